@@ -1,0 +1,241 @@
+/* xpoly_b200 -- C ABI of the B200-native simplex hot path.
+ *
+ * Drop-in boundary for the one hot path of stevenknown/xpoly's LP/MIP solvers:
+ * pricing -> min-ratio test -> tableau pivot (rank-1 elimination), FP64 and an
+ * exact fraction-free integer twin of the Rational simplex.  The reference has
+ * no FFI of its own (its API is C++ templates in src/com/lpsol.h); each entry
+ * point below names the reference interface it replaces, and
+ * xpoly_b200/host/xp_six.hpp wraps them with the reference's own signatures
+ * (SIX<Mat,T>::maxm/minm/TwoStageMethod/set_param, MIP<Mat,T>::maxm/minm).
+ * INTEGRATION.md shows the binding a maintainer adds.
+ *
+ * Conventions
+ *  - All matrices are dense row-major, element (r,c) at base[r*cols + c]
+ *    (the layout of xcom::Matrix<T>::m_mat, matt.h:152-156,289-295), so
+ *    FloatMat::get_matrix() / RMat::get_matrix() pointers pass straight in.
+ *  - Rationals are {int32 num; int32 den} pairs (xcom::Rational, rational.h:51-52).
+ *  - Return value >= 0 is the reference's own status code (lpsol.h:198-202,
+ *    :2082-2085); negative values are errors the reference cannot express.
+ *  - The library never frees or reallocates caller memory.  Device buffers are
+ *    owned by an xp_ctx; one ctx per host thread / CUDA stream.
+ *  - There is no CPU fallback: without a usable CUDA device every compute
+ *    entry point returns XP_ERR_CUDA.
+ */
+#ifndef XPOLY_B200_H
+#define XPOLY_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- status codes (lpsol.h:198-202) ---- */
+#define XP_SIX_SUCC 0
+#define XP_SIX_UNBOUND 1
+#define XP_SIX_NO_PRI_FEASIBLE_SOL 2
+#define XP_SIX_OPTIMAL_IS_INFEASIBLE 3
+#define XP_SIX_TIME_OUT 4
+/* ---- MIP status codes (lpsol.h:2082-2085) ---- */
+#define XP_IP_SUCC 0
+#define XP_IP_UNBOUND 1
+#define XP_IP_NO_PRI_FEASIBLE_SOL 2
+#define XP_IP_NO_BETTER_THAN_BEST_SOL 3
+/* ---- errors (never 0..4) ---- */
+#define XP_ERR_CUDA (-1)        /* CUDA runtime / no device; see xp_last_error */
+#define XP_ERR_BAD_ARG (-2)     /* dimensions / null pointers */
+#define XP_ERR_TOO_LARGE (-3)   /* LP does not fit the batched (shared-memory) path */
+#define XP_ERR_OVERFLOW (-4)    /* fraction-free path left int64 / result left int32 */
+#define XP_ERR_NCCL (-5)        /* NCCL unavailable or failed */
+#define XP_ERR_REFERENCE_UB (-100) /* the reference itself would hit undefined behaviour
+                                      (convertEq2Ineq lpsol.h:1232) */
+
+/* Pivot rule.  Only XP_RULE_REFERENCE has an oracle: lowest-index entering
+ * variable with c_j > 0 (lpsol.h:1054-1069), first strict minimum ratio row
+ * (lpsol.h:603-611), pair-tabu anti-cycling (lpsol.h:68-154). */
+#define XP_RULE_REFERENCE 0
+
+#define XP_NO_ITER_LIMIT 0xFFFFFFFFu /* SIX::set_param default, lpsol.h:260 */
+
+typedef struct xp_ctx xp_ctx;
+typedef struct {
+    int32_t num, den;
+} xp_rat;
+
+/* ------------------------------------------------------------------ context */
+int xp_ctx_create(int device, xp_ctx **out);
+void xp_ctx_destroy(xp_ctx *ctx);
+const char *xp_last_error(const xp_ctx *ctx);
+const char *xp_version(void);
+/* Kernel launches issued by this ctx since creation (for bench accounting). */
+uint64_t xp_ctx_launch_count(const xp_ctx *ctx);
+/* Device time in ms of the last solve call's kernel region, measured with CUDA
+ * events on the ctx stream (excludes H2D/D2H). */
+float xp_ctx_last_kernel_ms(const xp_ctx *ctx);
+void *xp_ctx_stream(const xp_ctx *ctx); /* cudaStream_t */
+
+/* ---------------------------------------------- kernel level: large FP64 LP
+ * Replaces SIX<FloatMat,Float>::solveSlackForm (lpsol.h:1007-1191) together
+ * with findPivotBV (:552), findPivotNVandBVPair (:670), pivot (:1455),
+ * PivotPairTab (:68) and is_feasible (:783) on an HBM-resident tableau.
+ *
+ * tableau m x C (C = rhs_idx+1) and tgtf 1 x C are updated in place exactly as
+ * the reference leaves them; nvset/bvset (rhs_idx bytes), bv2eq (rhs_idx),
+ * eq2bv (m) are the reference's Vector<bool>/Vector<INT> basis maps.
+ * vc_diag/vc_rhs: the diagonal and constant column of 'vc' (rhs_idx entries,
+ * the only parts is_feasible reads, lpsol.h:799); NULL means -1 / 0.
+ * sol: C entries.  pivot_log (optional): up to log_cap {nv, bv, row} triples.
+ */
+int xp_six_slack_f64(xp_ctx *ctx, double *tableau, double *tgtf, int m, int C, uint8_t *nvset,
+                     uint8_t *bvset, int32_t *bv2eq, int32_t *eq2bv, const double *vc_diag,
+                     const double *vc_rhs, uint32_t max_iter, int rule, double *maxv, double *sol,
+                     uint32_t *iters, int32_t *pivot_log, uint32_t log_cap);
+
+/* Device-resident handle for the same path: upload once, run K pivots at a
+ * time (resume semantics: the tabu table and iteration count persist until the
+ * next upload), download state.  This is what bench.py times for `value`. */
+typedef struct xp_lp_f64 xp_lp_f64;
+int xp_lp_f64_create(xp_ctx *ctx, int m, int C, xp_lp_f64 **out);
+void xp_lp_f64_destroy(xp_lp_f64 *lp);
+int xp_lp_f64_upload(xp_lp_f64 *lp, const double *tableau, const double *tgtf,
+                     const uint8_t *nvset, const uint8_t *bvset, const int32_t *bv2eq,
+                     const int32_t *eq2bv, const double *vc_diag, const double *vc_rhs);
+/* Build the slack form [A | I | b] of a normalised LP (leq m x (n+1), b >= 0)
+ * directly on the device: SIX::slack + the identity basis of stage1
+ * (lpsol.h:1405-1433, :1821-1841).  Requires C == n + m + 1. */
+int xp_lp_f64_upload_leq(xp_lp_f64 *lp, const double *leq, const double *tgtf, int n);
+/* Fill with the synthetic dense family of SURVEY 8(d) on the device
+ * (A_ij~U(0,1), b_i = 1 + U*n, c_j~U(0,1); counter-based generator). */
+int xp_lp_f64_fill_synthetic(xp_lp_f64 *lp, uint64_t seed);
+/* Run until a terminal status or until the total iteration count reaches
+ * max_iter (SIX_TIME_OUT).  Returns the status. */
+int xp_lp_f64_solve(xp_lp_f64 *lp, uint32_t max_iter, int rule);
+int xp_lp_f64_download(xp_lp_f64 *lp, double *tableau, double *tgtf, uint8_t *nvset,
+                       uint8_t *bvset, int32_t *bv2eq, int32_t *eq2bv, double *maxv, double *sol,
+                       uint32_t *iters, int32_t *pivot_log, uint32_t log_cap);
+/* Order-independent 64-bit checksum of the device tableau bits (parity at full size). */
+int xp_lp_f64_checksum(xp_lp_f64 *lp, uint64_t *sum_tableau, uint64_t *sum_tgtf);
+/* Column-sharded multi-GPU: attach an NCCL communicator built from a unique id
+ * that rank 0 obtained with xp_nccl_unique_id and shared out of band.  After
+ * this, create/upload/solve operate on this rank's column slice
+ * [rank*C/n, (rank+1)*C/n) plus a replica of the constant column. */
+int xp_nccl_unique_id(void *id128);
+int xp_ctx_attach_nccl(xp_ctx *ctx, const void *id128, int rank, int nranks);
+
+/* ------------------------------------------ TwoStageMethod level: batched FP64
+ * Replaces SIX<FloatMat,Float>::TwoStageMethod (lpsol.h:1906-1930: stage1,
+ * slack, constructBasicFeasibleSolution, solveSlackForm) for a batch of
+ * independent normalised LPs (x >= 0, no equalities), one CTA per LP with the
+ * tableau in shared memory.
+ *
+ * Uniform batch: every LP has leq m x (n+1) at leq + k*m*(n+1) and tgtf 1 x (n+1)
+ * at tgtf + k*(n+1).  Outputs per LP k (any may be NULL): status[k];
+ * maxv[k] = tgtf[rhs] (lpsol.h:1119); slack_sol[k*ldo .. ] (ldo = n+m+1 entries);
+ * tgtf_out[k*ldo ..] the final objective row (needed by minm, lpsol.h:1713-1716);
+ * eq2bv[k*m ..]; iters[k] main-loop iteration count; pivots[k] all pivot() calls.
+ */
+int xp_six_two_stage_f64_batch(xp_ctx *ctx, int batch, int m, int n, const double *leq,
+                               const double *tgtf, uint32_t max_iter, int rule, int32_t *status,
+                               double *maxv, double *slack_sol, double *tgtf_out, int32_t *eq2bv,
+                               uint32_t *iters, uint32_t *pivots);
+/* Same with device pointers for every array (inputs already resident in HBM). */
+int xp_six_two_stage_f64_batch_dev(xp_ctx *ctx, int batch, int m, int n, const double *d_leq,
+                                   const double *d_tgtf, uint32_t max_iter, int rule,
+                                   int32_t *d_status, double *d_maxv, double *d_slack_sol,
+                                   double *d_tgtf_out, int32_t *d_eq2bv, uint32_t *d_iters,
+                                   uint32_t *d_pivots);
+/* Ragged batch: LP k has ms[k] rows, ns[k] variables, data at leq + leq_off[k],
+ * tgtf + tgtf_off[k]; outputs use stride ldo >= max(ns+ms)+1 and ldm >= max(ms). */
+int xp_six_two_stage_f64_ragged(xp_ctx *ctx, int batch, const int32_t *ms, const int32_t *ns,
+                                const int64_t *leq_off, const int64_t *tgtf_off,
+                                const double *leq, size_t leq_len, const double *tgtf,
+                                size_t tgtf_len, uint32_t max_iter, int rule, int ldo, int ldm,
+                                int32_t *status, double *maxv, double *slack_sol,
+                                double *tgtf_out, int32_t *eq2bv, uint32_t *iters,
+                                uint32_t *pivots);
+
+/* ------------------------- TwoStageMethod level: batched exact (fraction-free)
+ * The exact twin of SIX<RMat,Rational>::TwoStageMethod: integer tableau N with
+ * one common denominator D per LP (a_ij = N_ij / D), int64 entries, 128-bit
+ * products, exact division; same pivot rule / tabu table / phase 1.  Inputs are
+ * integer matrices (int64).  Outputs are reduced num/den pairs (int64) equal to
+ * the reference's reduced Rational whenever the reference did not overflow
+ * int32 (its appro() path, rational.cpp:189-226).  status XP_ERR_OVERFLOW marks
+ * an LP whose entries left int64.
+ */
+int xp_six_two_stage_i64_batch(xp_ctx *ctx, int batch, int m, int n, const int64_t *leq,
+                               const int64_t *tgtf, uint32_t max_iter, int rule, int32_t *status,
+                               int64_t *maxv_num_den /* 2 per LP */,
+                               int64_t *slack_sol_num /* ldo per LP */,
+                               int64_t *slack_sol_den /* ldo per LP */,
+                               int64_t *tgtf_out_num, int64_t *tgtf_out_den, int32_t *eq2bv,
+                               uint32_t *iters, uint32_t *pivots);
+int xp_six_two_stage_i64_ragged(xp_ctx *ctx, int batch, const int32_t *ms, const int32_t *ns,
+                                const int64_t *leq_off, const int64_t *tgtf_off,
+                                const int64_t *leq, size_t leq_len, const int64_t *tgtf,
+                                size_t tgtf_len, uint32_t max_iter, int rule, int ldo, int ldm,
+                                int32_t *status, int64_t *maxv_num_den, int64_t *slack_sol_num,
+                                int64_t *slack_sol_den, int64_t *tgtf_out_num,
+                                int64_t *tgtf_out_den, int32_t *eq2bv, uint32_t *iters,
+                                uint32_t *pivots);
+
+/* ------------------------------------------------------------- entry level
+ * Replace SIX<FloatMat,Float>::maxm / minm (lpsol.h:1992 / :1661) and
+ * SIX<RMat,Rational>::maxm / minm: verify, normalize (eq -> ineq, free-variable
+ * split), [explicit dual for min], TwoStageMethod on the GPU, calcFinalSolution.
+ * tgtf 1 x (n+1); vc n x (n+1) or NULL (= -I | 0); eq k x (n+1) (k may be 0);
+ * leq m x (n+1).  sol: n+1 entries, written on XP_SIX_SUCC.  eq2bv_out
+ * (optional, capacity m + 2k): the final basis, which the reference only
+ * exposes through TwoStageMethod.
+ */
+int xp_six_maxm_f64(xp_ctx *ctx, int m, int n, const double *tgtf, const double *vc, int k,
+                    const double *eq, const double *leq, uint32_t max_iter, double *maxv,
+                    double *sol, int32_t *eq2bv_out);
+int xp_six_minm_f64(xp_ctx *ctx, int m, int n, const double *tgtf, const double *vc, int k,
+                    const double *eq, const double *leq, uint32_t max_iter, double *minv,
+                    double *sol, int32_t *eq2bv_out);
+int xp_six_maxm_rat(xp_ctx *ctx, int m, int n, const xp_rat *tgtf, const xp_rat *vc, int k,
+                    const xp_rat *eq, const xp_rat *leq, uint32_t max_iter, xp_rat *maxv,
+                    xp_rat *sol, int32_t *eq2bv_out);
+int xp_six_minm_rat(xp_ctx *ctx, int m, int n, const xp_rat *tgtf, const xp_rat *vc, int k,
+                    const xp_rat *eq, const xp_rat *leq, uint32_t max_iter, xp_rat *minv,
+                    xp_rat *sol, int32_t *eq2bv_out);
+
+/* Batched entry level (uniform shape, vc = -I, no equalities): what a caller
+ * with many independent LPs uses; `is_min` selects minm.  sol: batch x (n+1). */
+int xp_six_solve_f64_batch(xp_ctx *ctx, int is_min, int batch, int m, int n, const double *tgtf,
+                           const double *leq, uint32_t max_iter, int32_t *status, double *v,
+                           double *sol);
+int xp_six_solve_rat_batch(xp_ctx *ctx, int is_min, int batch, int m, int n, const xp_rat *tgtf,
+                           const xp_rat *leq, uint32_t max_iter, int32_t *status, xp_rat *v,
+                           xp_rat *sol);
+
+/* MIP<Mat,T>::maxm / minm (lpsol.h:2635 / :2680): depth-first branch & bound
+ * replayed on the host in the reference's order (fork_count, m_cur_best_v are
+ * order dependent, lpsol.h:2474-2497) with node LP relaxations solved on the
+ * GPU.  vc must be -I | 0 (MIP::verify, lpsol.h:2349-2358).  n_nodes (optional)
+ * returns the number of node LPs solved. */
+int xp_mip_solve_rat(xp_ctx *ctx, int is_min, int is_bin, int m, int n, const xp_rat *tgtf,
+                     int k, const xp_rat *eq, const xp_rat *leq, xp_rat *v, xp_rat *sol,
+                     int32_t *n_nodes);
+int xp_mip_solve_f64(xp_ctx *ctx, int is_min, int is_bin, int m, int n, const double *tgtf, int k,
+                     const double *eq, const double *leq, double *v, double *sol,
+                     int32_t *n_nodes);
+/* A batch of independent MIPs of one shape (config 5: knapsack-style B&B):
+ * all trees advance together, each wave of node relaxations is one batched
+ * GPU call, decisions are replayed per tree in DFS order. */
+int xp_mip_solve_rat_batch(xp_ctx *ctx, int is_min, int is_bin, int batch, int m, int n,
+                           const xp_rat *tgtf, const xp_rat *leq, int32_t *status, xp_rat *v,
+                           xp_rat *sol, int32_t *n_nodes);
+
+/* Lineq::has_solution (linsys.cpp:830-906) for a batch of independent
+ * dependence-feasibility systems of one shape (vc = -I, no equalities).
+ * result[k] = 1 / 0. */
+int xp_has_solution_rat_batch(xp_ctx *ctx, int batch, int m, int n, const xp_rat *leq,
+                              int is_int_sol, int is_unique_sol, int32_t *result);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XPOLY_B200_H */

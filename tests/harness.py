@@ -219,3 +219,33 @@ def appro_count(which):
 def bits(a):
     """float64 array -> uint64 view for bit-exact comparison."""
     return np.ascontiguousarray(a, dtype=np.float64).view(np.uint64)
+
+
+def slack_solve_oracle(kind, tab, tgtf, nvset, bvset, bv2eq, eq2bv, max_iter=NO_LIMIT,
+                       vc_diag=None, vc_rhs=None, log_cap=1 << 16):
+    """xo_slack_*: SIX::solveSlackForm alone on a caller-built slack form."""
+    lib = oracle()
+    m, Cc = tab.shape[0], tab.shape[1]
+    if kind == "f64":
+        tab = np.ascontiguousarray(tab, dtype=np.float64).copy()
+        tgtf = np.ascontiguousarray(tgtf, dtype=np.float64).copy()
+        maxv = np.zeros(1)
+        sol = np.zeros(Cc)
+    else:
+        tab = np.ascontiguousarray(tab, dtype=np.int32).copy()
+        tgtf = np.ascontiguousarray(tgtf, dtype=np.int32).copy()
+        maxv = np.zeros(2, dtype=np.int32)
+        sol = np.zeros((Cc, 2), dtype=np.int32)
+    nvset = np.ascontiguousarray(nvset, dtype=np.uint8).copy()
+    bvset = np.ascontiguousarray(bvset, dtype=np.uint8).copy()
+    bv2eq = np.ascontiguousarray(bv2eq, dtype=np.int32).copy()
+    eq2bv = np.ascontiguousarray(eq2bv, dtype=np.int32).copy()
+    iters = np.zeros(1, dtype=np.uint32)
+    log = np.zeros((max(log_cap, 1), 4), dtype=np.int32)
+    nlog = C.c_int(0)
+    st = getattr(lib, f"xo_slack_{kind}")(
+        m, Cc, P(tab), P(tgtf), P(nvset), P(bvset), P(bv2eq), P(eq2bv), P(vc_diag), P(vc_rhs),
+        C.c_uint32(max_iter), P(maxv), P(sol), P(iters), P(log), log_cap, C.byref(nlog))
+    return dict(status=st, tab=tab, tgtf=tgtf, nvset=nvset, bvset=bvset, bv2eq=bv2eq,
+                eq2bv=eq2bv, maxv=maxv, sol=sol, iters=int(iters[0]),
+                log=log[: min(nlog.value, log_cap), 1:].copy())

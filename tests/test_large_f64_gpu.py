@@ -1,0 +1,129 @@
+"""Parity of the HBM-resident FP64 path (xp_six_slack_f64 / xp_lp_f64_*) against
+the oracle's solveSlackForm, bit for bit: status, iteration count, pivot
+sequence, basis maps, whole tableau, objective row, solution."""
+import numpy as np
+import pytest
+
+import harness as H
+import xpoly_b200 as xp
+
+pytestmark = pytest.mark.gpu
+
+
+def assert_same_state(g, o, tag):
+    assert g["status"] == o["status"], (tag, g["status"], o["status"])
+    assert g["iters"] == o["iters"], (tag, g["iters"], o["iters"])
+    assert np.array_equal(g["log"], o["log"][: len(g["log"])]), (tag, "pivot sequence")
+    for k in ("eq2bv", "bv2eq", "nvset", "bvset"):
+        assert np.array_equal(g[k], o[k]), (tag, k)
+    for k in ("tab", "tgtf", "maxv", "sol"):
+        assert np.array_equal(H.bits(g[k]), H.bits(o[k])), (tag, k)
+
+
+def run_both(ctx, leq, tgtf, max_iter=H.NO_LIMIT, tag=None):
+    sf = xp.slack_form(leq, tgtf)
+    g = ctx.six_slack_f64(*sf, max_iter=max_iter, log_cap=1 << 16)
+    o = H.slack_solve_oracle("f64", *sf, max_iter=max_iter)
+    assert_same_state(g, o, tag)
+    return g
+
+
+@pytest.mark.parametrize("m,n", [(2, 2), (6, 5), (8, 7), (10, 9), (16, 15), (33, 20), (7, 40)])
+def test_small_dense_to_termination(ctx, m, n):
+    seen = set()
+    for seed in range(12):
+        leq, tg = H.gen_dense_lp(5000 + seed, m, n)
+        seen.add(run_both(ctx, leq, tg, tag=("dense", m, n, seed))["status"])
+    assert seen <= {0, 1, 3}
+
+
+@pytest.mark.parametrize("m,n", [(6, 5), (10, 9), (16, 15), (12, 30)])
+def test_mixed_sign_exhausts_tabu_table(ctx, m, n):
+    """Mixed-sign data drives the retry (disableNV), pass-2 ratio test and
+    findPivotNVandBVPair fallback paths; unbounded LPs exit by tabu exhaustion."""
+    seen = set()
+    for seed in range(10):
+        leq, tg = H.gen_mixed_lp(seed, m, n)
+        leq[:, n] = np.abs(leq[:, n])
+        seen.add(run_both(ctx, leq, tg, tag=("mixed", m, n, seed))["status"])
+    assert 1 in seen
+
+
+@pytest.mark.parametrize("K", [0, 1, 2, 5, 17])
+def test_bounded_iterations_state(ctx, K):
+    leq, tg = H.gen_dense_lp(777, 24, 23)
+    g = run_both(ctx, leq, tg, max_iter=K, tag=("K", K))
+    assert g["status"] in (0, 3, 4)
+
+
+def test_odd_column_count_scalar_path(ctx):
+    for seed in range(6):
+        leq, tg = H.gen_dense_lp(900 + seed, 9, 8)  # C = 8 + 9 + 1 = 18 even
+        run_both(ctx, leq, tg, tag=("even", seed))
+        leq, tg = H.gen_dense_lp(900 + seed, 9, 9)  # C = 19 odd
+        run_both(ctx, leq, tg, tag=("odd", seed))
+
+
+def test_c1_256x512_golden(ctx):
+    """256x255 seeded instance, 14 pivots, SIX_SUCC."""
+    leq, tg = H.gen_dense_lp(12345, 256, 255)
+    g = run_both(ctx, leq, tg, tag="c1")
+    assert g["status"] == 0 and g["iters"] == 14
+    assert [tuple(r) for r in g["log"][:5]] == [(0, 493, 238), (1, 408, 153), (2, 302, 47),
+                                                (5, 1, 153), (29, 2, 47)]
+
+
+def test_medium_wandering_regime(ctx):
+    """512 x 1024 tableau, 120 pivots: past pivot ~26 the tabu rule leaves the
+    feasible region; state must still match bit for bit."""
+    leq, tg = H.gen_dense_lp(4242, 512, 511)
+    run_both(ctx, leq, tg, max_iter=120, tag="wander")
+
+
+def test_resume_equals_single_run(ctx):
+    leq, tg = H.gen_dense_lp(31337, 128, 127)
+    sf = xp.slack_form(leq, tg)
+    lp = ctx.large_lp(*sf[0].shape)
+    lp.upload(*sf)
+    assert lp.solve(10) == xp.SIX_TIME_OUT
+    assert lp.solve(25) == xp.SIX_TIME_OUT
+    a = lp.download(log_cap=64)
+    o = H.slack_solve_oracle("f64", *sf, max_iter=25)
+    assert a["iters"] == 25 and np.array_equal(a["log"], o["log"])
+    assert np.array_equal(H.bits(a["tab"]), H.bits(o["tab"]))
+    assert np.array_equal(H.bits(a["tgtf"]), H.bits(o["tgtf"]))
+    lp.close()
+
+
+def test_upload_leq_device_slack_form(ctx):
+    leq, tg = H.gen_dense_lp(99, 40, 39)
+    sf = xp.slack_form(leq, tg)
+    lp = ctx.large_lp(*sf[0].shape)
+    lp.upload_leq(leq, tg)
+    st = lp.solve()
+    a = lp.download(log_cap=4096)
+    o = H.slack_solve_oracle("f64", *sf)
+    assert st == o["status"] and a["iters"] == o["iters"]
+    assert np.array_equal(H.bits(a["tab"]), H.bits(o["tab"]))
+    lp.close()
+
+
+def test_linearity_property_full_size_sample(ctx):
+    """Size-independent property used at BASELINE sizes: K pivots leave every
+    basic column a unit vector (up to round-off) and checksum is reproducible."""
+    m, n = 1024, 1023
+    lp = ctx.large_lp(m, n + m + 1)
+    lp.fill_synthetic(7)
+    lp.solve(20)
+    c1 = lp.checksum()
+    lp.fill_synthetic(7)
+    lp.solve(20)
+    c2 = lp.checksum()
+    assert c1 == c2
+    a = lp.download()
+    tab = a["tab"]
+    for r, bv in enumerate(a["eq2bv"]):
+        col = tab[:, bv]
+        assert abs(col[r] - 1.0) < 1e-9
+        assert np.abs(np.delete(col, r)).max() < 1e-9
+    lp.close()

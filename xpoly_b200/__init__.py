@@ -1,0 +1,220 @@
+"""xpoly_b200: ctypes binding of the B200-native simplex hot path (C ABI in
+include/xpoly_b200.h).  Python is only the test / bench harness language here;
+the product is libxpoly_b200.so plus the C++ adaptor in xpoly_b200/host/.
+
+There is no CPU fallback: if the shared library is missing, or no CUDA device
+is usable, the calls below raise.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libxpoly_b200.so")
+
+SIX_SUCC, SIX_UNBOUND, SIX_NO_PRI_FEASIBLE_SOL, SIX_OPTIMAL_IS_INFEASIBLE, SIX_TIME_OUT = range(5)
+IP_SUCC, IP_UNBOUND, IP_NO_PRI_FEASIBLE_SOL, IP_NO_BETTER_THAN_BEST_SOL = range(4)
+ERR_CUDA, ERR_BAD_ARG, ERR_TOO_LARGE, ERR_OVERFLOW, ERR_NCCL = -1, -2, -3, -4, -5
+ERR_REFERENCE_UB = -100
+RULE_REFERENCE = 0
+NO_ITER_LIMIT = 0xFFFFFFFF
+
+_vp = C.c_void_p
+_lib = None
+
+
+class XpolyError(RuntimeError):
+    pass
+
+
+def lib():
+    """The loaded C-ABI library.  Raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise XpolyError(
+                f"{LIB_PATH} is missing: run `python -m xpoly_b200.build` "
+                "(xpoly_b200 has no CPU fallback)")
+        _lib = C.CDLL(LIB_PATH)
+        _lib.xp_last_error.restype = C.c_char_p
+        _lib.xp_version.restype = C.c_char_p
+        _lib.xp_ctx_launch_count.restype = C.c_uint64
+        _lib.xp_ctx_last_kernel_ms.restype = C.c_float
+        _lib.xp_ctx_stream.restype = _vp
+        for name in ("xp_ctx_destroy", "xp_lp_f64_destroy"):
+            getattr(_lib, name).restype = None
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(_vp)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+class Context:
+    """One xp_ctx: a CUDA device + stream + reusable device scratch."""
+
+    def __init__(self, device=0):
+        self._h = _vp()
+        rc = lib().xp_ctx_create(int(device), C.byref(self._h))
+        if rc != 0:
+            msg = lib().xp_last_error(self._h).decode() if self._h else "xp_ctx_create failed"
+            if self._h:
+                lib().xp_ctx_destroy(self._h)
+                self._h = _vp()
+            raise XpolyError(msg)
+
+    def close(self):
+        if self._h:
+            lib().xp_ctx_destroy(self._h)
+            self._h = _vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def check(self, rc):
+        """Negative codes are errors; statuses (>= 0) pass through."""
+        if rc < 0 and rc not in (ERR_REFERENCE_UB, ERR_OVERFLOW, ERR_TOO_LARGE):
+            raise XpolyError(f"xpoly_b200 error {rc}: {lib().xp_last_error(self._h).decode()}")
+        return rc
+
+    @property
+    def launches(self):
+        return int(lib().xp_ctx_launch_count(self._h))
+
+    @property
+    def last_kernel_ms(self):
+        return float(lib().xp_ctx_last_kernel_ms(self._h))
+
+    @property
+    def stream(self):
+        return lib().xp_ctx_stream(self._h)
+
+    # ---- kernel level: SIX::solveSlackForm on a caller-built slack form ----
+    def six_slack_f64(self, tab, tgtf, nvset, bvset, bv2eq, eq2bv, max_iter=NO_ITER_LIMIT,
+                      vc_diag=None, vc_rhs=None, log_cap=0):
+        """In place on copies of the inputs; returns a dict of the outputs."""
+        tab = _f64(tab).copy()
+        tgtf = _f64(tgtf).copy()
+        m, Cc = tab.shape
+        nvset = np.ascontiguousarray(nvset, dtype=np.uint8).copy()
+        bvset = np.ascontiguousarray(bvset, dtype=np.uint8).copy()
+        bv2eq = np.ascontiguousarray(bv2eq, dtype=np.int32).copy()
+        eq2bv = np.ascontiguousarray(eq2bv, dtype=np.int32).copy()
+        maxv = np.zeros(1)
+        sol = np.zeros(Cc)
+        iters = np.zeros(1, dtype=np.uint32)
+        log = np.zeros((max(log_cap, 1), 3), dtype=np.int32)
+        st = self.check(lib().xp_six_slack_f64(
+            self._h, _p(tab), _p(tgtf), m, Cc, _p(nvset), _p(bvset), _p(bv2eq), _p(eq2bv),
+            _p(None if vc_diag is None else _f64(vc_diag)),
+            _p(None if vc_rhs is None else _f64(vc_rhs)), C.c_uint32(max_iter), RULE_REFERENCE,
+            _p(maxv), _p(sol), _p(iters), _p(log) if log_cap else None, C.c_uint32(log_cap)))
+        n_it = int(iters[0])
+        return dict(status=st, tab=tab, tgtf=tgtf, nvset=nvset, bvset=bvset, bv2eq=bv2eq,
+                    eq2bv=eq2bv, maxv=maxv, sol=sol, iters=n_it, log=log[:min(n_it, log_cap)])
+
+    def large_lp(self, m, Cc):
+        return LargeLP(self, m, Cc)
+
+
+class LargeLP:
+    """Device-resident FP64 slack-form LP (xp_lp_f64 handle)."""
+
+    def __init__(self, ctx, m, Cc):
+        self.ctx, self.m, self.C = ctx, m, Cc
+        self._h = _vp()
+        ctx.check(lib().xp_lp_f64_create(ctx._h, m, Cc, C.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            lib().xp_lp_f64_destroy(self._h)
+            self._h = _vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def upload(self, tab, tgtf, nvset, bvset, bv2eq, eq2bv, vc_diag=None, vc_rhs=None):
+        self.ctx.check(lib().xp_lp_f64_upload(
+            self._h, _p(_f64(tab)), _p(_f64(tgtf)),
+            _p(np.ascontiguousarray(nvset, dtype=np.uint8)),
+            _p(np.ascontiguousarray(bvset, dtype=np.uint8)),
+            _p(np.ascontiguousarray(bv2eq, dtype=np.int32)),
+            _p(np.ascontiguousarray(eq2bv, dtype=np.int32)),
+            _p(None if vc_diag is None else _f64(vc_diag)),
+            _p(None if vc_rhs is None else _f64(vc_rhs))))
+
+    def upload_leq(self, leq, tgtf):
+        leq = _f64(leq)
+        n = leq.shape[1] - 1
+        self.ctx.check(lib().xp_lp_f64_upload_leq(self._h, _p(leq), _p(_f64(tgtf)), n))
+
+    def fill_synthetic(self, seed):
+        self.ctx.check(lib().xp_lp_f64_fill_synthetic(self._h, C.c_uint64(seed)))
+
+    def solve(self, max_iter=NO_ITER_LIMIT):
+        return self.ctx.check(lib().xp_lp_f64_solve(self._h, C.c_uint32(max_iter), RULE_REFERENCE))
+
+    def checksum(self):
+        a, b = C.c_uint64(0), C.c_uint64(0)
+        self.ctx.check(lib().xp_lp_f64_checksum(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def download(self, want_tab=True, log_cap=0):
+        m, Cc = self.m, self.C
+        n = Cc - 1
+        tab = np.zeros((m, Cc)) if want_tab else None
+        tgtf = np.zeros(Cc)
+        nvset = np.zeros(n, dtype=np.uint8)
+        bvset = np.zeros(n, dtype=np.uint8)
+        bv2eq = np.zeros(n, dtype=np.int32)
+        eq2bv = np.zeros(m, dtype=np.int32)
+        maxv = np.zeros(1)
+        sol = np.zeros(Cc)
+        iters = np.zeros(1, dtype=np.uint32)
+        log = np.zeros((max(log_cap, 1), 3), dtype=np.int32)
+        self.ctx.check(lib().xp_lp_f64_download(
+            self._h, _p(tab), _p(tgtf), _p(nvset), _p(bvset), _p(bv2eq), _p(eq2bv), _p(maxv),
+            _p(sol), _p(iters), _p(log) if log_cap else None, C.c_uint32(log_cap)))
+        n_it = int(iters[0])
+        return dict(tab=tab, tgtf=tgtf, nvset=nvset, bvset=bvset, bv2eq=bv2eq, eq2bv=eq2bv,
+                    maxv=maxv, sol=sol, iters=n_it, log=log[:min(n_it, log_cap)])
+
+
+def slack_form(leq, tgtf):
+    """Host-side SIX::slack + identity basis (lpsol.h:1405-1433, :1821-1841) for a
+    normalised LP: returns tab [A | I | b], tgtf, nvset, bvset, bv2eq, eq2bv."""
+    leq = _f64(leq)
+    m, n1 = leq.shape
+    n = n1 - 1
+    Cc = n + m + 1
+    tab = np.zeros((m, Cc))
+    tab[:, :n] = leq[:, :n]
+    tab[:, n:n + m] = np.eye(m)
+    tab[:, Cc - 1] = leq[:, n]
+    tg = np.zeros(Cc)
+    tg[:n] = np.asarray(tgtf, dtype=np.float64)[:n]
+    tg[Cc - 1] = np.asarray(tgtf, dtype=np.float64)[n]
+    nvset = np.zeros(Cc - 1, dtype=np.uint8)
+    nvset[:n] = 1
+    bvset = (1 - nvset).astype(np.uint8)
+    bv2eq = np.full(Cc - 1, -1, dtype=np.int32)
+    bv2eq[n:] = np.arange(m, dtype=np.int32)
+    eq2bv = (n + np.arange(m)).astype(np.int32)
+    return tab, tg, nvset, bvset, bv2eq, eq2bv
