@@ -74,6 +74,10 @@ uint64_t xp_ctx_launch_count(const xp_ctx *ctx);
  * events on the ctx stream (excludes H2D/D2H). */
 float xp_ctx_last_kernel_ms(const xp_ctx *ctx);
 void *xp_ctx_stream(const xp_ctx *ctx); /* cudaStream_t */
+/* Page-locked host memory (cudaMallocHost) so uploads/downloads of a large
+ * tableau run at full PCIe rate; plain malloc'ed buffers work too, slower. */
+int xp_host_alloc(xp_ctx *ctx, size_t bytes, void **out);
+int xp_host_free(xp_ctx *ctx, void *p);
 
 /* ---------------------------------------------- kernel level: large FP64 LP
  * Replaces SIX<FloatMat,Float>::solveSlackForm (lpsol.h:1007-1191) together

@@ -1,0 +1,114 @@
+"""Parity of the one-CTA-per-LP FP64 kernel (xp_six_two_stage_f64_batch /
+_ragged) against the oracle's TwoStageMethod, bit for bit per LP: status,
+objective, slack solution, final objective row, basis, pivot count."""
+import numpy as np
+import pytest
+
+import harness as H
+import xpoly_b200 as xp
+
+pytestmark = pytest.mark.gpu
+
+
+def oracle_batch(lps, max_iter=H.NO_LIMIT):
+    return [H.two_stage("oracle", "f64", l, t, max_iter, want_log=True) for l, t in lps]
+
+
+def check_lp(g, k, o, m, n, tag):
+    assert g["status"][k] == o["status"], (tag, k, g["status"][k], o["status"])
+    assert g["pivots"][k] == len(o["log"]), (tag, k, "pivots", g["pivots"][k], len(o["log"]))
+    if o["status"] == H.SIX_NO_PRI:
+        return
+    Cc = o["cols"]
+    assert Cc == n + m + 1
+    assert np.array_equal(g["eq2bv"][k][:m], o["eq2bv"]), (tag, k, "eq2bv")
+    assert np.array_equal(H.bits(g["tgtf"][k][:Cc]), H.bits(o["tgtf"])), (tag, k, "tgtf")
+    assert np.array_equal(H.bits(g["maxv"][k:k + 1]), H.bits(o["maxv"])), (tag, k, "maxv")
+    assert np.array_equal(H.bits(g["slack_sol"][k][:Cc]), H.bits(o["slack_sol"])), (tag, k, "sol")
+
+
+def run_uniform(ctx, lps, max_iter=H.NO_LIMIT, tag=None):
+    leq = np.stack([l for l, _ in lps])
+    tg = np.stack([t for _, t in lps])
+    g = ctx.two_stage_f64_batch(leq, tg, max_iter)
+    m, n = leq.shape[1], leq.shape[2] - 1
+    for k, o in enumerate(oracle_batch(lps, max_iter)):
+        check_lp(g, k, o, m, n, tag)
+    return g
+
+
+def test_c2_shape_dense_32x64(ctx):
+    """Config 2 shape (tableau 32x64), SURVEY 8(d) distribution: status mix SUCC /
+    OPTIMAL_IS_INFEASIBLE / UNBOUND must match per LP."""
+    lps = [H.gen_dense_lp(2024 + k, 32, 31) for k in range(300)]
+    g = run_uniform(ctx, lps, tag="c2")
+    assert set(np.unique(g["status"])) <= {0, 1, 3}
+    assert (g["status"] == 0).sum() > 50 and (g["status"] == 3).sum() > 50
+
+
+@pytest.mark.parametrize("m,n", [(1, 1), (2, 2), (3, 7), (8, 7), (16, 15), (24, 23), (40, 20)])
+def test_phase1_and_mixed_sign(ctx, m, n):
+    """Negative constant terms / no positive cost force the auxiliary LP
+    (constructBasicFeasibleSolution): forced pivot, aux solve, xa pivot-out,
+    objective substitution, column deletion."""
+    lps = [H.gen_mixed_lp(100 * m + k, m, n, bneg=0.3) for k in range(60)]
+    lps += [H.gen_mixed_lp(7000 + 100 * m + k, m, n) for k in range(40)]
+    g = run_uniform(ctx, lps, tag=("phase1", m, n))
+    if m >= 8:
+        assert H.SIX_NO_PRI in set(g["status"].tolist())
+
+
+def test_bounded_iterations(ctx):
+    lps = [H.gen_dense_lp(5 + k, 16, 15) for k in range(40)]
+    for K in (0, 1, 3, 7):
+        run_uniform(ctx, lps, max_iter=K, tag=("K", K))
+
+
+def test_integer_data_dependence_style(ctx):
+    """Small integer data (A in {-1,0,1,2}, 30% dense, b in [0,20]) resembling
+    dependence polyhedra (second c2 family)."""
+    lps = [H.gen_int_lp(31 + k, 12, 8, alo=-1, ahi=2, density=0.3, blo=0, bhi=20) for k in range(200)]
+    run_uniform(ctx, lps, tag="dep")
+
+
+def test_ragged_batch(ctx):
+    r = np.random.RandomState(5)
+    lps = []
+    for k in range(150):
+        m, n = int(r.randint(1, 20)), int(r.randint(1, 20))
+        lps.append(H.gen_mixed_lp(900 + k, m, n, bneg=0.2) if k % 2 else H.gen_dense_lp(900 + k, m, n))
+    g = ctx.two_stage_f64_ragged(lps)
+    for k, o in enumerate(oracle_batch(lps)):
+        check_lp(g, k, o, lps[k][0].shape[0], lps[k][0].shape[1] - 1, "ragged")
+
+
+def test_c5_node_shape_51x102(ctx):
+    """B&B node relaxation shape (knapsack row + x_j <= 1 rows, 50 variables)."""
+    lps = []
+    for k in range(6):
+        r = np.random.RandomState(99 + k)
+        n = 50
+        w = r.randint(5, 41, size=n)
+        p = r.randint(5, 61, size=n)
+        leq = np.zeros((n + 1, n + 1))
+        leq[0, :n] = w
+        leq[0, n] = int(w.sum() // 3)
+        for j in range(n):
+            leq[1 + j, j] = 1
+            leq[1 + j, n] = 1
+        tg = np.zeros(n + 1)
+        tg[:n] = p
+        lps.append((leq, tg))
+    run_uniform(ctx, lps, tag="c5")
+
+
+def test_empty_batch_and_too_large(ctx):
+    out = ctx.two_stage_f64_batch(np.zeros((0, 4, 5)), np.zeros((0, 5)))
+    assert out["status"].shape == (0,)
+    import ctypes as C
+    big = np.zeros((1, 400, 401))
+    rc = xp.lib().xp_six_two_stage_f64_batch(ctx._h, 1, 400, 400, big.ctypes.data_as(C.c_void_p),
+                                             np.zeros((1, 401)).ctypes.data_as(C.c_void_p),
+                                             C.c_uint32(10), 0, None, None, None, None, None, None,
+                                             None)
+    assert rc == xp.ERR_TOO_LARGE

@@ -218,3 +218,56 @@ def slack_form(leq, tgtf):
     bv2eq[n:] = np.arange(m, dtype=np.int32)
     eq2bv = (n + np.arange(m)).astype(np.int32)
     return tab, tg, nvset, bvset, bv2eq, eq2bv
+
+
+def _two_stage_f64_batch(self, leq, tgtf, max_iter=NO_ITER_LIMIT, want=("status", "maxv", "slack_sol",
+                                                                       "tgtf", "eq2bv", "iters",
+                                                                       "pivots")):
+    """SIX::TwoStageMethod for a uniform batch: leq [B, m, n+1], tgtf [B, n+1]."""
+    leq = _f64(leq)
+    tgtf = _f64(tgtf)
+    B, m, n1 = leq.shape
+    n = n1 - 1
+    ldo = n + m + 1
+    out = dict(
+        status=np.zeros(B, dtype=np.int32) if "status" in want else None,
+        maxv=np.zeros(B) if "maxv" in want else None,
+        slack_sol=np.zeros((B, ldo)) if "slack_sol" in want else None,
+        tgtf=np.zeros((B, ldo)) if "tgtf" in want else None,
+        eq2bv=np.zeros((B, m), dtype=np.int32) if "eq2bv" in want else None,
+        iters=np.zeros(B, dtype=np.uint32) if "iters" in want else None,
+        pivots=np.zeros(B, dtype=np.uint32) if "pivots" in want else None)
+    self.check(lib().xp_six_two_stage_f64_batch(
+        self._h, B, m, n, _p(leq), _p(tgtf), C.c_uint32(max_iter), RULE_REFERENCE,
+        _p(out["status"]), _p(out["maxv"]), _p(out["slack_sol"]), _p(out["tgtf"]),
+        _p(out["eq2bv"]), _p(out["iters"]), _p(out["pivots"])))
+    return out
+
+
+def _two_stage_f64_ragged(self, lps, max_iter=NO_ITER_LIMIT):
+    """lps: list of (leq [m, n+1], tgtf [n+1]) with arbitrary per-LP shapes."""
+    B = len(lps)
+    ms = np.array([l.shape[0] for l, _ in lps], dtype=np.int32)
+    ns = np.array([l.shape[1] - 1 for l, _ in lps], dtype=np.int32)
+    leq_pool = np.concatenate([_f64(l).ravel() for l, _ in lps])
+    tg_pool = np.concatenate([_f64(t).ravel() for _, t in lps])
+    leq_off = np.zeros(B, dtype=np.int64)
+    tg_off = np.zeros(B, dtype=np.int64)
+    leq_off[1:] = np.cumsum(ms[:-1].astype(np.int64) * (ns[:-1] + 1))
+    tg_off[1:] = np.cumsum(ns[:-1].astype(np.int64) + 1)
+    ldo = int((ms + ns).max()) + 1
+    ldm = int(ms.max())
+    out = dict(status=np.zeros(B, dtype=np.int32), maxv=np.zeros(B), slack_sol=np.zeros((B, ldo)),
+               tgtf=np.zeros((B, ldo)), eq2bv=np.zeros((B, ldm), dtype=np.int32),
+               iters=np.zeros(B, dtype=np.uint32), pivots=np.zeros(B, dtype=np.uint32))
+    self.check(lib().xp_six_two_stage_f64_ragged(
+        self._h, B, _p(ms), _p(ns), _p(leq_off), _p(tg_off), _p(leq_pool),
+        C.c_size_t(leq_pool.size), _p(tg_pool), C.c_size_t(tg_pool.size), C.c_uint32(max_iter),
+        RULE_REFERENCE, ldo, ldm, _p(out["status"]), _p(out["maxv"]), _p(out["slack_sol"]),
+        _p(out["tgtf"]), _p(out["eq2bv"]), _p(out["iters"]), _p(out["pivots"])))
+    out["ms"], out["ns"] = ms, ns
+    return out
+
+
+Context.two_stage_f64_batch = _two_stage_f64_batch
+Context.two_stage_f64_ragged = _two_stage_f64_ragged

@@ -64,3 +64,19 @@ int xp_ctx_scratch(xp_ctx *ctx, size_t bytes, void **out)
     *out = ctx->scratch;
     return 0;
 }
+
+// Pinned host buffers for callers that want full-rate H2D/D2H on the large path.
+extern "C" int xp_host_alloc(xp_ctx *ctx, size_t bytes, void **out)
+{
+    if (!ctx || !out) return XP_ERR_BAD_ARG;
+    XP_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    XP_CUDA_OK(ctx, cudaMallocHost(out, bytes));
+    return 0;
+}
+
+extern "C" int xp_host_free(xp_ctx *ctx, void *p)
+{
+    if (!ctx) return XP_ERR_BAD_ARG;
+    XP_CUDA_OK(ctx, cudaFreeHost(p));
+    return 0;
+}

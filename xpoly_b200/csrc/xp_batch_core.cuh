@@ -1,0 +1,468 @@
+// One-CTA-per-LP simplex with the tableau in shared memory: the control
+// skeleton of SIX<Mat,T>::TwoStageMethod shared by the FP64 kernel
+// (xp_batch_f64.cu) and the exact fraction-free kernel (xp_batch_i64.cu).
+//
+// Reference (all /root/reference/src/com/lpsol.h): TwoStageMethod :1906-1930,
+// stage1 :1783-1844, slack :1405-1433, constructBasicFeasibleSolution :838-988,
+// solveSlackForm :1007-1191, findPivotBV :552-663, findPivotNVandBVPair
+// :670-773, PivotPairTab :68-154.
+//
+// The arithmetic (element type, pivot update, ratio comparison, feasibility
+// test, objective substitution) is supplied by an `Ops` policy.
+#pragma once
+
+#include "xp_common.cuh"
+
+struct XpBatchArgs {
+    int batch;
+    int m, n;                         // uniform shape (when ms == nullptr)
+    const int32_t *ms, *ns;           // ragged shapes (device) or nullptr
+    const int64_t *leq_off, *tgtf_off; // ragged element offsets (device) or nullptr
+    const void *leq, *tgtf;           // element pools (device)
+    uint32_t max_iter;
+    int ldo, ldm;                     // output strides (elements)
+    int32_t *status;
+    void *maxv, *slack_sol, *tgtf_out; // Ops-specific output layouts
+    void *slack_sol2, *tgtf_out2;      // (denominators, exact path)
+    int32_t *eq2bv;
+    uint32_t *iters, *pivots;
+    int maxm, maxn;                   // smem layout bounds
+    unsigned *queue;                  // atomic work counter
+};
+
+constexpr int XPB_BIG = 0x7fffffff;
+
+// Shared-memory resident solver state of one LP.
+template <class E>
+struct XpB {
+    E *tab, *tgtf, *fcol, *sol;
+    uint8_t *nvset;
+    int *bv2eq, *eq2bv;
+    uint32_t *tabu;
+    int *row_cnt, *col_cnt;
+    int *shi;    // 33 ints
+    void *shk;   // 33 ratio keys
+    int m, C, n, LD, W; // n = rhs_idx = C-1
+    unsigned pivots;
+};
+
+__host__ __device__ inline size_t xpb_align(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// Bytes of dynamic shared memory for bounds (maxm, maxn), element size es,
+// ratio-key size ks.  Layout mirrored in xpb_carve().
+inline size_t xpb_smem_bytes(int maxm, int maxn, size_t es, size_t ks)
+{
+    const int nmax = maxn + 1 + maxm;   // variables incl. the auxiliary one
+    const int LD = (nmax + 1) | 1;      // + constant column, odd => conflict-free column walks
+    const int W = (nmax + 31) / 32;
+    size_t b = 0;
+    b += xpb_align((size_t)maxm * LD * es, 16);  // tab
+    b += xpb_align((size_t)LD * es, 16) * 2;     // tgtf, sol
+    b += xpb_align((size_t)maxm * es, 16);       // fcol
+    b += xpb_align((size_t)33 * ks, 16);         // ratio keys
+    b += xpb_align((size_t)(nmax + 1) * 4, 16);  // bv2eq
+    b += xpb_align((size_t)maxm * 4, 16);        // eq2bv
+    b += xpb_align((size_t)nmax * W * 4, 16);    // tabu
+    b += xpb_align((size_t)nmax * 4, 16) * 2;    // row_cnt, col_cnt
+    b += xpb_align(33 * 4, 16);                  // shi
+    b += xpb_align((size_t)nmax + 1, 16);        // nvset
+    b += 64;                                     // misc scalars
+    return b;
+}
+
+#ifdef __CUDACC__
+
+template <class E, class K>
+__device__ inline void xpb_carve(XpB<E> &S, unsigned char *base, int maxm, int maxn, long long **misc)
+{
+    const int nmax = maxn + 1 + maxm;
+    const int LD = (nmax + 1) | 1;
+    const int W = (nmax + 31) / 32;
+    size_t o = 0;
+    S.tab = (E *)(base + o);
+    o += xpb_align((size_t)maxm * LD * sizeof(E), 16);
+    S.tgtf = (E *)(base + o);
+    o += xpb_align((size_t)LD * sizeof(E), 16);
+    S.sol = (E *)(base + o);
+    o += xpb_align((size_t)LD * sizeof(E), 16);
+    S.fcol = (E *)(base + o);
+    o += xpb_align((size_t)maxm * sizeof(E), 16);
+    S.shk = (void *)(base + o);
+    o += xpb_align((size_t)33 * sizeof(K), 16);
+    S.bv2eq = (int *)(base + o);
+    o += xpb_align((size_t)(nmax + 1) * 4, 16);
+    S.eq2bv = (int *)(base + o);
+    o += xpb_align((size_t)maxm * 4, 16);
+    S.tabu = (uint32_t *)(base + o);
+    o += xpb_align((size_t)nmax * W * 4, 16);
+    S.row_cnt = (int *)(base + o);
+    o += xpb_align((size_t)nmax * 4, 16);
+    S.col_cnt = (int *)(base + o);
+    o += xpb_align((size_t)nmax * 4, 16);
+    S.shi = (int *)(base + o);
+    o += xpb_align(33 * 4, 16);
+    S.nvset = (uint8_t *)(base + o);
+    o += xpb_align((size_t)nmax + 1, 16);
+    *misc = (long long *)(base + o);
+    S.LD = LD;
+    S.W = W;
+}
+
+template <class E>
+__device__ __forceinline__ bool xpb_tabu_get(const XpB<E> &S, int nv, int bv)
+{
+    return (S.tabu[nv * S.W + (bv >> 5)] >> (bv & 31)) & 1u;
+}
+
+// newPPT (lpsol.h:390-399): a fresh table per solveSlackForm call.
+template <class E>
+__device__ inline void xpb_tabu_reset(XpB<E> &S)
+{
+    for (int k = threadIdx.x; k < S.n * S.W; k += blockDim.x) S.tabu[k] = 0u;
+    for (int k = threadIdx.x; k < S.n; k += blockDim.x) {
+        S.row_cnt[k] = 0;
+        S.col_cnt[k] = 0;
+    }
+    __syncthreads();
+}
+
+// PivotPairTab::disableNV (lpsol.h:114-121).
+template <class E>
+__device__ inline void xpb_disable_nv(XpB<E> &S, int q)
+{
+    const int n = S.n;
+    for (int w = threadIdx.x; w < S.W; w += blockDim.x) {
+        const int base = w << 5;
+        uint32_t want = (n - base >= 32) ? 0xffffffffu : ((1u << (n - base)) - 1u);
+        if ((q >> 5) == w) want &= ~(1u << (q & 31));
+        uint32_t old = S.tabu[q * S.W + w];
+        uint32_t add = want & ~old;
+        S.tabu[q * S.W + w] = old | want;
+        while (add) {
+            int b = __ffs(add) - 1;
+            add &= add - 1;
+            S.col_cnt[base + b] += 1;
+        }
+    }
+    if (threadIdx.x == 0) S.row_cnt[q] = n - 1;
+    __syncthreads();
+}
+
+// Block arg-min over Ops::Key with the reference's "first strict minimum" rule.
+template <class Ops>
+__device__ inline typename Ops::Key xpb_block_best(typename Ops::Key x, void *shk)
+{
+    typedef typename Ops::Key K;
+    K *sh = (K *)shk;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x = Ops::better(x, Ops::shfl_xor(x, o));
+    __syncthreads();
+    if (lane == 0) sh[w] = x;
+    __syncthreads();
+    if (w == 0) {
+        K y = Ops::empty_key();
+        if (lane < nw) y = sh[lane];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) y = Ops::better(y, Ops::shfl_xor(y, o));
+        if (lane == 0) sh[32] = y;
+    }
+    __syncthreads();
+    return sh[32];
+}
+
+// findPivotBV (lpsol.h:552-663).  Returns the pivot ROW or -1.
+template <class Ops>
+__device__ inline int xpb_ratio_test(XpB<typename Ops::E> &S, int q)
+{
+    typedef typename Ops::Key K;
+    const int n = S.n;
+    K best = Ops::empty_key();
+    for (int i = threadIdx.x; i < S.m; i += blockDim.x) { // pass 1, :571-612
+        typename Ops::E a = S.tab[i * S.LD + q];
+        if (Ops::le_zero(a)) continue;
+        const int bv = S.eq2bv[i];
+        if (xpb_tabu_get(S, q, bv)) continue;
+        if (S.col_cnt[bv] >= n - 1) continue;
+        best = Ops::better(best, Ops::make_key(S.tab[i * S.LD + n], a, i));
+    }
+    best = xpb_block_best<Ops>(best, S.shk);
+    if (Ops::key_index(best) >= 0) return Ops::key_index(best);
+    best = Ops::empty_key();
+    for (int i = threadIdx.x; i < S.m; i += blockDim.x) { // pass 2, :623-658
+        const int bv = S.eq2bv[i];
+        if (xpb_tabu_get(S, q, bv)) continue;
+        if (S.col_cnt[bv] >= n - 1) continue;
+        typename Ops::E a = S.tab[i * S.LD + q];
+        if (Ops::is_zero(a)) continue;
+        best = Ops::better(best, Ops::make_key(S.tab[i * S.LD + n], a, i));
+    }
+    best = xpb_block_best<Ops>(best, S.shk);
+    return Ops::key_index(best);
+}
+
+// SIX::pivot bookkeeping common to both arithmetics (:1504-1510).
+template <class E>
+__device__ __forceinline__ void xpb_swap_basis(XpB<E> &S, int p, int q, int bv)
+{
+    S.nvset[q] = 0;
+    S.nvset[bv] = 1;
+    S.eq2bv[p] = q;
+    S.bv2eq[q] = p;
+    S.bv2eq[bv] = -1;
+}
+
+// solveSlackForm (lpsol.h:1007-1191).  Returns the SIX status; *iters = cnt.
+template <class Ops>
+__device__ inline int xpb_solve_loop(XpB<typename Ops::E> &S, uint32_t max_iter, uint32_t *iters)
+{
+    typedef typename Ops::E E;
+    const int tid = threadIdx.x;
+    xpb_tabu_reset(S);
+    const int n = S.n;
+    for (int j = tid; j < S.C; j += blockDim.x) S.sol[j] = Ops::zero(); // sol.reinit, :1028
+    uint32_t cnt = 0;
+    while (cnt < max_iter) {
+        int q = -1, p = -1;
+        for (;;) {
+            // pricing, :1054-1069
+            int best = XPB_BIG, anypos = 0;
+            for (int j = tid; j < n; j += blockDim.x) {
+                if (S.nvset[j] && Ops::pos(S.tgtf[j])) {
+                    anypos = 1;
+                    if (best == XPB_BIG && S.row_cnt[j] < n - 1) best = j;
+                }
+            }
+            best = xp_block_min_int(best, S.shi);
+            anypos = __syncthreads_or(anypos);
+            const int zlim = best == XPB_BIG ? n : best;
+            for (int j = tid; j < zlim; j += blockDim.x)
+                if (!S.nvset[j]) S.tgtf[j] = Ops::zero(); // :1059
+            __syncthreads();
+            if (best == XPB_BIG) {
+                if (!anypos) { // optimal exit, :1089-1127
+                    *iters = cnt;
+                    return Ops::optimal_exit(S);
+                }
+                // findPivotNVandBVPair, :670-773 (pass B skips the c_j > 0 columns
+                // that already failed in pass A: findPivotBV is pure)
+                int found = 0;
+                for (int pass = 0; pass < 2 && !found; pass++) {
+                    int last = -1;
+                    for (;;) {
+                        int cand = XPB_BIG;
+                        for (int j = last + 1 + tid; j < n; j += blockDim.x) {
+                            if (!S.nvset[j] || S.row_cnt[j] >= n - 1) continue;
+                            E c = S.tgtf[j];
+                            bool take = pass == 0 ? Ops::pos(c) : (!Ops::pos(c) && Ops::is_zero(c));
+                            if (take) {
+                                cand = j;
+                                break;
+                            }
+                        }
+                        cand = xp_block_min_int(cand, S.shi);
+                        if (cand == XPB_BIG) break;
+                        int r = xpb_ratio_test<Ops>(S, cand);
+                        if (r >= 0) {
+                            q = cand;
+                            p = r;
+                            found = 1;
+                            break;
+                        }
+                        last = cand;
+                    }
+                }
+                if (!found) {
+                    *iters = cnt;
+                    return XP_SIX_UNBOUND; // :1138-1141
+                }
+                break;
+            }
+            q = best;
+            p = xpb_ratio_test<Ops>(S, q);
+            if (p >= 0) break;
+            xpb_disable_nv(S, q); // :1146-1151
+        }
+        const int bv = S.eq2bv[p];
+        __syncthreads();
+        if (tid == 0) { // genPair, :1156
+            uint32_t *w = &S.tabu[q * S.W + (bv >> 5)];
+            const uint32_t bit = 1u << (bv & 31);
+            if (!(*w & bit)) {
+                *w |= bit;
+                S.row_cnt[q] += 1;
+                S.col_cnt[bv] += 1;
+            }
+        }
+        int rc = Ops::pivot(S, p, q); // :1170
+        if (rc) {
+            *iters = cnt;
+            return rc;
+        }
+        cnt++;
+    }
+    *iters = cnt;
+    return XP_SIX_TIME_OUT;
+}
+
+// TwoStageMethod for LP `k` of the batch.  Returns the status.
+template <class Ops>
+__device__ inline int xpb_two_stage(XpB<typename Ops::E> &S, const XpBatchArgs &A,
+                                    const typename Ops::In *leq, const typename Ops::In *tg,
+                                    int m, int n, uint32_t *iters)
+{
+    typedef typename Ops::E E;
+    const int tid = threadIdx.x;
+    const int LD = S.LD;
+    // stage1 decision, :1794-1803
+    int pos = 0, bneg = 0;
+    for (int j = tid; j < n; j += blockDim.x) pos |= Ops::in_pos(tg[j]);
+    for (int i = tid; i < m; i += blockDim.x) bneg |= Ops::in_neg(leq[(size_t)i * (n + 1) + n]);
+    pos = __syncthreads_or(pos);
+    bneg = __syncthreads_or(bneg);
+    const bool aux = !pos || bneg;
+    const int xa = n;                   // auxiliary variable index (if any)
+    const int s0 = aux ? n + 1 : n;     // first slack column
+    S.m = m;
+    S.n = s0 + m;
+    S.C = S.n + 1;
+    S.pivots = 0;
+    Ops::reset(S);
+    // slack form [A | (-1) | I | b], :860-875 / :1405-1433, and the identity basis
+    for (int e = tid; e < m * S.C; e += blockDim.x) {
+        const int i = e / S.C, j = e - i * S.C;
+        E v;
+        if (j < n) v = Ops::from_in(leq[(size_t)i * (n + 1) + j]);
+        else if (aux && j == xa) v = Ops::from_int(-1);
+        else if (j < S.n) v = Ops::from_int(j - s0 == i ? 1 : 0);
+        else v = Ops::from_in(leq[(size_t)i * (n + 1) + n]);
+        S.tab[i * LD + j] = v;
+    }
+    for (int j = tid; j < S.C; j += blockDim.x) {
+        E v = Ops::zero();
+        if (aux) {
+            if (j == xa) v = Ops::from_int(-1);
+        } else if (j < n) v = Ops::from_in(tg[j]);
+        else if (j == S.n) v = Ops::from_in(tg[n]);
+        S.tgtf[j] = v;
+        if (j < S.n) {
+            S.nvset[j] = j < s0;
+            S.bv2eq[j] = j < s0 ? -1 : j - s0;
+        }
+    }
+    for (int i = tid; i < m; i += blockDim.x) S.eq2bv[i] = s0 + i;
+    __syncthreads();
+
+    if (aux) {
+        // forced first pivot on the row of the first minimum constant term, :892-908
+        int prow = Ops::argmin_rhs(S);
+        int rc = Ops::pivot(S, prow, xa);
+        if (rc) return rc;
+        uint32_t it1 = 0;
+        int st = xpb_solve_loop<Ops>(S, A.max_iter, &it1);
+        if (st < 0) return st;
+        if (st != XP_SIX_SUCC) return XP_SIX_NO_PRI_FEASIBLE_SOL; // :912-915
+        if (!Ops::is_zero(S.tgtf[S.n])) return XP_SIX_NO_PRI_FEASIBLE_SOL; // :919-922
+        __syncthreads();
+        if (!S.nvset[xa]) { // xa still basic: pivot it out, :924-941
+            const int eqnum = S.bv2eq[xa];
+            int cand = XPB_BIG;
+            for (int j = tid; j < S.n; j += blockDim.x)
+                if (S.nvset[j] && !Ops::is_zero(S.tab[eqnum * LD + j])) {
+                    cand = j;
+                    break;
+                }
+            cand = xp_block_min_int(cand, S.shi);
+            if (cand == XPB_BIG) return XP_ERR_REFERENCE_UB; // reference ASSERTs (:937)
+            rc = Ops::pivot(S, eqnum, cand);
+            if (rc) return rc;
+        }
+        // restore the original objective by substitution (:944-953), then drop
+        // column xa and re-index the maps (:956-986)
+        rc = Ops::restore_objective(S, tg, n);
+        if (rc) return rc;
+        __syncthreads();
+        {
+            // shift columns (xa, C) one to the left; one warp per row, ascending
+            // 32-wide chunks (read chunk, then write it one slot lower)
+            const int lane = tid & 31, w = tid >> 5, nw = blockDim.x >> 5;
+            for (int i = w; i < m; i += nw) {
+                for (int j0 = xa + 1; j0 < S.C; j0 += 32) {
+                    const int j = j0 + lane;
+                    E t = Ops::zero();
+                    if (j < S.C) t = S.tab[i * LD + j];
+                    __syncwarp();
+                    if (j < S.C) S.tab[i * LD + j - 1] = t;
+                    __syncwarp();
+                }
+            }
+            if (w == 0) {
+                for (int j0 = xa + 1; j0 < S.C; j0 += 32) {
+                    const int j = j0 + lane;
+                    E t = Ops::zero();
+                    uint8_t nv = 0;
+                    int b2e = 0;
+                    if (j < S.C) t = S.tgtf[j];
+                    if (j < S.n) {
+                        nv = S.nvset[j];
+                        b2e = S.bv2eq[j];
+                    }
+                    __syncwarp();
+                    if (j < S.C) S.tgtf[j - 1] = t;
+                    if (j < S.n) {
+                        S.nvset[j - 1] = nv;
+                        S.bv2eq[j - 1] = b2e;
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+        for (int i = tid; i < m; i += blockDim.x)
+            if (S.eq2bv[i] > xa) S.eq2bv[i] -= 1;
+        S.n -= 1;
+        S.C -= 1;
+        __syncthreads();
+    }
+    return xpb_solve_loop<Ops>(S, A.max_iter, iters);
+}
+
+// Persistent CTAs pull LP indices from an atomic queue, so long-running LPs
+// (unbounded ones exit only after exhausting the tabu table) do not hold up
+// the rest of the grid.
+template <class Ops>
+__device__ inline void xpb_kernel_body(const XpBatchArgs &A)
+{
+    typedef typename Ops::E E;
+    extern __shared__ __align__(16) unsigned char xpb_smem[];
+    __shared__ int s_lp;
+    XpB<E> S;
+    long long *misc;
+    xpb_carve<E, typename Ops::Key>(S, xpb_smem, A.maxm, A.maxn, &misc);
+    Ops::bind(S, misc);
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_lp = (int)atomicAdd(A.queue, 1u);
+        __syncthreads();
+        const int k = s_lp;
+        if (k >= A.batch) break;
+        const int m = A.ms ? A.ms[k] : A.m;
+        const int n = A.ns ? A.ns[k] : A.n;
+        const typename Ops::In *leq = (const typename Ops::In *)A.leq +
+                                      (A.leq_off ? A.leq_off[k] : (int64_t)k * m * (n + 1));
+        const typename Ops::In *tg = (const typename Ops::In *)A.tgtf +
+                                     (A.tgtf_off ? A.tgtf_off[k] : (int64_t)k * (n + 1));
+        uint32_t iters = 0;
+        int st = xpb_two_stage<Ops>(S, A, leq, tg, m, n, &iters);
+        __syncthreads();
+        Ops::write_out(S, A, k, st);
+        if (threadIdx.x == 0) {
+            if (A.status) A.status[k] = st;
+            if (A.iters) A.iters[k] = iters;
+            if (A.pivots) A.pivots[k] = S.pivots;
+        }
+        if (A.eq2bv)
+            for (int i = threadIdx.x; i < m; i += blockDim.x) A.eq2bv[(size_t)k * A.ldm + i] = S.eq2bv[i];
+    }
+}
+
+#endif // __CUDACC__
