@@ -1,0 +1,407 @@
+#!/usr/bin/env python
+"""bench.py -- pivots/s of the simplex hot path on the config-3 workload
+(dense FP64 LP, 8192 x 16384 tableau) plus the config-2 batched figure.
+
+  python bench.py --gpus N --steps K --warmup W            (our arm)
+  python bench.py --impl reference --gpus N --steps K ...  (reference CPU arm)
+
+A "step" is one pass of the hot path over one batch of work: P simplex
+iterations (pricing -> ratio test -> rank-1 pivot) of the HBM-resident tableau.
+`value` is device-resident (inputs in HBM when the timed region starts); `e2e`
+goes through the C-ABI call a maintainer binds (xp_six_slack_f64) with pinned
+HOST buffers, host<->device copies inside the timed region.  Inputs (1 GiB) are
+larger than L2 (126 MB), so no flush is needed between iterations.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+M_ROWS = 8192          # config 3: leq 8192 x 8192 (8191 vars + rhs) -> tableau 8192 x 16384
+N_VARS = 8191
+BATCH_LPS = 100_000    # config 2: 100k LPs, leq 32 x 32 (31 vars) -> tableau 32 x 64
+BATCH_M, BATCH_N = 32, 31
+SEED = 20261017
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(np.max(mx)) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------- CPU side
+def cpu_pivot_rate(leq, tgtf, pivots, prefer_ref, setup_s=None):
+    """Pivots/s of the reference's CPU solver on the same LP, 1 thread (the
+    reference has no intra-LP parallelism).  kind 'reference' = oracle/_ref (the
+    unmodified reference; solve loop timed inside the checker; reference set-up measured with max_iter=0 and subtracted),
+    kind 'port' = oracle/xp_oracle.c solveSlackForm restatement."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import harness as H
+    import xpoly_b200 as xp
+    if prefer_ref and H.ref() is not None:
+        # SIX::TwoStageMethod timed inside the shim (excludes matrix fill / dump);
+        # its slack-form set-up is measured with max_iter=0 and subtracted.
+        H.ref().ref_last_two_stage_seconds.restype = C.c_double
+        t_setup = setup_s
+        if t_setup is None:  # warm minimum of two set-up-only runs
+            ts = []
+            for _ in range(2):
+                H.two_stage("ref", "f64", leq, tgtf, 0)
+                ts.append(H.ref().ref_last_two_stage_seconds())
+            t_setup = min(ts)
+        r = H.two_stage("ref", "f64", leq, tgtf, pivots)
+        t_run = H.ref().ref_last_two_stage_seconds()
+        dt = max(t_run - t_setup, 1e-9)
+        return pivots / dt, "reference", dict(eq2bv=r["eq2bv"], setup_s=t_setup, run_s=t_run)
+    sf = xp.slack_form(leq, tgtf)
+    H.oracle().xo_last_solve_seconds.restype = C.c_double
+    r = H.slack_solve_oracle("f64", *sf, max_iter=pivots, log_cap=0)
+    dt = max(H.oracle().xo_last_solve_seconds(), 1e-9)  # the solve loop alone
+    return pivots / dt, "port", dict(eq2bv=r["eq2bv"], setup_s=0.0, run_s=dt)
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from xpoly_b200.synth import dense_lp
+    leq, tgtf = dense_lp(SEED, args.m, args.n)
+    P = args.ref_pivots
+    rates = []
+    kind = "port"
+    setup = None
+    for s in range(args.warmup + args.steps):
+        rate, kind, info = cpu_pivot_rate(leq, tgtf, P, prefer_ref=not args.port, setup_s=setup)
+        setup = info["setup_s"]  # measured once (first warm-up step), reused afterwards
+        if s >= args.warmup:
+            rates.append(rate)
+    # whole-run rate over the timed steps
+    value = len(rates) / sum(1.0 / r for r in rates)
+    C_cols = args.n + args.m + 1
+    line = {
+        "impl": "reference", "metric": "pivots/s", "value": value, "unit": "pivots/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1000.0 * P / value, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"c3: dense FP64 LP, tableau {args.m}x{C_cols}, "
+                               f"{P} simplex iterations per step from the slack basis"},
+        "cpu_baseline": {"value": value, "unit": "pivots/s", "cores": 1, "kind": kind,
+                         "sample": f"{P} pivots of the same {args.m}x{C_cols} LP per step "
+                                   "(solve loop timed inside the checker; reference set-up measured with max_iter=0 and subtracted)"},
+        "e2e": {"value": value, "unit": "pivots/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ---------------------------------------------------------------- GPU side
+def run_batched(ctx, xp, torch, dev):
+    """Config 2: 100k LPs of tableau 32x64, one CTA per LP."""
+    B, m, n = BATCH_LPS, BATCH_M, BATCH_N
+    g = torch.Generator(device=dev)
+    g.manual_seed(SEED)
+    leq = torch.rand((B, m, n + 1), dtype=torch.float64, device=dev, generator=g)
+    leq[:, :, n] = 1.0 + leq[:, :, n] * n
+    tg = torch.rand((B, n + 1), dtype=torch.float64, device=dev, generator=g)
+    tg[:, n] = 0.0
+    status = torch.zeros(B, dtype=torch.int32, device=dev)
+    maxv = torch.zeros(B, dtype=torch.float64, device=dev)
+    pivots = torch.zeros(B, dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()
+    lib = xp.lib()
+
+    def once():
+        rc = lib.xp_six_two_stage_f64_batch_dev(
+            ctx._h, B, m, n, C.c_void_p(leq.data_ptr()), C.c_void_p(tg.data_ptr()),
+            C.c_uint32(xp.NO_ITER_LIMIT), 0, C.c_void_p(status.data_ptr()),
+            C.c_void_p(maxv.data_ptr()), None, None, None, None, C.c_void_p(pivots.data_ptr()))
+        ctx.check(rc)
+        return ctx.last_kernel_ms
+    for _ in range(3):
+        once()
+    ms = [once() for _ in range(5)]
+    dev_ms = float(np.median(ms))
+    st = status.cpu().numpy()
+    tot_piv = int(pivots.cpu().numpy().astype(np.int64).sum())
+    # end to end through the host-pointer C-ABI call (H2D of all LPs, D2H of results)
+    h_leq = leq.cpu().numpy()
+    h_tg = tg.cpu().numpy()
+    t_e2e = []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        out = ctx.two_stage_f64_batch(h_leq, h_tg, want=("status", "maxv"))
+        t_e2e.append(time.perf_counter() - t0)
+    e2e_s = float(np.median(t_e2e))
+    smem_bytes = tot_piv * 2.0 * (m + 1) * (n + m + 1) * 8
+    return {
+        "metric": "small LPs/s", "workload": f"c2: {B} LPs, tableau {m}x{n + m + 1}, FP64",
+        "value": B / (dev_ms * 1e-3), "unit": "LPs/s", "ms": dev_ms,
+        "pivots_total": tot_piv, "pivots_per_s": tot_piv / (dev_ms * 1e-3),
+        "smem_algorithmic_GBps": smem_bytes / (dev_ms * 1e-3) / 1e9,
+        "status_mix": {str(k): int((st == k).sum()) for k in np.unique(st)},
+        "e2e": {"value": B / e2e_s, "unit": "LPs/s",
+                "h2d_bytes_per_step": int(h_leq.nbytes + h_tg.nbytes),
+                "d2h_bytes_per_step": int(B * 12)},
+        "status_matches_e2e": bool(np.array_equal(out["status"], st)),
+    }
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import xpoly_b200 as xp
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (xpoly_b200 has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    ctx = xp.Context(local_rank)
+    lib = xp.lib()
+    m, n = args.m, args.n
+    Ccols = n + m + 1
+    P = args.pivots
+    if world > 1:
+        from xpoly_b200 import sharded
+        lp = sharded.ShardedLP(ctx, m, Ccols, rank, world, dist)
+    else:
+        lp = ctx.large_lp(m, Ccols)
+    lp.fill_synthetic(SEED)
+    lib.xp_lp_f64_profile(lp._h, 1)
+
+    done = 0
+
+    def step():
+        nonlocal done
+        st = lp.solve(done + P)
+        done += P
+        if st != xp.SIX_TIME_OUT:  # LP terminated: restart from a fresh instance
+            lp.fill_synthetic(SEED + done)
+            done = 0
+        return ctx.last_kernel_ms
+
+    for _ in range(args.warmup):
+        step()
+    lib.xp_lp_f64_profile(lp._h, 1)  # reset the per-launch accumulators
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    launches0 = ctx.launches
+    t0 = time.perf_counter()
+    dev_ms = 0.0
+    for _ in range(args.steps):
+        dev_ms += step()
+    barrier()
+    wall_s = time.perf_counter() - t0
+    clocks = sampler.stop()
+    launches = ctx.launches - launches0
+    if world > 1:
+        t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms = float(t.item())
+    total_pivots = args.steps * P
+    value = total_pivots / (dev_ms * 1e-3)
+
+    n_sw, sw_ms, gap_ms = C.c_uint64(0), C.c_double(0), C.c_double(0)
+    lib.xp_lp_f64_profile_read(lp._h, C.byref(n_sw), C.byref(sw_ms), C.byref(gap_ms))
+    lib.xp_lp_f64_profile(lp._h, 0)
+    peak, peak_src = measured_peak_gbs()
+    local_cols = lp.local_cols if world > 1 else Ccols
+    alg_bytes = 2.0 * (m + 1) * local_cols * 8  # read+write of every entry
+    sweep_avg_ms = sw_ms.value / max(n_sw.value, 1)
+    achieved = alg_bytes / (sweep_avg_ms * 1e-3) / 1e9 if sweep_avg_ms > 0 else 0.0
+    traffic = None
+    prof = os.path.join(ROOT, "profiles", "r01_sweep_ncu_full.json")
+    if os.path.exists(prof) and world == 1:
+        try:
+            traffic = json.load(open(prof)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": "k_sweep (rank-1 update + next-column extraction)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "peak_source": peak_src, "traffic": traffic,
+                "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": sweep_avg_ms,
+                "launches_timed": int(n_sw.value),
+                "sweep_share_of_step": sw_ms.value / dev_ms if dev_ms > 0 else None,
+                "whole_pivot_frac_of_peak": value * alg_bytes / 1e9 / peak,
+                "whole_pivot_frac_of_8TBps": value * alg_bytes / 8e12}
+
+    line = {
+        "metric": "pivots/s", "value": value, "unit": "pivots/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": f"c3: dense FP64 LP, tableau {m}x{Ccols}, {P} simplex iterations "
+                               "per step (reference pivot rule), HBM-resident"
+                               + (f", column-sharded over {world} GPUs" if world > 1 else ""),
+                   "l2": "inputs (1 GiB) larger than L2 (126 MB): no flush between iterations",
+                   "pivots_per_step": P},
+        "gpu_launches": int(launches), "wall_s": wall_s, "clocks": clocks, "roofline": roofline,
+    }
+
+    if world == 1:
+        # ---- e2e: the C-ABI call with pinned host buffers (H2D + K pivots + D2H per step)
+        tab_bytes = m * Ccols * 8
+        hp = C.c_void_p()
+        ctx.check(lib.xp_host_alloc(ctx._h, C.c_size_t(tab_bytes), C.byref(hp)))
+        h_tab = np.ctypeslib.as_array(C.cast(hp, C.POINTER(C.c_double)), shape=(m, Ccols))
+        lp.fill_synthetic(SEED)
+        st0 = lp.download(want_tab=False)
+        ctx.check(lib.xp_lp_f64_download(lp._h, hp, None, None, None, None, None, None, None, None,
+                                         None, 0))
+        lp.close()
+        tg, nv, bvs = st0["tgtf"].copy(), st0["nvset"].copy(), st0["bvset"].copy()
+        b2e, e2b = st0["bv2eq"].copy(), st0["eq2bv"].copy()
+        maxv, sol = np.zeros(1), np.zeros(Ccols)
+        iters = np.zeros(1, dtype=np.uint32)
+        p = lambda a: a.ctypes.data_as(C.c_void_p)
+
+        def e2e_step():
+            t0 = time.perf_counter()
+            st = lib.xp_six_slack_f64(ctx._h, hp, p(tg), m, Ccols, p(nv), p(bvs), p(b2e), p(e2b),
+                                      None, None, C.c_uint32(P), 0, p(maxv), p(sol), p(iters),
+                                      None, 0)
+            ctx.check(st)
+            return time.perf_counter() - t0, int(iters[0])
+        e2e_step()
+        ts, its = [], 0
+        for _ in range(max(2, min(args.steps, 4))):
+            dt, it = e2e_step()
+            ts.append(dt)
+            its += it
+        e2e_value = its / sum(ts)
+        small = Ccols * 8 + (Ccols - 1) * (1 + 1 + 4) + m * 4
+        line["e2e"] = {"value": e2e_value, "unit": "pivots/s",
+                       "h2d_bytes_per_step": int(tab_bytes + small),
+                       "d2h_bytes_per_step": int(tab_bytes + small + Ccols * 8),
+                       "ms_per_step": 1000.0 * sum(ts) / len(ts), "pivots_per_step": P,
+                       "api": "xp_six_slack_f64 (pinned host buffers)"}
+        # ---- CPU baseline on a bounded sample of the same workload (rank 0, N=1)
+        if not args.no_cpu:
+            from xpoly_b200.synth import dense_lp
+            leq, tgtf = dense_lp(SEED, m, n)
+            Kc = args.cpu_pivots
+            rate, kind, info = cpu_pivot_rate(leq, tgtf, Kc, prefer_ref=False)
+            chk = ctx.large_lp(m, Ccols)
+            chk.fill_synthetic(SEED)
+            chk.solve(Kc)
+            same = bool(np.array_equal(chk.download(want_tab=False)["eq2bv"], info["eq2bv"]))
+            chk.close()
+            line["cpu_baseline"] = {
+                "value": rate, "unit": "pivots/s", "cores": 1, "kind": kind,
+                "sample": f"{Kc} pivots of the same {m}x{Ccols} LP (single thread; the reference "
+                          "has no intra-LP parallelism); solve loop timed inside the checker",
+                "basis_after_sample_matches_gpu": same}
+        ctx.check(lib.xp_host_free(ctx._h, hp))
+        if not args.no_batched:
+            line["batched"] = run_batched(ctx, xp, torch, dev)
+    else:
+        line["e2e"] = None
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--pivots", type=int, default=25, help="simplex iterations per step")
+    ap.add_argument("--m", type=int, default=M_ROWS)
+    ap.add_argument("--n", type=int, default=N_VARS)
+    ap.add_argument("--cpu-pivots", type=int, default=12)
+    ap.add_argument("--ref-pivots", type=int, default=2)
+    ap.add_argument("--port", action="store_true", help="reference arm: force the oracle port")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-batched", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

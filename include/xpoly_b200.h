@@ -118,6 +118,12 @@ int xp_lp_f64_solve(xp_lp_f64 *lp, uint32_t max_iter, int rule);
 int xp_lp_f64_download(xp_lp_f64 *lp, double *tableau, double *tgtf, uint8_t *nvset,
                        uint8_t *bvset, int32_t *bv2eq, int32_t *eq2bv, double *maxv, double *sol,
                        uint32_t *iters, int32_t *pivot_log, uint32_t log_cap);
+/* Per-launch timing of the rank-1 sweep kernel with CUDA events on the ctx
+ * stream (bench.py's roofline leg).  sweep_ms sums the sweep launches that did
+ * real work since enable; gap_ms the time between consecutive sweeps (select
+ * kernel + launch gaps). */
+int xp_lp_f64_profile(xp_lp_f64 *lp, int enable);
+int xp_lp_f64_profile_read(xp_lp_f64 *lp, uint64_t *n_sweeps, double *sweep_ms, double *gap_ms);
 /* Order-independent 64-bit checksum of the device tableau bits (parity at full size). */
 int xp_lp_f64_checksum(xp_lp_f64 *lp, uint64_t *sum_tableau, uint64_t *sum_tgtf);
 /* Column-sharded multi-GPU: attach an NCCL communicator built from a unique id

@@ -27,6 +27,7 @@
 
 #include <stdint.h>
 #include <string.h>
+#include <time.h>
 
 namespace xcom {
 extern LONGLONG g_appro_count;  // rational.cpp:188 (non-static)
@@ -39,6 +40,14 @@ template <> bool MIP<FloatMat, Float>::dump_end_six(UINT, Float, FloatMat &) { r
 using namespace xcom;
 
 namespace {
+
+double g_last_seconds = 0.0;
+double now_s()
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
 
 void fill_f64(FloatMat & M, int r, int c, const double * src)
 {
@@ -97,6 +106,9 @@ void dump_rat(const RMat & M, int32_t * dst, size_t cap)
 extern "C" {
 
 long long ref_appro_count(void) { return (long long)g_appro_count; }
+
+// Wall time of the last ref_two_stage_f64's SIX::TwoStageMethod call alone.
+double ref_last_two_stage_seconds(void) { return g_last_seconds; }
 
 // SIX<FloatMat,Float>::maxm / minm  (lpsol.h:1992 / :1661).
 // leq m x (n+1), tgtf 1 x (n+1), vc n x (n+1) or NULL (= -I | 0), eq k x (n+1) or k=0.
@@ -158,7 +170,9 @@ int ref_two_stage_f64(int m, int n, const double * leq, const double * tgtf, uns
     Vector<bool> nv, bv;
     Vector<INT> b2e, e2b;
     INT rhs = n;
+    double t0 = now_s();
     UINT st = six.TwoStageMethod(L, V, T, S, val, nv, bv, b2e, e2b, rhs);
+    g_last_seconds = now_s() - t0;
     size_t cap = (size_t)n + m + 2;
     dims[0] = L.get_row_size();
     dims[1] = L.get_col_size();

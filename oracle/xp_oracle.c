@@ -11,6 +11,7 @@
 #include <stddef.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 /* ------------------------------------------------------------------ Float */
 #define XO_EPS 0.00000000000000001 /* INFINITESIMAL, flty.h:46 */
@@ -309,6 +310,15 @@ void xo_mt64_uniform(uint64_t seed, size_t count, double *out)
     }
 }
 
+static double g_xo_last_seconds = 0.0;
+double xo_last_solve_seconds(void) { return g_xo_last_seconds; }
+static double xo_now(void)
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+
 /* ------------------------------------------------------- C entry points */
 #define DEFINE_ENTRIES(SFX, TY)                                                                   \
     int xo_six_solve_##SFX(int is_min, int m, int n, const TY *leq, const TY *tgtf,               \
@@ -395,7 +405,9 @@ void xo_mt64_uniform(uint64_t seed, size_t count, double *out)
         S.log = pivot_log;                                                                        \
         S.log_cap = log_cap;                                                                      \
         S.phase = XO_PH_MAIN;                                                                     \
+        double t0__ = xo_now();                                                                   \
         int st = solve_slack_##SFX(&S, maxv, sol);                                                \
+        g_xo_last_seconds = xo_now() - t0__;                                                      \
         memcpy(tab, S.tab.a, (size_t)m * (size_t)C * sizeof(TY));                                 \
         memcpy(tgtf, S.tgtf.a, (size_t)C * sizeof(TY));                                           \
         memcpy(nvset, S.nvset, (size_t)rhs);                                                      \

@@ -98,6 +98,9 @@ int xo_mip_solve_rat(int is_min, int is_bin, int m, int n, const xo_rat *leq, co
 int xo_has_solution_rat(int m, int n, const xo_rat *leq, int k, const xo_rat *eq, int is_int_sol,
                         int is_unique_sol);
 
+/* Wall time of the last xo_slack_* solve loop alone (bench.py cpu_baseline). */
+double xo_last_solve_seconds(void);
+
 /* std::mt19937_64 + uniform_real_distribution<double>(0,1) stream (libstdc++). */
 void xo_mt64_uniform(uint64_t seed, size_t count, double *out);
 

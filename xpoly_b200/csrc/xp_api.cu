@@ -35,6 +35,7 @@ extern "C" void xp_ctx_destroy(xp_ctx *ctx)
     if (ctx->stream) {
         cudaSetDevice(ctx->device);
         cudaStreamSynchronize(ctx->stream);
+        xp_large_release_cached(ctx);
         if (ctx->scratch) cudaFree(ctx->scratch);
         cudaEventDestroy(ctx->ev0);
         cudaEventDestroy(ctx->ev1);

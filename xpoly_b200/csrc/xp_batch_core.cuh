@@ -13,6 +13,8 @@
 
 #include "xp_common.cuh"
 
+#include <cstring>
+
 struct XpBatchArgs {
     int batch;
     int m, n;                         // uniform shape (when ms == nullptr)
@@ -44,6 +46,7 @@ struct XpB {
     void *shk;   // 33 ratio keys
     int m, C, n, LD, W; // n = rhs_idx = C-1
     unsigned pivots;
+    long long *misc;    // 8 spare 64-bit shared slots (exact path: D, overflow flag)
 };
 
 __host__ __device__ inline size_t xpb_align(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -104,6 +107,7 @@ __device__ inline void xpb_carve(XpB<E> &S, unsigned char *base, int maxm, int m
     S.nvset = (uint8_t *)(base + o);
     o += xpb_align((size_t)nmax + 1, 16);
     *misc = (long long *)(base + o);
+    S.misc = *misc;
     S.LD = LD;
     S.W = W;
 }
@@ -466,3 +470,131 @@ __device__ inline void xpb_kernel_body(const XpBatchArgs &A)
 }
 
 #endif // __CUDACC__
+
+// ---------------------------------------------------------------------------
+// Host plumbing shared by the FP64 and exact entry points: stage inputs in the
+// ctx scratch block, launch, copy results back.  All pools hold 8-byte elements.
+// ---------------------------------------------------------------------------
+struct XpBatchHost {
+    int batch = 0;
+    int m = 0, n = 0;                       // uniform shape, or
+    const int32_t *ms = nullptr, *ns = nullptr; // ragged shapes (host)
+    const int64_t *leq_off = nullptr, *tgtf_off = nullptr;
+    const void *leq = nullptr, *tgtf = nullptr; // host pools
+    size_t leq_len = 0, tgtf_len = 0;       // elements
+    uint32_t max_iter = 0;
+    int ldo = 0, ldm = 0;
+    int maxv_elems = 1;                     // 8-byte elements per LP in maxv
+    // host outputs (any may be null)
+    int32_t *status = nullptr;
+    void *maxv = nullptr, *slack_sol = nullptr, *slack_sol2 = nullptr;
+    void *tgtf_out = nullptr, *tgtf_out2 = nullptr;
+    int32_t *eq2bv = nullptr;
+    uint32_t *iters = nullptr, *pivots = nullptr;
+};
+
+typedef int (*XpBatchLaunch)(xp_ctx *ctx, XpBatchArgs &A);
+
+inline int xpb_host_run(xp_ctx *ctx, const XpBatchHost &H, XpBatchLaunch launch)
+{
+    auto pad = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const size_t B = (size_t)H.batch;
+    int maxm = H.m, maxn = H.n;
+    if (H.ms) {
+        maxm = maxn = 0;
+        for (int k = 0; k < H.batch; k++) {
+            if (H.ms[k] < 1 || H.ns[k] < 1) return XP_ERR_BAD_ARG;
+            maxm = H.ms[k] > maxm ? H.ms[k] : maxm;
+            maxn = H.ns[k] > maxn ? H.ns[k] : maxn;
+            if (H.ms[k] + H.ns[k] + 1 > H.ldo) return XP_ERR_BAD_ARG;
+        }
+        if (H.ldm < maxm) return XP_ERR_BAD_ARG;
+    }
+    XP_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    const size_t ldo = (size_t)H.ldo, ldm = (size_t)H.ldm;
+    size_t total = 1024 + pad(H.leq_len * 8) + pad(H.tgtf_len * 8) + 4 * pad(B * ldo * 8) +
+                   pad(B * 8 * H.maxv_elems) + pad(B * ldm * 4) + 5 * pad(B * 4) +
+                   2 * pad(B * 8) + 8192;
+    void *scr = nullptr;
+    int rc = xp_ctx_scratch(ctx, total, &scr);
+    if (rc) return rc;
+    unsigned char *base = (unsigned char *)scr;
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        off = (off + 255) & ~(size_t)255;
+        void *p = base + off;
+        off += bytes;
+        return p;
+    };
+    unsigned *queue = (unsigned *)take(256);
+    void *d_leq = take(H.leq_len * 8), *d_tg = take(H.tgtf_len * 8);
+    int32_t *d_ms = nullptr, *d_ns = nullptr;
+    int64_t *d_lo = nullptr, *d_to = nullptr;
+    cudaStream_t s = ctx->stream;
+    if (H.ms) {
+        d_ms = (int32_t *)take(B * 4);
+        d_ns = (int32_t *)take(B * 4);
+        d_lo = (int64_t *)take(B * 8);
+        d_to = (int64_t *)take(B * 8);
+        XP_CUDA_OK(ctx, cudaMemcpyAsync(d_ms, H.ms, B * 4, cudaMemcpyHostToDevice, s));
+        XP_CUDA_OK(ctx, cudaMemcpyAsync(d_ns, H.ns, B * 4, cudaMemcpyHostToDevice, s));
+        XP_CUDA_OK(ctx, cudaMemcpyAsync(d_lo, H.leq_off, B * 8, cudaMemcpyHostToDevice, s));
+        XP_CUDA_OK(ctx, cudaMemcpyAsync(d_to, H.tgtf_off, B * 8, cudaMemcpyHostToDevice, s));
+    }
+    void *d_sol = H.slack_sol ? take(B * ldo * 8) : nullptr;
+    void *d_sol2 = H.slack_sol2 ? take(B * ldo * 8) : nullptr;
+    void *d_tgo = H.tgtf_out ? take(B * ldo * 8) : nullptr;
+    void *d_tgo2 = H.tgtf_out2 ? take(B * ldo * 8) : nullptr;
+    void *d_maxv = H.maxv ? take(B * 8 * H.maxv_elems) : nullptr;
+    int32_t *d_e2b = H.eq2bv ? (int32_t *)take(B * ldm * 4) : nullptr;
+    int32_t *d_st = H.status ? (int32_t *)take(B * 4) : nullptr;
+    uint32_t *d_it = H.iters ? (uint32_t *)take(B * 4) : nullptr;
+    uint32_t *d_pv = H.pivots ? (uint32_t *)take(B * 4) : nullptr;
+    XP_CUDA_OK(ctx, cudaMemcpyAsync(d_leq, H.leq, H.leq_len * 8, cudaMemcpyHostToDevice, s));
+    XP_CUDA_OK(ctx, cudaMemcpyAsync(d_tg, H.tgtf, H.tgtf_len * 8, cudaMemcpyHostToDevice, s));
+    XpBatchArgs A;
+    memset(&A, 0, sizeof A);
+    A.batch = H.batch;
+    A.m = H.m;
+    A.n = H.n;
+    A.ms = d_ms;
+    A.ns = d_ns;
+    A.leq_off = d_lo;
+    A.tgtf_off = d_to;
+    A.leq = d_leq;
+    A.tgtf = d_tg;
+    A.max_iter = H.max_iter;
+    A.ldo = H.ldo;
+    A.ldm = H.ldm;
+    A.status = d_st;
+    A.maxv = d_maxv;
+    A.slack_sol = d_sol;
+    A.slack_sol2 = d_sol2;
+    A.tgtf_out = d_tgo;
+    A.tgtf_out2 = d_tgo2;
+    A.eq2bv = d_e2b;
+    A.iters = d_it;
+    A.pivots = d_pv;
+    A.maxm = maxm;
+    A.maxn = maxn;
+    A.queue = queue;
+    XP_CUDA_OK(ctx, cudaEventRecord(ctx->ev0, s));
+    rc = launch(ctx, A);
+    if (rc) return rc;
+    XP_CUDA_OK(ctx, cudaEventRecord(ctx->ev1, s));
+#define XPB_D2H(dst, src, bytes) \
+    if (dst) XP_CUDA_OK(ctx, cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyDeviceToHost, s))
+    XPB_D2H(H.status, d_st, B * 4);
+    XPB_D2H(H.maxv, d_maxv, B * 8 * H.maxv_elems);
+    XPB_D2H(H.slack_sol, d_sol, B * ldo * 8);
+    XPB_D2H(H.slack_sol2, d_sol2, B * ldo * 8);
+    XPB_D2H(H.tgtf_out, d_tgo, B * ldo * 8);
+    XPB_D2H(H.tgtf_out2, d_tgo2, B * ldo * 8);
+    XPB_D2H(H.eq2bv, d_e2b, B * ldm * 4);
+    XPB_D2H(H.iters, d_it, B * 4);
+    XPB_D2H(H.pivots, d_pv, B * 4);
+#undef XPB_D2H
+    XP_CUDA_OK(ctx, cudaStreamSynchronize(s));
+    XP_CUDA_OK(ctx, cudaEventElapsedTime(&ctx->last_kernel_ms, ctx->ev0, ctx->ev1));
+    return 0;
+}

@@ -261,26 +261,6 @@ extern "C" int xp_six_two_stage_f64_batch_dev(xp_ctx *ctx, int batch, int m, int
     return 0;
 }
 
-namespace {
-
-// Scratch carving helper: bump allocator over the ctx scratch block.
-struct Bump {
-    unsigned char *base;
-    size_t off = 0;
-    template <class T>
-    T *take(size_t count)
-    {
-        off = (off + 255) & ~(size_t)255;
-        T *p = (T *)(base + off);
-        off += count * sizeof(T);
-        return p;
-    }
-};
-
-size_t pad256(size_t b) { return (b + 255) & ~(size_t)255; }
-
-} // namespace
-
 // ---- host-pointer entry (uniform shape) ----
 extern "C" int xp_six_two_stage_f64_batch(xp_ctx *ctx, int batch, int m, int n, const double *leq,
                                           const double *tgtf, uint32_t max_iter, int rule,
@@ -291,66 +271,25 @@ extern "C" int xp_six_two_stage_f64_batch(xp_ctx *ctx, int batch, int m, int n, 
     if (!ctx || batch < 0 || m < 1 || n < 1 || !leq || !tgtf) return XP_ERR_BAD_ARG;
     if (rule != XP_RULE_REFERENCE) return XP_ERR_BAD_ARG;
     if (batch == 0) return 0;
-    XP_CUDA_OK(ctx, cudaSetDevice(ctx->device));
-    const size_t B = (size_t)batch, ldo = (size_t)n + m + 1;
-    const size_t b_leq = pad256(B * m * (n + 1) * 8), b_tg = pad256(B * (n + 1) * 8);
-    const size_t b_out = pad256(B * ldo * 8);
-    size_t total = 512 + b_leq + b_tg + 2 * b_out + pad256(B * 8) + pad256(B * m * 4) +
-                   3 * pad256(B * 4) + 4096;
-    void *scr = nullptr;
-    int rc = xp_ctx_scratch(ctx, total, &scr);
-    if (rc) return rc;
-    Bump bp{(unsigned char *)scr};
-    unsigned *queue = bp.take<unsigned>(64);
-    double *d_leq = bp.take<double>(B * m * (n + 1));
-    double *d_tg = bp.take<double>(B * (n + 1));
-    double *d_sol = slack_sol ? bp.take<double>(B * ldo) : nullptr;
-    double *d_tgo = tgtf_out ? bp.take<double>(B * ldo) : nullptr;
-    double *d_maxv = maxv ? bp.take<double>(B) : nullptr;
-    int32_t *d_e2b = eq2bv ? bp.take<int32_t>(B * m) : nullptr;
-    int32_t *d_st = status ? bp.take<int32_t>(B) : nullptr;
-    uint32_t *d_it = iters ? bp.take<uint32_t>(B) : nullptr;
-    uint32_t *d_pv = pivots ? bp.take<uint32_t>(B) : nullptr;
-    cudaStream_t s = ctx->stream;
-    XP_CUDA_OK(ctx, cudaMemcpyAsync(d_leq, leq, B * m * (n + 1) * 8, cudaMemcpyHostToDevice, s));
-    XP_CUDA_OK(ctx, cudaMemcpyAsync(d_tg, tgtf, B * (n + 1) * 8, cudaMemcpyHostToDevice, s));
-    XpBatchArgs A;
-    memset(&A, 0, sizeof A);
-    A.batch = batch;
-    A.m = m;
-    A.n = n;
-    A.leq = d_leq;
-    A.tgtf = d_tg;
-    A.max_iter = max_iter;
-    A.ldo = (int)ldo;
-    A.ldm = m;
-    A.status = d_st;
-    A.maxv = d_maxv;
-    A.slack_sol = d_sol;
-    A.tgtf_out = d_tgo;
-    A.eq2bv = d_e2b;
-    A.iters = d_it;
-    A.pivots = d_pv;
-    A.maxm = m;
-    A.maxn = n;
-    A.queue = queue;
-    XP_CUDA_OK(ctx, cudaEventRecord(ctx->ev0, s));
-    rc = launch_f64(ctx, A);
-    if (rc) return rc;
-    XP_CUDA_OK(ctx, cudaEventRecord(ctx->ev1, s));
-#define D2H(dst, src, bytes) \
-    if (dst) XP_CUDA_OK(ctx, cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyDeviceToHost, s))
-    D2H(status, d_st, B * 4);
-    D2H(maxv, d_maxv, B * 8);
-    D2H(slack_sol, d_sol, B * ldo * 8);
-    D2H(tgtf_out, d_tgo, B * ldo * 8);
-    D2H(eq2bv, d_e2b, B * m * 4);
-    D2H(iters, d_it, B * 4);
-    D2H(pivots, d_pv, B * 4);
-#undef D2H
-    XP_CUDA_OK(ctx, cudaStreamSynchronize(s));
-    XP_CUDA_OK(ctx, cudaEventElapsedTime(&ctx->last_kernel_ms, ctx->ev0, ctx->ev1));
-    return 0;
+    XpBatchHost H;
+    H.batch = batch;
+    H.m = m;
+    H.n = n;
+    H.leq = leq;
+    H.tgtf = tgtf;
+    H.leq_len = (size_t)batch * m * (n + 1);
+    H.tgtf_len = (size_t)batch * (n + 1);
+    H.max_iter = max_iter;
+    H.ldo = n + m + 1;
+    H.ldm = m;
+    H.status = status;
+    H.maxv = maxv;
+    H.slack_sol = slack_sol;
+    H.tgtf_out = tgtf_out;
+    H.eq2bv = eq2bv;
+    H.iters = iters;
+    H.pivots = pivots;
+    return xpb_host_run(ctx, H, launch_f64);
 }
 
 // ---- host-pointer entry (ragged shapes) ----
@@ -367,79 +306,25 @@ extern "C" int xp_six_two_stage_f64_ragged(xp_ctx *ctx, int batch, const int32_t
         return XP_ERR_BAD_ARG;
     if (rule != XP_RULE_REFERENCE) return XP_ERR_BAD_ARG;
     if (batch == 0) return 0;
-    int maxm = 0, maxn = 0, maxc = 0;
-    for (int k = 0; k < batch; k++) {
-        if (ms[k] < 1 || ns[k] < 1) return XP_ERR_BAD_ARG;
-        maxm = ms[k] > maxm ? ms[k] : maxm;
-        maxn = ns[k] > maxn ? ns[k] : maxn;
-        maxc = ms[k] + ns[k] + 1 > maxc ? ms[k] + ns[k] + 1 : maxc;
-    }
-    if (ldo < maxc || ldm < maxm) return XP_ERR_BAD_ARG;
-    XP_CUDA_OK(ctx, cudaSetDevice(ctx->device));
-    const size_t B = (size_t)batch;
-    size_t total = 512 + pad256(leq_len * 8) + pad256(tgtf_len * 8) + 2 * pad256(B * ldo * 8) +
-                   pad256(B * 8) + pad256(B * ldm * 4) + 5 * pad256(B * 4) + 2 * pad256(B * 8) +
-                   8192;
-    void *scr = nullptr;
-    int rc = xp_ctx_scratch(ctx, total, &scr);
-    if (rc) return rc;
-    Bump bp{(unsigned char *)scr};
-    unsigned *queue = bp.take<unsigned>(64);
-    double *d_leq = bp.take<double>(leq_len);
-    double *d_tg = bp.take<double>(tgtf_len);
-    int32_t *d_ms = bp.take<int32_t>(B), *d_ns = bp.take<int32_t>(B);
-    int64_t *d_lo = bp.take<int64_t>(B), *d_to = bp.take<int64_t>(B);
-    double *d_sol = slack_sol ? bp.take<double>(B * ldo) : nullptr;
-    double *d_tgo = tgtf_out ? bp.take<double>(B * ldo) : nullptr;
-    double *d_maxv = maxv ? bp.take<double>(B) : nullptr;
-    int32_t *d_e2b = eq2bv ? bp.take<int32_t>(B * ldm) : nullptr;
-    int32_t *d_st = status ? bp.take<int32_t>(B) : nullptr;
-    uint32_t *d_it = iters ? bp.take<uint32_t>(B) : nullptr;
-    uint32_t *d_pv = pivots ? bp.take<uint32_t>(B) : nullptr;
-    cudaStream_t s = ctx->stream;
-    XP_CUDA_OK(ctx, cudaMemcpyAsync(d_leq, leq, leq_len * 8, cudaMemcpyHostToDevice, s));
-    XP_CUDA_OK(ctx, cudaMemcpyAsync(d_tg, tgtf, tgtf_len * 8, cudaMemcpyHostToDevice, s));
-    XP_CUDA_OK(ctx, cudaMemcpyAsync(d_ms, ms, B * 4, cudaMemcpyHostToDevice, s));
-    XP_CUDA_OK(ctx, cudaMemcpyAsync(d_ns, ns, B * 4, cudaMemcpyHostToDevice, s));
-    XP_CUDA_OK(ctx, cudaMemcpyAsync(d_lo, leq_off, B * 8, cudaMemcpyHostToDevice, s));
-    XP_CUDA_OK(ctx, cudaMemcpyAsync(d_to, tgtf_off, B * 8, cudaMemcpyHostToDevice, s));
-    XpBatchArgs A;
-    memset(&A, 0, sizeof A);
-    A.batch = batch;
-    A.ms = d_ms;
-    A.ns = d_ns;
-    A.leq_off = d_lo;
-    A.tgtf_off = d_to;
-    A.leq = d_leq;
-    A.tgtf = d_tg;
-    A.max_iter = max_iter;
-    A.ldo = ldo;
-    A.ldm = ldm;
-    A.status = d_st;
-    A.maxv = d_maxv;
-    A.slack_sol = d_sol;
-    A.tgtf_out = d_tgo;
-    A.eq2bv = d_e2b;
-    A.iters = d_it;
-    A.pivots = d_pv;
-    A.maxm = maxm;
-    A.maxn = maxn;
-    A.queue = queue;
-    XP_CUDA_OK(ctx, cudaEventRecord(ctx->ev0, s));
-    rc = launch_f64(ctx, A);
-    if (rc) return rc;
-    XP_CUDA_OK(ctx, cudaEventRecord(ctx->ev1, s));
-#define D2H(dst, src, bytes) \
-    if (dst) XP_CUDA_OK(ctx, cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyDeviceToHost, s))
-    D2H(status, d_st, B * 4);
-    D2H(maxv, d_maxv, B * 8);
-    D2H(slack_sol, d_sol, B * ldo * 8);
-    D2H(tgtf_out, d_tgo, B * ldo * 8);
-    D2H(eq2bv, d_e2b, B * ldm * 4);
-    D2H(iters, d_it, B * 4);
-    D2H(pivots, d_pv, B * 4);
-#undef D2H
-    XP_CUDA_OK(ctx, cudaStreamSynchronize(s));
-    XP_CUDA_OK(ctx, cudaEventElapsedTime(&ctx->last_kernel_ms, ctx->ev0, ctx->ev1));
-    return 0;
+    XpBatchHost H;
+    H.batch = batch;
+    H.ms = ms;
+    H.ns = ns;
+    H.leq_off = leq_off;
+    H.tgtf_off = tgtf_off;
+    H.leq = leq;
+    H.tgtf = tgtf;
+    H.leq_len = leq_len;
+    H.tgtf_len = tgtf_len;
+    H.max_iter = max_iter;
+    H.ldo = ldo;
+    H.ldm = ldm;
+    H.status = status;
+    H.maxv = maxv;
+    H.slack_sol = slack_sol;
+    H.tgtf_out = tgtf_out;
+    H.eq2bv = eq2bv;
+    H.iters = iters;
+    H.pivots = pivots;
+    return xpb_host_run(ctx, H, launch_f64);
 }

@@ -520,10 +520,16 @@ struct xp_lp_f64 {
     xp_ctx *ctx;
     LpDev d;
     LpState *h_st; // pinned
-    bool has_vc;
     double *vc_diag, *vc_rhs;
-    uint8_t *h_tmp;
+    // optional per-launch timing of the sweep kernel (CUDA events on the ctx stream)
+    bool profile = false;
+    std::vector<cudaEvent_t> evs;
+    uint64_t prof_sweeps = 0;
+    unsigned cnt_at_entry = 0;
+    double prof_sweep_ms = 0.0, prof_gap_ms = 0.0;
 };
+
+constexpr int PROF_MAX_SWEEPS = 4096;
 
 static int sweep_launch(xp_lp_f64 *lp)
 {
@@ -586,7 +592,6 @@ extern "C" int xp_lp_f64_create(xp_ctx *ctx, int m, int C, xp_lp_f64 **out)
 #undef ALLOC
     XP_CUDA_OK(ctx, cudaMemset(d.st, 0, sizeof(LpState)));
     XP_CUDA_OK(ctx, cudaMallocHost((void **)&lp->h_st, sizeof(LpState)));
-    lp->h_tmp = nullptr;
     *out = lp;
     return 0;
 }
@@ -601,6 +606,7 @@ extern "C" void xp_lp_f64_destroy(xp_lp_f64 *lp)
                     d.sol,    lp->vc_diag, lp->vc_rhs, d.nvset,     d.bv2eq,     d.eq2bv,
                     d.tabu,   d.row_cnt,   d.col_cnt,  d.log,       d.st};
     for (void *p : ptrs) cudaFree(p);
+    for (cudaEvent_t e : lp->evs) cudaEventDestroy(e);
     cudaFreeHost(lp->h_st);
     delete lp;
 }
@@ -696,14 +702,26 @@ extern "C" int xp_lp_f64_solve(xp_lp_f64 *lp, uint32_t max_iter, int rule)
     XP_CUDA_OK(ctx, cudaEventRecord(ctx->ev0, s));
     k_init<<<1, 32, 0, s>>>(d, max_iter, 0);
     ctx->launches++;
+    if (lp->profile) {
+        XP_CUDA_OK(ctx, cudaMemcpyAsync(lp->h_st, d.st, sizeof(LpState), cudaMemcpyDeviceToHost, s));
+        XP_CUDA_OK(ctx, cudaStreamSynchronize(s));
+        lp->cnt_at_entry = lp->h_st->cnt;
+    }
     // Each select+sweep pair is one simplex iteration; batches run without any
     // host round trip, the host only polls the status word between batches.
     int batch = 8;
+    int n_prof = 0; // sweeps bracketed by events in this call
     for (;;) {
         for (int b = 0; b < batch; b++) {
             k_select<<<1, SEL_THREADS, 0, s>>>(d);
             ctx->launches++;
+            const bool prof = lp->profile && n_prof < PROF_MAX_SWEEPS;
+            if (prof) XP_CUDA_OK(ctx, cudaEventRecord(lp->evs[2 * n_prof], s));
             sweep_launch(lp);
+            if (prof) {
+                XP_CUDA_OK(ctx, cudaEventRecord(lp->evs[2 * n_prof + 1], s));
+                n_prof++;
+            }
         }
         XP_CUDA_OK(ctx, cudaGetLastError());
         XP_CUDA_OK(ctx, cudaMemcpyAsync(lp->h_st, d.st, sizeof(LpState), cudaMemcpyDeviceToHost, s));
@@ -712,6 +730,21 @@ extern "C" int xp_lp_f64_solve(xp_lp_f64 *lp, uint32_t max_iter, int rule)
         if (batch < 64) batch *= 2;
         unsigned long long left = (unsigned long long)max_iter - lp->h_st->cnt;
         if ((unsigned long long)batch > left + 1) batch = (int)(left + 1);
+    }
+    if (lp->profile) {
+        // only the first (iterations done in this call) sweeps did real work
+        long long real = (long long)lp->h_st->cnt - (long long)lp->cnt_at_entry;
+        if (real > n_prof) real = n_prof;
+        for (long long k = 0; k < real; k++) {
+            float ms = 0.f;
+            XP_CUDA_OK(ctx, cudaEventElapsedTime(&ms, lp->evs[2 * k], lp->evs[2 * k + 1]));
+            lp->prof_sweep_ms += ms;
+            lp->prof_sweeps++;
+            if (k > 0) {
+                XP_CUDA_OK(ctx, cudaEventElapsedTime(&ms, lp->evs[2 * k - 1], lp->evs[2 * k]));
+                lp->prof_gap_ms += ms;
+            }
+        }
     }
     if (lp->h_st->status == XPI_OPT_PENDING) {
         k_feas_sol<<<ctx->sm_count, 256, 0, s>>>(d);
@@ -725,6 +758,30 @@ extern "C" int xp_lp_f64_solve(xp_lp_f64 *lp, uint32_t max_iter, int rule)
     XP_CUDA_OK(ctx, cudaStreamSynchronize(s));
     XP_CUDA_OK(ctx, cudaEventElapsedTime(&ctx->last_kernel_ms, ctx->ev0, ctx->ev1));
     return lp->h_st->status;
+}
+
+extern "C" int xp_lp_f64_profile(xp_lp_f64 *lp, int enable)
+{
+    if (!lp) return XP_ERR_BAD_ARG;
+    xp_ctx *ctx = lp->ctx;
+    if (enable && lp->evs.empty()) {
+        lp->evs.resize(2 * PROF_MAX_SWEEPS);
+        for (auto &e : lp->evs) XP_CUDA_OK(ctx, cudaEventCreate(&e));
+    }
+    lp->profile = enable != 0;
+    lp->prof_sweeps = 0;
+    lp->prof_sweep_ms = lp->prof_gap_ms = 0.0;
+    return 0;
+}
+
+extern "C" int xp_lp_f64_profile_read(xp_lp_f64 *lp, uint64_t *n_sweeps, double *sweep_ms,
+                                      double *gap_ms)
+{
+    if (!lp) return XP_ERR_BAD_ARG;
+    if (n_sweeps) *n_sweeps = lp->prof_sweeps;
+    if (sweep_ms) *sweep_ms = lp->prof_sweep_ms;
+    if (gap_ms) *gap_ms = lp->prof_gap_ms;
+    return 0;
 }
 
 extern "C" int xp_lp_f64_download(xp_lp_f64 *lp, double *tableau, double *tgtf, uint8_t *nvset,
@@ -798,19 +855,30 @@ extern "C" int xp_six_slack_f64(xp_ctx *ctx, double *tableau, double *tgtf, int 
                                 int32_t *pivot_log, uint32_t log_cap)
 {
     if (!ctx || !tableau || !tgtf || !nvset || !bv2eq || !eq2bv) return XP_ERR_BAD_ARG;
-    xp_lp_f64 *lp = nullptr;
-    int rc = xp_lp_f64_create(ctx, m, C, &lp);
-    if (rc) return rc;
-    rc = xp_lp_f64_upload(lp, tableau, tgtf, nvset, bvset, bv2eq, eq2bv, vc_diag, vc_rhs);
-    int st = rc;
-    if (!rc) {
-        st = xp_lp_f64_solve(lp, max_iter, rule);
-        if (st >= 0) {
-            rc = xp_lp_f64_download(lp, tableau, tgtf, nvset, bvset, bv2eq, eq2bv, maxv, sol, iters,
-                                    pivot_log, log_cap);
-            if (rc) st = rc;
-        }
+    // Device buffers are kept on the ctx between calls of the same shape.
+    xp_lp_f64 *lp = (xp_lp_f64 *)ctx->cached_lp;
+    int rc = 0;
+    if (!lp || lp->d.m != m || lp->d.C != C) {
+        if (lp) xp_lp_f64_destroy(lp);
+        ctx->cached_lp = nullptr;
+        lp = nullptr;
+        rc = xp_lp_f64_create(ctx, m, C, &lp);
+        if (rc) return rc;
+        ctx->cached_lp = lp;
     }
-    xp_lp_f64_destroy(lp);
+    rc = xp_lp_f64_upload(lp, tableau, tgtf, nvset, bvset, bv2eq, eq2bv, vc_diag, vc_rhs);
+    if (rc) return rc;
+    int st = xp_lp_f64_solve(lp, max_iter, rule);
+    if (st >= 0) {
+        rc = xp_lp_f64_download(lp, tableau, tgtf, nvset, bvset, bv2eq, eq2bv, maxv, sol, iters,
+                                pivot_log, log_cap);
+        if (rc) st = rc;
+    }
     return st;
+}
+
+void xp_large_release_cached(xp_ctx *ctx)
+{
+    if (ctx->cached_lp) xp_lp_f64_destroy((xp_lp_f64 *)ctx->cached_lp);
+    ctx->cached_lp = nullptr;
 }
