@@ -271,3 +271,56 @@ def _two_stage_f64_ragged(self, lps, max_iter=NO_ITER_LIMIT):
 
 Context.two_stage_f64_batch = _two_stage_f64_batch
 Context.two_stage_f64_ragged = _two_stage_f64_ragged
+
+
+def _two_stage_i64_batch(self, leq, tgtf, max_iter=NO_ITER_LIMIT):
+    """Exact (fraction-free) TwoStageMethod for a uniform batch of integer LPs:
+    leq [B, m, n+1], tgtf [B, n+1] (integer valued).  Outputs are reduced
+    num/den int64 pairs."""
+    leq = np.ascontiguousarray(leq, dtype=np.int64)
+    tgtf = np.ascontiguousarray(tgtf, dtype=np.int64)
+    B, m, n1 = leq.shape
+    n = n1 - 1
+    ldo = n + m + 1
+    out = dict(status=np.zeros(B, dtype=np.int32), maxv=np.zeros((B, 2), dtype=np.int64),
+               sol_num=np.zeros((B, ldo), dtype=np.int64), sol_den=np.zeros((B, ldo), dtype=np.int64),
+               tgtf_num=np.zeros((B, ldo), dtype=np.int64), tgtf_den=np.zeros((B, ldo), dtype=np.int64),
+               eq2bv=np.zeros((B, m), dtype=np.int32), iters=np.zeros(B, dtype=np.uint32),
+               pivots=np.zeros(B, dtype=np.uint32))
+    self.check(lib().xp_six_two_stage_i64_batch(
+        self._h, B, m, n, _p(leq), _p(tgtf), C.c_uint32(max_iter), RULE_REFERENCE,
+        _p(out["status"]), _p(out["maxv"]), _p(out["sol_num"]), _p(out["sol_den"]),
+        _p(out["tgtf_num"]), _p(out["tgtf_den"]), _p(out["eq2bv"]), _p(out["iters"]),
+        _p(out["pivots"])))
+    return out
+
+
+def _two_stage_i64_ragged(self, lps, max_iter=NO_ITER_LIMIT):
+    B = len(lps)
+    ms = np.array([l.shape[0] for l, _ in lps], dtype=np.int32)
+    ns = np.array([l.shape[1] - 1 for l, _ in lps], dtype=np.int32)
+    leq_pool = np.concatenate([np.asarray(l, dtype=np.int64).ravel() for l, _ in lps])
+    tg_pool = np.concatenate([np.asarray(t, dtype=np.int64).ravel() for _, t in lps])
+    leq_off = np.zeros(B, dtype=np.int64)
+    tg_off = np.zeros(B, dtype=np.int64)
+    leq_off[1:] = np.cumsum(ms[:-1].astype(np.int64) * (ns[:-1] + 1))
+    tg_off[1:] = np.cumsum(ns[:-1].astype(np.int64) + 1)
+    ldo = int((ms + ns).max()) + 1
+    ldm = int(ms.max())
+    out = dict(status=np.zeros(B, dtype=np.int32), maxv=np.zeros((B, 2), dtype=np.int64),
+               sol_num=np.zeros((B, ldo), dtype=np.int64), sol_den=np.zeros((B, ldo), dtype=np.int64),
+               tgtf_num=np.zeros((B, ldo), dtype=np.int64), tgtf_den=np.zeros((B, ldo), dtype=np.int64),
+               eq2bv=np.zeros((B, ldm), dtype=np.int32), iters=np.zeros(B, dtype=np.uint32),
+               pivots=np.zeros(B, dtype=np.uint32))
+    self.check(lib().xp_six_two_stage_i64_ragged(
+        self._h, B, _p(ms), _p(ns), _p(leq_off), _p(tg_off), _p(leq_pool),
+        C.c_size_t(leq_pool.size), _p(tg_pool), C.c_size_t(tg_pool.size), C.c_uint32(max_iter),
+        RULE_REFERENCE, ldo, ldm, _p(out["status"]), _p(out["maxv"]), _p(out["sol_num"]),
+        _p(out["sol_den"]), _p(out["tgtf_num"]), _p(out["tgtf_den"]), _p(out["eq2bv"]),
+        _p(out["iters"]), _p(out["pivots"])))
+    out["ms"], out["ns"] = ms, ns
+    return out
+
+
+Context.two_stage_i64_batch = _two_stage_i64_batch
+Context.two_stage_i64_ragged = _two_stage_i64_ragged
