@@ -126,13 +126,6 @@ int xp_lp_f64_profile(xp_lp_f64 *lp, int enable);
 int xp_lp_f64_profile_read(xp_lp_f64 *lp, uint64_t *n_sweeps, double *sweep_ms, double *gap_ms);
 /* Order-independent 64-bit checksum of the device tableau bits (parity at full size). */
 int xp_lp_f64_checksum(xp_lp_f64 *lp, uint64_t *sum_tableau, uint64_t *sum_tgtf);
-/* Column-sharded multi-GPU: attach an NCCL communicator built from a unique id
- * that rank 0 obtained with xp_nccl_unique_id and shared out of band.  After
- * this, create/upload/solve operate on this rank's column slice
- * [rank*C/n, (rank+1)*C/n) plus a replica of the constant column. */
-int xp_nccl_unique_id(void *id128);
-int xp_ctx_attach_nccl(xp_ctx *ctx, const void *id128, int rank, int nranks);
-
 /* ------------------------------------------ TwoStageMethod level: batched FP64
  * Replaces SIX<FloatMat,Float>::TwoStageMethod (lpsol.h:1906-1930: stage1,
  * slack, constructBasicFeasibleSolution, solveSlackForm) for a batch of

@@ -236,6 +236,7 @@ static int r_eq(xo_rat a, xo_rat b) { return a.num == b.num && a.den == b.den; }
 #define T_REDUCE(a) (a)                  /* Float::reduce is a no-op, flty.h:93 */
 #define T_IS_INT(a) f_is_int(a)
 #define T_TRUNC(a) ((int)(a))            /* Float::typecast2int, flty.h:85-88 */
+#define T_IS_EXACT_ZERO(a) ((a) == 0.0)
 #include "xp_oracle_six.inc"
 #undef T
 #undef FN
@@ -254,6 +255,7 @@ static int r_eq(xo_rat a, xo_rat b) { return a.num == b.num && a.den == b.den; }
 #undef T_REDUCE
 #undef T_IS_INT
 #undef T_TRUNC
+#undef T_IS_EXACT_ZERO
 
 /* --------------------------------------------- instantiate: Rational */
 #define T xo_rat
@@ -273,6 +275,7 @@ static int r_eq(xo_rat a, xo_rat b) { return a.num == b.num && a.den == b.den; }
 #define T_REDUCE(a) r_reduce(a)
 #define T_IS_INT(a) ((a).den == 1)       /* RMat::is_imat, xmat.cpp:603-616 */
 #define T_TRUNC(a) ((a).num / (a).den)   /* Rational::typecast2int, rational.h:62 */
+#define T_IS_EXACT_ZERO(a) ((a).num == 0)
 #include "xp_oracle_six.inc"
 #undef T
 #undef FN

@@ -1,0 +1,227 @@
+"""Entry-level parity (SIX::maxm / minm, MIP::maxm / minm, Lineq::has_solution)
+of the C ABI against the oracle: status, objective and solution -- bit-exact for
+FP64, exact num/den for rationals (on LPs where the reference stayed exact)."""
+import numpy as np
+import pytest
+
+import harness as H
+import xpoly_b200 as xp
+
+pytestmark = pytest.mark.gpu
+
+
+def same_f64(g, o, tag):
+    assert g["status"] == o["status"], (tag, g["status"], o["status"])
+    assert np.array_equal(H.bits(g["v"]), H.bits(o["v"])), (tag, g["v"], o["v"])
+    if o["status"] == 0:
+        assert np.array_equal(H.bits(g["sol"]), H.bits(o["sol"])), tag
+
+
+def same_rat(g, o, tag):
+    assert g["status"] == o["status"], (tag, g["status"], o["status"])
+    assert np.array_equal(g["v"], o["v"]), (tag, g["v"], o["v"])
+    if o["status"] == 0:
+        assert np.array_equal(g["sol"], o["sol"]), tag
+
+
+def cover_lp(seed):
+    r = np.random.RandomState(seed)
+    m, n = r.randint(3, 10), r.randint(2, 8)
+    A = r.randint(0, 4, size=(m, n)).astype(float)
+    leq = np.zeros((m, n + 1))
+    leq[:, :n] = -A
+    leq[:, n] = -r.randint(1, 10, size=m)
+    tg = np.zeros(n + 1)
+    tg[:n] = r.randint(1, 6, size=n)
+    return leq, tg
+
+
+def test_example_float_golden(ctx):
+    """src/example/example.cpp:54-93: max 2x1-x2 s.t. 2x1-x2<=2, x1-5x2<=-4 => 2 at (14/9, 10/9)."""
+    leq = np.array([[2, -1, 2], [1, -5, -4]], dtype=float)
+    tg = np.array([2, -1, 0], dtype=float)
+    g = ctx.six_solve("f64", 0, leq, tg)
+    assert g["status"] == 0 and g["v"][0] == 2.0
+    assert g["sol"].tolist() == [1.5555555555555556, 1.1111111111111112, 1.0]
+
+
+def test_example_rational_golden(ctx):
+    """src/example/example.cpp:106-181: max unbounded, min = 23 at (10,5,3,2,3)."""
+    import json, os
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_vectors.json")))
+    ex = gold["example_rational"]
+    leq = np.array(ex["leq"], dtype=np.int64)
+    tg = np.array(ex["tgtf"], dtype=np.int64)
+    gmax = ctx.six_solve("rat", 0, leq, tg)
+    gmin = ctx.six_solve("rat", 1, leq, tg)
+    assert gmax["status"] == ex["max"]["status"] == xp.SIX_UNBOUND
+    assert gmin["status"] == 0 and gmin["v"].tolist() == ex["min"]["v"] == [23, 1]
+    assert gmin["sol"].tolist() == ex["min"]["sol"]
+
+
+def test_maxm_minm_f64_vs_oracle(ctx):
+    for seed in range(120):
+        leq, tg = cover_lp(seed)
+        for is_min in (0, 1):
+            same_f64(ctx.six_solve("f64", is_min, leq, tg),
+                     H.six_solve("oracle", "f64", is_min, leq, tg), ("cover", seed, is_min))
+        leq, tg = H.gen_mixed_lp(seed, 9, 7, bneg=0.3)
+        for is_min in (0, 1):
+            same_f64(ctx.six_solve("f64", is_min, leq, tg),
+                     H.six_solve("oracle", "f64", is_min, leq, tg), ("mixed", seed, is_min))
+
+
+def test_maxm_minm_rat_vs_oracle(ctx):
+    n_checked = 0
+    for seed in range(150):
+        for leq, tg in (cover_lp(seed), H.gen_int_lp(seed, 10, 8, alo=-2, ahi=3, density=0.6,
+                                                      blo=-4, bhi=15)):
+            for is_min in (0, 1):
+                a0 = H.appro_count("oracle")
+                o = H.six_solve("oracle", "rat", is_min, H.to_rat(leq), H.to_rat(tg))
+                if H.appro_count("oracle") != a0:
+                    continue
+                same_rat(ctx.six_solve("rat", is_min, leq.astype(np.int64), tg.astype(np.int64)), o,
+                         (seed, is_min))
+                n_checked += 1
+    assert n_checked > 500
+
+
+def test_equalities_and_free_variables(ctx):
+    """eq rows go through convertEq2Ineq (including its mis-indexed column,
+    lpsol.h:1232); free variables (zero vc column) are split v = v' - v''."""
+    r = np.random.RandomState(1)
+    seen_ub = 0
+    for seed in range(120):
+        m, n = r.randint(3, 8), r.randint(2, 6)
+        leq, tg = H.gen_int_lp(seed, m, n, alo=-2, ahi=3, density=0.7)
+        k = r.randint(1, 3)
+        E = np.zeros((k, n + 1))
+        E[:, :n] = r.randint(-2, 3, size=(k, n))
+        E[:, n] = r.randint(0, 6, size=k)
+        o = H.six_solve("oracle", "f64", 0, leq, tg, None, E)
+        g = ctx.six_solve("f64", 0, leq, tg, eq=E)
+        if o["status"] == xp.ERR_REFERENCE_UB:
+            seen_ub += 1
+            assert g["status"] == xp.ERR_REFERENCE_UB
+        else:
+            same_f64(g, o, ("eq", seed))
+        vc = np.zeros((n, n + 1))
+        for i in range(n):
+            if r.uniform() < 0.6:
+                vc[i, i] = -1
+        for is_min in (0, 1):
+            same_f64(ctx.six_solve("f64", is_min, leq, tg, vc=vc),
+                     H.six_solve("oracle", "f64", is_min, leq, tg, vc), ("free", seed, is_min))
+    assert seen_ub > 0
+
+
+def test_large_lp_through_entry_goes_to_hbm_path(ctx):
+    """An LP too large for shared memory is routed to the HBM-resident path,
+    including the host-mediated phase 1 (negative right-hand sides)."""
+    leq, tg = H.gen_dense_lp(3, 150, 149)
+    same_f64(ctx.six_solve("f64", 0, leq, tg), H.six_solve("oracle", "f64", 0, leq, tg), "large")
+    leq2 = leq.copy()
+    leq2[::7, -1] = -0.5
+    leq2[::7, :-1] *= -1.0
+    same_f64(ctx.six_solve("f64", 0, leq2, tg, max_iter=60),
+             H.six_solve("oracle", "f64", 0, leq2, tg, max_iter=60), "large-phase1")
+
+
+def test_batched_entry_f64_and_rat(ctx):
+    lps = [H.gen_dense_lp(2024 + k, 16, 15) for k in range(64)]
+    leq = np.stack([l for l, _ in lps])
+    tg = np.stack([t for _, t in lps])
+    for is_min in (0, 1):
+        g = ctx.six_solve_batch("f64", is_min, leq, tg)
+        for k, (l, t) in enumerate(lps):
+            o = H.six_solve("oracle", "f64", is_min, l, t)
+            same_f64(dict(status=g["status"][k], v=g["v"][k:k + 1], sol=g["sol"][k]), o, (k, is_min))
+    lps = [cover_lp(900 + k) if k % 2 else H.gen_int_lp(k, 8, 6) for k in range(40)]
+    lps = [(l, t) for l, t in lps if l.shape == lps[1][0].shape]
+    leq = np.stack([l for l, _ in lps]).astype(np.int64)
+    tg = np.stack([t for _, t in lps]).astype(np.int64)
+    for is_min in (0, 1):
+        g = ctx.six_solve_batch("rat", is_min, leq, tg)
+        for k, (l, t) in enumerate(lps):
+            o = H.six_solve("oracle", "rat", is_min, H.to_rat(l), H.to_rat(t))
+            same_rat(dict(status=g["status"][k], v=g["v"][k], sol=g["sol"][k]), o, (k, is_min))
+
+
+def knapsack(n, seed):
+    r = np.random.RandomState(seed)
+    w = r.randint(5, 41, size=n)
+    p = r.randint(5, 61, size=n)
+    leq = np.zeros((n + 1, n + 1), dtype=np.int64)
+    leq[0, :n] = w
+    leq[0, n] = int(w.sum() // 3)
+    for j in range(n):
+        leq[1 + j, j] = 1
+        leq[1 + j, n] = 1
+    tg = np.zeros(n + 1, dtype=np.int64)
+    tg[:n] = p
+    return leq, tg
+
+
+def test_mip_rat_vs_oracle(ctx):
+    for seed in range(80):
+        r = np.random.RandomState(seed)
+        m, n = r.randint(2, 7), r.randint(2, 6)
+        leq, tg = H.gen_int_lp(seed, m, n, alo=-1, ahi=4, density=0.8, blo=1, bhi=25)
+        for is_min in (0, 1):
+            o = H.mip_solve("oracle", "rat", is_min, 0, H.to_rat(leq), H.to_rat(tg))
+            g = ctx.mip_solve("rat", is_min, 0, leq.astype(np.int64), tg.astype(np.int64))
+            same_rat(g, o, ("mip", seed, is_min))
+            assert g["nodes"] == o["nodes"], ("nodes", seed, is_min)
+
+
+def test_mip_f64_vs_oracle(ctx):
+    for seed in range(40):
+        r = np.random.RandomState(seed)
+        m, n = r.randint(2, 7), r.randint(2, 6)
+        leq, tg = H.gen_int_lp(seed, m, n, alo=-1, ahi=4, density=0.8, blo=1, bhi=25)
+        o = H.mip_solve("oracle", "f64", 0, 0, leq, tg)
+        same_f64(ctx.mip_solve("f64", 0, 0, leq, tg), o, ("mipf", seed))
+
+
+def test_c5_knapsack_bnb(ctx):
+    """Config 5 family.  n <= 50 solves; n = 200 has the reference answer
+    IP_UNBOUND after one node."""
+    for n, seed in ((10, 109), (30, 129), (50, 149)):
+        leq, tg = knapsack(n, seed)
+        o = H.mip_solve("oracle", "rat", 0, 0, H.to_rat(leq), H.to_rat(tg))
+        g = ctx.mip_solve("rat", 0, 0, leq, tg)
+        same_rat(g, o, ("knap", n))
+        assert g["nodes"] == o["nodes"]
+    leq, tg = knapsack(200, 99)
+    g = ctx.mip_solve("rat", 0, 0, leq, tg)
+    o = H.mip_solve("oracle", "rat", 0, 0, H.to_rat(leq), H.to_rat(tg))
+    assert g["status"] == o["status"] == xp.IP_UNBOUND and g["nodes"] == o["nodes"] == 1
+
+
+def test_mip_batch_lockstep_equals_individual(ctx):
+    lps = [knapsack(12, 300 + k) for k in range(24)]
+    leq = np.stack([l for l, _ in lps])
+    tg = np.stack([t for _, t in lps])
+    g = ctx.mip_solve_rat_batch(0, 0, leq, tg)
+    for k, (l, t) in enumerate(lps):
+        o = H.mip_solve("oracle", "rat", 0, 0, H.to_rat(l), H.to_rat(t))
+        same_rat(dict(status=g["status"][k], v=g["v"][k], sol=g["sol"][k]), o, ("batch", k))
+        assert g["nodes"][k] == o["nodes"]
+
+
+def test_has_solution_dependence_queries(ctx):
+    """SURVEY Appendix A6 (A true, B false, C false) + random systems vs the oracle."""
+    A = [[-1, 0, -1], [1, 0, 10], [0, -1, -1], [0, 1, 10], [1, -1, 1], [-1, 1, -1]]
+    Cc = [[-1, 0, -1], [1, 0, 10], [0, -1, -1], [0, 1, 10], [2, -2, 1], [-2, 2, -1]]
+    res = ctx.has_solution_batch(np.array([A, Cc], dtype=np.int64))
+    assert res.tolist() == [1, 0]
+    B = [[-1, 0, -1], [1, 0, 10], [0, -1, -1], [0, 1, 10], [1, -1, -20]]
+    assert ctx.has_solution_batch(np.array([B], dtype=np.int64)).tolist() == [0]
+    lps = [H.gen_int_lp(k, 6, 4, alo=-1, ahi=4, density=0.8, blo=1, bhi=25)[0] for k in range(100)]
+    res = ctx.has_solution_batch(np.stack(lps).astype(np.int64))
+    for k, l in enumerate(lps):
+        assert res[k] == H.has_solution("oracle", H.to_rat(l)), k
+    res2 = ctx.has_solution_batch(np.stack(lps).astype(np.int64), is_int=False, is_unique=False)
+    for k, l in enumerate(lps):
+        assert res2[k] == H.has_solution("oracle", H.to_rat(l), is_int=False, is_unique=False), k

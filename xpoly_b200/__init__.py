@@ -324,3 +324,97 @@ def _two_stage_i64_ragged(self, lps, max_iter=NO_ITER_LIMIT):
 
 Context.two_stage_i64_batch = _two_stage_i64_batch
 Context.two_stage_i64_ragged = _two_stage_i64_ragged
+
+
+# --------------------------------------------------------------- entry level
+def _rat(a):
+    """int (..., 2) array of num/den pairs, or an integer array (den = 1)."""
+    a = np.asarray(a)
+    if a.dtype != np.int32 or a.shape[-1:] != (2,):
+        out = np.empty(a.shape + (2,), dtype=np.int32)
+        out[..., 0] = a
+        out[..., 1] = 1
+        a = out
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _six_solve(self, kind, is_min, leq, tgtf, vc=None, eq=None, max_iter=NO_ITER_LIMIT):
+    """SIX::maxm / minm.  kind 'f64' (float64 arrays) or 'rat' (int32 num/den pairs)."""
+    if kind == "f64":
+        conv, v = _f64, np.zeros(1)
+    else:
+        conv, v = _rat, np.zeros(2, dtype=np.int32)
+    leq = None if leq is None else conv(leq)
+    eq = None if eq is None else conv(eq)
+    tgtf = conv(tgtf)
+    vc = None if vc is None else conv(vc)
+    n = tgtf.shape[0] - 1
+    m = 0 if leq is None else leq.shape[0]
+    k = 0 if eq is None else eq.shape[0]
+    sol = np.zeros((n + 1,) + tgtf.shape[1:], dtype=tgtf.dtype)
+    e2b = np.zeros(m + 2 * k + n + 2, dtype=np.int32)
+    fn = getattr(lib(), f"xp_six_{'minm' if is_min else 'maxm'}_{kind}")
+    st = self.check(fn(self._h, m, n, _p(tgtf), _p(vc), k, _p(eq), _p(leq), C.c_uint32(max_iter),
+                       _p(v), _p(sol), _p(e2b)))
+    return dict(status=st, v=v, sol=sol, eq2bv=e2b)
+
+
+def _six_solve_batch(self, kind, is_min, leq, tgtf, max_iter=NO_ITER_LIMIT):
+    conv = _f64 if kind == "f64" else _rat
+    leq, tgtf = conv(leq), conv(tgtf)
+    B, m, n1 = leq.shape[:3]
+    status = np.zeros(B, dtype=np.int32)
+    v = np.zeros((B,) + tgtf.shape[2:], dtype=tgtf.dtype)
+    sol = np.zeros((B, n1) + tgtf.shape[2:], dtype=tgtf.dtype)
+    fn = getattr(lib(), f"xp_six_solve_{kind}_batch")
+    self.check(fn(self._h, int(is_min), B, m, n1 - 1, _p(tgtf), _p(leq), C.c_uint32(max_iter),
+                  _p(status), _p(v), _p(sol)))
+    return dict(status=status, v=v, sol=sol)
+
+
+def _mip_solve(self, kind, is_min, is_bin, leq, tgtf, eq=None):
+    if kind == "f64":
+        conv, v = _f64, np.zeros(1)
+    else:
+        conv, v = _rat, np.zeros(2, dtype=np.int32)
+    leq = None if leq is None else conv(leq)
+    eq = None if eq is None else conv(eq)
+    tgtf = conv(tgtf)
+    n = tgtf.shape[0] - 1
+    m = 0 if leq is None else leq.shape[0]
+    k = 0 if eq is None else eq.shape[0]
+    sol = np.zeros((n + 1,) + tgtf.shape[1:], dtype=tgtf.dtype)
+    nodes = C.c_int32(0)
+    fn = getattr(lib(), f"xp_mip_solve_{kind}")
+    st = self.check(fn(self._h, int(is_min), int(is_bin), m, n, _p(tgtf), k, _p(eq), _p(leq),
+                       _p(v), _p(sol), C.byref(nodes)))
+    return dict(status=st, v=v, sol=sol, nodes=nodes.value)
+
+
+def _mip_solve_rat_batch(self, is_min, is_bin, leq, tgtf):
+    leq, tgtf = _rat(leq), _rat(tgtf)
+    B, m, n1 = leq.shape[:3]
+    status = np.zeros(B, dtype=np.int32)
+    v = np.zeros((B, 2), dtype=np.int32)
+    sol = np.zeros((B, n1, 2), dtype=np.int32)
+    nodes = np.zeros(B, dtype=np.int32)
+    self.check(lib().xp_mip_solve_rat_batch(self._h, int(is_min), int(is_bin), B, m, n1 - 1,
+                                            _p(tgtf), _p(leq), _p(status), _p(v), _p(sol),
+                                            _p(nodes)))
+    return dict(status=status, v=v, sol=sol, nodes=nodes)
+
+
+def _has_solution_batch(self, leq, is_int=True, is_unique=True):
+    leq = _rat(leq)
+    B, m, n1 = leq.shape[:3]
+    res = np.zeros(B, dtype=np.int32)
+    self.check(lib().xp_has_solution_rat_batch(self._h, B, m, n1 - 1, _p(leq), int(is_int),
+                                               int(is_unique), _p(res)))
+    return res
+
+
+Context.six_solve = _six_solve
+Context.six_solve_batch = _six_solve_batch
+Context.mip_solve = _mip_solve
+Context.mip_solve_rat_batch = _mip_solve_rat_batch
+Context.has_solution_batch = _has_solution_batch

@@ -37,6 +37,7 @@ extern "C" void xp_ctx_destroy(xp_ctx *ctx)
         cudaStreamSynchronize(ctx->stream);
         xp_large_release_cached(ctx);
         if (ctx->scratch) cudaFree(ctx->scratch);
+        if (ctx->gws) cudaFree(ctx->gws);
         cudaEventDestroy(ctx->ev0);
         cudaEventDestroy(ctx->ev1);
         cudaStreamDestroy(ctx->stream);
@@ -63,6 +64,22 @@ int xp_ctx_scratch(xp_ctx *ctx, size_t bytes, void **out)
         ctx->scratch_bytes = want;
     }
     *out = ctx->scratch;
+    return 0;
+}
+
+int xp_ctx_gws(xp_ctx *ctx, size_t bytes, void **out)
+{
+    if (bytes > ctx->gws_bytes) {
+        if (ctx->gws) {
+            XP_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+            XP_CUDA_OK(ctx, cudaFree(ctx->gws));
+            ctx->gws = nullptr;
+            ctx->gws_bytes = 0;
+        }
+        XP_CUDA_OK(ctx, cudaMalloc(&ctx->gws, bytes));
+        ctx->gws_bytes = bytes;
+    }
+    *out = ctx->gws;
     return 0;
 }
 

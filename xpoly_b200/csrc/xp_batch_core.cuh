@@ -30,6 +30,10 @@ struct XpBatchArgs {
     uint32_t *iters, *pivots;
     int maxm, maxn;                   // smem layout bounds
     unsigned *queue;                  // atomic work counter
+    // LPs too large for shared memory: the same state block carved out of a
+    // per-CTA slab of global memory instead (L2-resident for c5-sized tableaux).
+    unsigned char *gws;
+    size_t gws_stride;
 };
 
 constexpr int XPB_BIG = 0x7fffffff;
@@ -441,7 +445,8 @@ __device__ inline void xpb_kernel_body(const XpBatchArgs &A)
     __shared__ int s_lp;
     XpB<E> S;
     long long *misc;
-    xpb_carve<E, typename Ops::Key>(S, xpb_smem, A.maxm, A.maxn, &misc);
+    unsigned char *state = A.gws ? A.gws + (size_t)blockIdx.x * A.gws_stride : xpb_smem;
+    xpb_carve<E, typename Ops::Key>(S, state, A.maxm, A.maxn, &misc);
     Ops::bind(S, misc);
     for (;;) {
         __syncthreads();

@@ -296,8 +296,20 @@ int launch_i64(xp_ctx *ctx, XpBatchArgs &A)
 {
     const size_t smem = xpb_smem_bytes(A.maxm, A.maxn, sizeof(i64), sizeof(KeyI64));
     if (smem > ctx->smem_optin) {
-        ctx->err = "LP too large for the shared-memory batched path";
-        return XP_ERR_TOO_LARGE;
+        // Same kernel, state slab in global memory: one 1024-thread CTA per LP.
+        const size_t stride = (smem + 255) & ~(size_t)255;
+        long long g = 2LL * ctx->sm_count;
+        if (g > A.batch) g = A.batch;
+        void *ws = nullptr;
+        int rc = xp_ctx_gws(ctx, stride * (size_t)g, &ws);
+        if (rc) return rc;
+        A.gws = (unsigned char *)ws;
+        A.gws_stride = stride;
+        XP_CUDA_OK(ctx, cudaMemsetAsync(A.queue, 0, sizeof(unsigned), ctx->stream));
+        k_batch_i64<1024><<<(unsigned)g, 1024, 0, ctx->stream>>>(A);
+        ctx->launches++;
+        XP_CUDA_OK(ctx, cudaGetLastError());
+        return 0;
     }
     XP_CUDA_OK(ctx, cudaMemsetAsync(A.queue, 0, sizeof(unsigned), ctx->stream));
     const int th = pick_threads_i64(A.maxm, A.maxn);

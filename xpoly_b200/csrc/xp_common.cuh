@@ -31,6 +31,9 @@ struct xp_ctx {
     void *scratch = nullptr;
     size_t scratch_bytes = 0;
     void *cached_lp = nullptr; // xp_lp_f64 reused by xp_six_slack_f64
+    // global-memory state slabs of the batched kernels (LPs beyond shared memory)
+    void *gws = nullptr;
+    size_t gws_bytes = 0;
 };
 
 #define XP_CUDA_OK(ctx, expr)                                                                  \
@@ -144,4 +147,5 @@ __device__ __forceinline__ int xp_block_min_int(int x, int *sh)
 
 // host-side helpers shared by the translation units
 int xp_ctx_scratch(xp_ctx *ctx, size_t bytes, void **out);
+int xp_ctx_gws(xp_ctx *ctx, size_t bytes, void **out);
 void xp_large_release_cached(xp_ctx *ctx);

@@ -1,0 +1,755 @@
+// Entry-level C ABI: SIX<Mat,T>::maxm / minm, MIP<Mat,T>::maxm / minm and
+// Lineq::has_solution over raw row-major arrays.  The host half (verify,
+// normalize, dual, calcFinalSolution, B&B bookkeeping) is xp_host_six.hpp; every
+// TwoStageMethod (slack form, phase 1, solveSlackForm) runs on the GPU:
+//   - LPs that fit shared memory go to the one-CTA-per-LP kernels, many per launch;
+//   - larger FP64 LPs go to the HBM-resident path (host-mediated phase 1).
+// There is no CPU solve path in here.
+#include "xp_batch_core.cuh"
+
+#include "../host/xp_host_six.hpp"
+
+#include <vector>
+
+using namespace xph;
+
+namespace {
+
+// ---------------------------------------------------------------- FP64 side
+typedef TwoStageResult<F64> ResF;
+
+bool fits_smem(const xp_ctx *ctx, int m, int n, size_t key_bytes)
+{
+    return xpb_smem_bytes(m, n, 8, key_bytes) <= ctx->smem_optin;
+}
+
+// SIX::pivot (lpsol.h:1455-1511) on the host, FP64, used only by the
+// host-mediated phase 1 of LPs too large for shared memory (two pivots per solve).
+void host_pivot(std::vector<double> &tab, std::vector<double> &tg, int m, int C, int rhs, int p,
+                int q, std::vector<uint8_t> &nvset, std::vector<int32_t> &bv2eq,
+                std::vector<int32_t> &eq2bv)
+{
+    const int bv = eq2bv[p];
+    double *rowp = &tab[(size_t)p * C];
+    const double r = 1.0 / rowp[q];
+    if (!F64::eq(r, 1.0)) {
+        const bool z = F64::eq(r, 0.0);
+        for (int j = 0; j < C; j++) rowp[j] = z ? 0.0 : rowp[j] * r;
+    }
+    const double cq = tg[q];
+    for (int i = 0; i < m; i++) {
+        if (i == p) continue;
+        double *row = &tab[(size_t)i * C];
+        const double f = -row[q];
+        for (int j = 0; j < C; j++) {
+            const double v = f * rowp[j];
+            row[j] = row[j] + v;
+        }
+    }
+    const bool cz = F64::eq(cq, 0.0), c1 = F64::eq(cq, 1.0);
+    for (int j = 0; j < C; j++) {
+        double t = rowp[j] * -1.0;
+        if (j >= rhs) t = -t;
+        t = cz ? 0.0 : (c1 ? t : t * cq);
+        tg[j] = t + tg[j];
+    }
+    nvset[q] = 0;
+    nvset[bv] = 1;
+    eq2bv[p] = q;
+    bv2eq[q] = p;
+    bv2eq[bv] = -1;
+}
+
+// TwoStageMethod (lpsol.h:1906-1930) for one FP64 LP on the HBM-resident path.
+int two_stage_large_f64(xp_ctx *ctx, const Mat<F64> &leq, const Mat<F64> &tg, uint32_t max_iter,
+                        ResF &R)
+{
+    const int m = leq.r, n = leq.c - 1;
+    bool pos = false, bneg = false;
+    for (int j = 0; j < n; j++) pos |= tg.at(0, j) > 0.0;
+    for (int i = 0; i < m; i++) bneg |= leq.at(i, n) < 0.0;
+    const bool aux = !pos || bneg; // stage1, :1794-1803
+    const int Cm = n + m + 1;
+    R.slack_sol.assign(Cm, 0.0);
+    R.tgtf.assign(Cm, 0.0);
+    R.eq2bv.assign(m, 0);
+    R.maxv = 0.0;
+    xp_lp_f64 *lp = nullptr;
+    int rc;
+    if (!aux) {
+        rc = xp_lp_f64_create(ctx, m, Cm, &lp);
+        if (rc) return rc;
+        rc = xp_lp_f64_upload_leq(lp, leq.a.data(), tg.a.data(), n);
+        int st = rc ? rc : xp_lp_f64_solve(lp, max_iter, XP_RULE_REFERENCE);
+        if (st >= 0)
+            rc = xp_lp_f64_download(lp, nullptr, R.tgtf.data(), nullptr, nullptr, nullptr,
+                                    R.eq2bv.data(), &R.maxv, R.slack_sol.data(), nullptr, nullptr, 0);
+        xp_lp_f64_destroy(lp);
+        R.status = (st >= 0 && rc) ? rc : st;
+        return 0;
+    }
+    // ---- constructBasicFeasibleSolution, lpsol.h:838-988, host-mediated ----
+    const int xa = n, s0 = n + 1, rhs = n + 1 + m, C = rhs + 1;
+    std::vector<double> tab((size_t)m * C, 0.0), tgt(C, 0.0), sol(C, 0.0);
+    std::vector<uint8_t> nvset(rhs, 0), bvset(rhs, 0);
+    std::vector<int32_t> bv2eq(rhs, -1), eq2bv(m, 0);
+    for (int i = 0; i < m; i++) {
+        for (int j = 0; j < n; j++) tab[(size_t)i * C + j] = leq.at(i, j);
+        tab[(size_t)i * C + xa] = -1.0;
+        tab[(size_t)i * C + s0 + i] = 1.0;
+        tab[(size_t)i * C + rhs] = leq.at(i, n);
+        eq2bv[i] = s0 + i;
+        bv2eq[s0 + i] = i;
+    }
+    for (int j = 0; j < s0; j++) nvset[j] = 1;
+    tgt[xa] = -1.0;
+    int prow = 0; // row of the first minimum constant term, :894-904
+    for (int i = 1; i < m; i++)
+        if (tab[(size_t)prow * C + rhs] > tab[(size_t)i * C + rhs]) prow = i;
+    host_pivot(tab, tgt, m, C, rhs, prow, xa, nvset, bv2eq, eq2bv);
+    for (int j = 0; j < rhs; j++) bvset[j] = !nvset[j];
+    double maxv = 0.0;
+    uint32_t iters = 0;
+    int st = xp_six_slack_f64(ctx, tab.data(), tgt.data(), m, C, nvset.data(), bvset.data(),
+                              bv2eq.data(), eq2bv.data(), nullptr, nullptr, max_iter,
+                              XP_RULE_REFERENCE, &maxv, sol.data(), &iters, nullptr, 0);
+    if (st < 0) return st;
+    if (st != XP_SIX_SUCC || !F64::eq(maxv, 0.0)) { // :912-922
+        R.status = XP_SIX_NO_PRI_FEASIBLE_SOL;
+        return 0;
+    }
+    if (!nvset[xa]) { // :924-941
+        const int eqnum = bv2eq[xa];
+        int cand = -1;
+        for (int j = 0; j < rhs; j++)
+            if (nvset[j] && !F64::eq(tab[(size_t)eqnum * C + j], 0.0)) {
+                cand = j;
+                break;
+            }
+        if (cand < 0) {
+            R.status = XP_ERR_REFERENCE_UB;
+            return 0;
+        }
+        host_pivot(tab, tgt, m, C, rhs, eqnum, cand, nvset, bv2eq, eq2bv);
+    }
+    // restore the original objective by substitution, :944-953 (FloatMat::substit)
+    for (int j = 0; j < C; j++) tgt[j] = j < n ? tg.at(0, j) : (j == rhs ? tg.at(0, n) : 0.0);
+    for (int i = 0; i < rhs; i++) {
+        const double ci = tgt[i];
+        if (F64::eq(ci, 0.0) || nvset[i]) continue;
+        const double *ex = &tab[(size_t)bv2eq[i] * C];
+        const double ev = ex[i];
+        const bool skip = F64::eq(ev, 0.0);
+        double s = -1.0;
+        if (!F64::eq(ci, ev)) s = (-ci) / ev;
+        const bool sz = F64::eq(s, 0.0), s1 = F64::eq(s, 1.0);
+        for (int j = 0; j < C; j++) {
+            double tj = tgt[j];
+            if (j >= rhs) tj = tj * -1.0;
+            if (!skip) {
+                double x = sz ? 0.0 : (s1 ? ex[j] : ex[j] * s);
+                tj = x + tj;
+            }
+            if (j >= rhs) tj = tj * -1.0;
+            tgt[j] = tj;
+        }
+    }
+    // drop column xa, re-index the maps, :956-986
+    std::vector<double> tab2((size_t)m * Cm), tg2(Cm);
+    for (int i = 0; i < m; i++)
+        for (int j = 0, k = 0; j < C; j++)
+            if (j != xa) tab2[(size_t)i * Cm + k++] = tab[(size_t)i * C + j];
+    std::vector<uint8_t> nv2(Cm - 1), bvs2(Cm - 1);
+    std::vector<int32_t> b2e2(Cm - 1);
+    for (int j = 0, k = 0; j < C; j++)
+        if (j != xa) {
+            tg2[k] = tgt[j];
+            if (j < rhs) {
+                nv2[k] = nvset[j];
+                bvs2[k] = !nvset[j];
+                b2e2[k] = bv2eq[j];
+            }
+            k++;
+        }
+    for (int i = 0; i < m; i++)
+        if (eq2bv[i] > xa) eq2bv[i]--;
+    st = xp_six_slack_f64(ctx, tab2.data(), tg2.data(), m, Cm, nv2.data(), bvs2.data(), b2e2.data(),
+                          eq2bv.data(), nullptr, nullptr, max_iter, XP_RULE_REFERENCE, &R.maxv,
+                          R.slack_sol.data(), &iters, nullptr, 0);
+    if (st < 0) return st;
+    R.status = st;
+    R.tgtf = tg2;
+    R.eq2bv = eq2bv;
+    return 0;
+}
+
+// TwoStageMethod for a set of normalised FP64 LPs: one ragged batched launch for
+// everything that fits shared memory, the HBM-resident path for the rest.
+int two_stage_many_f64(xp_ctx *ctx, const std::vector<const Mat<F64> *> &leqs,
+                       const std::vector<const Mat<F64> *> &tgs, uint32_t max_iter,
+                       std::vector<ResF> &out)
+{
+    const int B = (int)leqs.size();
+    out.assign(B, ResF());
+    std::vector<int> small;
+    for (int k = 0; k < B; k++) {
+        const int m = leqs[k]->r, n = leqs[k]->c - 1;
+        if (m < 1 || n < 1) {
+            out[k].status = XP_ERR_BAD_ARG;
+            continue;
+        }
+        if (fits_smem(ctx, m, n, 16)) small.push_back(k);
+        else {
+            int rc = two_stage_large_f64(ctx, *leqs[k], *tgs[k], max_iter, out[k]);
+            if (rc) return rc;
+        }
+    }
+    if (small.empty()) return 0;
+    const int S = (int)small.size();
+    std::vector<int32_t> ms(S), ns(S);
+    std::vector<int64_t> lo(S), to(S);
+    size_t ll = 0, tl = 0;
+    int ldo = 0, ldm = 0;
+    for (int s = 0; s < S; s++) {
+        const Mat<F64> &L = *leqs[small[s]];
+        ms[s] = L.r;
+        ns[s] = L.c - 1;
+        lo[s] = (int64_t)ll;
+        to[s] = (int64_t)tl;
+        ll += L.a.size();
+        tl += (size_t)L.c;
+        ldo = std::max(ldo, L.r + L.c);
+        ldm = std::max(ldm, L.r);
+    }
+    std::vector<double> lp(ll), tp(tl), maxv(S), sol((size_t)S * ldo), tgo((size_t)S * ldo);
+    std::vector<int32_t> status(S), e2b((size_t)S * ldm);
+    for (int s = 0; s < S; s++) {
+        const Mat<F64> &L = *leqs[small[s]], &T = *tgs[small[s]];
+        std::copy(L.a.begin(), L.a.end(), lp.begin() + lo[s]);
+        std::copy(T.a.begin(), T.a.end(), tp.begin() + to[s]);
+    }
+    int rc = xp_six_two_stage_f64_ragged(ctx, S, ms.data(), ns.data(), lo.data(), to.data(),
+                                         lp.data(), ll, tp.data(), tl, max_iter, XP_RULE_REFERENCE,
+                                         ldo, ldm, status.data(), maxv.data(), sol.data(),
+                                         tgo.data(), e2b.data(), nullptr, nullptr);
+    if (rc) return rc;
+    for (int s = 0; s < S; s++) {
+        ResF &R = out[small[s]];
+        const int Cm = ms[s] + ns[s] + 1;
+        R.status = status[s];
+        R.maxv = maxv[s];
+        R.slack_sol.assign(sol.begin() + (size_t)s * ldo, sol.begin() + (size_t)s * ldo + Cm);
+        R.tgtf.assign(tgo.begin() + (size_t)s * ldo, tgo.begin() + (size_t)s * ldo + Cm);
+        R.eq2bv.assign(e2b.begin() + (size_t)s * ldm, e2b.begin() + (size_t)s * ldm + ms[s]);
+    }
+    return 0;
+}
+
+// --------------------------------------------------------------- exact side
+typedef TwoStageResult<Q> ResQ;
+
+long long lcm_ll(long long a, long long b, bool &ovf)
+{
+    long long g = Q::gcdll(a, b);
+    __int128 l = (__int128)(a / g) * b;
+    if (l > (__int128)0x7fffffffffffffffLL) {
+        ovf = true;
+        return 1;
+    }
+    return (long long)l;
+}
+
+// TwoStageMethod for a set of normalised exact LPs.  Rows (and the objective)
+// are scaled to integers by the lcm of their denominators -- a positive row
+// scaling changes no pivoting decision -- and the results are scaled back:
+// slack i of a row scaled by k_i reads s_i = s'_i / k_i, its objective
+// coefficient c(s_i) = c'(s'_i) * k_i / k_0, everything else divides by k_0.
+int two_stage_group_q(xp_ctx *ctx, const std::vector<const Mat<Q> *> &leqs,
+                      const std::vector<const Mat<Q> *> &tgs, const std::vector<int> &live,
+                      uint32_t max_iter, std::vector<ResQ> &out);
+
+// LPs that fit shared memory go out as one ragged launch; the others (c5's
+// 201 x 402 root tableau) as a second one whose CTAs keep their state in a
+// global-memory slab (one maxm/maxn bound per launch decides which).
+int two_stage_many_q(xp_ctx *ctx, const std::vector<const Mat<Q> *> &leqs,
+                     const std::vector<const Mat<Q> *> &tgs, uint32_t max_iter,
+                     std::vector<ResQ> &out)
+{
+    const int B = (int)leqs.size();
+    out.assign(B, ResQ());
+    std::vector<int> small, big;
+    for (int k = 0; k < B; k++) {
+        const Mat<Q> &L = *leqs[k];
+        if (L.r < 1 || L.c < 2) {
+            out[k].status = XP_ERR_BAD_ARG;
+            continue;
+        }
+        (fits_smem(ctx, L.r, L.c - 1, 24) ? small : big).push_back(k);
+    }
+    int rc = two_stage_group_q(ctx, leqs, tgs, small, max_iter, out);
+    if (rc) return rc;
+    return two_stage_group_q(ctx, leqs, tgs, big, max_iter, out);
+}
+
+int two_stage_group_q(xp_ctx *ctx, const std::vector<const Mat<Q> *> &leqs,
+                      const std::vector<const Mat<Q> *> &tgs, const std::vector<int> &live,
+                      uint32_t max_iter, std::vector<ResQ> &out)
+{
+    const int B = (int)leqs.size();
+    std::vector<int32_t> ms(B), ns(B);
+    std::vector<int64_t> lo(B), to(B);
+    std::vector<std::vector<long long>> scale(B); // k_1..k_m then k_0
+    size_t ll = 0, tl = 0;
+    int ldo = 0, ldm = 0;
+    const int S = (int)live.size();
+    if (S == 0) return 0;
+    for (int s = 0; s < S; s++) {
+        const Mat<Q> &L = *leqs[live[s]];
+        ms[s] = L.r;
+        ns[s] = L.c - 1;
+        lo[s] = (int64_t)ll;
+        to[s] = (int64_t)tl;
+        ll += L.a.size();
+        tl += (size_t)L.c;
+        ldo = std::max(ldo, L.r + L.c);
+        ldm = std::max(ldm, L.r);
+    }
+    std::vector<int64_t> lp(ll), tp(tl);
+    for (int s = 0; s < S; s++) {
+        const Mat<Q> &L = *leqs[live[s]], &T = *tgs[live[s]];
+        std::vector<long long> &sc = scale[live[s]];
+        sc.assign(L.r + 1, 1);
+        bool ovf = false;
+        for (int i = 0; i < L.r; i++) {
+            long long k = 1;
+            for (int j = 0; j < L.c; j++) k = lcm_ll(k, L.at(i, j).den, ovf);
+            sc[i] = k;
+            for (int j = 0; j < L.c; j++) {
+                __int128 v = (__int128)L.at(i, j).num * (k / L.at(i, j).den);
+                if (v > (__int128)0x7fffffffffffffffLL || v < -(__int128)0x7fffffffffffffffLL) ovf = true;
+                lp[lo[s] + (size_t)i * L.c + j] = (int64_t)v;
+            }
+        }
+        long long k0 = 1;
+        for (int j = 0; j < T.c; j++) k0 = lcm_ll(k0, T.at(0, j).den, ovf);
+        sc[L.r] = k0;
+        for (int j = 0; j < T.c; j++) {
+            __int128 v = (__int128)T.at(0, j).num * (k0 / T.at(0, j).den);
+            if (v > (__int128)0x7fffffffffffffffLL || v < -(__int128)0x7fffffffffffffffLL) ovf = true;
+            tp[to[s] + j] = (int64_t)v;
+        }
+        if (ovf) out[live[s]].status = XP_ERR_OVERFLOW;
+    }
+    std::vector<int64_t> maxv((size_t)S * 2), sn((size_t)S * ldo), sd((size_t)S * ldo),
+        tn((size_t)S * ldo), td((size_t)S * ldo);
+    std::vector<int32_t> status(S), e2b((size_t)S * ldm);
+    int rc = xp_six_two_stage_i64_ragged(ctx, S, ms.data(), ns.data(), lo.data(), to.data(),
+                                         lp.data(), ll, tp.data(), tl, max_iter, XP_RULE_REFERENCE,
+                                         ldo, ldm, status.data(), maxv.data(), sn.data(), sd.data(),
+                                         tn.data(), td.data(), e2b.data(), nullptr, nullptr);
+    if (rc) return rc;
+    for (int s = 0; s < S; s++) {
+        ResQ &R = out[live[s]];
+        if (R.status == XP_ERR_OVERFLOW) continue; // input scaling already overflowed
+        const int m = ms[s], n = ns[s], Cm = m + n + 1;
+        const std::vector<long long> &sc = scale[live[s]];
+        const Q::T k0 = Q::from_int(sc[m]);
+        R.status = status[s];
+        R.maxv = Q::div(Q::make(maxv[2 * (size_t)s], maxv[2 * (size_t)s + 1]), k0);
+        R.slack_sol.resize(Cm);
+        R.tgtf.resize(Cm);
+        for (int j = 0; j < Cm; j++) {
+            const size_t o = (size_t)s * ldo + j;
+            Q::T sv = Q::make(sn[o], sd[o] ? sd[o] : 1), tv = Q::make(tn[o], td[o] ? td[o] : 1);
+            if (j >= n && j < n + m) {
+                const Q::T ki = Q::from_int(sc[j - n]);
+                sv = Q::div(sv, ki);
+                tv = Q::mul(tv, ki);
+            }
+            R.slack_sol[j] = sv;
+            R.tgtf[j] = Q::div(tv, k0);
+        }
+        R.eq2bv.assign(e2b.begin() + (size_t)s * ldm, e2b.begin() + (size_t)s * ldm + m);
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------- plumbing
+Mat<F64> mat_f64(int r, int c, const double *src)
+{
+    Mat<F64> M(r, c);
+    if (src) std::copy(src, src + (size_t)r * c, M.a.begin());
+    return M;
+}
+Mat<Q> mat_q(int r, int c, const xp_rat *src)
+{
+    Mat<Q> M(r, c);
+    if (src)
+        for (size_t e = 0; e < (size_t)r * c; e++)
+            M.a[e] = Q::make(src[e].num, src[e].den ? src[e].den : 1);
+    return M;
+}
+bool to_rat(Q::T v, xp_rat *o)
+{
+    if (v.num > 0x7fffffffLL || v.num < -0x7fffffffLL || v.den > 0x7fffffffLL) return false;
+    o->num = (int32_t)v.num;
+    o->den = (int32_t)v.den;
+    return true;
+}
+
+template <class P>
+struct Many;
+template <>
+struct Many<F64> {
+    static int run(xp_ctx *c, const std::vector<const Mat<F64> *> &l,
+                   const std::vector<const Mat<F64> *> &t, uint32_t it, std::vector<ResF> &o)
+    {
+        return two_stage_many_f64(c, l, t, it, o);
+    }
+};
+template <>
+struct Many<Q> {
+    static int run(xp_ctx *c, const std::vector<const Mat<Q> *> &l,
+                   const std::vector<const Mat<Q> *> &t, uint32_t it, std::vector<ResQ> &o)
+    {
+        return two_stage_many_q(c, l, t, it, o);
+    }
+};
+
+// One SIX::maxm / minm.
+template <class P>
+int solve_one(xp_ctx *ctx, bool is_min, const Mat<P> &tg, const Mat<P> &vc, const Mat<P> &eq,
+              const Mat<P> &leq, uint32_t max_iter, typename P::T &v,
+              std::vector<typename P::T> &sol, std::vector<int32_t> *eq2bv)
+{
+    SixJob<P> job;
+    int st = job.prepare(is_min, tg, vc, eq, leq);
+    v = P::zero();
+    if (st) return st;
+    std::vector<TwoStageResult<P>> R;
+    std::vector<const Mat<P> *> l{&job.lp_leq}, t{&job.lp_tgtf};
+    int rc = Many<P>::run(ctx, l, t, max_iter, R);
+    if (rc) return rc;
+    if (eq2bv) *eq2bv = R[0].eq2bv;
+    return job.finish(R[0], v, sol);
+}
+
+// A set of B&B trees advanced in lockstep: one batched GPU call per wave of node
+// relaxations, decisions replayed per tree in DFS order (MipTree).
+template <class P>
+int run_trees(xp_ctx *ctx, std::vector<MipTree<P>> &trees)
+{
+    for (;;) {
+        std::vector<int> act;
+        std::vector<SixJob<P>> jobs;
+        for (int t = 0; t < (int)trees.size(); t++) {
+            if (trees[t].done) continue;
+            for (;;) { // node LPs whose host preparation already fails are fed back at once
+                if (trees[t].done) break;
+                const typename MipTree<P>::Frame &f = trees[t].top();
+                SixJob<P> job;
+                int st = job.prepare(!trees[t].is_max, trees[t].tgtf, trees[t].vc, f.eq, f.leq);
+                if (st == 0) {
+                    act.push_back(t);
+                    jobs.push_back(std::move(job));
+                    break;
+                }
+                trees[t].feed(st, P::zero(), std::vector<typename P::T>());
+            }
+        }
+        if (act.empty()) return 0;
+        std::vector<const Mat<P> *> l, tg;
+        for (auto &j : jobs) {
+            l.push_back(&j.lp_leq);
+            tg.push_back(&j.lp_tgtf);
+        }
+        std::vector<TwoStageResult<P>> R;
+        int rc = Many<P>::run(ctx, l, tg, 10000u, R); // six.set_param(m_indent, 10000), :2441
+        if (rc) return rc;
+        for (size_t k = 0; k < act.size(); k++) {
+            typename P::T v;
+            std::vector<typename P::T> sol;
+            int st = jobs[k].finish(R[k], v, sol);
+            trees[act[k]].feed(st, v, sol);
+        }
+    }
+}
+
+int mip_status(int st) { return st; }
+
+} // namespace
+
+// ============================================================== C entry points
+#define XP_ENTRY_GUARD(ctx) \
+    if (!(ctx)) return XP_ERR_BAD_ARG; \
+    XP_CUDA_OK(ctx, cudaSetDevice((ctx)->device)); \
+    Q::overflow() = false;
+
+static int six_f64(xp_ctx *ctx, bool is_min, int m, int n, const double *tgtf, const double *vc,
+                   int k, const double *eq, const double *leq, uint32_t max_iter, double *v,
+                   double *sol, int32_t *eq2bv_out)
+{
+    XP_ENTRY_GUARD(ctx);
+    if (n < 1 || (m < 1 && k < 1) || !tgtf || !v) return XP_ERR_BAD_ARG;
+    Mat<F64> T = mat_f64(1, n + 1, tgtf), V = vc ? mat_f64(n, n + 1, vc) : default_vc<F64>(n);
+    Mat<F64> E = k > 0 ? mat_f64(k, n + 1, eq) : Mat<F64>(), L = m > 0 ? mat_f64(m, n + 1, leq) : Mat<F64>();
+    std::vector<double> s;
+    std::vector<int32_t> e2b;
+    int st = solve_one<F64>(ctx, is_min, T, V, E, L, max_iter, *v, s, &e2b);
+    if (st == XP_SIX_SUCC && sol) std::copy(s.begin(), s.begin() + n + 1, sol);
+    if (eq2bv_out) std::copy(e2b.begin(), e2b.end(), eq2bv_out);
+    return st;
+}
+
+extern "C" int xp_six_maxm_f64(xp_ctx *ctx, int m, int n, const double *tgtf, const double *vc,
+                               int k, const double *eq, const double *leq, uint32_t max_iter,
+                               double *maxv, double *sol, int32_t *eq2bv_out)
+{
+    return six_f64(ctx, false, m, n, tgtf, vc, k, eq, leq, max_iter, maxv, sol, eq2bv_out);
+}
+extern "C" int xp_six_minm_f64(xp_ctx *ctx, int m, int n, const double *tgtf, const double *vc,
+                               int k, const double *eq, const double *leq, uint32_t max_iter,
+                               double *minv, double *sol, int32_t *eq2bv_out)
+{
+    return six_f64(ctx, true, m, n, tgtf, vc, k, eq, leq, max_iter, minv, sol, eq2bv_out);
+}
+
+static int six_rat(xp_ctx *ctx, bool is_min, int m, int n, const xp_rat *tgtf, const xp_rat *vc,
+                   int k, const xp_rat *eq, const xp_rat *leq, uint32_t max_iter, xp_rat *v,
+                   xp_rat *sol, int32_t *eq2bv_out)
+{
+    XP_ENTRY_GUARD(ctx);
+    if (n < 1 || (m < 1 && k < 1) || !tgtf || !v) return XP_ERR_BAD_ARG;
+    Mat<Q> T = mat_q(1, n + 1, tgtf), V = vc ? mat_q(n, n + 1, vc) : default_vc<Q>(n);
+    Mat<Q> E = k > 0 ? mat_q(k, n + 1, eq) : Mat<Q>(), L = m > 0 ? mat_q(m, n + 1, leq) : Mat<Q>();
+    Q::T val;
+    std::vector<Q::T> s;
+    std::vector<int32_t> e2b;
+    int st = solve_one<Q>(ctx, is_min, T, V, E, L, max_iter, val, s, &e2b);
+    v->num = 0;
+    v->den = 1;
+    if (st == XP_SIX_SUCC) {
+        bool ok = to_rat(val, v);
+        for (int j = 0; j <= n && sol; j++) ok &= to_rat(s[j], &sol[j]);
+        if (!ok) return XP_ERR_OVERFLOW;
+    }
+    if (eq2bv_out) std::copy(e2b.begin(), e2b.end(), eq2bv_out);
+    return st;
+}
+
+extern "C" int xp_six_maxm_rat(xp_ctx *ctx, int m, int n, const xp_rat *tgtf, const xp_rat *vc,
+                               int k, const xp_rat *eq, const xp_rat *leq, uint32_t max_iter,
+                               xp_rat *maxv, xp_rat *sol, int32_t *eq2bv_out)
+{
+    return six_rat(ctx, false, m, n, tgtf, vc, k, eq, leq, max_iter, maxv, sol, eq2bv_out);
+}
+extern "C" int xp_six_minm_rat(xp_ctx *ctx, int m, int n, const xp_rat *tgtf, const xp_rat *vc,
+                               int k, const xp_rat *eq, const xp_rat *leq, uint32_t max_iter,
+                               xp_rat *minv, xp_rat *sol, int32_t *eq2bv_out)
+{
+    return six_rat(ctx, true, m, n, tgtf, vc, k, eq, leq, max_iter, minv, sol, eq2bv_out);
+}
+
+// ---- batched entry level: uniform shape, vc = -I, no equalities ----
+template <class P, class In, class Out, class MK, class WR>
+static int solve_batch(xp_ctx *ctx, int is_min, int batch, int m, int n, const In *tgtf,
+                       const In *leq, uint32_t max_iter, int32_t *status, Out *v, Out *sol, MK mk,
+                       WR wr)
+{
+    XP_ENTRY_GUARD(ctx);
+    if (batch < 0 || m < 1 || n < 1 || !tgtf || !leq) return XP_ERR_BAD_ARG;
+    const Mat<P> V = default_vc<P>(n), E;
+    std::vector<SixJob<P>> jobs(batch);
+    std::vector<int> st0(batch);
+    std::vector<const Mat<P> *> l, t;
+    std::vector<int> idx;
+    for (int b = 0; b < batch; b++) {
+        Mat<P> T = mk(1, n + 1, tgtf + (size_t)b * (n + 1));
+        Mat<P> L = mk(m, n + 1, leq + (size_t)b * m * (n + 1));
+        st0[b] = jobs[b].prepare(is_min != 0, T, V, E, L);
+        if (st0[b] == 0) {
+            l.push_back(&jobs[b].lp_leq);
+            t.push_back(&jobs[b].lp_tgtf);
+            idx.push_back(b);
+        }
+    }
+    std::vector<TwoStageResult<P>> R;
+    int rc = Many<P>::run(ctx, l, t, max_iter, R);
+    if (rc) return rc;
+    for (int b = 0; b < batch; b++)
+        if (st0[b] && status) status[b] = st0[b];
+    for (size_t k = 0; k < idx.size(); k++) {
+        const int b = idx[k];
+        typename P::T val;
+        std::vector<typename P::T> s;
+        int st = jobs[b].finish(R[k], val, s);
+        st = wr(st, val, s, v ? v + b : nullptr, sol ? sol + (size_t)b * (n + 1) : nullptr, n + 1);
+        if (status) status[b] = st;
+    }
+    return 0;
+}
+
+extern "C" int xp_six_solve_f64_batch(xp_ctx *ctx, int is_min, int batch, int m, int n,
+                                      const double *tgtf, const double *leq, uint32_t max_iter,
+                                      int32_t *status, double *v, double *sol)
+{
+    return solve_batch<F64, double, double>(
+        ctx, is_min, batch, m, n, tgtf, leq, max_iter, status, v, sol, mat_f64,
+        [](int st, double val, const std::vector<double> &s, double *vo, double *so, int n1) {
+            if (vo) *vo = val;
+            if (st == XP_SIX_SUCC && so) std::copy(s.begin(), s.begin() + n1, so);
+            return st;
+        });
+}
+
+extern "C" int xp_six_solve_rat_batch(xp_ctx *ctx, int is_min, int batch, int m, int n,
+                                      const xp_rat *tgtf, const xp_rat *leq, uint32_t max_iter,
+                                      int32_t *status, xp_rat *v, xp_rat *sol)
+{
+    return solve_batch<Q, xp_rat, xp_rat>(
+        ctx, is_min, batch, m, n, tgtf, leq, max_iter, status, v, sol, mat_q,
+        [](int st, Q::T val, const std::vector<Q::T> &s, xp_rat *vo, xp_rat *so, int n1) {
+            bool ok = true;
+            if (vo) {
+                vo->num = 0;
+                vo->den = 1;
+                if (st == XP_SIX_SUCC) ok &= to_rat(val, vo);
+            }
+            if (st == XP_SIX_SUCC && so)
+                for (int j = 0; j < n1; j++) ok &= to_rat(s[j], so + j);
+            return ok ? st : XP_ERR_OVERFLOW;
+        });
+}
+
+// ---- MIP ----
+extern "C" int xp_mip_solve_rat(xp_ctx *ctx, int is_min, int is_bin, int m, int n,
+                                const xp_rat *tgtf, int k, const xp_rat *eq, const xp_rat *leq,
+                                xp_rat *v, xp_rat *sol, int32_t *n_nodes)
+{
+    XP_ENTRY_GUARD(ctx);
+    if (n < 1 || (m < 1 && k < 1) || !tgtf || !v) return XP_ERR_BAD_ARG;
+    std::vector<MipTree<Q>> trees(1);
+    trees[0].start(mat_q(1, n + 1, tgtf), default_vc<Q>(n), k > 0 ? mat_q(k, n + 1, eq) : Mat<Q>(),
+                   m > 0 ? mat_q(m, n + 1, leq) : Mat<Q>(), !is_min, is_bin != 0);
+    int rc = run_trees<Q>(ctx, trees);
+    if (rc) return rc;
+    if (n_nodes) *n_nodes = trees[0].nodes;
+    int st = trees[0].ret_status;
+    // RecusivePart shares one `v` down the whole recursion (lpsol.h:2426-2447), so on a
+    // failing status the caller still sees the value of the last node LP solved.
+    v->num = 0;
+    v->den = 1;
+    bool ok = to_rat(trees[0].v, v);
+    if (st == XP_IP_SUCC) {
+        for (int j = 0; j <= n && sol; j++) ok &= to_rat(trees[0].sol[j], &sol[j]);
+        if (!ok || !Q::ok()) return XP_ERR_OVERFLOW;
+    }
+    return mip_status(st);
+}
+
+extern "C" int xp_mip_solve_f64(xp_ctx *ctx, int is_min, int is_bin, int m, int n,
+                                const double *tgtf, int k, const double *eq, const double *leq,
+                                double *v, double *sol, int32_t *n_nodes)
+{
+    XP_ENTRY_GUARD(ctx);
+    if (n < 1 || (m < 1 && k < 1) || !tgtf || !v) return XP_ERR_BAD_ARG;
+    std::vector<MipTree<F64>> trees(1);
+    trees[0].start(mat_f64(1, n + 1, tgtf), default_vc<F64>(n),
+                   k > 0 ? mat_f64(k, n + 1, eq) : Mat<F64>(),
+                   m > 0 ? mat_f64(m, n + 1, leq) : Mat<F64>(), !is_min, is_bin != 0);
+    int rc = run_trees<F64>(ctx, trees);
+    if (rc) return rc;
+    if (n_nodes) *n_nodes = trees[0].nodes;
+    int st = trees[0].ret_status;
+    *v = trees[0].v;
+    if (st == XP_IP_SUCC && sol) std::copy(trees[0].sol.begin(), trees[0].sol.begin() + n + 1, sol);
+    return st;
+}
+
+extern "C" int xp_mip_solve_rat_batch(xp_ctx *ctx, int is_min, int is_bin, int batch, int m, int n,
+                                      const xp_rat *tgtf, const xp_rat *leq, int32_t *status,
+                                      xp_rat *v, xp_rat *sol, int32_t *n_nodes)
+{
+    XP_ENTRY_GUARD(ctx);
+    if (batch < 0 || m < 1 || n < 1 || !tgtf || !leq) return XP_ERR_BAD_ARG;
+    std::vector<MipTree<Q>> trees(batch);
+    for (int b = 0; b < batch; b++)
+        trees[b].start(mat_q(1, n + 1, tgtf + (size_t)b * (n + 1)), default_vc<Q>(n), Mat<Q>(),
+                       mat_q(m, n + 1, leq + (size_t)b * m * (n + 1)), !is_min, is_bin != 0);
+    int rc = run_trees<Q>(ctx, trees);
+    if (rc) return rc;
+    for (int b = 0; b < batch; b++) {
+        int st = trees[b].ret_status;
+        if (n_nodes) n_nodes[b] = trees[b].nodes;
+        bool vok = true;
+        if (v) {
+            v[b].num = 0;
+            v[b].den = 1;
+            vok = to_rat(trees[b].v, &v[b]);
+        }
+        if (st == XP_IP_SUCC) {
+            bool ok = vok;
+            for (int j = 0; j <= n && sol; j++) ok &= to_rat(trees[b].sol[j], &sol[(size_t)b * (n + 1) + j]);
+            if (!ok) st = XP_ERR_OVERFLOW;
+        }
+        if (status) status[b] = st;
+    }
+    return 0;
+}
+
+// ---- Lineq::has_solution (linsys.cpp:830-906), batched ----
+extern "C" int xp_has_solution_rat_batch(xp_ctx *ctx, int batch, int m, int n, const xp_rat *leq,
+                                         int is_int_sol, int is_unique_sol, int32_t *result)
+{
+    XP_ENTRY_GUARD(ctx);
+    if (batch < 0 || m < 1 || n < 1 || !leq || !result) return XP_ERR_BAD_ARG;
+    std::vector<Mat<Q>> Ls(batch), Ts(batch);
+    const Mat<Q> V = default_vc<Q>(n), E;
+    for (int b = 0; b < batch; b++) {
+        Ls[b] = mat_q(m, n + 1, leq + (size_t)b * m * (n + 1));
+        Ts[b] = Mat<Q>(1, n + 1); // all-ones objective, reviseTargetFunc (lpsol.h:2052-2074)
+        for (int j = 0; j < n; j++)
+            if (!Ls[b].col_all_eq(j, Q::zero())) Ts[b].at(0, j) = Q::from_int(1);
+        result[b] = 0;
+    }
+    std::vector<int> pending(batch);
+    for (int b = 0; b < batch; b++) pending[b] = b;
+    for (int pass = 0; pass < 2 && !pending.empty(); pass++) { // max first, then min
+        const bool is_min = pass == 1;
+        std::vector<int> st(pending.size());
+        if (is_int_sol) {
+            std::vector<MipTree<Q>> trees(pending.size());
+            for (size_t k = 0; k < pending.size(); k++)
+                trees[k].start(Ts[pending[k]], V, E, Ls[pending[k]], !is_min, false);
+            int rc = run_trees<Q>(ctx, trees);
+            if (rc) return rc;
+            for (size_t k = 0; k < pending.size(); k++) st[k] = trees[k].ret_status;
+        } else {
+            std::vector<SixJob<Q>> jobs(pending.size());
+            std::vector<const Mat<Q> *> l, t;
+            for (size_t k = 0; k < pending.size(); k++) {
+                int e = jobs[k].prepare(is_min, Ts[pending[k]], V, E, Ls[pending[k]]);
+                if (e) return e;
+                l.push_back(&jobs[k].lp_leq);
+                t.push_back(&jobs[k].lp_tgtf);
+            }
+            std::vector<ResQ> R;
+            int rc = two_stage_many_q(ctx, l, t, XP_NO_ITER_LIMIT, R);
+            if (rc) return rc;
+            for (size_t k = 0; k < pending.size(); k++) {
+                Q::T val;
+                std::vector<Q::T> s;
+                st[k] = jobs[k].finish(R[k], val, s);
+            }
+        }
+        std::vector<int> next;
+        for (size_t k = 0; k < pending.size(); k++) {
+            if (st[k] < 0) return st[k];
+            // IP_SUCC == SIX_SUCC == 0 and IP_UNBOUND == SIX_UNBOUND == 1
+            if (st[k] == 0 || (!is_unique_sol && st[k] == 1)) result[pending[k]] = 1;
+            else next.push_back(pending[k]);
+        }
+        pending.swap(next);
+    }
+    return 0;
+}

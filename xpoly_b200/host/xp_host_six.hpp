@@ -63,6 +63,7 @@ struct F64 {
     }
     static int trunc(T a) { return (int)a; } // Float::typecast2int, flty.h:85-88
     static bool ok() { return true; }
+    static bool div_by_zero_is_ub(T a) { return a == 0.0; } // 1/0 = inf, then 0*inf = NaN downstream
 };
 
 // -------------------------------------------------------------------- Q policy
@@ -132,6 +133,7 @@ struct Q {
     static bool is_int(T a) { return a.den == 1; } // RMat::is_imat, xmat.cpp:603
     static int trunc(T a) { return (int)(a.num / a.den); } // Rational::typecast2int
     static bool ok() { return !overflow(); }
+    static bool div_by_zero_is_ub(T a) { return a.num == 0; } // Rational 1/0: den = 0 garbage
 };
 
 // ------------------------------------------------------------------- matrices
@@ -259,7 +261,7 @@ int eq_to_ineq(Mat<P> &leq, const Mat<P> &eq, int rhs_idx)
                 if (mm >= tp.c) return XP_ERR_REFERENCE_UB; // reference reads out of bounds
                 T tpv = tp.at(0, mm); // sic: the row counter is used as a column index
                 if (!P::eq(tpv, P::from_int(1))) {
-                    if (std::is_same<P, Q>::value && tpv.num == 0) return XP_ERR_REFERENCE_UB;
+                    if (P::div_by_zero_is_ub(tpv)) return XP_ERR_REFERENCE_UB;
                     tp.mul_row(0, P::div(P::from_int(1), tpv));
                 }
                 tp.mul_row(0, v);
@@ -336,7 +338,7 @@ void final_solution(std::vector<typename P::T> &sol, typename P::T &v,
                     std::vector<typename P::T> &slack_sol, const std::vector<int32_t> &vcmap,
                     const Mat<P> &orig_tgtf, int m_rhs_idx)
 {
-    for (size_t i = 0; i + 2 < vcmap.size() + 0 && i < vcmap.size(); i += 3)
+    for (size_t i = 0; i + 2 < vcmap.size(); i += 3)
         slack_sol[vcmap[i]] = P::sub(slack_sol[vcmap[i + 1]], slack_sol[vcmap[i + 2]]);
     sol.assign(orig_tgtf.c, P::zero());
     for (int i = 0; i < m_rhs_idx; i++) sol[i] = slack_sol[i];
@@ -353,67 +355,70 @@ Mat<P> default_vc(int n)
     return V;
 }
 
-// SIX::maxm, lpsol.h:1992-2033.
+// One SIX::maxm / SIX::minm call split around the GPU part, so that many of them
+// can share one batched TwoStageMethod launch:
+//   prepare()  verify + normalize (+ explicit dual for min)       [host]
+//   -> lp_leq / lp_tgtf go to the two-stage solver                [GPU]
+//   finish()   calcFinalSolution                                  [host]
+// maxm: lpsol.h:1992-2033.  minm: lpsol.h:1661-1732 + calcDualMaxm :1585-1655.
 template <class P>
-int six_maxm(const TwoStageFn<P> &solver, const Mat<P> &tgtf, const Mat<P> &vc, const Mat<P> &eq,
-             const Mat<P> &leq, uint32_t max_iter, typename P::T &maxv,
-             std::vector<typename P::T> &sol, std::vector<int32_t> *eq2bv)
-{
-    const int maxc = !eq.empty() ? eq.c : leq.c; // verify, :1516-1558
-    const int m_rhs = maxc - 1;
-    maxv = P::zero();
-    Normalized<P> N;
-    int st = normalize(N, vc, eq, leq, tgtf, m_rhs);
-    if (st) return st;
-    if (!N.std_vc) return XP_ERR_BAD_ARG;
-    TwoStageResult<P> R = solver(N.leq, N.tgtf, max_iter);
-    if (eq2bv) *eq2bv = R.eq2bv;
-    if (R.status == XP_SIX_SUCC) {
-        std::vector<typename P::T> ss = R.slack_sol;
-        ss.resize((size_t)N.rhs_idx + N.leq.r + 2, P::zero());
-        final_solution<P>(sol, maxv, ss, N.vcmap, tgtf, m_rhs);
-        maxv = P::reduce(maxv);
-        if (!P::ok()) return XP_ERR_OVERFLOW;
-    }
-    return R.status;
-}
-
-// SIX::minm via the explicit dual, lpsol.h:1661-1732 + calcDualMaxm :1585-1655.
-template <class P>
-int six_minm(const TwoStageFn<P> &solver, const Mat<P> &tgtf, const Mat<P> &vc, const Mat<P> &eq,
-             const Mat<P> &leq, uint32_t max_iter, typename P::T &minv,
-             std::vector<typename P::T> &sol, std::vector<int32_t> *eq2bv)
-{
+struct SixJob {
     typedef typename P::T T;
-    const int maxc = !eq.empty() ? eq.c : leq.c;
-    const int m_rhs = maxc - 1;
-    minv = P::zero();
+    bool is_min = false;
+    Mat<P> tgtf_orig;
     Normalized<P> N;
-    int st = normalize(N, vc, eq, leq, tgtf, m_rhs);
-    if (st) return st;
-    if (!N.std_vc) return XP_ERR_BAD_ARG;
-    const int nd_rhs = N.rhs_idx, rows = N.leq.r;
-    const int dn = rows, dm = nd_rhs; // dual: one variable per primal row (:1602-1629)
-    Mat<P> dleq(dm, dn + 1), dtg(1, dn + 1);
-    for (int i = 0; i < dm; i++)
-        for (int j = 0; j < dn; j++) dleq.at(i, j) = N.leq.at(j, i);
-    dleq.mul_all(P::from_int(-1)); // :1607 (also negates the grown zero column)
-    for (int i = 0; i < dm; i++) dleq.at(i, dn) = N.tgtf.at(0, i);
-    for (int j = 0; j < dn; j++) dtg.at(0, j) = N.leq.at(j, nd_rhs);
-    dtg.mul_all(P::from_int(-1)); // :1619
-    TwoStageResult<P> R = solver(dleq, dtg, max_iter);
-    if (eq2bv) *eq2bv = R.eq2bv;
-    if (R.status == XP_SIX_SUCC) {
-        // y_i = -(coefficient of dual slack i in the final dual objective row), :1713-1716
-        std::vector<T> tmp((size_t)dm + 1 + 2 * m_rhs + 4, P::zero());
-        for (int k = 0; k < dm; k++) tmp[k] = P::neg(R.tgtf[dn + k]);
-        T v;
-        final_solution<P>(sol, v, tmp, N.vcmap, tgtf, m_rhs);
-        minv = P::reduce(v);
-        if (!P::ok()) return XP_ERR_OVERFLOW;
+    int m_rhs = 0, dn = 0, dm = 0;
+    Mat<P> lp_leq, lp_tgtf; // the normalised LP handed to TwoStageMethod
+
+    int prepare(bool minimise, const Mat<P> &tgtf, const Mat<P> &vc, const Mat<P> &eq,
+                const Mat<P> &leq)
+    {
+        is_min = minimise;
+        tgtf_orig = tgtf;
+        const int maxc = !eq.empty() ? eq.c : leq.c; // verify, :1516-1558
+        m_rhs = maxc - 1;
+        int st = normalize(N, vc, eq, leq, tgtf, m_rhs);
+        if (st) return st;
+        if (!N.std_vc) return XP_ERR_BAD_ARG;
+        if (!is_min) {
+            lp_leq = N.leq;
+            lp_tgtf = N.tgtf;
+            return 0;
+        }
+        const int nd_rhs = N.rhs_idx, rows = N.leq.r;
+        dn = rows; // dual: one variable per primal row (:1602-1629)
+        dm = nd_rhs;
+        lp_leq = Mat<P>(dm, dn + 1);
+        lp_tgtf = Mat<P>(1, dn + 1);
+        for (int i = 0; i < dm; i++)
+            for (int j = 0; j < dn; j++) lp_leq.at(i, j) = N.leq.at(j, i);
+        lp_leq.mul_all(P::from_int(-1)); // :1607 (also negates the grown zero column)
+        for (int i = 0; i < dm; i++) lp_leq.at(i, dn) = N.tgtf.at(0, i);
+        for (int j = 0; j < dn; j++) lp_tgtf.at(0, j) = N.leq.at(j, nd_rhs);
+        lp_tgtf.mul_all(P::from_int(-1)); // :1619
+        return 0;
     }
-    return R.status;
-}
+
+    // Returns the SIX status; v / sol are written on XP_SIX_SUCC (v = 0 otherwise).
+    int finish(const TwoStageResult<P> &R, T &v, std::vector<T> &sol) const
+    {
+        v = P::zero();
+        if (R.status != XP_SIX_SUCC) return R.status;
+        if (!is_min) {
+            std::vector<T> ss = R.slack_sol;
+            ss.resize((size_t)N.rhs_idx + N.leq.r + 2, P::zero());
+            final_solution<P>(sol, v, ss, N.vcmap, tgtf_orig, m_rhs);
+        } else {
+            // y_i = -(coefficient of dual slack i in the final dual objective row), :1713-1716
+            std::vector<T> tmp((size_t)dm + 1 + 2 * m_rhs + 4, P::zero());
+            for (int k = 0; k < dm; k++) tmp[k] = P::neg(R.tgtf[dn + k]);
+            final_solution<P>(sol, v, tmp, N.vcmap, tgtf_orig, m_rhs);
+        }
+        v = P::reduce(v);
+        if (!P::ok()) return XP_ERR_OVERFLOW;
+        return XP_SIX_SUCC;
+    }
+};
 
 // ------------------------------------------------------------------------ MIP
 // MIP<Mat,T>::RecusivePart (lpsol.h:2426-2612) unrolled into a resumable state
