@@ -47,7 +47,7 @@ extern "C" {
 #define XP_ERR_BAD_ARG (-2)     /* dimensions / null pointers */
 #define XP_ERR_TOO_LARGE (-3)   /* LP does not fit the batched (shared-memory) path */
 #define XP_ERR_OVERFLOW (-4)    /* fraction-free path left int64 / result left int32 */
-#define XP_ERR_NCCL (-5)        /* NCCL unavailable or failed */
+#define XP_ERR_PEER (-5)        /* sharded LP: a peer GPU did not answer in time */
 #define XP_ERR_REFERENCE_UB (-100) /* the reference itself would hit undefined behaviour
                                       (convertEq2Ineq lpsol.h:1232) */
 
@@ -126,6 +126,29 @@ int xp_lp_f64_profile(xp_lp_f64 *lp, int enable);
 int xp_lp_f64_profile_read(xp_lp_f64 *lp, uint64_t *n_sweeps, double *sweep_ms, double *gap_ms);
 /* Order-independent 64-bit checksum of the device tableau bits (parity at full size). */
 int xp_lp_f64_checksum(xp_lp_f64 *lp, uint64_t *sum_tableau, uint64_t *sum_tgtf);
+/* Column-sharded multi-GPU, one process per GPU.  Rank r of nranks
+ * owns a contiguous column slice of the tableau and of the objective row; the
+ * constant column, basis maps and tabu table are replicated.  Per pivot the
+ * select kernel exchanges one 8-byte pricing candidate per rank (lowest index
+ * wins) and the sweep kernel writes the entering column (m+1 doubles) into
+ * every peer's exchange block -- NVLink peer memory mapped with CUDA IPC, no
+ * host or library collective on the pivot path.  Set-up: every rank creates its
+ * shard, the XP_PEER_HANDLE_BYTES handles are all-gathered out of band (any
+ * channel: torch.distributed, MPI, a file), every rank attaches.  upload /
+ * fill / solve / download / checksum then work as for one GPU: upload takes the
+ * full arrays and keeps this rank's slice, download writes only this rank's
+ * columns of `tableau` / `tgtf` (replicated state is returned whole), and the
+ * per-rank checksums add up (mod 2^64) to the single-GPU checksum.  All ranks
+ * must issue the same calls in the same order. */
+#define XP_MAX_RANKS 8
+#define XP_PEER_HANDLE_BYTES 64
+int xp_lp_f64_create_sharded(xp_ctx *ctx, int m, int C, int rank, int nranks, xp_lp_f64 **out);
+int xp_lp_f64_local_cols(const xp_lp_f64 *lp, int *col0, int *ncols);
+int xp_lp_f64_peer_handle(xp_lp_f64 *lp, void *handle /* XP_PEER_HANDLE_BYTES */);
+int xp_lp_f64_peer_attach(xp_lp_f64 *lp, const void *handles /* nranks x XP_PEER_HANDLE_BYTES */);
+/* Same-process variant (several shards driven by threads of one process). */
+int xp_lp_f64_peer_attach_local(xp_lp_f64 *lp, xp_lp_f64 *const *all /* nranks, rank order */);
+
 /* ------------------------------------------ TwoStageMethod level: batched FP64
  * Replaces SIX<FloatMat,Float>::TwoStageMethod (lpsol.h:1906-1930: stage1,
  * slack, constructBasicFeasibleSolution, solveSlackForm) for a batch of

@@ -1,0 +1,148 @@
+"""Column-sharded HBM path: G shards of one LP exchange the pricing
+candidate and the entering column through peer memory inside the kernels.  The
+merged result must be bit-identical to the oracle (and hence to one GPU).
+
+* in-process: G shards on cuda:0, one host thread + stream per shard
+  (xp_lp_f64_peer_attach_local) -- runs on a single-GPU box;
+* multi-process: torchrun, one process per GPU, CUDA IPC handles all-gathered
+  with torch.distributed -- skipped with fewer than 2 GPUs."""
+import os
+import subprocess
+import sys
+import threading
+
+import numpy as np
+import pytest
+
+import harness as H
+import xpoly_b200 as xp
+from xpoly_b200 import sharded
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def solve_sharded_inproc(G, sf, max_iters, device=0):
+    """Returns one merged result dict per entry of max_iters (successive resumes)."""
+    tab, tg = sf[0], sf[1]
+    m, Cc = tab.shape
+    ctxs = [xp.Context(device) for _ in range(G)]
+    lps = [c.large_lp(m, Cc, r, G) for r, c in enumerate(ctxs)]
+    for lp in lps:
+        lp.peer_attach_local(lps)
+        lp.upload(*sf)
+    outs = []
+    for K in max_iters:
+        st = [None] * G
+        err = [None] * G
+
+        def run(r):
+            try:
+                st[r] = lps[r].solve(K)
+            except Exception as e:  # noqa: BLE001
+                err[r] = e
+        th = [threading.Thread(target=run, args=(r,)) for r in range(G)]
+        [t.start() for t in th]
+        [t.join() for t in th]
+        assert not any(err), err
+        assert len(set(st)) == 1, st
+        parts = [lp.download(log_cap=1 << 16) for lp in lps]
+        merged = dict(parts[0])
+        merged["status"] = st[0]
+        merged["tab"] = np.zeros((m, Cc))
+        merged["tgtf"] = np.zeros(Cc)
+        for lp, part in zip(lps, parts):
+            sl = slice(lp.col0, lp.col0 + lp.local_cols)
+            merged["tab"][:, sl] = part["tab"][:, sl]
+            merged["tgtf"][sl] = part["tgtf"][sl]
+            for k in ("eq2bv", "bv2eq", "nvset", "bvset", "log", "sol", "maxv"):  # replicated state
+                assert np.array_equal(part[k], parts[0][k]), (k, lp.rank)
+            assert part["iters"] == parts[0]["iters"]
+        merged["checksums"] = [lp.checksum() for lp in lps]
+        outs.append(merged)
+    for lp in lps:
+        lp.close()
+    for c in ctxs:
+        c.close()
+    return outs
+
+
+def assert_same_state(g, o, tag):
+    assert g["status"] == o["status"], (tag, g["status"], o["status"])
+    assert g["iters"] == o["iters"], (tag, g["iters"], o["iters"])
+    assert np.array_equal(g["log"], o["log"][: len(g["log"])]), (tag, "pivot sequence")
+    for k in ("eq2bv", "bv2eq", "nvset", "bvset"):
+        assert np.array_equal(g[k], o[k]), (tag, k)
+    for k in ("tab", "tgtf", "maxv", "sol"):
+        assert np.array_equal(H.bits(g[k]), H.bits(o[k])), (tag, k)
+
+
+def test_shard_bounds_cover_and_match_device():
+    for Cc in (4, 5, 18, 19, 64, 1000, 16384):
+        for G in (1, 2, 3, 4, 8):
+            if (Cc + 1) // 2 < G:
+                continue
+            b = sharded.shard_bounds(Cc, G)
+            assert b[0][0] == 0 and b[-1][1] == Cc
+            assert all(b[r][1] == b[r + 1][0] for r in range(G - 1))
+            assert all(lo % 2 == 0 and hi > lo for lo, hi in b)
+
+
+@pytest.mark.parametrize("G", [2, 3, 4])
+def test_inproc_dense_to_termination(G):
+    seen = set()
+    for seed, (m, n) in enumerate([(16, 15), (24, 23), (33, 20), (9, 9), (40, 64)]):
+        leq, tg = H.gen_dense_lp(7000 + seed, m, n)
+        sf = xp.slack_form(leq, tg)
+        g = solve_sharded_inproc(G, sf, [H.NO_LIMIT])[0]
+        o = H.slack_solve_oracle("f64", *sf)
+        assert_same_state(g, o, ("dense", G, m, n))
+        seen.add(g["status"])
+    assert seen <= {0, 1, 3}
+
+
+@pytest.mark.parametrize("G", [2, 4])
+def test_inproc_mixed_sign_slow_paths(G):
+    """disableNV retries, the pass-2 ratio test and the findPivotNVandBVPair search
+    all need columns that were not pre-extracted: the collective slow fetch."""
+    seen = set()
+    for seed in range(6):
+        m, n = [(6, 5), (10, 9), (12, 30)][seed % 3]
+        leq, tg = H.gen_mixed_lp(seed, m, n)
+        leq[:, n] = np.abs(leq[:, n])
+        sf = xp.slack_form(leq, tg)
+        g = solve_sharded_inproc(G, sf, [H.NO_LIMIT])[0]
+        assert_same_state(g, H.slack_solve_oracle("f64", *sf), ("mixed", G, seed))
+        seen.add(g["status"])
+    assert 1 in seen
+
+
+def test_inproc_bounded_resume_and_checksum(ctx):
+    """Run K pivots, resume to 3K: same bits as the oracle at each stop, and the
+    shard checksums add up to the single-GPU checksum (mod 2^64)."""
+    leq, tg = H.gen_dense_lp(4242, 96, 95)
+    sf = xp.slack_form(leq, tg)
+    outs = solve_sharded_inproc(4, sf, [5, 15])
+    one = ctx.large_lp(*sf[0].shape)
+    one.upload(*sf)
+    for K, g in zip((5, 15), outs):
+        assert_same_state(g, H.slack_solve_oracle("f64", *sf, max_iter=K), ("resume", K))
+        one.solve(K)
+        ref = one.checksum()
+        for k in (0, 1):
+            assert sum(c[k] for c in g["checksums"]) % (1 << 64) == ref[k]
+    one.close()
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_multiprocess_ipc(world):
+    import torch
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    port = 29650 + world
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", str(port),
+           os.path.join(ROOT, "tests", "sharded_worker.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "SHARDED_WORKER_OK" in r.stdout

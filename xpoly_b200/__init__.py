@@ -15,7 +15,8 @@ LIB_PATH = os.path.join(_HERE, "libxpoly_b200.so")
 
 SIX_SUCC, SIX_UNBOUND, SIX_NO_PRI_FEASIBLE_SOL, SIX_OPTIMAL_IS_INFEASIBLE, SIX_TIME_OUT = range(5)
 IP_SUCC, IP_UNBOUND, IP_NO_PRI_FEASIBLE_SOL, IP_NO_BETTER_THAN_BEST_SOL = range(4)
-ERR_CUDA, ERR_BAD_ARG, ERR_TOO_LARGE, ERR_OVERFLOW, ERR_NCCL = -1, -2, -3, -4, -5
+ERR_CUDA, ERR_BAD_ARG, ERR_TOO_LARGE, ERR_OVERFLOW, ERR_PEER = -1, -2, -3, -4, -5
+MAX_RANKS, PEER_HANDLE_BYTES = 8, 64
 ERR_REFERENCE_UB = -100
 RULE_REFERENCE = 0
 NO_ITER_LIMIT = 0xFFFFFFFF
@@ -127,17 +128,38 @@ class Context:
         return dict(status=st, tab=tab, tgtf=tgtf, nvset=nvset, bvset=bvset, bv2eq=bv2eq,
                     eq2bv=eq2bv, maxv=maxv, sol=sol, iters=n_it, log=log[:min(n_it, log_cap)])
 
-    def large_lp(self, m, Cc):
-        return LargeLP(self, m, Cc)
+    def large_lp(self, m, Cc, rank=0, nranks=1):
+        return LargeLP(self, m, Cc, rank, nranks)
 
 
 class LargeLP:
-    """Device-resident FP64 slack-form LP (xp_lp_f64 handle)."""
+    """Device-resident FP64 slack-form LP (xp_lp_f64 handle); with nranks > 1 this
+    is rank `rank`'s column shard (see xpoly_b200/sharded.py for the handshake)."""
 
-    def __init__(self, ctx, m, Cc):
-        self.ctx, self.m, self.C = ctx, m, Cc
+    def __init__(self, ctx, m, Cc, rank=0, nranks=1):
+        self.ctx, self.m, self.C, self.rank, self.nranks = ctx, m, Cc, rank, nranks
         self._h = _vp()
-        ctx.check(lib().xp_lp_f64_create(ctx._h, m, Cc, C.byref(self._h)))
+        if nranks == 1:
+            ctx.check(lib().xp_lp_f64_create(ctx._h, m, Cc, C.byref(self._h)))
+        else:
+            ctx.check(lib().xp_lp_f64_create_sharded(ctx._h, m, Cc, rank, nranks, C.byref(self._h)))
+        c0, nc = C.c_int(0), C.c_int(0)
+        ctx.check(lib().xp_lp_f64_local_cols(self._h, C.byref(c0), C.byref(nc)))
+        self.col0, self.local_cols = c0.value, nc.value
+
+    def peer_handle(self):
+        buf = np.zeros(PEER_HANDLE_BYTES, dtype=np.uint8)
+        self.ctx.check(lib().xp_lp_f64_peer_handle(self._h, _p(buf)))
+        return buf
+
+    def peer_attach(self, handles):
+        """handles: uint8 [nranks, PEER_HANDLE_BYTES] in rank order (all-gathered)."""
+        h = np.ascontiguousarray(handles, dtype=np.uint8).reshape(self.nranks, PEER_HANDLE_BYTES)
+        self.ctx.check(lib().xp_lp_f64_peer_attach(self._h, _p(h)))
+
+    def peer_attach_local(self, shards):
+        arr = (_vp * self.nranks)(*[s._h for s in shards])
+        self.ctx.check(lib().xp_lp_f64_peer_attach_local(self._h, arr))
 
     def close(self):
         if self._h:

@@ -1,20 +1,30 @@
-// HBM-resident FP64 simplex: SIX<FloatMat,Float>::solveSlackForm on the device.
+// HBM-resident FP64 simplex: SIX<FloatMat,Float>::solveSlackForm on the device,
+// on one GPU or column-sharded over up to 8 GPUs (one process per GPU).
 //
 // Reference semantics (all in /root/reference/src/com/lpsol.h):
 //   solveSlackForm :1007-1191, findPivotBV :552-663, findPivotNVandBVPair
 //   :670-773, pivot :1455-1511, PivotPairTab :68-154, is_feasible :783-822.
 //
 // Two kernels per simplex iteration, no host round trip inside a batch:
-//   k_select  (1 CTA)  pricing (+ the reference's zeroing of basic reduced
-//             costs), ratio test on the already-extracted entering column, tabu
-//             table upkeep, pivot-row scaling, objective-row update, basis swap
-//             and a side-effect-free peek at the NEXT entering column.
+//   k_select  (1 CTA)  completes the pricing exchange, runs the ratio test on the
+//             already-extracted entering column, keeps the tabu table, scales
+//             the pivot row, updates the objective row and the replicated
+//             constant column, swaps the basis, and prices the NEXT iteration
+//             (side-effect free) so the sweep can extract that column.
 //   k_sweep   (grid)   the rank-1 update a[i][j] += (-a[i][q]) * row_p[j] as a
-//             128-bit row-major stream; while streaming it also extracts the
-//             updated NEXT entering column and the constant column into
-//             contiguous buffers, so the next ratio test never touches the
-//             tableau with a strided read.
+//             128-bit row-major stream; while streaming it extracts the updated
+//             NEXT entering column into a contiguous buffer (and, sharded, into
+//             every peer's buffer over NVLink), so the next ratio test never
+//             touches the tableau with a strided read.
 // Algorithmic HBM bytes per pivot: 2*(m+1)*C*8 (read+write of every entry).
+//
+// Column sharding: rank g owns columns [lo_g, hi_g) of the tableau
+// and of the objective row; the constant column, the basis maps and the tabu
+// table are replicated and kept identical by construction (every rank takes the
+// same decisions from the same bits).  The only data that cross GPUs per pivot
+// are one 8-byte candidate word per rank (pricing arg-min, lowest index wins)
+// and the entering column (m+1 doubles), both written straight into the peers'
+// exchange blocks (CUDA IPC mappings) by the kernels themselves.
 //
 // The pair-tabu table is a bit matrix (n x n bits) plus per-row / per-column
 // population counters, which makes canBeNVCandidate / canBeBVCandidate O(1)
@@ -26,26 +36,51 @@
 
 namespace {
 
+constexpr int MAXR = XP_MAX_RANKS;
+constexpr int SEL_THREADS = 1024;
+constexpr int PT = 8; // independent loads in flight per thread in k_select
+constexpr int INT_BIG = 0x7fffffff;
+constexpr unsigned long long SPIN_LIMIT = 6000000000ULL; // ~3 s of SM clocks
+
 struct LpState {
     int status;
     unsigned cnt;
     unsigned max_iter;
     int sweep_pending;
-    int p;      // pivot row of the pending sweep
-    int q;      // entering column of the pending sweep
-    int q_next; // column the pending sweep extracts (-1: none)
-    int cur;    // colbuf[cur] holds (after the pending sweep) column col_tag
-    int col_tag;
+    int p;        // pivot row of the pending sweep
+    int q_next;   // column the pending sweep extracts (global index, -1: none)
     unsigned n_log;
     int infeasible;
+    unsigned xseq; // candidate exchanges initiated so far
+    unsigned xs;   // slow-path column fetches so far
+    unsigned swp;  // sweeps issued so far (slot parity, `done` tag)
+    unsigned fe;   // feasibility-chain epoch
+    int fast;      // exchange #xseq is in flight and sweep #swp extracts its column
     int pad;
     double maxv;
+    double tg_rhs; // replica of the objective row's constant term
 };
 
+// Exchange block of one rank (one cudaMalloc, exported over CUDA IPC).  Every
+// word has a single writer; sequence numbers only grow.
+struct XHdr {
+    unsigned long long cand[2][MAXR]; // (seq << 32) | anypos << 31 | candidate, by rank
+    unsigned long long done[MAXR];    // sweep number whose extracted column is in slot[rank]
+    unsigned long long arrive[MAXR];  // slow fetch: rank reached fetch #xs
+    unsigned long long xflag[MAXR];   // slow fetch: owner's column #xs is in xslot
+    unsigned long long feas_in;       // feasibility chain: partial sums from rank-1 are in feas[]
+    unsigned long long feas_res[MAXR]; // (epoch << 1) | infeasible, broadcast by the last rank
+};
+constexpr size_t XHDR_BYTES = 1024;
+static_assert(sizeof(XHdr) <= XHDR_BYTES, "exchange header");
+
 struct LpDev {
-    int m, C, n; // n = rhs_idx = C-1
-    int W;       // tabu words per row
-    double *tab, *tgtf, *prow, *colbuf[2], *rhsbuf, *sol;
+    int m, C, n;  // global shape; n = rhs_idx = C-1
+    int W;        // tabu words per row
+    int rank, G;  // column shard
+    int col0, Cl; // first local column, local width (row stride of tab)
+    int mpad;     // doubles per exchanged column (m+1 padded)
+    double *tab, *tgtf, *prow, *fcol, *rhsbuf, *sol;
     const double *vc_diag, *vc_rhs; // may be null
     uint8_t *nvset;
     int32_t *bv2eq, *eq2bv;
@@ -53,61 +88,168 @@ struct LpDev {
     int32_t *row_cnt, *col_cnt;
     int32_t *log;
     unsigned log_cap;
+    unsigned *feas_ctr, *sweep_ctr;
     LpState *st;
+    unsigned char *xb[MAXR]; // exchange blocks: xb[rank] is local, the rest peer mappings
 };
 
-constexpr int SEL_THREADS = 1024;
-constexpr int INT_BIG = 0x7fffffff;
+// ---- exchange-block addressing ----
+__host__ __device__ __forceinline__ size_t xoff_slot(const LpDev &d, int r, int par)
+{
+    return XHDR_BYTES + ((size_t)(r * 2 + par) * d.mpad) * sizeof(double);
+}
+__host__ __device__ __forceinline__ size_t xoff_xslot(const LpDev &d)
+{
+    return XHDR_BYTES + ((size_t)(MAXR * 2) * d.mpad) * sizeof(double);
+}
+__host__ __device__ __forceinline__ size_t xoff_feas(const LpDev &d)
+{
+    return XHDR_BYTES + ((size_t)(MAXR * 2 + 1) * d.mpad) * sizeof(double);
+}
+__host__ __device__ __forceinline__ size_t xblock_bytes(const LpDev &d)
+{
+    return XHDR_BYTES + ((size_t)(MAXR * 2 + 2) * d.mpad) * sizeof(double);
+}
+// Column range of rank r: even split in units of two columns (128-bit accesses).
+__host__ __device__ __forceinline__ int shard_lo(int C, int G, int r)
+{
+    long long pairs = (C + 1) / 2;
+    long long lo = 2 * (pairs * r / G);
+    return lo > C ? C : (int)lo;
+}
+__device__ __forceinline__ int owner_of(const LpDev &d, int j)
+{
+    int r = (int)(((long long)(j / 2) * d.G) / ((d.C + 1) / 2));
+    while (r + 1 < d.G && shard_lo(d.C, d.G, r + 1) <= j) r++;
+    while (r > 0 && shard_lo(d.C, d.G, r) > j) r--;
+    return r;
+}
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ double ld_cg(const double *p) { return __ldcg(p); }
+
+// Threads 0..G-1 each write `w` to the word at byte offset `off` of rank t's
+// block.  Callers __syncthreads() first when the word guards data.
+__device__ __forceinline__ void publish(const LpDev &d, size_t off, unsigned long long w)
+{
+    if ((int)threadIdx.x < d.G) {
+        __threadfence_system();
+        st_release_sys((unsigned long long *)(d.xb[threadIdx.x] + off), w);
+    }
+}
+// Thread t < cnt waits until pred(word t at local offset off + 8*t).  Returns
+// false on timeout (block-uniform).
+template <class Pred>
+__device__ __forceinline__ bool wait_words(const LpDev &d, size_t off, int first, int cnt, Pred pred)
+{
+    int bad = 0;
+    if ((int)threadIdx.x < cnt) {
+        const unsigned long long *w =
+            (const unsigned long long *)(d.xb[d.rank] + off) + first + threadIdx.x;
+        const unsigned long long t0 = clock64();
+        unsigned spins = 0;
+        while (!pred(ld_acquire_sys(w))) {
+            if ((++spins & 1023u) == 0 && clock64() - t0 > SPIN_LIMIT) {
+                bad = 1;
+                break;
+            }
+        }
+    }
+    return !__syncthreads_or(bad);
+}
 
 __device__ __forceinline__ bool tabu_get(const LpDev &d, int nv, int bv)
 {
     return (d.tabu[(size_t)nv * d.W + (bv >> 5)] >> (bv & 31)) & 1u;
 }
 
-// Strided read of column j into dst (slow path only: start of a solve, after a
-// disableNV retry, and inside the fallback pair search).
-__device__ void gather_col(const LpDev &d, int j, double *dst)
+// Pricing over the local slice (lpsol.h:1054-1069): lowest eligible index with
+// c_j > 0, and whether any non-basic c_j > 0 exists at all.  Only j > after.
+__device__ __forceinline__ void price_local(const LpDev &d, int after, int mode, int &best, int &anypos)
 {
-    for (int i = threadIdx.x; i < d.m; i += blockDim.x) dst[i] = d.tab[(size_t)i * d.C + j];
-    __syncthreads();
+    // mode 0: c_j > 0 (pricing / pair-search pass A); mode 1: c_j == 0 tolerant (pass B)
+    const int tid = threadIdx.x;
+    const int nl = min(d.Cl, d.n - d.col0); // local columns that are variables
+    best = INT_BIG;
+    anypos = 0;
+    for (int base = 0; base < nl; base += SEL_THREADS * PT) {
+        double c[PT];
+        int nv[PT], rc[PT];
+#pragma unroll
+        for (int u = 0; u < PT; u++) {
+            const int jl = base + u * SEL_THREADS + tid;
+            const bool ok = jl < nl;
+            const int g = d.col0 + (ok ? jl : 0);
+            c[u] = ok ? d.tgtf[jl] : 0.0;
+            nv[u] = ok ? d.nvset[g] : 0;
+            rc[u] = ok ? d.row_cnt[g] : INT_BIG;
+        }
+#pragma unroll
+        for (int u = 0; u < PT; u++) {
+            const int g = d.col0 + base + u * SEL_THREADS + tid;
+            if (!nv[u]) continue;
+            const bool pos = c[u] > 0.0;
+            if (pos) anypos = 1;
+            const bool take = mode == 0 ? pos : (!pos && xp_feq(c[u], 0.0));
+            if (take && g > after && best == INT_BIG && rc[u] < d.n - 1) best = g;
+        }
+    }
 }
 
-// findPivotBV (lpsol.h:552-663) on a contiguous copy of column q.
-// Returns the pivot ROW or -1.
+// findPivotBV (lpsol.h:552-663) on a contiguous copy of column q (col) and the
+// replicated constant column.  Returns the pivot ROW or -1.
 __device__ int ratio_test(const LpDev &d, int q, const double *col, XpMinIdx *shm)
 {
-    const int n = d.n;
-    XpMinIdx best;
-    best.v = 0.0;
-    best.i = -1;
-    for (int i = threadIdx.x; i < d.m; i += blockDim.x) { // pass 1, :571-612
-        double a = col[i];
-        if (xp_fle(a, 0.0)) continue;
-        int bv = d.eq2bv[i];
-        if (tabu_get(d, q, bv)) continue;
-        if (d.col_cnt[bv] >= n - 1) continue; // !canBeBVCandidate
-        XpMinIdx c;
-        c.v = xp_div(d.rhsbuf[i], a);
-        c.i = i;
-        best = xp_better(best, c);
+    const int n = d.n, tid = threadIdx.x;
+    for (int pass = 0; pass < 2; pass++) {
+        XpMinIdx best;
+        best.v = 0.0;
+        best.i = -1;
+        for (int base = 0; base < d.m; base += SEL_THREADS * PT) {
+            double a[PT], rh[PT];
+            int bv[PT];
+#pragma unroll
+            for (int u = 0; u < PT; u++) {
+                const int i = base + u * SEL_THREADS + tid;
+                const bool ok = i < d.m;
+                a[u] = ok ? ld_cg(col + i) : 0.0;
+                rh[u] = ok ? d.rhsbuf[i] : 0.0;
+                bv[u] = ok ? d.eq2bv[i] : -1;
+            }
+            uint32_t tw[PT];
+            int cc[PT];
+#pragma unroll
+            for (int u = 0; u < PT; u++) {
+                // pass 1 (:571-612) takes a > 0 (tolerant), pass 2 (:623-658) any a != 0
+                const bool cand = bv[u] >= 0 && (pass == 0 ? !xp_fle(a[u], 0.0) : !xp_feq(a[u], 0.0));
+                tw[u] = cand ? d.tabu[(size_t)q * d.W + (bv[u] >> 5)] : 0xffffffffu;
+                cc[u] = cand ? d.col_cnt[bv[u]] : INT_BIG;
+                if (!cand) bv[u] = -1;
+            }
+#pragma unroll
+            for (int u = 0; u < PT; u++) {
+                if (bv[u] < 0) continue;
+                if ((tw[u] >> (bv[u] & 31)) & 1u) continue; // is_handle(q, bv)
+                if (cc[u] >= n - 1) continue;               // !canBeBVCandidate
+                XpMinIdx c;
+                c.v = xp_div(rh[u], a[u]);
+                c.i = base + u * SEL_THREADS + tid;
+                best = xp_better(best, c);
+            }
+        }
+        best = xp_block_argmin(best, shm);
+        if (best.i >= 0) return best.i;
     }
-    best = xp_block_argmin(best, shm);
-    if (best.i >= 0) return best.i;
-    best.v = 0.0;
-    best.i = -1;
-    for (int i = threadIdx.x; i < d.m; i += blockDim.x) { // pass 2, :623-658
-        int bv = d.eq2bv[i];
-        if (tabu_get(d, q, bv)) continue;
-        if (d.col_cnt[bv] >= n - 1) continue;
-        double a = col[i];
-        if (xp_feq(a, 0.0)) continue;
-        XpMinIdx c;
-        c.v = xp_div(d.rhsbuf[i], a);
-        c.i = i;
-        best = xp_better(best, c);
-    }
-    best = xp_block_argmin(best, shm);
-    return best.i;
+    return -1;
 }
 
 // PivotPairTab::disableNV (lpsol.h:114-121) with counter upkeep.
@@ -132,17 +274,102 @@ __device__ void disable_nv(const LpDev &d, int q)
     __syncthreads();
 }
 
+struct SelCtx {
+    unsigned xseq, xs;
+    bool ok; // false after a peer timeout
+};
+
+// All-ranks arg-min of the local pricing result (lowest index wins; `anypos`
+// is OR-ed).  Split in two halves so the exchange of the next iteration can be
+// in flight during the sweep.
+__device__ __forceinline__ void cand_publish(const LpDev &d, SelCtx &x, int best, int anypos)
+{
+    x.xseq++;
+    const unsigned long long w = ((unsigned long long)x.xseq << 32) |
+                                 ((unsigned long long)(anypos ? 1u : 0u) << 31) |
+                                 (unsigned long long)(unsigned)best;
+    __syncthreads();
+    publish(d, offsetof(XHdr, cand) + (size_t)(x.xseq & 1) * MAXR * 8 + (size_t)d.rank * 8, w);
+}
+__device__ __forceinline__ void cand_complete(const LpDev &d, SelCtx &x, int &q, int &anypos)
+{
+    const unsigned seq = x.xseq;
+    const size_t off = offsetof(XHdr, cand) + (size_t)(seq & 1) * MAXR * 8;
+    if (!wait_words(d, off, 0, d.G, [seq](unsigned long long w) { return (unsigned)(w >> 32) == seq; }))
+        x.ok = false;
+    const unsigned long long *w = (const unsigned long long *)(d.xb[d.rank] + off);
+    q = INT_BIG;
+    anypos = 0;
+    for (int r = 0; r < d.G; r++) {
+        const unsigned long long v = ld_acquire_sys(w + r);
+        q = min(q, (int)(v & 0x7fffffffu));
+        anypos |= (int)((v >> 31) & 1u);
+    }
+    __syncthreads(); // every thread has read the words before anyone publishes the next exchange
+}
+
+// Slow path: column j as of now, from its owner's tableau, to every rank's
+// xslot ([m] carries c_j).  Collective; used at the start of a solve, after a
+// disableNV retry and inside the pair search.
+__device__ const double *fetch_col(const LpDev &d, SelCtx &x, int j)
+{
+    double *mine = (double *)(d.xb[d.rank] + xoff_xslot(d));
+    x.xs++;
+    const unsigned xs = x.xs;
+    const int owner = d.G > 1 ? owner_of(d, j) : 0;
+    if (d.G > 1) {
+        __syncthreads();
+        publish(d, offsetof(XHdr, arrive) + (size_t)d.rank * 8, xs);
+    }
+    if (owner == d.rank) {
+        if (d.G > 1 &&
+            !wait_words(d, offsetof(XHdr, arrive), 0, d.G, [xs](unsigned long long w) { return w >= xs; }))
+            x.ok = false;
+        const int jl = j - d.col0;
+        for (int base = 0; base < d.m + 1; base += SEL_THREADS * PT) {
+            double v[PT];
+#pragma unroll
+            for (int u = 0; u < PT; u++) {
+                const int i = base + u * SEL_THREADS + threadIdx.x;
+                v[u] = i < d.m ? d.tab[(size_t)i * d.Cl + jl] : (i == d.m ? d.tgtf[jl] : 0.0);
+            }
+#pragma unroll
+            for (int u = 0; u < PT; u++) {
+                const int i = base + u * SEL_THREADS + threadIdx.x;
+                if (i > d.m) continue;
+                for (int r = 0; r < d.G; r++) ((double *)(d.xb[r] + xoff_xslot(d)))[i] = v[u];
+            }
+        }
+        if (d.G > 1) {
+            __syncthreads();
+            publish(d, offsetof(XHdr, xflag) + (size_t)d.rank * 8, xs);
+        }
+    }
+    if (d.G > 1) {
+        if (!wait_words(d, offsetof(XHdr, xflag), owner, 1, [xs](unsigned long long w) { return w >= xs; }))
+            x.ok = false;
+    } else {
+        __syncthreads();
+    }
+    return mine;
+}
+
 __global__ void __launch_bounds__(SEL_THREADS, 1) k_select(LpDev d)
 {
     __shared__ XpMinIdx shm[33];
     __shared__ int shi[33];
     LpState *st = d.st;
     const int tid = threadIdx.x;
-    const int n = d.n, C = d.C;
+    const int n = d.n, m = d.m, Cl = d.Cl;
 
     const int status0 = st->status;
     const unsigned cnt0 = st->cnt, max_iter = st->max_iter;
-    int cur = st->cur, col_tag = st->col_tag;
+    const int fast0 = st->fast;
+    const unsigned swp0 = st->swp;
+    SelCtx x;
+    x.xseq = st->xseq;
+    x.xs = st->xs;
+    x.ok = true;
     __syncthreads();
     if (tid == 0) st->sweep_pending = 0;
     if (status0 != XPI_RUNNING) return;
@@ -150,31 +377,60 @@ __global__ void __launch_bounds__(SEL_THREADS, 1) k_select(LpDev d)
         if (tid == 0) st->status = XP_SIX_TIME_OUT;
         return;
     }
+#define SEL_EXIT(code)                  \
+    do {                                \
+        if (tid == 0) {                 \
+            st->status = (code);        \
+            st->xseq = x.xseq;          \
+            st->xs = x.xs;              \
+            st->fast = 0;               \
+        }                               \
+        return;                         \
+    } while (0)
 
     int q = -1, p = -1;
+    const double *col = nullptr;
+    bool first = true;
     for (;;) {
         // ---- pricing, :1054-1069 ----
-        int best = INT_BIG;
-        int anypos = 0;
-        for (int j = tid; j < n; j += blockDim.x) {
-            if (d.nvset[j] && d.tgtf[j] > 0.0) {
-                anypos = 1;
-                if (best == INT_BIG && d.row_cnt[j] < n - 1) best = j; // canBeNVCandidate
-            }
+        int best, anypos;
+        if (!(first && fast0)) {
+            int lb, la;
+            price_local(d, -1, 0, lb, la);
+            lb = xp_block_min_int(lb, shi);
+            la = __syncthreads_or(la);
+            if (d.G > 1) cand_publish(d, x, lb, la);
+            best = lb;
+            anypos = la;
         }
-        best = xp_block_min_int(best, shi);
-        anypos = __syncthreads_or(anypos);
+        if (d.G > 1) {
+            cand_complete(d, x, best, anypos);
+            if (!x.ok) SEL_EXIT(XP_ERR_PEER);
+        } else if (first && fast0) {
+            best = st->q_next < 0 ? INT_BIG : st->q_next;
+            anypos = st->pad;
+        }
         // basic columns scanned before the break have their reduced cost forced to 0 (:1059)
-        const int zlim = best == INT_BIG ? n : best;
-        for (int j = tid; j < zlim; j += blockDim.x)
-            if (!d.nvset[j]) d.tgtf[j] = 0.0;
-        __syncthreads();
-
-        if (best == INT_BIG) {
-            if (!anypos) { // optimal exit; feasibility is checked by k_feas_*
-                if (tid == 0) st->status = XPI_OPT_PENDING;
-                return;
+        {
+            const int zlim = (best == INT_BIG ? n : best) - d.col0;
+            const int zl = min(zlim, Cl);
+            for (int base = 0; base < zl; base += SEL_THREADS * PT) {
+                int nv[PT];
+#pragma unroll
+                for (int u = 0; u < PT; u++) {
+                    const int jl = base + u * SEL_THREADS + tid;
+                    nv[u] = jl < zl ? d.nvset[d.col0 + jl] : 1;
+                }
+#pragma unroll
+                for (int u = 0; u < PT; u++) {
+                    const int jl = base + u * SEL_THREADS + tid;
+                    if (!nv[u]) d.tgtf[jl] = 0.0;
+                }
             }
+            __syncthreads();
+        }
+        if (best == INT_BIG) {
+            if (!anypos) SEL_EXIT(XPI_OPT_PENDING); // optimal exit; feasibility is checked by k_feas_*
             // ---- findPivotNVandBVPair, :670-773 ----
             // Pass A: eligible c_j > 0; pass B additionally c_j == 0 (tolerant).
             // findPivotBV is pure, so the c_j > 0 columns that failed in pass A
@@ -183,21 +439,18 @@ __global__ void __launch_bounds__(SEL_THREADS, 1) k_select(LpDev d)
             for (int pass = 0; pass < 2 && !found; pass++) {
                 int last = -1;
                 for (;;) {
-                    int cand = INT_BIG;
-                    for (int j = last + 1 + tid; j < n; j += blockDim.x) {
-                        if (!d.nvset[j] || d.row_cnt[j] >= n - 1) continue;
-                        double c = d.tgtf[j];
-                        bool take = pass == 0 ? (c > 0.0) : (!(c > 0.0) && xp_feq(c, 0.0));
-                        if (take) {
-                            cand = j;
-                            break;
-                        }
-                    }
+                    int cand, dummy;
+                    price_local(d, last, pass, cand, dummy);
                     cand = xp_block_min_int(cand, shi);
+                    if (d.G > 1) {
+                        cand_publish(d, x, cand, 0);
+                        cand_complete(d, x, cand, dummy);
+                        if (!x.ok) SEL_EXIT(XP_ERR_PEER);
+                    }
                     if (cand == INT_BIG) break;
-                    gather_col(d, cand, d.colbuf[cur]);
-                    col_tag = cand;
-                    int r = ratio_test(d, cand, d.colbuf[cur], shm);
+                    col = fetch_col(d, x, cand);
+                    if (!x.ok) SEL_EXIT(XP_ERR_PEER);
+                    int r = ratio_test(d, cand, col, shm);
                     if (r >= 0) {
                         q = cand;
                         p = r;
@@ -207,31 +460,35 @@ __global__ void __launch_bounds__(SEL_THREADS, 1) k_select(LpDev d)
                     last = cand;
                 }
             }
-            if (!found) {
-                if (tid == 0) {
-                    st->status = XP_SIX_UNBOUND;
-                    st->col_tag = col_tag;
-                }
-                return;
-            }
+            if (!found) SEL_EXIT(XP_SIX_UNBOUND);
             break;
         }
         q = best;
-        if (col_tag != q) {
-            gather_col(d, q, d.colbuf[cur]);
-            col_tag = q;
+        if (first && fast0) {
+            const int owner = d.G > 1 ? owner_of(d, q) : 0;
+            if (d.G > 1 && owner != d.rank) {
+                const unsigned w = swp0;
+                if (!wait_words(d, offsetof(XHdr, done), owner, 1,
+                                [w](unsigned long long v) { return v >= w; }))
+                    SEL_EXIT(XP_ERR_PEER);
+            }
+            col = (const double *)(d.xb[d.rank] + xoff_slot(d, owner, swp0 & 1));
+        } else {
+            col = fetch_col(d, x, q);
+            if (!x.ok) SEL_EXIT(XP_ERR_PEER);
         }
-        p = ratio_test(d, q, d.colbuf[cur], shm);
+        first = false;
+        p = ratio_test(d, q, col, shm);
         if (p >= 0) break;
         disable_nv(d, q); // :1146-1151, retry without counting an iteration
     }
 
     // ---- genPair (:1156) + pivot bookkeeping ----
-    const double *col = d.colbuf[cur];
     const int bv = d.eq2bv[p];
-    const double pv = col[p];
-    const double cq = d.tgtf[q];
-    __syncthreads(); // everyone has read eq2bv[p], tgtf[q] before they change
+    const double pv = ld_cg(col + p);
+    const double cq = ld_cg(col + m); // c_q travels with the column
+    const double rhs_p = d.rhsbuf[p];
+    __syncthreads(); // everyone has read eq2bv[p], rhsbuf[p] before they change
     if (tid == 0) {
         uint32_t *w = &d.tabu[(size_t)q * d.W + (bv >> 5)];
         uint32_t bit = 1u << (bv & 31);
@@ -252,44 +509,81 @@ __global__ void __launch_bounds__(SEL_THREADS, 1) k_select(LpDev d)
     const double r = xp_div(1.0, pv);
     const bool r_one = xp_feq(r, 1.0), r_zero = xp_feq(r, 0.0);
     const bool cq_zero = xp_feq(cq, 0.0), cq_one = xp_feq(cq, 1.0);
-    double *rowp = d.tab + (size_t)p * C;
-    for (int j = tid; j < C; j += blockDim.x) {
-        double x = xp_scale(rowp[j], r, r_one, r_zero); // mulOfRow(eqnum, 1/pivot)
-        rowp[j] = x;
-        d.prow[j] = x;
-        double t = xp_mul(x, -1.0);                     // nvexp.mul(-1)
-        if (j >= n) t = -t;                             // constant column keeps its sign
-        t = cq_zero ? 0.0 : (cq_one ? t : xp_mul(t, cq)); // nvexp.mul(tgtf[nv])
-        d.tgtf[j] = xp_add(t, d.tgtf[j]);               // tgtf.addRowToRow
+    const double prow_rhs = xp_scale(rhs_p, r, r_one, r_zero);
+    // multipliers f_i = -a[i][q] for the sweep, and the replicated constant column
+    for (int base = 0; base < m; base += SEL_THREADS * PT) {
+        double a[PT], rh[PT];
+#pragma unroll
+        for (int u = 0; u < PT; u++) {
+            const int i = base + u * SEL_THREADS + tid;
+            a[u] = i < m ? ld_cg(col + i) : 0.0;
+            rh[u] = i < m ? d.rhsbuf[i] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < PT; u++) {
+            const int i = base + u * SEL_THREADS + tid;
+            if (i >= m) continue;
+            const double f = -a[u];
+            d.fcol[i] = f;
+            d.rhsbuf[i] = i == p ? prow_rhs : xp_add(rh[u], xp_mul(f, prow_rhs));
+        }
     }
-    if (tid == 0) { // :1504-1510
+    double *rowp = d.tab + (size_t)p * Cl;
+    for (int base = 0; base < Cl; base += SEL_THREADS * PT) {
+        double xr[PT], tg[PT];
+#pragma unroll
+        for (int u = 0; u < PT; u++) {
+            const int jl = base + u * SEL_THREADS + tid;
+            xr[u] = jl < Cl ? rowp[jl] : 0.0;
+            tg[u] = jl < Cl ? d.tgtf[jl] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < PT; u++) {
+            const int jl = base + u * SEL_THREADS + tid;
+            if (jl >= Cl) continue;
+            const double xv = xp_scale(xr[u], r, r_one, r_zero); // mulOfRow(eqnum, 1/pivot)
+            rowp[jl] = xv;
+            d.prow[jl] = xv;
+            double t = xp_mul(xv, -1.0);                      // nvexp.mul(-1)
+            if (d.col0 + jl >= n) t = -t;                     // constant column keeps its sign
+            t = cq_zero ? 0.0 : (cq_one ? t : xp_mul(t, cq)); // nvexp.mul(tgtf[nv])
+            d.tgtf[jl] = xp_add(t, tg[u]);                    // tgtf.addRowToRow
+        }
+    }
+    if (tid == 0) { // :1504-1510, and the replica of tgtf[rhs]
         d.nvset[q] = 0;
         d.nvset[bv] = 1;
         d.eq2bv[p] = q;
         d.bv2eq[q] = p;
         d.bv2eq[bv] = -1;
+        double t = -xp_mul(prow_rhs, -1.0);
+        t = cq_zero ? 0.0 : (cq_one ? t : xp_mul(t, cq));
+        st->tg_rhs = xp_add(t, st->tg_rhs);
     }
     __syncthreads();
-    // ---- peek: the column the NEXT iteration will price in (no side effects) ----
-    int nxt = INT_BIG;
+    // ---- price the NEXT iteration (no side effects) and start its exchange ----
+    int nxt = INT_BIG, anyn = 0, fast1 = 0;
     if (cnt0 + 1 < max_iter) {
-        for (int j = tid; j < n; j += blockDim.x) {
-            if (d.nvset[j] && d.tgtf[j] > 0.0 && d.row_cnt[j] < n - 1) {
-                nxt = j;
-                break;
-            }
-        }
+        price_local(d, -1, 0, nxt, anyn);
+        nxt = xp_block_min_int(nxt, shi);
+        anyn = __syncthreads_or(anyn);
+        fast1 = 1;
+        if (nxt != INT_BIG && tid < d.G) // c_q of my candidate rides in slot[rank][par][m]
+            ((double *)(d.xb[tid] + xoff_slot(d, d.rank, (swp0 + 1) & 1)))[m] = d.tgtf[nxt - d.col0];
+        if (d.G > 1) cand_publish(d, x, nxt, anyn);
     }
-    nxt = xp_block_min_int(nxt, shi);
     if (tid == 0) {
         st->p = p;
-        st->q = q;
         st->q_next = nxt == INT_BIG ? -1 : nxt;
-        st->cur = cur ^ 1; // the sweep reads colbuf[cur], writes colbuf[cur^1]
-        st->col_tag = nxt == INT_BIG ? -1 : nxt;
+        st->pad = anyn;
         st->cnt = cnt0 + 1;
+        st->swp = swp0 + 1;
+        st->fast = fast1;
+        st->xseq = x.xseq;
+        st->xs = x.xs;
         st->sweep_pending = 1;
     }
+#undef SEL_EXIT
 }
 
 // Rank-1 update + extraction.  Each thread owns VEC adjacent columns and walks
@@ -301,27 +595,27 @@ __global__ void __launch_bounds__(THREADS) k_sweep(LpDev d, int rows_per_cta)
     extern __shared__ double s_f[];
     const LpState *st = d.st;
     if (!st->sweep_pending) return;
-    const int p = st->p, qn = st->q_next, C = d.C, n = d.n, m = d.m;
-    const double *fcol = d.colbuf[st->cur ^ 1];
-    double *ncol = d.colbuf[st->cur];
+    const int p = st->p, Cl = d.Cl, m = d.m;
+    const int qn = st->q_next < 0 ? -1 : st->q_next - d.col0; // local index of my candidate
+    const size_t slot = xoff_slot(d, d.rank, st->swp & 1);
     const int r0 = blockIdx.y * rows_per_cta;
     const int r1 = min(m, r0 + rows_per_cta);
-    for (int i = r0 + threadIdx.x; i < r1; i += THREADS) s_f[i - r0] = -fcol[i];
+    for (int i = r0 + threadIdx.x; i < r1; i += THREADS) s_f[i - r0] = d.fcol[i];
     __syncthreads();
     const int j0 = (blockIdx.x * THREADS + threadIdx.x) * VEC;
-    if (j0 >= C) return;
 
-    if (VEC == 2) {
+    if (j0 >= Cl) {
+        // nothing to update in this thread
+    } else if (VEC == 2) {
         const double2 pr = *reinterpret_cast<const double2 *>(d.prow + j0);
         const int exq = (qn == j0) ? 0 : (qn == j0 + 1 ? 1 : -1);
-        const int exr = (n == j0) ? 0 : (n == j0 + 1 ? 1 : -1);
         double *base = d.tab + j0;
         int i = r0;
         for (; i + UNROLL <= r1; i += UNROLL) {
             double2 a[UNROLL];
 #pragma unroll
             for (int u = 0; u < UNROLL; u++)
-                a[u] = *reinterpret_cast<const double2 *>(base + (size_t)(i + u) * C);
+                a[u] = *reinterpret_cast<const double2 *>(base + (size_t)(i + u) * Cl);
 #pragma unroll
             for (int u = 0; u < UNROLL; u++) {
                 const double f = s_f[i + u - r0];
@@ -329,33 +623,52 @@ __global__ void __launch_bounds__(THREADS) k_sweep(LpDev d, int rows_per_cta)
                 v.x = xp_add(a[u].x, xp_mul(f, pr.x));
                 v.y = xp_add(a[u].y, xp_mul(f, pr.y));
                 if (i + u == p) v = a[u]; // row p was rewritten by k_select
-                *reinterpret_cast<double2 *>(base + (size_t)(i + u) * C) = v;
-                if (exq >= 0) ncol[i + u] = exq ? v.y : v.x;
-                if (exr >= 0) d.rhsbuf[i + u] = exr ? v.y : v.x;
+                *reinterpret_cast<double2 *>(base + (size_t)(i + u) * Cl) = v;
+                if (exq >= 0) {
+                    const double e = exq ? v.y : v.x;
+                    for (int r = 0; r < d.G; r++) ((double *)(d.xb[r] + slot))[i + u] = e;
+                }
             }
         }
         for (; i < r1; i++) {
-            double2 a = *reinterpret_cast<const double2 *>(base + (size_t)i * C);
+            double2 a = *reinterpret_cast<const double2 *>(base + (size_t)i * Cl);
             const double f = s_f[i - r0];
             double2 v;
             v.x = xp_add(a.x, xp_mul(f, pr.x));
             v.y = xp_add(a.y, xp_mul(f, pr.y));
             if (i == p) v = a;
-            *reinterpret_cast<double2 *>(base + (size_t)i * C) = v;
-            if (exq >= 0) ncol[i] = exq ? v.y : v.x;
-            if (exr >= 0) d.rhsbuf[i] = exr ? v.y : v.x;
+            *reinterpret_cast<double2 *>(base + (size_t)i * Cl) = v;
+            if (exq >= 0) {
+                const double e = exq ? v.y : v.x;
+                for (int r = 0; r < d.G; r++) ((double *)(d.xb[r] + slot))[i] = e;
+            }
         }
     } else {
         const double pr = d.prow[j0];
-        const bool exq = qn == j0, exr = n == j0;
+        const bool exq = qn == j0;
         double *base = d.tab + j0;
         for (int i = r0; i < r1; i++) {
-            double a = base[(size_t)i * C];
+            double a = base[(size_t)i * Cl];
             double v = xp_add(a, xp_mul(s_f[i - r0], pr));
             if (i == p) v = a;
-            base[(size_t)i * C] = v;
-            if (exq) ncol[i] = v;
-            if (exr) d.rhsbuf[i] = v;
+            base[(size_t)i * Cl] = v;
+            if (exq)
+                for (int r = 0; r < d.G; r++) ((double *)(d.xb[r] + slot))[i] = v;
+        }
+    }
+    if (d.G > 1) {
+        // The last CTA to finish tells every rank that sweep #swp is complete on this
+        // rank, i.e. that slot[rank][swp & 1] holds my candidate's column everywhere.
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence_system();
+            if (atomicAdd(d.sweep_ctr, 1u) == gridDim.x * gridDim.y - 1) {
+                *d.sweep_ctr = 0;
+                __threadfence_system();
+                for (int r = 0; r < d.G; r++)
+                    st_release_sys((unsigned long long *)(d.xb[r] + offsetof(XHdr, done)) + d.rank,
+                                   (unsigned long long)st->swp);
+            }
         }
     }
 }
@@ -381,31 +694,91 @@ __global__ void k_feas_sol(LpDev d)
 
 // One thread per row: the reference's left-to-right sum (:805-809).  Terms of
 // non-basic columns are exact +-0 products and cannot change the running sum,
-// so only basic columns are visited (same value, bit for bit).
+// so only basic columns are visited (same value, bit for bit).  Sharded: the
+// running sums travel rank to rank in column order (feas[] of the next rank).
 __global__ void k_feas_rows(LpDev d)
 {
     LpState *st = d.st;
     if (st->status != XPI_OPT_PENDING) return;
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= d.m) return;
-    const double *row = d.tab + (size_t)i * d.C;
-    double sum = 0.0;
-    for (int j = 0; j < d.n; j++) {
-        if (d.nvset[j]) continue;
-        sum = xp_add(sum, xp_mul(row[j], d.sol[j]));
+    __shared__ int s_bad;
+    const unsigned long long ep = (unsigned long long)st->fe + 1;
+    if (threadIdx.x == 0) s_bad = 0;
+    if (d.G > 1 && d.rank > 0) {
+        if (threadIdx.x == 0) {
+            const unsigned long long *w =
+                (const unsigned long long *)(d.xb[d.rank] + offsetof(XHdr, feas_in));
+            const unsigned long long t0 = clock64();
+            while (ld_acquire_sys(w) < ep)
+                if (clock64() - t0 > SPIN_LIMIT) {
+                    s_bad = 1;
+                    break;
+                }
+        }
     }
-    if (!xp_feq(sum, row[d.n])) atomicOr(&st->infeasible, 1);
+    __syncthreads();
+    if (s_bad) {
+        if (threadIdx.x == 0) st->infeasible = 2; // peer timeout
+        return;
+    }
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < d.m) {
+        const double *row = d.tab + (size_t)i * d.Cl;
+        double sum = 0.0;
+        if (d.G > 1 && d.rank > 0) sum = ld_cg((const double *)(d.xb[d.rank] + xoff_feas(d)) + i);
+        const int nl = min(d.Cl, d.n - d.col0);
+        for (int jl = 0; jl < nl; jl++) {
+            const int g = d.col0 + jl;
+            if (d.nvset[g]) continue;
+            sum = xp_add(sum, xp_mul(row[jl], d.sol[g]));
+        }
+        if (d.rank + 1 < d.G) ((double *)(d.xb[d.rank + 1] + xoff_feas(d)))[i] = sum;
+        else if (!xp_feq(sum, d.rhsbuf[i])) atomicOr(&st->infeasible, 1);
+    }
+    if (d.G > 1 && d.rank + 1 < d.G) { // last CTA hands the chain to the next rank
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence_system();
+            if (atomicAdd(d.feas_ctr, 1u) == gridDim.x - 1) {
+                *d.feas_ctr = 0;
+                __threadfence_system();
+                st_release_sys((unsigned long long *)(d.xb[d.rank + 1] + offsetof(XHdr, feas_in)), ep);
+            }
+        }
+    }
 }
 
 __global__ void k_feas_done(LpDev d)
 {
     LpState *st = d.st;
     if (st->status != XPI_OPT_PENDING) return;
-    if (st->infeasible) {
+    const unsigned long long ep = (unsigned long long)st->fe + 1;
+    int inf = st->infeasible;
+    if (d.G > 1) {
+        // every rank checked the variable bounds (replicated); the row sums end on the last rank
+        if (d.rank == d.G - 1) {
+            for (int r = 0; r < d.G; r++) {
+                __threadfence_system();
+                st_release_sys((unsigned long long *)(d.xb[r] + offsetof(XHdr, feas_res)), (ep << 2) | (unsigned)inf);
+            }
+        }
+        const unsigned long long *w = (const unsigned long long *)(d.xb[d.rank] + offsetof(XHdr, feas_res));
+        const unsigned long long t0 = clock64();
+        unsigned long long v;
+        while (((v = ld_acquire_sys(w)) >> 2) < ep)
+            if (clock64() - t0 > SPIN_LIMIT) {
+                v = (ep << 2) | 2u;
+                break;
+            }
+        inf |= (int)(v & 3u);
+    }
+    st->fe = (unsigned)ep;
+    if (inf & 2) {
+        st->status = XP_ERR_PEER;
+    } else if (inf) {
         st->status = XP_SIX_OPTIMAL_IS_INFEASIBLE;
     } else {
         st->status = XP_SIX_SUCC;
-        st->maxv = d.tgtf[d.n]; // :1119
+        st->maxv = st->tg_rhs; // :1119
     }
 }
 
@@ -420,16 +793,15 @@ __global__ void k_init(LpDev d, unsigned max_iter, int fresh)
             d.row_cnt[k] = 0;
             d.col_cnt[k] = 0;
         }
-        for (int k = t; k < d.m; k += stride) d.rhsbuf[k] = d.tab[(size_t)k * d.C + d.n];
         for (int k = t; k < d.C; k += stride) d.sol[k] = 0.0; // sol.reinit, :1028
     }
     if (t == 0) {
         if (fresh) {
             st->cnt = 0;
             st->n_log = 0;
-            st->cur = 0;
-            st->col_tag = -1;
             st->infeasible = 0;
+            st->fast = 0;
+            st->q_next = -1;
             st->maxv = 0.0; // :1027
             st->status = XPI_RUNNING;
         } else if (st->status == XP_SIX_TIME_OUT && st->cnt < max_iter) {
@@ -440,29 +812,53 @@ __global__ void k_init(LpDev d, unsigned max_iter, int fresh)
     }
 }
 
-__global__ void k_slack_form(double *tab, double *tgtf, const double *leq, const double *tg, int m,
-                             int n, uint8_t *nvset, int32_t *bv2eq, int32_t *eq2bv)
+// SIX::slack (lpsol.h:1405-1433) + identity basis (:1821-1841): [A | I | b],
+// local slice [col0, col0+Cl) plus the replicated constant column.
+template <class Gen>
+__device__ __forceinline__ void fill_slack_form(const LpDev &d, int nvars, Gen gen)
 {
-    // SIX::slack (lpsol.h:1405-1433) + identity basis (:1821-1841): [A | I | b]
-    const int C = n + m + 1;
-    size_t total = (size_t)m * C;
+    const int m = d.m, n = nvars, C = d.C;
+    const size_t total = (size_t)m * d.Cl;
     for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
          e += (size_t)gridDim.x * blockDim.x) {
-        int i = (int)(e / C), j = (int)(e % C);
+        const int i = (int)(e / d.Cl), j = d.col0 + (int)(e % d.Cl);
         double v;
-        if (j < n) v = leq[(size_t)i * (n + 1) + j];
+        if (j < n) v = gen(i, j);
         else if (j < n + m) v = (j - n == i) ? 1.0 : 0.0;
-        else v = leq[(size_t)i * (n + 1) + n];
-        tab[e] = v;
+        else v = gen(i, n);
+        d.tab[e] = v;
     }
     for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < C; j += gridDim.x * blockDim.x) {
-        tgtf[j] = j < n ? tg[j] : (j < n + m ? 0.0 : tg[n]);
+        if (j >= d.col0 && j < d.col0 + d.Cl) d.tgtf[j - d.col0] = j < n ? gen(m, j) : (j < n + m ? 0.0 : gen(m, n));
         if (j < n + m) {
-            nvset[j] = j < n;
-            bv2eq[j] = j < n ? -1 : j - n;
+            d.nvset[j] = j < n;
+            d.bv2eq[j] = j < n ? -1 : j - n;
         }
-        if (j < m) eq2bv[j] = n + j;
+        if (j < m) {
+            d.eq2bv[j] = n + j;
+            d.rhsbuf[j] = gen(j, n);
+        }
+        if (j == 0) d.st->tg_rhs = gen(m, n);
     }
+}
+
+struct GenLeq { // entries of the caller's leq (rows 0..m-1) and objective (row m)
+    const double *leq, *tg;
+    int m, n;
+    __device__ __forceinline__ double operator()(int i, int j) const
+    {
+        return i < m ? leq[(size_t)i * (n + 1) + j] : tg[j];
+    }
+};
+
+__global__ void k_slack_form(LpDev d, const double *leq, const double *tg, int n)
+{
+    GenLeq g;
+    g.leq = leq;
+    g.tg = tg;
+    g.m = d.m;
+    g.n = n;
+    fill_slack_form(d, n, g);
 }
 
 __device__ __forceinline__ uint64_t mix64(uint64_t z)
@@ -477,38 +873,43 @@ __device__ __forceinline__ double u01(uint64_t seed, uint64_t idx)
     return (double)(mix64(seed ^ mix64(idx)) >> 11) * (1.0 / 9007199254740992.0);
 }
 
-__global__ void k_fill_synth(double *tab, double *tgtf, int m, int n, uint64_t seed, uint8_t *nvset,
-                             int32_t *bv2eq, int32_t *eq2bv)
+struct GenSynth { // SURVEY 8(d) dense family: A_ij~U(0,1), b_i = 1+U*n, c_j~U(0,1), c_rhs = 0
+    uint64_t seed;
+    int m, n;
+    __device__ __forceinline__ double operator()(int i, int j) const
+    {
+        if (i == m) return j < n ? u01(seed, (uint64_t)m * (n + 1) + j) : 0.0;
+        const double u = u01(seed, (uint64_t)i * (n + 1) + j);
+        return j < n ? u : 1.0 + u * n;
+    }
+};
+
+__global__ void k_fill_synth(LpDev d, int n, uint64_t seed)
 {
-    // SURVEY 8(d) dense family in slack form: A_ij~U(0,1), b_i = 1+U*n, c_j~U(0,1)
-    const int C = n + m + 1;
-    size_t total = (size_t)m * C;
-    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
-         e += (size_t)gridDim.x * blockDim.x) {
-        int i = (int)(e / C), j = (int)(e % C);
-        double v;
-        if (j < n) v = u01(seed, (uint64_t)i * (n + 1) + j);
-        else if (j < n + m) v = (j - n == i) ? 1.0 : 0.0;
-        else v = 1.0 + u01(seed, (uint64_t)i * (n + 1) + n) * n;
-        tab[e] = v;
-    }
-    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < C; j += gridDim.x * blockDim.x) {
-        tgtf[j] = j < n ? u01(seed, (uint64_t)m * (n + 1) + j) : 0.0;
-        if (j < n + m) {
-            nvset[j] = j < n;
-            bv2eq[j] = j < n ? -1 : j - n;
-        }
-        if (j < m) eq2bv[j] = n + j;
-    }
+    GenSynth g;
+    g.seed = seed;
+    g.m = d.m;
+    g.n = n;
+    fill_slack_form(d, n, g);
 }
 
-__global__ void k_checksum(const double *a, size_t nelem, unsigned long long *out)
+// replicas after a raw upload (the caller's full arrays)
+__global__ void k_set_tg_rhs(LpDev d, double v) { d.st->tg_rhs = v; }
+__global__ void k_rhs_from_tab(LpDev d)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < d.m; i += gridDim.x * blockDim.x)
+        d.rhsbuf[i] = d.tab[(size_t)i * d.Cl + (d.n - d.col0)];
+}
+
+__global__ void k_checksum(const double *a, int rows, int Cl, int col0, int C, unsigned long long *out)
 {
     unsigned long long s = 0;
+    const size_t nelem = (size_t)rows * Cl;
     for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < nelem;
          e += (size_t)gridDim.x * blockDim.x) {
+        const size_t i = e / Cl, j = col0 + e % Cl;
         unsigned long long b = (unsigned long long)__double_as_longlong(a[e]);
-        s += mix64(b ^ mix64((uint64_t)e)); // position-keyed, order-independent sum
+        s += mix64(b ^ mix64((uint64_t)(i * C + j))); // keyed by the GLOBAL position: shard sums add up
     }
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if ((threadIdx.x & 31) == 0) atomicAdd(out, s);
@@ -521,6 +922,9 @@ struct xp_lp_f64 {
     LpDev d;
     LpState *h_st; // pinned
     double *vc_diag, *vc_rhs;
+    unsigned char *xblock = nullptr;       // this rank's exchange block
+    void *peer_map[MAXR] = {nullptr};      // IPC mappings to close
+    bool attached = false;
     // optional per-launch timing of the sweep kernel (CUDA events on the ctx stream)
     bool profile = false;
     std::vector<cudaEvent_t> evs;
@@ -535,10 +939,10 @@ static int sweep_launch(xp_lp_f64 *lp)
 {
     xp_ctx *ctx = lp->ctx;
     const LpDev &d = lp->d;
-    const int m = d.m, C = d.C;
-    if ((C & 1) == 0) {
+    const int m = d.m, Cl = d.Cl;
+    if ((Cl & 1) == 0) {
         constexpr int TH = 256;
-        int ctiles = (C / 2 + TH - 1) / TH;
+        int ctiles = (Cl / 2 + TH - 1) / TH;
         // aim for >= 8 CTAs per SM worth of row tiles, 8..64 rows per CTA
         int want = ctx->sm_count * 8;
         int rpc = (int)(((long long)m * ctiles + want - 1) / want);
@@ -548,7 +952,7 @@ static int sweep_launch(xp_lp_f64 *lp)
         k_sweep<2, TH, 8><<<grid, TH, rpc * sizeof(double), ctx->stream>>>(d, rpc);
     } else {
         constexpr int TH = 128;
-        int ctiles = (C + TH - 1) / TH;
+        int ctiles = (Cl + TH - 1) / TH;
         int rpc = 16;
         dim3 grid(ctiles, (m + rpc - 1) / rpc);
         k_sweep<1, TH, 1><<<grid, TH, rpc * sizeof(double), ctx->stream>>>(d, rpc);
@@ -557,9 +961,11 @@ static int sweep_launch(xp_lp_f64 *lp)
     return 0;
 }
 
-extern "C" int xp_lp_f64_create(xp_ctx *ctx, int m, int C, xp_lp_f64 **out)
+static int lp_create(xp_ctx *ctx, int m, int C, int rank, int G, xp_lp_f64 **out)
 {
-    if (!ctx || !out || m < 1 || C < 2) return XP_ERR_BAD_ARG;
+    if (!ctx || !out || m < 1 || C < 2 || G < 1 || G > MAXR || rank < 0 || rank >= G)
+        return XP_ERR_BAD_ARG;
+    if (G > 1 && (C + 1) / 2 < G) return XP_ERR_BAD_ARG;
     XP_CUDA_OK(ctx, cudaSetDevice(ctx->device));
     xp_lp_f64 *lp = new xp_lp_f64();
     lp->ctx = ctx;
@@ -569,14 +975,18 @@ extern "C" int xp_lp_f64_create(xp_ctx *ctx, int m, int C, xp_lp_f64 **out)
     d.C = C;
     d.n = C - 1;
     d.W = (d.n + 31) / 32;
+    d.rank = rank;
+    d.G = G;
+    d.col0 = shard_lo(C, G, rank);
+    d.Cl = (rank + 1 < G ? shard_lo(C, G, rank + 1) : C) - d.col0;
+    d.mpad = (m + 1 + 15) & ~15;
     d.log_cap = 1u << 16;
-    const size_t n = d.n;
+    const size_t n = d.n, Cl = d.Cl;
 #define ALLOC(ptr, bytes) XP_CUDA_OK(ctx, cudaMalloc((void **)&(ptr), (bytes)))
-    ALLOC(d.tab, (size_t)m * C * sizeof(double));
-    ALLOC(d.tgtf, C * sizeof(double));
-    ALLOC(d.prow, C * sizeof(double));
-    ALLOC(d.colbuf[0], m * sizeof(double));
-    ALLOC(d.colbuf[1], m * sizeof(double));
+    ALLOC(d.tab, (size_t)m * Cl * sizeof(double));
+    ALLOC(d.tgtf, Cl * sizeof(double));
+    ALLOC(d.prow, Cl * sizeof(double));
+    ALLOC(d.fcol, m * sizeof(double));
     ALLOC(d.rhsbuf, m * sizeof(double));
     ALLOC(d.sol, C * sizeof(double));
     ALLOC(lp->vc_diag, n * sizeof(double));
@@ -588,11 +998,94 @@ extern "C" int xp_lp_f64_create(xp_ctx *ctx, int m, int C, xp_lp_f64 **out)
     ALLOC(d.row_cnt, n * sizeof(int32_t));
     ALLOC(d.col_cnt, n * sizeof(int32_t));
     ALLOC(d.log, (size_t)d.log_cap * 3 * sizeof(int32_t));
+    ALLOC(d.feas_ctr, 16);
     ALLOC(d.st, sizeof(LpState));
+    ALLOC(lp->xblock, xblock_bytes(d));
 #undef ALLOC
     XP_CUDA_OK(ctx, cudaMemset(d.st, 0, sizeof(LpState)));
+    XP_CUDA_OK(ctx, cudaMemset(d.feas_ctr, 0, 16));
+    d.sweep_ctr = d.feas_ctr + 1;
+    XP_CUDA_OK(ctx, cudaMemset(lp->xblock, 0, xblock_bytes(d)));
+    d.xb[rank] = lp->xblock;
+    lp->attached = G == 1;
     XP_CUDA_OK(ctx, cudaMallocHost((void **)&lp->h_st, sizeof(LpState)));
     *out = lp;
+    return 0;
+}
+
+extern "C" int xp_lp_f64_create(xp_ctx *ctx, int m, int C, xp_lp_f64 **out)
+{
+    return lp_create(ctx, m, C, 0, 1, out);
+}
+
+extern "C" int xp_lp_f64_create_sharded(xp_ctx *ctx, int m, int C, int rank, int nranks,
+                                        xp_lp_f64 **out)
+{
+    return lp_create(ctx, m, C, rank, nranks, out);
+}
+
+extern "C" int xp_lp_f64_local_cols(const xp_lp_f64 *lp, int *col0, int *ncols)
+{
+    if (!lp) return XP_ERR_BAD_ARG;
+    if (col0) *col0 = lp->d.col0;
+    if (ncols) *ncols = lp->d.Cl;
+    return 0;
+}
+
+extern "C" int xp_lp_f64_peer_handle(xp_lp_f64 *lp, void *handle)
+{
+    if (!lp || !handle) return XP_ERR_BAD_ARG;
+    static_assert(sizeof(cudaIpcMemHandle_t) <= XP_PEER_HANDLE_BYTES, "handle size");
+    xp_ctx *ctx = lp->ctx;
+    XP_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    XP_CUDA_OK(ctx, cudaIpcGetMemHandle(&h, lp->xblock));
+    memset(handle, 0, XP_PEER_HANDLE_BYTES);
+    memcpy(handle, &h, sizeof h);
+    return 0;
+}
+
+extern "C" int xp_lp_f64_peer_attach(xp_lp_f64 *lp, const void *handles)
+{
+    if (!lp || !handles) return XP_ERR_BAD_ARG;
+    xp_ctx *ctx = lp->ctx;
+    LpDev &d = lp->d;
+    XP_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    for (int r = 0; r < d.G; r++) {
+        if (r == d.rank) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const unsigned char *)handles + (size_t)r * XP_PEER_HANDLE_BYTES, sizeof h);
+        void *p = nullptr;
+        XP_CUDA_OK(ctx, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        lp->peer_map[r] = p;
+        d.xb[r] = (unsigned char *)p;
+    }
+    lp->attached = true;
+    return 0;
+}
+
+// Same-process variant (tests, single-process multi-device hosts): `all` holds
+// the nranks handles in rank order; devices get peer access enabled if they differ.
+extern "C" int xp_lp_f64_peer_attach_local(xp_lp_f64 *lp, xp_lp_f64 *const *all)
+{
+    if (!lp || !all) return XP_ERR_BAD_ARG;
+    xp_ctx *ctx = lp->ctx;
+    LpDev &d = lp->d;
+    XP_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    for (int r = 0; r < d.G; r++) {
+        if (!all[r] || all[r]->d.G != d.G || all[r]->d.rank != r || all[r]->d.m != d.m ||
+            all[r]->d.C != d.C)
+            return XP_ERR_BAD_ARG;
+        if (r == d.rank) continue;
+        const int pd = all[r]->ctx->device;
+        if (pd != ctx->device) {
+            cudaError_t e = cudaDeviceEnablePeerAccess(pd, 0);
+            if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+            else XP_CUDA_OK(ctx, e);
+        }
+        d.xb[r] = all[r]->xblock;
+    }
+    lp->attached = true;
     return 0;
 }
 
@@ -602,9 +1095,11 @@ extern "C" void xp_lp_f64_destroy(xp_lp_f64 *lp)
     LpDev &d = lp->d;
     cudaSetDevice(lp->ctx->device);
     cudaStreamSynchronize(lp->ctx->stream);
-    void *ptrs[] = {d.tab,    d.tgtf,      d.prow,     d.colbuf[0], d.colbuf[1], d.rhsbuf,
-                    d.sol,    lp->vc_diag, lp->vc_rhs, d.nvset,     d.bv2eq,     d.eq2bv,
-                    d.tabu,   d.row_cnt,   d.col_cnt,  d.log,       d.st};
+    for (int r = 0; r < MAXR; r++)
+        if (lp->peer_map[r]) cudaIpcCloseMemHandle(lp->peer_map[r]);
+    void *ptrs[] = {d.tab,     d.tgtf,    d.prow,  d.fcol,     d.rhsbuf,  d.sol, lp->vc_diag,
+                    lp->vc_rhs, d.nvset,  d.bv2eq, d.eq2bv,    d.tabu,    d.row_cnt,
+                    d.col_cnt, d.log,     d.st,    d.feas_ctr, lp->xblock};
     for (void *p : ptrs) cudaFree(p);
     for (cudaEvent_t e : lp->evs) cudaEventDestroy(e);
     cudaFreeHost(lp->h_st);
@@ -620,6 +1115,7 @@ static int lp_reset(xp_lp_f64 *lp)
     return 0;
 }
 
+// Full (global) host arrays in; every rank keeps its column slice and the replicas.
 extern "C" int xp_lp_f64_upload(xp_lp_f64 *lp, const double *tableau, const double *tgtf,
                                 const uint8_t *nvset, const uint8_t *bvset, const int32_t *bv2eq,
                                 const int32_t *eq2bv, const double *vc_diag, const double *vc_rhs)
@@ -630,12 +1126,22 @@ extern "C" int xp_lp_f64_upload(xp_lp_f64 *lp, const double *tableau, const doub
     LpDev &d = lp->d;
     XP_CUDA_OK(ctx, cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream;
-    XP_CUDA_OK(ctx, cudaMemcpyAsync(d.tab, tableau, (size_t)d.m * d.C * sizeof(double),
-                                    cudaMemcpyHostToDevice, s));
-    XP_CUDA_OK(ctx, cudaMemcpyAsync(d.tgtf, tgtf, d.C * sizeof(double), cudaMemcpyHostToDevice, s));
+    const size_t pitch = (size_t)d.C * sizeof(double);
+    XP_CUDA_OK(ctx, cudaMemcpy2DAsync(d.tab, (size_t)d.Cl * sizeof(double), tableau + d.col0, pitch,
+                                      (size_t)d.Cl * sizeof(double), d.m, cudaMemcpyHostToDevice, s));
+    if (d.col0 + d.Cl == d.C) { // the constant column is in my slice
+        k_rhs_from_tab<<<(d.m + 255) / 256, 256, 0, s>>>(d);
+        ctx->launches++;
+    } else {
+        XP_CUDA_OK(ctx, cudaMemcpy2DAsync(d.rhsbuf, sizeof(double), tableau + d.n, pitch,
+                                          sizeof(double), d.m, cudaMemcpyHostToDevice, s));
+    }
+    XP_CUDA_OK(ctx, cudaMemcpyAsync(d.tgtf, tgtf + d.col0, d.Cl * sizeof(double), cudaMemcpyHostToDevice, s));
     XP_CUDA_OK(ctx, cudaMemcpyAsync(d.nvset, nvset, d.n, cudaMemcpyHostToDevice, s));
     XP_CUDA_OK(ctx, cudaMemcpyAsync(d.bv2eq, bv2eq, d.n * sizeof(int32_t), cudaMemcpyHostToDevice, s));
     XP_CUDA_OK(ctx, cudaMemcpyAsync(d.eq2bv, eq2bv, d.m * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    k_set_tg_rhs<<<1, 1, 0, s>>>(d, tgtf[d.n]);
+    ctx->launches++;
     d.vc_diag = d.vc_rhs = nullptr;
     if (vc_diag) {
         XP_CUDA_OK(ctx, cudaMemcpyAsync(lp->vc_diag, vc_diag, d.n * sizeof(double),
@@ -667,8 +1173,7 @@ extern "C" int xp_lp_f64_upload_leq(xp_lp_f64 *lp, const double *leq, const doub
     XP_CUDA_OK(ctx, cudaMemcpyAsync(d_leq, leq, (size_t)m * (n + 1) * sizeof(double),
                                     cudaMemcpyHostToDevice, s));
     XP_CUDA_OK(ctx, cudaMemcpyAsync(d_tg, tgtf, (n + 1) * sizeof(double), cudaMemcpyHostToDevice, s));
-    k_slack_form<<<ctx->sm_count * 4, 256, 0, s>>>(d.tab, d.tgtf, d_leq, d_tg, m, n, d.nvset,
-                                                   d.bv2eq, d.eq2bv);
+    k_slack_form<<<ctx->sm_count * 4, 256, 0, s>>>(d, d_leq, d_tg, n);
     ctx->launches++;
     d.vc_diag = d.vc_rhs = nullptr;
     XP_CUDA_OK(ctx, cudaGetLastError());
@@ -683,8 +1188,7 @@ extern "C" int xp_lp_f64_fill_synthetic(xp_lp_f64 *lp, uint64_t seed)
     const int m = d.m, n = d.C - 1 - m;
     if (n < 1) return XP_ERR_BAD_ARG;
     XP_CUDA_OK(ctx, cudaSetDevice(ctx->device));
-    k_fill_synth<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(d.tab, d.tgtf, m, n, seed, d.nvset,
-                                                             d.bv2eq, d.eq2bv);
+    k_fill_synth<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(d, n, seed);
     ctx->launches++;
     d.vc_diag = d.vc_rhs = nullptr;
     XP_CUDA_OK(ctx, cudaGetLastError());
@@ -697,6 +1201,10 @@ extern "C" int xp_lp_f64_solve(xp_lp_f64 *lp, uint32_t max_iter, int rule)
     if (rule != XP_RULE_REFERENCE) return XP_ERR_BAD_ARG;
     xp_ctx *ctx = lp->ctx;
     LpDev &d = lp->d;
+    if (!lp->attached) {
+        ctx->err = "sharded LP: peers not attached (xp_lp_f64_peer_attach)";
+        return XP_ERR_BAD_ARG;
+    }
     XP_CUDA_OK(ctx, cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream;
     XP_CUDA_OK(ctx, cudaEventRecord(ctx->ev0, s));
@@ -709,6 +1217,8 @@ extern "C" int xp_lp_f64_solve(xp_lp_f64 *lp, uint32_t max_iter, int rule)
     }
     // Each select+sweep pair is one simplex iteration; batches run without any
     // host round trip, the host only polls the status word between batches.
+    // Every rank of a sharded LP sees the same status words, hence issues the
+    // same launches.
     int batch = 8;
     int n_prof = 0; // sweeps bracketed by events in this call
     for (;;) {
@@ -757,6 +1267,7 @@ extern "C" int xp_lp_f64_solve(xp_lp_f64 *lp, uint32_t max_iter, int rule)
     XP_CUDA_OK(ctx, cudaEventRecord(ctx->ev1, s));
     XP_CUDA_OK(ctx, cudaStreamSynchronize(s));
     XP_CUDA_OK(ctx, cudaEventElapsedTime(&ctx->last_kernel_ms, ctx->ev0, ctx->ev1));
+    if (lp->h_st->status == XP_ERR_PEER) ctx->err = "sharded LP: timed out waiting for a peer GPU";
     return lp->h_st->status;
 }
 
@@ -784,6 +1295,8 @@ extern "C" int xp_lp_f64_profile_read(xp_lp_f64 *lp, uint64_t *n_sweeps, double 
     return 0;
 }
 
+// Full-size host arrays out: a sharded rank writes only its own columns of
+// `tableau` / `tgtf` (the caller merges ranks); the replicated state is complete.
 extern "C" int xp_lp_f64_download(xp_lp_f64 *lp, double *tableau, double *tgtf, uint8_t *nvset,
                                   uint8_t *bvset, int32_t *bv2eq, int32_t *eq2bv, double *maxv,
                                   double *sol, uint32_t *iters, int32_t *pivot_log, uint32_t log_cap)
@@ -795,8 +1308,11 @@ extern "C" int xp_lp_f64_download(xp_lp_f64 *lp, double *tableau, double *tgtf, 
     cudaStream_t s = ctx->stream;
 #define D2H(dst, src, bytes) \
     if (dst) XP_CUDA_OK(ctx, cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyDeviceToHost, s))
-    D2H(tableau, d.tab, (size_t)d.m * d.C * sizeof(double));
-    D2H(tgtf, d.tgtf, d.C * sizeof(double));
+    if (tableau)
+        XP_CUDA_OK(ctx, cudaMemcpy2DAsync(tableau + d.col0, (size_t)d.C * sizeof(double), d.tab,
+                                          (size_t)d.Cl * sizeof(double), (size_t)d.Cl * sizeof(double),
+                                          d.m, cudaMemcpyDeviceToHost, s));
+    D2H(tgtf ? tgtf + d.col0 : nullptr, d.tgtf, d.Cl * sizeof(double));
     D2H(nvset, d.nvset, (size_t)d.n);
     D2H(bv2eq, d.bv2eq, d.n * sizeof(int32_t));
     D2H(eq2bv, d.eq2bv, d.m * sizeof(int32_t));
@@ -835,8 +1351,8 @@ extern "C" int xp_lp_f64_checksum(xp_lp_f64 *lp, uint64_t *sum_tableau, uint64_t
     if (rc) return rc;
     unsigned long long *acc = (unsigned long long *)scr;
     XP_CUDA_OK(ctx, cudaMemsetAsync(acc, 0, 16, ctx->stream));
-    k_checksum<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(d.tab, (size_t)d.m * d.C, acc);
-    k_checksum<<<8, 256, 0, ctx->stream>>>(d.tgtf, (size_t)d.C, acc + 1);
+    k_checksum<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(d.tab, d.m, d.Cl, d.col0, d.C, acc);
+    k_checksum<<<8, 256, 0, ctx->stream>>>(d.tgtf, 1, d.Cl, d.col0, d.C, acc + 1);
     ctx->launches += 2;
     unsigned long long h[2];
     XP_CUDA_OK(ctx, cudaMemcpyAsync(h, acc, 16, cudaMemcpyDeviceToHost, ctx->stream));
