@@ -118,10 +118,19 @@ int xp_lp_f64_solve(xp_lp_f64 *lp, uint32_t max_iter, int rule);
 int xp_lp_f64_download(xp_lp_f64 *lp, double *tableau, double *tgtf, uint8_t *nvset,
                        uint8_t *bvset, int32_t *bv2eq, int32_t *eq2bv, double *maxv, double *sol,
                        uint32_t *iters, int32_t *pivot_log, uint32_t log_cap);
-/* Per-launch timing of the rank-1 sweep kernel with CUDA events on the ctx
- * stream (bench.py's roofline leg).  sweep_ms sums the sweep launches that did
- * real work since enable; gap_ms the time between consecutive sweeps (select
- * kernel + launch gaps). */
+/* Pivots per pass over the tableau (1..XP_MAX_BLOCK, 0 = automatic).  The
+ * tableau in HBM is brought up to date every k pivots by one kernel that applies
+ * the k pending rank-1 updates to each entry in the reference's order (same
+ * roundings, hence the same bits); k = 1 is the reference's own schedule of one
+ * full read+write of the tableau per pivot (lpsol.h:1481-1490).  Takes effect at
+ * the next upload / solve. */
+#define XP_MAX_BLOCK 32
+int xp_lp_f64_set_block(xp_lp_f64 *lp, int pivots_per_flush);
+int xp_ctx_set_block(xp_ctx *ctx, int pivots_per_flush); /* for xp_six_slack_f64 */
+/* Per-launch timing of the tableau-update kernel (k_flush) with CUDA events on
+ * the ctx stream (bench.py's roofline leg).  sweep_ms sums the launches that did
+ * real work since enable; gap_ms the time between consecutive ones (the panel
+ * kernels k_pcol / k_prow of the pivots in between + launch gaps). */
 int xp_lp_f64_profile(xp_lp_f64 *lp, int enable);
 int xp_lp_f64_profile_read(xp_lp_f64 *lp, uint64_t *n_sweeps, double *sweep_ms, double *gap_ms);
 /* Order-independent 64-bit checksum of the device tableau bits (parity at full size). */

@@ -20,11 +20,19 @@ def assert_same_state(g, o, tag):
         assert np.array_equal(H.bits(g[k]), H.bits(o[k])), (tag, k)
 
 
-def run_both(ctx, leq, tgtf, max_iter=H.NO_LIMIT, tag=None):
+BLOCKS = (0, 1, 3, 32)  # pivots per tableau pass: automatic, the reference's schedule, odd, maximum
+
+
+def run_both(ctx, leq, tgtf, max_iter=H.NO_LIMIT, tag=None, blocks=BLOCKS):
     sf = xp.slack_form(leq, tgtf)
-    g = ctx.six_slack_f64(*sf, max_iter=max_iter, log_cap=1 << 16)
     o = H.slack_solve_oracle("f64", *sf, max_iter=max_iter)
-    assert_same_state(g, o, tag)
+    try:
+        for k in blocks:
+            ctx.set_block(k)
+            g = ctx.six_slack_f64(*sf, max_iter=max_iter, log_cap=1 << 16)
+            assert_same_state(g, o, (tag, "block", k))
+    finally:
+        ctx.set_block(0)
     return g
 
 

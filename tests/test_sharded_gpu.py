@@ -22,7 +22,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def solve_sharded_inproc(G, sf, max_iters, device=0):
+def solve_sharded_inproc(G, sf, max_iters, device=0, block=0):
     """Returns one merged result dict per entry of max_iters (successive resumes)."""
     tab, tg = sf[0], sf[1]
     m, Cc = tab.shape
@@ -30,6 +30,7 @@ def solve_sharded_inproc(G, sf, max_iters, device=0):
     lps = [c.large_lp(m, Cc, r, G) for r, c in enumerate(ctxs)]
     for lp in lps:
         lp.peer_attach_local(lps)
+        lp.set_block(block)
         lp.upload(*sf)
     outs = []
     for K in max_iters:
@@ -94,7 +95,7 @@ def test_inproc_dense_to_termination(G):
     for seed, (m, n) in enumerate([(16, 15), (24, 23), (33, 20), (9, 9), (40, 64)]):
         leq, tg = H.gen_dense_lp(7000 + seed, m, n)
         sf = xp.slack_form(leq, tg)
-        g = solve_sharded_inproc(G, sf, [H.NO_LIMIT])[0]
+        g = solve_sharded_inproc(G, sf, [H.NO_LIMIT], block=(0, 1, 5, 32)[seed % 4])[0]
         o = H.slack_solve_oracle("f64", *sf)
         assert_same_state(g, o, ("dense", G, m, n))
         seen.add(g["status"])
@@ -111,7 +112,7 @@ def test_inproc_mixed_sign_slow_paths(G):
         leq, tg = H.gen_mixed_lp(seed, m, n)
         leq[:, n] = np.abs(leq[:, n])
         sf = xp.slack_form(leq, tg)
-        g = solve_sharded_inproc(G, sf, [H.NO_LIMIT])[0]
+        g = solve_sharded_inproc(G, sf, [H.NO_LIMIT], block=(0, 1, 7)[seed % 3])[0]
         assert_same_state(g, H.slack_solve_oracle("f64", *sf), ("mixed", G, seed))
         seen.add(g["status"])
     assert 1 in seen
@@ -122,7 +123,7 @@ def test_inproc_bounded_resume_and_checksum(ctx):
     shard checksums add up to the single-GPU checksum (mod 2^64)."""
     leq, tg = H.gen_dense_lp(4242, 96, 95)
     sf = xp.slack_form(leq, tg)
-    outs = solve_sharded_inproc(4, sf, [5, 15])
+    outs = solve_sharded_inproc(4, sf, [5, 15], block=4)
     one = ctx.large_lp(*sf[0].shape)
     one.upload(*sf)
     for K, g in zip((5, 15), outs):

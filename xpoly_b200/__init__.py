@@ -128,6 +128,10 @@ class Context:
         return dict(status=st, tab=tab, tgtf=tgtf, nvset=nvset, bvset=bvset, bv2eq=bv2eq,
                     eq2bv=eq2bv, maxv=maxv, sol=sol, iters=n_it, log=log[:min(n_it, log_cap)])
 
+    def set_block(self, k):
+        """Pivots per pass over the tableau for six_slack_f64 (0 = automatic)."""
+        self.check(lib().xp_ctx_set_block(self._h, int(k)))
+
     def large_lp(self, m, Cc, rank=0, nranks=1):
         return LargeLP(self, m, Cc, rank, nranks)
 
@@ -146,6 +150,9 @@ class LargeLP:
         c0, nc = C.c_int(0), C.c_int(0)
         ctx.check(lib().xp_lp_f64_local_cols(self._h, C.byref(c0), C.byref(nc)))
         self.col0, self.local_cols = c0.value, nc.value
+
+    def set_block(self, k):
+        self.ctx.check(lib().xp_lp_f64_set_block(self._h, int(k)))
 
     def peer_handle(self):
         buf = np.zeros(PEER_HANDLE_BYTES, dtype=np.uint8)

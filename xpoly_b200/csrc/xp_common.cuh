@@ -24,13 +24,11 @@ struct xp_ctx {
     uint64_t launches = 0;
     float last_kernel_ms = 0.f;
     std::string err;
-    // NCCL (column-sharded large-LP path); see xp_nccl.cu
-    void *nccl_comm = nullptr;
-    int rank = 0, nranks = 1;
     // reusable device scratch
     void *scratch = nullptr;
     size_t scratch_bytes = 0;
     void *cached_lp = nullptr; // xp_lp_f64 reused by xp_six_slack_f64
+    int slack_block = 0;       // pivots per flush for xp_six_slack_f64 (0 = automatic)
     // global-memory state slabs of the batched kernels (LPs beyond shared memory)
     void *gws = nullptr;
     size_t gws_bytes = 0;

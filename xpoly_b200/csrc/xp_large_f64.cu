@@ -5,26 +5,44 @@
 //   solveSlackForm :1007-1191, findPivotBV :552-663, findPivotNVandBVPair
 //   :670-773, pivot :1455-1511, PivotPairTab :68-154, is_feasible :783-822.
 //
-// Two kernels per simplex iteration, no host round trip inside a batch:
-//   k_select  (1 CTA)  completes the pricing exchange, runs the ratio test on the
-//             already-extracted entering column, keeps the tabu table, scales
-//             the pivot row, updates the objective row and the replicated
-//             constant column, swaps the basis, and prices the NEXT iteration
-//             (side-effect free) so the sweep can extract that column.
-//   k_sweep   (grid)   the rank-1 update a[i][j] += (-a[i][q]) * row_p[j] as a
-//             128-bit row-major stream; while streaming it extracts the updated
-//             NEXT entering column into a contiguous buffer (and, sharded, into
-//             every peer's buffer over NVLink), so the next ratio test never
-//             touches the tableau with a strided read.
-// Algorithmic HBM bytes per pivot: 2*(m+1)*C*8 (read+write of every entry).
+// Blocked (delayed-update) formulation.  The reference touches every tableau
+// entry once per pivot: a[i][j] = a[i][j] + (-a[i][q]) * row_p[j], product
+// rounded, then sum rounded (lpsol.h:1485-1489).  Here the tableau in HBM is
+// only brought up to date every k pivots ("flush"); in between, the k pivot rows
+// P[s][.] and multiplier columns F[s][.] = -a[.][q_s] are kept aside and the few
+// entries the next decision needs -- the entering column (m values) and the
+// leaving row (C values) -- are evaluated on demand by replaying the pending
+// updates on them in order:
+//     v = A[i][j];  for s = 0..t-1:  v = (i == p_s) ? P[s][j] : add(v, mul(F[s][i], P[s][j]))
+// which is, operation for operation and rounding for rounding, what the
+// reference would have stored.  The flush applies the same recurrence to every
+// entry in one pass.  Pivot sequence and every bit of the state are therefore
+// unchanged, while the tableau streams through HBM once per k pivots instead of
+// once per pivot.  k = 1 is the reference's own schedule.
 //
-// Column sharding: rank g owns columns [lo_g, hi_g) of the tableau
-// and of the objective row; the constant column, the basis maps and the tabu
-// table are replicated and kept identical by construction (every rank takes the
-// same decisions from the same bits).  The only data that cross GPUs per pivot
-// are one 8-byte candidate word per rank (pricing arg-min, lowest index wins)
-// and the entering column (m+1 doubles), both written straight into the peers'
-// exchange blocks (CUDA IPC mappings) by the kernels themselves.
+// Kernels (no host round trip inside a block):
+//   k_pcol   (grid over rows)     entering column now (strided read + replay),
+//            its multipliers F[t], both passes of the ratio test as block
+//            arg-mins; the last CTA reduces, keeps the tabu table and swaps the basis.
+//   k_prow   (grid over columns)  leaving row now (read + replay), scaled into
+//            P[t]; objective row and replicated constant column updated; pricing
+//            of the next iteration; the last CTA reduces (and, sharded, runs
+//            the all-ranks arg-min of the candidates).
+//   k_flush  (grid over tiles)    the rank-t update of the whole tableau slice as a
+//            128-bit row-major stream, P in registers, F in shared memory.
+// Rare paths (ratio test fails -> disableNV and re-price, findPivotNVandBVPair,
+// start of a solve) run on one CTA ("slow path") with the same device functions.
+//
+// Algorithmic HBM bytes per pivot: 2*(m+1)*C*8; bytes actually
+// moved per pivot: that / k plus O((m + C) * k).
+//
+// Column sharding: rank g owns columns [lo_g, hi_g) of the tableau,
+// of P and of the objective row; the constant column, F, the basis maps and the
+// tabu table are replicated and kept identical by construction (every rank
+// takes the same decisions from the same bits).  Per pivot the owner of the
+// entering column writes its m+1 values straight into every peer's F buffer and
+// each rank publishes one 8-byte pricing candidate (lowest index wins) -- stores
+// into CUDA-IPC-mapped peer memory over NVLink issued by the kernels themselves.
 //
 // The pair-tabu table is a bit matrix (n x n bits) plus per-row / per-column
 // population counters, which makes canBeNVCandidate / canBeBVCandidate O(1)
@@ -37,8 +55,8 @@
 namespace {
 
 constexpr int MAXR = XP_MAX_RANKS;
-constexpr int SEL_THREADS = 1024;
-constexpr int PT = 8; // independent loads in flight per thread in k_select
+constexpr int KMAX = XP_MAX_BLOCK; // pivots per flush, upper bound
+constexpr int TH = 256;            // threads per CTA of the panel kernels / the slow path
 constexpr int INT_BIG = 0x7fffffff;
 constexpr unsigned long long SPIN_LIMIT = 6000000000ULL; // ~3 s of SM clocks
 
@@ -46,17 +64,24 @@ struct LpState {
     int status;
     unsigned cnt;
     unsigned max_iter;
-    int sweep_pending;
-    int p;        // pivot row of the pending sweep
-    int q_next;   // column the pending sweep extracts (global index, -1: none)
+    int t;     // pivots pending in the open block (rows of P / F in use)
+    int kblk;  // block size
+    int blk;   // blocks flushed so far (parity selects the F buffer)
+    int q;     // entering column of the next step (INT_BIG: none)
+    int anypos;
+    int slow;  // next k_pcol must price / search on one CTA
+    int pivot_pending;
+    int p, bv, s0p; // pivot row, leaving variable, last_piv[p] before this step
+    int zero_upto;  // basic columns j < zero_upto still owe the reference's tgtf[j] = 0 (:1059)
     unsigned n_log;
     int infeasible;
-    unsigned xseq; // candidate exchanges initiated so far
+    unsigned xseq; // candidate exchanges so far
     unsigned xs;   // slow-path column fetches so far
-    unsigned swp;  // sweeps issued so far (slot parity, `done` tag)
+    unsigned cseq; // entering columns published so far
     unsigned fe;   // feasibility-chain epoch
-    int fast;      // exchange #xseq is in flight and sweep #swp extracts its column
-    int pad;
+    int n_touched;
+    int touched[KMAX]; // rows with last_piv >= 0
+    double r, cq, prow_rhs;
     double maxv;
     double tg_rhs; // replica of the objective row's constant term
 };
@@ -65,50 +90,58 @@ struct LpState {
 // word has a single writer; sequence numbers only grow.
 struct XHdr {
     unsigned long long cand[2][MAXR]; // (seq << 32) | anypos << 31 | candidate, by rank
-    unsigned long long done[MAXR];    // sweep number whose extracted column is in slot[rank]
+    unsigned long long colflag[MAXR]; // column event number whose data the rank has pushed
     unsigned long long arrive[MAXR];  // slow fetch: rank reached fetch #xs
-    unsigned long long xflag[MAXR];   // slow fetch: owner's column #xs is in xslot
     unsigned long long feas_in;       // feasibility chain: partial sums from rank-1 are in feas[]
-    unsigned long long feas_res[MAXR]; // (epoch << 1) | infeasible, broadcast by the last rank
+    unsigned long long feas_res;      // (epoch << 2) | flags, broadcast by the last rank
 };
 constexpr size_t XHDR_BYTES = 1024;
 static_assert(sizeof(XHdr) <= XHDR_BYTES, "exchange header");
+
+struct PartA {
+    double v1, v2;
+    int i1, i2;
+    int pad[2];
+};
 
 struct LpDev {
     int m, C, n;  // global shape; n = rhs_idx = C-1
     int W;        // tabu words per row
     int rank, G;  // column shard
-    int col0, Cl; // first local column, local width (row stride of tab)
-    int mpad;     // doubles per exchanged column (m+1 padded)
-    double *tab, *tgtf, *prow, *fcol, *rhsbuf, *sol;
+    int col0, Cl; // first local column, local width (row stride of tab and P)
+    int mpad;     // doubles per F row (m+1 padded)
+    int gridA, gridB;
+    double *tab, *tgtf, *P, *rhsbuf, *sol;
     const double *vc_diag, *vc_rhs; // may be null
     uint8_t *nvset;
-    int32_t *bv2eq, *eq2bv;
+    int32_t *bv2eq, *eq2bv, *last_piv;
     uint32_t *tabu;
     int32_t *row_cnt, *col_cnt;
     int32_t *log;
     unsigned log_cap;
-    unsigned *feas_ctr, *sweep_ctr;
+    PartA *partA;
+    int2 *partB;
+    unsigned *ctr; // [0] pcol ticket, [1] prow ticket, [2] flush ticket, [3] feas ticket
     LpState *st;
     unsigned char *xb[MAXR]; // exchange blocks: xb[rank] is local, the rest peer mappings
 };
 
 // ---- exchange-block addressing ----
-__host__ __device__ __forceinline__ size_t xoff_slot(const LpDev &d, int r, int par)
+__host__ __device__ __forceinline__ size_t xoff_F(const LpDev &d, int par, int s)
 {
-    return XHDR_BYTES + ((size_t)(r * 2 + par) * d.mpad) * sizeof(double);
-}
-__host__ __device__ __forceinline__ size_t xoff_xslot(const LpDev &d)
-{
-    return XHDR_BYTES + ((size_t)(MAXR * 2) * d.mpad) * sizeof(double);
+    return XHDR_BYTES + ((size_t)(par * KMAX + s) * d.mpad) * sizeof(double);
 }
 __host__ __device__ __forceinline__ size_t xoff_feas(const LpDev &d)
 {
-    return XHDR_BYTES + ((size_t)(MAXR * 2 + 1) * d.mpad) * sizeof(double);
+    return XHDR_BYTES + ((size_t)(2 * KMAX) * d.mpad) * sizeof(double);
 }
 __host__ __device__ __forceinline__ size_t xblock_bytes(const LpDev &d)
 {
-    return XHDR_BYTES + ((size_t)(MAXR * 2 + 2) * d.mpad) * sizeof(double);
+    return XHDR_BYTES + ((size_t)(2 * KMAX + 1) * d.mpad) * sizeof(double);
+}
+__device__ __forceinline__ double *Fptr(const LpDev &d, int r, int par, int s)
+{
+    return (double *)(d.xb[r] + xoff_F(d, par, s));
 }
 // Column range of rank r: even split in units of two columns (128-bit accesses).
 __host__ __device__ __forceinline__ int shard_lo(int C, int G, int r)
@@ -119,6 +152,7 @@ __host__ __device__ __forceinline__ int shard_lo(int C, int G, int r)
 }
 __device__ __forceinline__ int owner_of(const LpDev &d, int j)
 {
+    if (d.G == 1) return 0;
     int r = (int)(((long long)(j / 2) * d.G) / ((d.C + 1) / 2));
     while (r + 1 < d.G && shard_lo(d.C, d.G, r + 1) <= j) r++;
     while (r > 0 && shard_lo(d.C, d.G, r) > j) r--;
@@ -146,7 +180,7 @@ __device__ __forceinline__ void publish(const LpDev &d, size_t off, unsigned lon
         st_release_sys((unsigned long long *)(d.xb[threadIdx.x] + off), w);
     }
 }
-// Thread t < cnt waits until pred(word t at local offset off + 8*t).  Returns
+// Thread t < cnt waits until pred(word first+t at local offset off).  Returns
 // false on timeout (block-uniform).
 template <class Pred>
 __device__ __forceinline__ bool wait_words(const LpDev &d, size_t off, int first, int cnt, Pred pred)
@@ -167,93 +201,156 @@ __device__ __forceinline__ bool wait_words(const LpDev &d, size_t off, int first
     return !__syncthreads_or(bad);
 }
 
-__device__ __forceinline__ bool tabu_get(const LpDev &d, int nv, int bv)
+// ---------------------------------------------------------------------------
+// Replay of the pending updates (see the header comment).
+// ---------------------------------------------------------------------------
+// Entry (i, ql) now, at step t; pq[s] = P[s][ql].
+__device__ __forceinline__ double cur_in_col(const LpDev &d, int par, int t, int i, int ql,
+                                             const double *pq)
 {
-    return (d.tabu[(size_t)nv * d.W + (bv >> 5)] >> (bv & 31)) & 1u;
+    const int s0 = d.last_piv[i];
+    double v = s0 >= 0 ? pq[s0] : d.tab[(size_t)i * d.Cl + ql];
+    for (int s = s0 + 1; s < t; s++) v = xp_add(v, xp_mul(ld_cg(Fptr(d, d.rank, par, s) + i), pq[s]));
+    return v;
+}
+// Entry (p, jl) now, at step t; fp[s] = F[s][p], s0 = last_piv[p].
+__device__ __forceinline__ double cur_in_row(const LpDev &d, int t, int p, int s0, int jl,
+                                             const double *fp)
+{
+    double v = s0 >= 0 ? d.P[(size_t)s0 * d.Cl + jl] : d.tab[(size_t)p * d.Cl + jl];
+    for (int s = s0 + 1; s < t; s++) v = xp_add(v, xp_mul(fp[s], d.P[(size_t)s * d.Cl + jl]));
+    return v;
 }
 
-// Pricing over the local slice (lpsol.h:1054-1069): lowest eligible index with
-// c_j > 0, and whether any non-basic c_j > 0 exists at all.  Only j > after.
-__device__ __forceinline__ void price_local(const LpDev &d, int after, int mode, int &best, int &anypos)
+// Ratio-test keys of one row (lpsol.h:571-612 pass 1, :623-658 pass 2).
+__device__ __forceinline__ void ratio_keys(const LpDev &d, int q, int i, double a, XpMinIdx &b1,
+                                           XpMinIdx &b2)
 {
-    // mode 0: c_j > 0 (pricing / pair-search pass A); mode 1: c_j == 0 tolerant (pass B)
-    const int tid = threadIdx.x;
-    const int nl = min(d.Cl, d.n - d.col0); // local columns that are variables
+    if (xp_feq(a, 0.0)) return; // neither pass takes a == 0 (tolerant)
+    const int bv = d.eq2bv[i];
+    if ((d.tabu[(size_t)q * d.W + (bv >> 5)] >> (bv & 31)) & 1u) return; // is_handle(q, bv)
+    if (d.col_cnt[bv] >= d.n - 1) return;                                // !canBeBVCandidate
+    XpMinIdx c;
+    c.v = xp_div(d.rhsbuf[i], a);
+    c.i = i;
+    b2 = xp_better(b2, c);
+    if (a > 0.0) b1 = xp_better(b1, c); // !(a <= 0) with the tolerant ==
+}
+
+// ---------------------------------------------------------------------------
+// One-CTA ("slow path") building blocks.  Sharded: every rank runs them at the
+// same logical point, so the exchanges inside are collective.
+// ---------------------------------------------------------------------------
+struct Seq {
+    unsigned xseq, xs, cseq;
+    bool ok; // false after a peer timeout
+};
+
+// All-ranks arg-min of a pricing result (lowest index wins; anypos is OR-ed).
+__device__ void cand_exchange(const LpDev &d, Seq &x, int &best, int &anypos)
+{
+    if (d.G == 1) return;
+    x.xseq++;
+    const unsigned seq = x.xseq;
+    const unsigned long long w = ((unsigned long long)seq << 32) |
+                                 ((unsigned long long)(anypos ? 1u : 0u) << 31) |
+                                 (unsigned long long)(unsigned)best;
+    const size_t off = offsetof(XHdr, cand) + (size_t)(seq & 1) * MAXR * 8;
+    __syncthreads();
+    publish(d, off + (size_t)d.rank * 8, w);
+    if (!wait_words(d, off, 0, d.G, [seq](unsigned long long v) { return (unsigned)(v >> 32) == seq; }))
+        x.ok = false;
+    const unsigned long long *wp = (const unsigned long long *)(d.xb[d.rank] + off);
     best = INT_BIG;
     anypos = 0;
-    for (int base = 0; base < nl; base += SEL_THREADS * PT) {
-        double c[PT];
-        int nv[PT], rc[PT];
-#pragma unroll
-        for (int u = 0; u < PT; u++) {
-            const int jl = base + u * SEL_THREADS + tid;
-            const bool ok = jl < nl;
-            const int g = d.col0 + (ok ? jl : 0);
-            c[u] = ok ? d.tgtf[jl] : 0.0;
-            nv[u] = ok ? d.nvset[g] : 0;
-            rc[u] = ok ? d.row_cnt[g] : INT_BIG;
-        }
-#pragma unroll
-        for (int u = 0; u < PT; u++) {
-            const int g = d.col0 + base + u * SEL_THREADS + tid;
-            if (!nv[u]) continue;
-            const bool pos = c[u] > 0.0;
-            if (pos) anypos = 1;
-            const bool take = mode == 0 ? pos : (!pos && xp_feq(c[u], 0.0));
-            if (take && g > after && best == INT_BIG && rc[u] < d.n - 1) best = g;
-        }
+    for (int r = 0; r < d.G; r++) {
+        const unsigned long long v = ld_acquire_sys(wp + r);
+        best = min(best, (int)(v & 0x7fffffffu));
+        anypos |= (int)((v >> 31) & 1u);
     }
+    __syncthreads(); // everyone has read the words before the next exchange may start
 }
 
-// findPivotBV (lpsol.h:552-663) on a contiguous copy of column q (col) and the
-// replicated constant column.  Returns the pivot ROW or -1.
-__device__ int ratio_test(const LpDev &d, int q, const double *col, XpMinIdx *shm)
+// Pricing over the local slice (lpsol.h:1054-1069 / the candidate scans of
+// findPivotNVandBVPair): lowest eligible index > after.
+// mode 0: c_j > 0; mode 1: c_j == 0 (tolerant) and not > 0.
+__device__ void sp_price(const LpDev &d, int after, int mode, int *shi, int &best, int &anypos)
 {
-    const int n = d.n, tid = threadIdx.x;
-    for (int pass = 0; pass < 2; pass++) {
-        XpMinIdx best;
-        best.v = 0.0;
-        best.i = -1;
-        for (int base = 0; base < d.m; base += SEL_THREADS * PT) {
-            double a[PT], rh[PT];
-            int bv[PT];
-#pragma unroll
-            for (int u = 0; u < PT; u++) {
-                const int i = base + u * SEL_THREADS + tid;
-                const bool ok = i < d.m;
-                a[u] = ok ? ld_cg(col + i) : 0.0;
-                rh[u] = ok ? d.rhsbuf[i] : 0.0;
-                bv[u] = ok ? d.eq2bv[i] : -1;
-            }
-            uint32_t tw[PT];
-            int cc[PT];
-#pragma unroll
-            for (int u = 0; u < PT; u++) {
-                // pass 1 (:571-612) takes a > 0 (tolerant), pass 2 (:623-658) any a != 0
-                const bool cand = bv[u] >= 0 && (pass == 0 ? !xp_fle(a[u], 0.0) : !xp_feq(a[u], 0.0));
-                tw[u] = cand ? d.tabu[(size_t)q * d.W + (bv[u] >> 5)] : 0xffffffffu;
-                cc[u] = cand ? d.col_cnt[bv[u]] : INT_BIG;
-                if (!cand) bv[u] = -1;
-            }
-#pragma unroll
-            for (int u = 0; u < PT; u++) {
-                if (bv[u] < 0) continue;
-                if ((tw[u] >> (bv[u] & 31)) & 1u) continue; // is_handle(q, bv)
-                if (cc[u] >= n - 1) continue;               // !canBeBVCandidate
-                XpMinIdx c;
-                c.v = xp_div(rh[u], a[u]);
-                c.i = base + u * SEL_THREADS + tid;
-                best = xp_better(best, c);
-            }
-        }
-        best = xp_block_argmin(best, shm);
-        if (best.i >= 0) return best.i;
+    const int nl = min(d.Cl, d.n - d.col0);
+    best = INT_BIG;
+    anypos = 0;
+    for (int jl = threadIdx.x; jl < nl; jl += blockDim.x) {
+        const int g = d.col0 + jl;
+        if (!d.nvset[g]) continue;
+        const double c = d.tgtf[jl];
+        const bool pos = c > 0.0;
+        if (pos) anypos = 1;
+        const bool take = mode == 0 ? pos : (!pos && xp_feq(c, 0.0));
+        if (take && g > after && best == INT_BIG && d.row_cnt[g] < d.n - 1) best = g;
     }
-    return -1;
+    best = xp_block_min_int(best, shi);
+    anypos = __syncthreads_or(anypos);
+}
+
+// tgtf[j] = 0 for basic j < limit (lpsol.h:1059), local slice.
+__device__ void sp_zero(const LpDev &d, int limit)
+{
+    const int zl = min(min(limit, d.n) - d.col0, d.Cl);
+    for (int jl = threadIdx.x; jl < zl; jl += blockDim.x)
+        if (!d.nvset[d.col0 + jl]) d.tgtf[jl] = 0.0;
+    __syncthreads();
+}
+
+// Column q as of now into F[par][t] of every rank ([m] carries c_q).
+__device__ void sp_column(const LpDev &d, Seq &x, int par, int t, int q, double *s_pq)
+{
+    const int owner = owner_of(d, q);
+    x.cseq++;
+    if (d.G > 1) { // nobody may still be reading F[par][t] from an earlier fetch of this step
+        x.xs++;
+        const unsigned xs = x.xs;
+        __syncthreads();
+        publish(d, offsetof(XHdr, arrive) + (size_t)d.rank * 8, xs);
+        if (owner == d.rank &&
+            !wait_words(d, offsetof(XHdr, arrive), 0, d.G, [xs](unsigned long long w) { return w >= xs; }))
+            x.ok = false;
+    }
+    if (owner == d.rank) {
+        const int ql = q - d.col0;
+        __syncthreads();
+        if ((int)threadIdx.x < t) s_pq[threadIdx.x] = d.P[(size_t)threadIdx.x * d.Cl + ql];
+        __syncthreads();
+        for (int i = threadIdx.x; i <= d.m; i += blockDim.x) {
+            const double v = i < d.m ? -cur_in_col(d, par, t, i, ql, s_pq) : d.tgtf[ql];
+            for (int r = 0; r < d.G; r++) Fptr(d, r, par, t)[i] = v;
+        }
+        __syncthreads();
+        if (d.G > 1) publish(d, offsetof(XHdr, colflag) + (size_t)d.rank * 8, x.cseq);
+    }
+    if (d.G > 1) {
+        const unsigned cs = x.cseq;
+        if (!wait_words(d, offsetof(XHdr, colflag), owner, 1, [cs](unsigned long long w) { return w >= cs; }))
+            x.ok = false;
+    }
+    __syncthreads();
+}
+
+// findPivotBV (lpsol.h:552-663) on F[par][t] (= -column).  Returns the pivot ROW or -1.
+__device__ int sp_ratio(const LpDev &d, int par, int t, int q, XpMinIdx *shm)
+{
+    XpMinIdx b1, b2;
+    b1.v = b2.v = 0.0;
+    b1.i = b2.i = -1;
+    const double *f = Fptr(d, d.rank, par, t);
+    for (int i = threadIdx.x; i < d.m; i += blockDim.x) ratio_keys(d, q, i, -ld_cg(f + i), b1, b2);
+    b1 = xp_block_argmin(b1, shm);
+    if (b1.i >= 0) return b1.i;
+    b2 = xp_block_argmin(b2, shm);
+    return b2.i;
 }
 
 // PivotPairTab::disableNV (lpsol.h:114-121) with counter upkeep.
-__device__ void disable_nv(const LpDev &d, int q)
+__device__ void sp_disable_nv(const LpDev &d, int q)
 {
     const int n = d.n;
     for (int w = threadIdx.x; w < d.W; w += blockDim.x) {
@@ -274,402 +371,424 @@ __device__ void disable_nv(const LpDev &d, int q)
     __syncthreads();
 }
 
-struct SelCtx {
-    unsigned xseq, xs;
-    bool ok; // false after a peer timeout
-};
-
-// All-ranks arg-min of the local pricing result (lowest index wins; `anypos`
-// is OR-ed).  Split in two halves so the exchange of the next iteration can be
-// in flight during the sweep.
-__device__ __forceinline__ void cand_publish(const LpDev &d, SelCtx &x, int best, int anypos)
+// genPair (:1156), the pivot log, and the basis swap of SIX::pivot (:1504-1510);
+// leaves the scalars k_prow needs in the state.  One CTA.
+__device__ void sp_commit_pivot(const LpDev &d, LpState *st, const Seq &x, int par, int t, int q, int p)
 {
-    x.xseq++;
-    const unsigned long long w = ((unsigned long long)x.xseq << 32) |
-                                 ((unsigned long long)(anypos ? 1u : 0u) << 31) |
-                                 (unsigned long long)(unsigned)best;
     __syncthreads();
-    publish(d, offsetof(XHdr, cand) + (size_t)(x.xseq & 1) * MAXR * 8 + (size_t)d.rank * 8, w);
-}
-__device__ __forceinline__ void cand_complete(const LpDev &d, SelCtx &x, int &q, int &anypos)
-{
-    const unsigned seq = x.xseq;
-    const size_t off = offsetof(XHdr, cand) + (size_t)(seq & 1) * MAXR * 8;
-    if (!wait_words(d, off, 0, d.G, [seq](unsigned long long w) { return (unsigned)(w >> 32) == seq; }))
-        x.ok = false;
-    const unsigned long long *w = (const unsigned long long *)(d.xb[d.rank] + off);
-    q = INT_BIG;
-    anypos = 0;
-    for (int r = 0; r < d.G; r++) {
-        const unsigned long long v = ld_acquire_sys(w + r);
-        q = min(q, (int)(v & 0x7fffffffu));
-        anypos |= (int)((v >> 31) & 1u);
-    }
-    __syncthreads(); // every thread has read the words before anyone publishes the next exchange
-}
-
-// Slow path: column j as of now, from its owner's tableau, to every rank's
-// xslot ([m] carries c_j).  Collective; used at the start of a solve, after a
-// disableNV retry and inside the pair search.
-__device__ const double *fetch_col(const LpDev &d, SelCtx &x, int j)
-{
-    double *mine = (double *)(d.xb[d.rank] + xoff_xslot(d));
-    x.xs++;
-    const unsigned xs = x.xs;
-    const int owner = d.G > 1 ? owner_of(d, j) : 0;
-    if (d.G > 1) {
-        __syncthreads();
-        publish(d, offsetof(XHdr, arrive) + (size_t)d.rank * 8, xs);
-    }
-    if (owner == d.rank) {
-        if (d.G > 1 &&
-            !wait_words(d, offsetof(XHdr, arrive), 0, d.G, [xs](unsigned long long w) { return w >= xs; }))
-            x.ok = false;
-        const int jl = j - d.col0;
-        for (int base = 0; base < d.m + 1; base += SEL_THREADS * PT) {
-            double v[PT];
-#pragma unroll
-            for (int u = 0; u < PT; u++) {
-                const int i = base + u * SEL_THREADS + threadIdx.x;
-                v[u] = i < d.m ? d.tab[(size_t)i * d.Cl + jl] : (i == d.m ? d.tgtf[jl] : 0.0);
-            }
-#pragma unroll
-            for (int u = 0; u < PT; u++) {
-                const int i = base + u * SEL_THREADS + threadIdx.x;
-                if (i > d.m) continue;
-                for (int r = 0; r < d.G; r++) ((double *)(d.xb[r] + xoff_xslot(d)))[i] = v[u];
-            }
-        }
-        if (d.G > 1) {
-            __syncthreads();
-            publish(d, offsetof(XHdr, xflag) + (size_t)d.rank * 8, xs);
-        }
-    }
-    if (d.G > 1) {
-        if (!wait_words(d, offsetof(XHdr, xflag), owner, 1, [xs](unsigned long long w) { return w >= xs; }))
-            x.ok = false;
-    } else {
-        __syncthreads();
-    }
-    return mine;
-}
-
-__global__ void __launch_bounds__(SEL_THREADS, 1) k_select(LpDev d)
-{
-    __shared__ XpMinIdx shm[33];
-    __shared__ int shi[33];
-    LpState *st = d.st;
-    const int tid = threadIdx.x;
-    const int n = d.n, m = d.m, Cl = d.Cl;
-
-    const int status0 = st->status;
-    const unsigned cnt0 = st->cnt, max_iter = st->max_iter;
-    const int fast0 = st->fast;
-    const unsigned swp0 = st->swp;
-    SelCtx x;
-    x.xseq = st->xseq;
-    x.xs = st->xs;
-    x.ok = true;
-    __syncthreads();
-    if (tid == 0) st->sweep_pending = 0;
-    if (status0 != XPI_RUNNING) return;
-    if (cnt0 >= max_iter) { // while (cnt < m_max_iter), :1039
-        if (tid == 0) st->status = XP_SIX_TIME_OUT;
-        return;
-    }
-#define SEL_EXIT(code)                  \
-    do {                                \
-        if (tid == 0) {                 \
-            st->status = (code);        \
-            st->xseq = x.xseq;          \
-            st->xs = x.xs;              \
-            st->fast = 0;               \
-        }                               \
-        return;                         \
-    } while (0)
-
-    int q = -1, p = -1;
-    const double *col = nullptr;
-    bool first = true;
-    for (;;) {
-        // ---- pricing, :1054-1069 ----
-        int best, anypos;
-        if (!(first && fast0)) {
-            int lb, la;
-            price_local(d, -1, 0, lb, la);
-            lb = xp_block_min_int(lb, shi);
-            la = __syncthreads_or(la);
-            if (d.G > 1) cand_publish(d, x, lb, la);
-            best = lb;
-            anypos = la;
-        }
-        if (d.G > 1) {
-            cand_complete(d, x, best, anypos);
-            if (!x.ok) SEL_EXIT(XP_ERR_PEER);
-        } else if (first && fast0) {
-            best = st->q_next < 0 ? INT_BIG : st->q_next;
-            anypos = st->pad;
-        }
-        // basic columns scanned before the break have their reduced cost forced to 0 (:1059)
-        {
-            const int zlim = (best == INT_BIG ? n : best) - d.col0;
-            const int zl = min(zlim, Cl);
-            for (int base = 0; base < zl; base += SEL_THREADS * PT) {
-                int nv[PT];
-#pragma unroll
-                for (int u = 0; u < PT; u++) {
-                    const int jl = base + u * SEL_THREADS + tid;
-                    nv[u] = jl < zl ? d.nvset[d.col0 + jl] : 1;
-                }
-#pragma unroll
-                for (int u = 0; u < PT; u++) {
-                    const int jl = base + u * SEL_THREADS + tid;
-                    if (!nv[u]) d.tgtf[jl] = 0.0;
-                }
-            }
-            __syncthreads();
-        }
-        if (best == INT_BIG) {
-            if (!anypos) SEL_EXIT(XPI_OPT_PENDING); // optimal exit; feasibility is checked by k_feas_*
-            // ---- findPivotNVandBVPair, :670-773 ----
-            // Pass A: eligible c_j > 0; pass B additionally c_j == 0 (tolerant).
-            // findPivotBV is pure, so the c_j > 0 columns that failed in pass A
-            // are not retried in pass B (same outcome, less work).
-            int found = 0;
-            for (int pass = 0; pass < 2 && !found; pass++) {
-                int last = -1;
-                for (;;) {
-                    int cand, dummy;
-                    price_local(d, last, pass, cand, dummy);
-                    cand = xp_block_min_int(cand, shi);
-                    if (d.G > 1) {
-                        cand_publish(d, x, cand, 0);
-                        cand_complete(d, x, cand, dummy);
-                        if (!x.ok) SEL_EXIT(XP_ERR_PEER);
-                    }
-                    if (cand == INT_BIG) break;
-                    col = fetch_col(d, x, cand);
-                    if (!x.ok) SEL_EXIT(XP_ERR_PEER);
-                    int r = ratio_test(d, cand, col, shm);
-                    if (r >= 0) {
-                        q = cand;
-                        p = r;
-                        found = 1;
-                        break;
-                    }
-                    last = cand;
-                }
-            }
-            if (!found) SEL_EXIT(XP_SIX_UNBOUND);
-            break;
-        }
-        q = best;
-        if (first && fast0) {
-            const int owner = d.G > 1 ? owner_of(d, q) : 0;
-            if (d.G > 1 && owner != d.rank) {
-                const unsigned w = swp0;
-                if (!wait_words(d, offsetof(XHdr, done), owner, 1,
-                                [w](unsigned long long v) { return v >= w; }))
-                    SEL_EXIT(XP_ERR_PEER);
-            }
-            col = (const double *)(d.xb[d.rank] + xoff_slot(d, owner, swp0 & 1));
-        } else {
-            col = fetch_col(d, x, q);
-            if (!x.ok) SEL_EXIT(XP_ERR_PEER);
-        }
-        first = false;
-        p = ratio_test(d, q, col, shm);
-        if (p >= 0) break;
-        disable_nv(d, q); // :1146-1151, retry without counting an iteration
-    }
-
-    // ---- genPair (:1156) + pivot bookkeeping ----
-    const int bv = d.eq2bv[p];
-    const double pv = ld_cg(col + p);
-    const double cq = ld_cg(col + m); // c_q travels with the column
-    const double rhs_p = d.rhsbuf[p];
-    __syncthreads(); // everyone has read eq2bv[p], rhsbuf[p] before they change
-    if (tid == 0) {
+    if (threadIdx.x == 0) {
+        const double *f = Fptr(d, d.rank, par, t);
+        const int bv = d.eq2bv[p];
+        const double pv = -ld_cg(f + p);
+        const double cq = ld_cg(f + d.m);
         uint32_t *w = &d.tabu[(size_t)q * d.W + (bv >> 5)];
-        uint32_t bit = 1u << (bv & 31);
+        const uint32_t bit = 1u << (bv & 31);
         if (!(*w & bit)) {
             *w |= bit;
             d.row_cnt[q] += 1;
             d.col_cnt[bv] += 1;
         }
-        unsigned k = st->n_log;
+        const unsigned k = st->n_log;
         if (k < d.log_cap) {
             d.log[3 * k] = q;
             d.log[3 * k + 1] = bv;
             d.log[3 * k + 2] = p;
         }
         st->n_log = k + 1;
-    }
-    // ---- pivot, steps on row p and the objective row (:1471-1501) ----
-    const double r = xp_div(1.0, pv);
-    const bool r_one = xp_feq(r, 1.0), r_zero = xp_feq(r, 0.0);
-    const bool cq_zero = xp_feq(cq, 0.0), cq_one = xp_feq(cq, 1.0);
-    const double prow_rhs = xp_scale(rhs_p, r, r_one, r_zero);
-    // multipliers f_i = -a[i][q] for the sweep, and the replicated constant column
-    for (int base = 0; base < m; base += SEL_THREADS * PT) {
-        double a[PT], rh[PT];
-#pragma unroll
-        for (int u = 0; u < PT; u++) {
-            const int i = base + u * SEL_THREADS + tid;
-            a[u] = i < m ? ld_cg(col + i) : 0.0;
-            rh[u] = i < m ? d.rhsbuf[i] : 0.0;
-        }
-#pragma unroll
-        for (int u = 0; u < PT; u++) {
-            const int i = base + u * SEL_THREADS + tid;
-            if (i >= m) continue;
-            const double f = -a[u];
-            d.fcol[i] = f;
-            d.rhsbuf[i] = i == p ? prow_rhs : xp_add(rh[u], xp_mul(f, prow_rhs));
-        }
-    }
-    double *rowp = d.tab + (size_t)p * Cl;
-    for (int base = 0; base < Cl; base += SEL_THREADS * PT) {
-        double xr[PT], tg[PT];
-#pragma unroll
-        for (int u = 0; u < PT; u++) {
-            const int jl = base + u * SEL_THREADS + tid;
-            xr[u] = jl < Cl ? rowp[jl] : 0.0;
-            tg[u] = jl < Cl ? d.tgtf[jl] : 0.0;
-        }
-#pragma unroll
-        for (int u = 0; u < PT; u++) {
-            const int jl = base + u * SEL_THREADS + tid;
-            if (jl >= Cl) continue;
-            const double xv = xp_scale(xr[u], r, r_one, r_zero); // mulOfRow(eqnum, 1/pivot)
-            rowp[jl] = xv;
-            d.prow[jl] = xv;
-            double t = xp_mul(xv, -1.0);                      // nvexp.mul(-1)
-            if (d.col0 + jl >= n) t = -t;                     // constant column keeps its sign
-            t = cq_zero ? 0.0 : (cq_one ? t : xp_mul(t, cq)); // nvexp.mul(tgtf[nv])
-            d.tgtf[jl] = xp_add(t, tg[u]);                    // tgtf.addRowToRow
-        }
-    }
-    if (tid == 0) { // :1504-1510, and the replica of tgtf[rhs]
+        const double r = xp_div(1.0, pv); // mulOfRow(eqnum, 1 / pivot), :1471
+        st->r = r;
+        st->cq = cq;
+        st->prow_rhs = xp_scale(d.rhsbuf[p], r, xp_feq(r, 1.0), xp_feq(r, 0.0));
+        st->q = q;
+        st->p = p;
+        st->bv = bv;
+        st->s0p = d.last_piv[p];
         d.nvset[q] = 0;
         d.nvset[bv] = 1;
         d.eq2bv[p] = q;
         d.bv2eq[q] = p;
         d.bv2eq[bv] = -1;
-        double t = -xp_mul(prow_rhs, -1.0);
-        t = cq_zero ? 0.0 : (cq_one ? t : xp_mul(t, cq));
-        st->tg_rhs = xp_add(t, st->tg_rhs);
-    }
-    __syncthreads();
-    // ---- price the NEXT iteration (no side effects) and start its exchange ----
-    int nxt = INT_BIG, anyn = 0, fast1 = 0;
-    if (cnt0 + 1 < max_iter) {
-        price_local(d, -1, 0, nxt, anyn);
-        nxt = xp_block_min_int(nxt, shi);
-        anyn = __syncthreads_or(anyn);
-        fast1 = 1;
-        if (nxt != INT_BIG && tid < d.G) // c_q of my candidate rides in slot[rank][par][m]
-            ((double *)(d.xb[tid] + xoff_slot(d, d.rank, (swp0 + 1) & 1)))[m] = d.tgtf[nxt - d.col0];
-        if (d.G > 1) cand_publish(d, x, nxt, anyn);
-    }
-    if (tid == 0) {
-        st->p = p;
-        st->q_next = nxt == INT_BIG ? -1 : nxt;
-        st->pad = anyn;
-        st->cnt = cnt0 + 1;
-        st->swp = swp0 + 1;
-        st->fast = fast1;
+        st->pivot_pending = 1;
         st->xseq = x.xseq;
         st->xs = x.xs;
-        st->sweep_pending = 1;
+        st->cseq = x.cseq;
     }
-#undef SEL_EXIT
 }
 
-// Rank-1 update + extraction.  Each thread owns VEC adjacent columns and walks
-// `rows_per_cta` rows; the pivot-row slice lives in registers, the multipliers
-// -a[i][q] for the CTA's rows are staged in shared memory.
-template <int VEC, int THREADS, int UNROLL>
-__global__ void __launch_bounds__(THREADS) k_sweep(LpDev d, int rows_per_cta)
+__device__ void sp_exit(LpState *st, const Seq &x, int code)
 {
-    extern __shared__ double s_f[];
-    const LpState *st = d.st;
-    if (!st->sweep_pending) return;
-    const int p = st->p, Cl = d.Cl, m = d.m;
-    const int qn = st->q_next < 0 ? -1 : st->q_next - d.col0; // local index of my candidate
-    const size_t slot = xoff_slot(d, d.rank, st->swp & 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        st->status = code;
+        st->xseq = x.xseq;
+        st->xs = x.xs;
+        st->cseq = x.cseq;
+    }
+}
+
+// The part of solveSlackForm's loop body (:1054-1156) that picks (q, p), on
+// one CTA.  failed_q >= 0: the ratio test on that column just failed.
+__device__ void sp_select(const LpDev &d, LpState *st, Seq &x, int par, int t, int failed_q,
+                          XpMinIdx *shm, int *shi, double *s_pq)
+{
+    const int n = d.n;
+    // zeroing owed by an earlier fast-path scan (same basis since): make it physical
+    const int owed = st->zero_upto;
+    __syncthreads();
+    if (owed > 0) sp_zero(d, owed);
+    if (threadIdx.x == 0) st->zero_upto = 0;
+    if (failed_q >= 0) sp_disable_nv(d, failed_q); // :1146-1151, retry without counting an iteration
+    int q = -1, p = -1;
+    for (;;) {
+        int best, anypos;
+        sp_price(d, -1, 0, shi, best, anypos);
+        cand_exchange(d, x, best, anypos);
+        if (!x.ok) return sp_exit(st, x, XP_ERR_PEER);
+        sp_zero(d, best == INT_BIG ? n : best);
+        if (best == INT_BIG) {
+            if (!anypos) return sp_exit(st, x, XPI_OPT_PENDING); // feasibility: k_feas_*
+            // ---- findPivotNVandBVPair, :670-773 ----
+            // Pass A: eligible c_j > 0; pass B additionally c_j == 0 (tolerant).
+            // findPivotBV is pure, so the c_j > 0 columns that failed in pass A
+            // are not retried in pass B (same outcome, less work).
+            bool found = false;
+            for (int pass = 0; pass < 2 && !found; pass++) {
+                int last = -1;
+                for (;;) {
+                    int cand, dummy;
+                    sp_price(d, last, pass, shi, cand, dummy);
+                    cand_exchange(d, x, cand, dummy);
+                    if (!x.ok) return sp_exit(st, x, XP_ERR_PEER);
+                    if (cand == INT_BIG) break;
+                    sp_column(d, x, par, t, cand, s_pq);
+                    if (!x.ok) return sp_exit(st, x, XP_ERR_PEER);
+                    const int r = sp_ratio(d, par, t, cand, shm);
+                    if (r >= 0) {
+                        q = cand;
+                        p = r;
+                        found = true;
+                        break;
+                    }
+                    last = cand;
+                }
+            }
+            if (!found) return sp_exit(st, x, XP_SIX_UNBOUND); // :1138-1141
+            break;
+        }
+        sp_column(d, x, par, t, best, s_pq);
+        if (!x.ok) return sp_exit(st, x, XP_ERR_PEER);
+        p = sp_ratio(d, par, t, best, shm);
+        if (p >= 0) {
+            q = best;
+            break;
+        }
+        sp_disable_nv(d, best);
+    }
+    sp_commit_pivot(d, st, x, par, t, q, p);
+}
+
+// ---------------------------------------------------------------------------
+// k_pcol: entering column, multipliers, ratio test.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(TH) k_pcol(LpDev d)
+{
+    __shared__ XpMinIdx shm[33];
+    __shared__ int shi[33];
+    __shared__ double s_pq[KMAX];
+    __shared__ int s_flag;
+    LpState *st = d.st;
+    const int tid = threadIdx.x;
+    if (st->status != XPI_RUNNING) return;
+    if (st->cnt >= st->max_iter) { // while (cnt < m_max_iter), :1039
+        if (blockIdx.x == 0 && tid == 0) st->status = XP_SIX_TIME_OUT;
+        return;
+    }
+    const int t = st->t, par = st->blk & 1;
+    Seq x;
+    x.xseq = st->xseq;
+    x.xs = st->xs;
+    x.cseq = st->cseq;
+    x.ok = true;
+    if (st->slow) { // decided by the previous kernel; only CTA 0 works
+        if (blockIdx.x == 0) sp_select(d, st, x, par, t, -1, shm, shi, s_pq);
+        return;
+    }
+    const int q = st->q;
+    const int owner = owner_of(d, q);
+    const bool mine = owner == d.rank;
+    const int ql = q - d.col0;
+    const unsigned cs = x.cseq + 1;
+    if (mine) {
+        if (tid < t) s_pq[tid] = d.P[(size_t)tid * d.Cl + ql];
+        __syncthreads();
+    } else {
+        if (!wait_words(d, offsetof(XHdr, colflag), owner, 1, [cs](unsigned long long w) { return w >= cs; })) {
+            if (tid == 0) st->status = XP_ERR_PEER;
+            return;
+        }
+    }
+    XpMinIdx b1, b2;
+    b1.v = b2.v = 0.0;
+    b1.i = b2.i = -1;
+    double *fmine = Fptr(d, d.rank, par, t);
+    for (int i = blockIdx.x * TH + tid; i < d.m; i += gridDim.x * TH) {
+        double a;
+        if (mine) {
+            a = cur_in_col(d, par, t, i, ql, s_pq);
+            for (int r = 0; r < d.G; r++) Fptr(d, r, par, t)[i] = -a;
+        } else {
+            a = -ld_cg(fmine + i);
+        }
+        ratio_keys(d, q, i, a, b1, b2);
+    }
+    if (mine && blockIdx.x == 0 && tid == 0) {
+        const double cq = d.tgtf[ql];
+        for (int r = 0; r < d.G; r++) Fptr(d, r, par, t)[d.m] = cq;
+    }
+    b1 = xp_block_argmin(b1, shm);
+    b2 = xp_block_argmin(b2, shm);
+    if (tid == 0) {
+        PartA pa;
+        pa.v1 = b1.v;
+        pa.i1 = b1.i;
+        pa.v2 = b2.v;
+        pa.i2 = b2.i;
+        pa.pad[0] = pa.pad[1] = 0;
+        d.partA[blockIdx.x] = pa;
+        if (d.G > 1 && mine) __threadfence_system();
+        else __threadfence();
+        s_flag = atomicAdd(&d.ctr[0], 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!s_flag) return;
+    // ---- last CTA: everything above is complete on this rank ----
+    __threadfence();
+    if (tid == 0) d.ctr[0] = 0;
+    x.cseq = cs;
+    if (d.G > 1 && mine) publish(d, offsetof(XHdr, colflag) + (size_t)d.rank * 8, cs);
+    b1.i = b2.i = -1;
+    b1.v = b2.v = 0.0;
+    for (int k = tid; k < (int)gridDim.x; k += TH) {
+        const PartA *pa = &d.partA[k];
+        XpMinIdx c;
+        c.v = __ldcg(&pa->v1);
+        c.i = __ldcg(&pa->i1);
+        b1 = xp_better(b1, c);
+        c.v = __ldcg(&pa->v2);
+        c.i = __ldcg(&pa->i2);
+        b2 = xp_better(b2, c);
+    }
+    b1 = xp_block_argmin(b1, shm);
+    b2 = xp_block_argmin(b2, shm);
+    const int p = b1.i >= 0 ? b1.i : b2.i;
+    if (p < 0) sp_select(d, st, x, par, t, q, shm, shi, s_pq);
+    else sp_commit_pivot(d, st, x, par, t, q, p);
+}
+
+// ---------------------------------------------------------------------------
+// k_prow: leaving row -> P[t], objective row, constant column, next pricing.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(TH) k_prow(LpDev d)
+{
+    __shared__ int shi[33];
+    __shared__ double s_fp[KMAX];
+    __shared__ int s_flag;
+    LpState *st = d.st;
+    const int tid = threadIdx.x;
+    if (!st->pivot_pending || st->status != XPI_RUNNING) return;
+    const int t = st->t, par = st->blk & 1, n = d.n, Cl = d.Cl;
+    const int p = st->p, q = st->q, bv = st->bv, s0p = st->s0p, zero_upto = st->zero_upto;
+    const double r = st->r, cq = st->cq, prow_rhs = st->prow_rhs;
+    const bool r_one = xp_feq(r, 1.0), r_zero = xp_feq(r, 0.0);
+    const bool cq_zero = xp_feq(cq, 0.0), cq_one = xp_feq(cq, 1.0);
+    if (tid < t) s_fp[tid] = ld_cg(Fptr(d, d.rank, par, tid) + p);
+    __syncthreads();
+    int cand = INT_BIG, anypos = 0;
+    double *Pt = d.P + (size_t)t * Cl;
+    for (int jl = blockIdx.x * TH + tid; jl < Cl; jl += gridDim.x * TH) {
+        const int g = d.col0 + jl;
+        const double v = cur_in_row(d, t, p, s0p, jl, s_fp);
+        const double xv = xp_scale(v, r, r_one, r_zero); // mulOfRow(eqnum, 1/pivot), :1471
+        Pt[jl] = xv;
+        double tg = d.tgtf[jl];
+        const int nvg = g < n ? d.nvset[g] : 0;
+        // the zeroing the pricing scan of this iteration owed (:1059), judged on the
+        // basis as it was at that scan: bv was basic, q was not
+        if (g < zero_upto && (g == bv || (!nvg && g != q))) tg = 0.0;
+        double tt = xp_mul(xv, -1.0);                        // nvexp.mul(-1), :1496
+        if (g >= n) tt = -tt;                                // constant column keeps its sign
+        tt = cq_zero ? 0.0 : (cq_one ? tt : xp_mul(tt, cq)); // nvexp.mul(tgtf[nv])
+        const double tn = xp_add(tt, tg);                    // tgtf.addRowToRow, :1501
+        d.tgtf[jl] = tn;
+        if (nvg && tn > 0.0) { // pricing of the next iteration, :1054-1069
+            anypos = 1;
+            if (cand == INT_BIG && d.row_cnt[g] < n - 1) cand = g;
+        }
+    }
+    const double *ft = Fptr(d, d.rank, par, t);
+    for (int i = blockIdx.x * TH + tid; i < d.m; i += gridDim.x * TH)
+        d.rhsbuf[i] = i == p ? prow_rhs : xp_add(d.rhsbuf[i], xp_mul(ld_cg(ft + i), prow_rhs));
+    cand = xp_block_min_int(cand, shi);
+    anypos = __syncthreads_or(anypos);
+    if (tid == 0) {
+        d.partB[blockIdx.x] = make_int2(cand, anypos);
+        __threadfence();
+        s_flag = atomicAdd(&d.ctr[1], 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!s_flag) return;
+    // ---- last CTA ----
+    __threadfence();
+    if (tid == 0) d.ctr[1] = 0;
+    cand = INT_BIG;
+    anypos = 0;
+    for (int k = tid; k < (int)gridDim.x; k += TH) {
+        const int2 pb = __ldcg(&d.partB[k]);
+        cand = min(cand, pb.x);
+        anypos |= pb.y;
+    }
+    cand = xp_block_min_int(cand, shi);
+    anypos = __syncthreads_or(anypos);
+    Seq x;
+    x.xseq = st->xseq;
+    x.xs = st->xs;
+    x.cseq = st->cseq;
+    x.ok = true;
+    cand_exchange(d, x, cand, anypos);
+    const bool optimal = cand == INT_BIG && !anypos;
+    if (optimal) { // the scan found nothing: every basic reduced cost is forced to 0 (:1059)
+        __syncthreads();
+        sp_zero(d, n);
+    }
+    if (tid == 0) {
+        double tt = -xp_mul(prow_rhs, -1.0); // replica of the constant term of the objective row
+        tt = cq_zero ? 0.0 : (cq_one ? tt : xp_mul(tt, cq));
+        st->tg_rhs = xp_add(tt, st->tg_rhs);
+        d.last_piv[p] = t;
+        if (s0p < 0) st->touched[st->n_touched++] = p;
+        st->t = t + 1;
+        st->cnt += 1;
+        st->pivot_pending = 0;
+        st->q = cand;
+        st->anypos = anypos;
+        st->xseq = x.xseq;
+        if (!x.ok) {
+            st->status = XP_ERR_PEER;
+        } else if (optimal) {
+            st->zero_upto = 0;
+            st->status = XPI_OPT_PENDING; // feasibility is checked by k_feas_*
+        } else {
+            st->zero_upto = cand == INT_BIG ? n : cand;
+            st->slow = cand == INT_BIG; // some c_j > 0 but none eligible: pair search
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// k_flush: apply the t pending pivots to the tableau slice.
+// Each thread owns VEC adjacent columns and keeps P[0..KB)[cols] in registers;
+// the CTA walks `rows_per_cta` rows whose multipliers sit in shared memory.
+// ---------------------------------------------------------------------------
+template <int KB, int VEC, int THREADS, int UNROLL>
+__global__ void __launch_bounds__(THREADS) k_flush(LpDev d, int rows_per_cta)
+{
+    extern __shared__ double s_f[]; // [rows_per_cta][KB], then last_piv as ints
+    __shared__ int s_flag;
+    LpState *st = d.st;
+    const int t = st->t;
+    if (t == 0) return;
+    if (t < st->kblk && st->status == XPI_RUNNING) return; // block still open
+    const int par = st->blk & 1, Cl = d.Cl, m = d.m;
+    int *s_lp = (int *)(s_f + (size_t)rows_per_cta * KB);
     const int r0 = blockIdx.y * rows_per_cta;
     const int r1 = min(m, r0 + rows_per_cta);
-    for (int i = r0 + threadIdx.x; i < r1; i += THREADS) s_f[i - r0] = d.fcol[i];
+    for (int e = threadIdx.x; e < (r1 - r0) * KB; e += THREADS) {
+        const int i = e / KB, s = e - i * KB;
+        s_f[e] = s < t ? ld_cg(Fptr(d, d.rank, par, s) + r0 + i) : 0.0;
+    }
+    for (int i = r0 + threadIdx.x; i < r1; i += THREADS) s_lp[i - r0] = d.last_piv[i];
     __syncthreads();
     const int j0 = (blockIdx.x * THREADS + threadIdx.x) * VEC;
-
-    if (j0 >= Cl) {
-        // nothing to update in this thread
-    } else if (VEC == 2) {
-        const double2 pr = *reinterpret_cast<const double2 *>(d.prow + j0);
-        const int exq = (qn == j0) ? 0 : (qn == j0 + 1 ? 1 : -1);
-        double *base = d.tab + j0;
-        int i = r0;
-        for (; i + UNROLL <= r1; i += UNROLL) {
-            double2 a[UNROLL];
+    if (j0 < Cl) {
+        double pr[KB][VEC];
 #pragma unroll
-            for (int u = 0; u < UNROLL; u++)
-                a[u] = *reinterpret_cast<const double2 *>(base + (size_t)(i + u) * Cl);
+        for (int s = 0; s < KB; s++) {
+            if (s < t) {
+                if (VEC == 2) {
+                    const double2 v = *reinterpret_cast<const double2 *>(d.P + (size_t)s * Cl + j0);
+                    pr[s][0] = v.x;
+                    pr[s][VEC - 1] = v.y;
+                } else {
+                    pr[s][0] = d.P[(size_t)s * Cl + j0];
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < VEC; c++) pr[s][c] = 0.0;
+            }
+        }
+        double *base = d.tab + j0;
+        for (int i = r0; i < r1; i += UNROLL) {
+            double a[UNROLL][VEC];
 #pragma unroll
             for (int u = 0; u < UNROLL; u++) {
-                const double f = s_f[i + u - r0];
-                double2 v;
-                v.x = xp_add(a[u].x, xp_mul(f, pr.x));
-                v.y = xp_add(a[u].y, xp_mul(f, pr.y));
-                if (i + u == p) v = a[u]; // row p was rewritten by k_select
-                *reinterpret_cast<double2 *>(base + (size_t)(i + u) * Cl) = v;
-                if (exq >= 0) {
-                    const double e = exq ? v.y : v.x;
-                    for (int r = 0; r < d.G; r++) ((double *)(d.xb[r] + slot))[i + u] = e;
+                if (i + u < r1) {
+                    if (VEC == 2) {
+                        const double2 v = *reinterpret_cast<const double2 *>(base + (size_t)(i + u) * Cl);
+                        a[u][0] = v.x;
+                        a[u][VEC - 1] = v.y;
+                    } else {
+                        a[u][0] = base[(size_t)(i + u) * Cl];
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < UNROLL; u++) {
+                if (i + u >= r1) continue;
+                const double *f = s_f + (size_t)(i + u - r0) * KB;
+                const int s0 = s_lp[i + u - r0];
+                if (s0 < 0) {
+#pragma unroll
+                    for (int s = 0; s < KB; s++) {
+                        if (s < t) {
+                            const double fs = f[s];
+#pragma unroll
+                            for (int c = 0; c < VEC; c++) a[u][c] = xp_add(a[u][c], xp_mul(fs, pr[s][c]));
+                        }
+                    }
+                } else { // this row was a pivot row at step s0: restart from P[s0]
+#pragma unroll
+                    for (int c = 0; c < VEC; c++) {
+                        double v = d.P[(size_t)s0 * Cl + j0 + c];
+                        for (int s = s0 + 1; s < t; s++)
+                            v = xp_add(v, xp_mul(f[s], d.P[(size_t)s * Cl + j0 + c]));
+                        a[u][c] = v;
+                    }
+                }
+                if (VEC == 2) {
+                    double2 v;
+                    v.x = a[u][0];
+                    v.y = a[u][VEC - 1];
+                    *reinterpret_cast<double2 *>(base + (size_t)(i + u) * Cl) = v;
+                } else {
+                    base[(size_t)(i + u) * Cl] = a[u][0];
                 }
             }
         }
-        for (; i < r1; i++) {
-            double2 a = *reinterpret_cast<const double2 *>(base + (size_t)i * Cl);
-            const double f = s_f[i - r0];
-            double2 v;
-            v.x = xp_add(a.x, xp_mul(f, pr.x));
-            v.y = xp_add(a.y, xp_mul(f, pr.y));
-            if (i == p) v = a;
-            *reinterpret_cast<double2 *>(base + (size_t)i * Cl) = v;
-            if (exq >= 0) {
-                const double e = exq ? v.y : v.x;
-                for (int r = 0; r < d.G; r++) ((double *)(d.xb[r] + slot))[i] = e;
-            }
-        }
-    } else {
-        const double pr = d.prow[j0];
-        const bool exq = qn == j0;
-        double *base = d.tab + j0;
-        for (int i = r0; i < r1; i++) {
-            double a = base[(size_t)i * Cl];
-            double v = xp_add(a, xp_mul(s_f[i - r0], pr));
-            if (i == p) v = a;
-            base[(size_t)i * Cl] = v;
-            if (exq)
-                for (int r = 0; r < d.G; r++) ((double *)(d.xb[r] + slot))[i] = v;
-        }
     }
-    if (d.G > 1) {
-        // The last CTA to finish tells every rank that sweep #swp is complete on this
-        // rank, i.e. that slot[rank][swp & 1] holds my candidate's column everywhere.
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            __threadfence_system();
-            if (atomicAdd(d.sweep_ctr, 1u) == gridDim.x * gridDim.y - 1) {
-                *d.sweep_ctr = 0;
-                __threadfence_system();
-                for (int r = 0; r < d.G; r++)
-                    st_release_sys((unsigned long long *)(d.xb[r] + offsetof(XHdr, done)) + d.rank,
-                                   (unsigned long long)st->swp);
-            }
-        }
+    // the last CTA closes the block
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_flag = atomicAdd(&d.ctr[2], 1u) == gridDim.x * gridDim.y - 1;
+    }
+    __syncthreads();
+    if (!s_flag) return;
+    if (threadIdx.x == 0) {
+        d.ctr[2] = 0;
+        for (int k = 0; k < st->n_touched; k++) d.last_piv[st->touched[k]] = -1;
+        st->n_touched = 0;
+        st->t = 0;
+        st->blk += 1;
     }
 }
 
@@ -717,7 +836,7 @@ __global__ void k_feas_rows(LpDev d)
     }
     __syncthreads();
     if (s_bad) {
-        if (threadIdx.x == 0) st->infeasible = 2; // peer timeout
+        if (threadIdx.x == 0) atomicOr(&st->infeasible, 2); // peer timeout
         return;
     }
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -738,8 +857,8 @@ __global__ void k_feas_rows(LpDev d)
         __syncthreads();
         if (threadIdx.x == 0) {
             __threadfence_system();
-            if (atomicAdd(d.feas_ctr, 1u) == gridDim.x - 1) {
-                *d.feas_ctr = 0;
+            if (atomicAdd(&d.ctr[3], 1u) == gridDim.x - 1) {
+                d.ctr[3] = 0;
                 __threadfence_system();
                 st_release_sys((unsigned long long *)(d.xb[d.rank + 1] + offsetof(XHdr, feas_in)), ep);
             }
@@ -758,7 +877,8 @@ __global__ void k_feas_done(LpDev d)
         if (d.rank == d.G - 1) {
             for (int r = 0; r < d.G; r++) {
                 __threadfence_system();
-                st_release_sys((unsigned long long *)(d.xb[r] + offsetof(XHdr, feas_res)), (ep << 2) | (unsigned)inf);
+                st_release_sys((unsigned long long *)(d.xb[r] + offsetof(XHdr, feas_res)),
+                               (ep << 2) | (unsigned)inf);
             }
         }
         const unsigned long long *w = (const unsigned long long *)(d.xb[d.rank] + offsetof(XHdr, feas_res));
@@ -782,7 +902,7 @@ __global__ void k_feas_done(LpDev d)
     }
 }
 
-__global__ void k_init(LpDev d, unsigned max_iter, int fresh)
+__global__ void k_init(LpDev d, unsigned max_iter, int kblk, int fresh)
 {
     LpState *st = d.st;
     int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -794,21 +914,27 @@ __global__ void k_init(LpDev d, unsigned max_iter, int fresh)
             d.col_cnt[k] = 0;
         }
         for (int k = t; k < d.C; k += stride) d.sol[k] = 0.0; // sol.reinit, :1028
+        for (int k = t; k < d.m; k += stride) d.last_piv[k] = -1;
     }
     if (t == 0) {
         if (fresh) {
             st->cnt = 0;
             st->n_log = 0;
             st->infeasible = 0;
-            st->fast = 0;
-            st->q_next = -1;
+            st->t = 0;
+            st->n_touched = 0;
+            st->q = INT_BIG;
+            st->slow = 1; // first pricing of a solve runs on the slow path
+            st->pivot_pending = 0;
+            st->zero_upto = 0;
             st->maxv = 0.0; // :1027
             st->status = XPI_RUNNING;
-        } else if (st->status == XP_SIX_TIME_OUT && st->cnt < max_iter) {
-            st->status = XPI_RUNNING; // resume after a bounded run
+            st->kblk = kblk > 0 ? kblk : 1;
+        } else {
+            if (st->status == XP_SIX_TIME_OUT && st->cnt < max_iter) st->status = XPI_RUNNING; // resume
+            if (kblk > 0 && st->t == 0) st->kblk = kblk;
         }
         st->max_iter = max_iter;
-        st->sweep_pending = 0;
     }
 }
 
@@ -829,7 +955,8 @@ __device__ __forceinline__ void fill_slack_form(const LpDev &d, int nvars, Gen g
         d.tab[e] = v;
     }
     for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < C; j += gridDim.x * blockDim.x) {
-        if (j >= d.col0 && j < d.col0 + d.Cl) d.tgtf[j - d.col0] = j < n ? gen(m, j) : (j < n + m ? 0.0 : gen(m, n));
+        if (j >= d.col0 && j < d.col0 + d.Cl)
+            d.tgtf[j - d.col0] = j < n ? gen(m, j) : (j < n + m ? 0.0 : gen(m, n));
         if (j < n + m) {
             d.nvset[j] = j < n;
             d.bv2eq[j] = j < n ? -1 : j - n;
@@ -922,43 +1049,66 @@ struct xp_lp_f64 {
     LpDev d;
     LpState *h_st; // pinned
     double *vc_diag, *vc_rhs;
-    unsigned char *xblock = nullptr;       // this rank's exchange block
-    void *peer_map[MAXR] = {nullptr};      // IPC mappings to close
+    unsigned char *xblock = nullptr;  // this rank's exchange block
+    void *peer_map[MAXR] = {nullptr}; // IPC mappings to close
     bool attached = false;
-    // optional per-launch timing of the sweep kernel (CUDA events on the ctx stream)
+    int kblk = 0; // 0: automatic
+    // optional per-launch timing of the flush kernel (CUDA events on the ctx stream)
     bool profile = false;
     std::vector<cudaEvent_t> evs;
     uint64_t prof_sweeps = 0;
-    unsigned cnt_at_entry = 0;
     double prof_sweep_ms = 0.0, prof_gap_ms = 0.0;
 };
 
 constexpr int PROF_MAX_SWEEPS = 4096;
 
-static int sweep_launch(xp_lp_f64 *lp)
+static int auto_block(const LpDev &d)
+{
+    const long long cells = (long long)d.m * d.Cl;
+    if (cells >= (4LL << 20)) return 16;
+    if (cells >= (1LL << 18)) return 8;
+    return 4;
+}
+
+template <int KB>
+static void flush_launch_kb(xp_ctx *ctx, const LpDev &d)
+{
+    const int m = d.m, Cl = d.Cl;
+    constexpr int THR = 256;
+    const bool vec2 = (Cl & 1) == 0 && KB <= 16;
+    int ctiles = vec2 ? (Cl / 2 + THR - 1) / THR : (Cl + THR - 1) / THR;
+    int want = ctx->sm_count * 8; // >= 8 CTAs per SM worth of row tiles, 8..64 rows per CTA
+    int rpc = (int)(((long long)m * ctiles + want - 1) / want);
+    rpc = rpc < 8 ? 8 : (rpc > 64 ? 64 : rpc);
+    rpc = (rpc + 7) & ~7;
+    dim3 grid(ctiles, (m + rpc - 1) / rpc);
+    size_t smem = (size_t)rpc * KB * sizeof(double) + (size_t)rpc * sizeof(int);
+    if (vec2) k_flush<KB, (KB <= 16 ? 2 : 1), THR, (KB <= 4 ? 8 : 4)><<<grid, THR, smem, ctx->stream>>>(d, rpc);
+    else k_flush<KB, 1, THR, 4><<<grid, THR, smem, ctx->stream>>>(d, rpc);
+    ctx->launches++;
+}
+
+static void flush_launch(xp_lp_f64 *lp, int kblk)
 {
     xp_ctx *ctx = lp->ctx;
     const LpDev &d = lp->d;
-    const int m = d.m, Cl = d.Cl;
-    if ((Cl & 1) == 0) {
-        constexpr int TH = 256;
-        int ctiles = (Cl / 2 + TH - 1) / TH;
-        // aim for >= 8 CTAs per SM worth of row tiles, 8..64 rows per CTA
-        int want = ctx->sm_count * 8;
-        int rpc = (int)(((long long)m * ctiles + want - 1) / want);
-        rpc = rpc < 8 ? 8 : (rpc > 64 ? 64 : rpc);
-        rpc = (rpc + 7) & ~7;
-        dim3 grid(ctiles, (m + rpc - 1) / rpc);
-        k_sweep<2, TH, 8><<<grid, TH, rpc * sizeof(double), ctx->stream>>>(d, rpc);
-    } else {
-        constexpr int TH = 128;
-        int ctiles = (Cl + TH - 1) / TH;
-        int rpc = 16;
-        dim3 grid(ctiles, (m + rpc - 1) / rpc);
-        k_sweep<1, TH, 1><<<grid, TH, rpc * sizeof(double), ctx->stream>>>(d, rpc);
-    }
-    ctx->launches++;
-    return 0;
+    if (kblk <= 1) flush_launch_kb<1>(ctx, d);
+    else if (kblk <= 2) flush_launch_kb<2>(ctx, d);
+    else if (kblk <= 4) flush_launch_kb<4>(ctx, d);
+    else if (kblk <= 8) flush_launch_kb<8>(ctx, d);
+    else if (kblk <= 12) flush_launch_kb<12>(ctx, d);
+    else if (kblk <= 16) flush_launch_kb<16>(ctx, d);
+    else if (kblk <= 24) flush_launch_kb<24>(ctx, d);
+    else flush_launch_kb<32>(ctx, d);
+}
+
+template <int KB>
+static cudaError_t preload_flush()
+{
+    cudaFuncAttributes fa;
+    cudaError_t e = cudaFuncGetAttributes(&fa, k_flush<KB, 1, 256, 4>);
+    if (e != cudaSuccess) return e;
+    return cudaFuncGetAttributes(&fa, k_flush<KB, (KB <= 16 ? 2 : 1), 256, (KB <= 4 ? 8 : 4)>);
 }
 
 static int lp_create(xp_ctx *ctx, int m, int C, int rank, int G, xp_lp_f64 **out)
@@ -981,12 +1131,16 @@ static int lp_create(xp_ctx *ctx, int m, int C, int rank, int G, xp_lp_f64 **out
     d.Cl = (rank + 1 < G ? shard_lo(C, G, rank + 1) : C) - d.col0;
     d.mpad = (m + 1 + 15) & ~15;
     d.log_cap = 1u << 16;
+    d.gridA = (m + TH - 1) / TH;
+    if (d.gridA > 64) d.gridA = 64;
+    int span = d.Cl > m ? d.Cl : m;
+    d.gridB = (span + TH - 1) / TH;
+    if (d.gridB > 128) d.gridB = 128;
     const size_t n = d.n, Cl = d.Cl;
 #define ALLOC(ptr, bytes) XP_CUDA_OK(ctx, cudaMalloc((void **)&(ptr), (bytes)))
     ALLOC(d.tab, (size_t)m * Cl * sizeof(double));
     ALLOC(d.tgtf, Cl * sizeof(double));
-    ALLOC(d.prow, Cl * sizeof(double));
-    ALLOC(d.fcol, m * sizeof(double));
+    ALLOC(d.P, (size_t)KMAX * Cl * sizeof(double));
     ALLOC(d.rhsbuf, m * sizeof(double));
     ALLOC(d.sol, C * sizeof(double));
     ALLOC(lp->vc_diag, n * sizeof(double));
@@ -994,21 +1148,42 @@ static int lp_create(xp_ctx *ctx, int m, int C, int rank, int G, xp_lp_f64 **out
     ALLOC(d.nvset, n + 1);
     ALLOC(d.bv2eq, n * sizeof(int32_t));
     ALLOC(d.eq2bv, m * sizeof(int32_t));
+    ALLOC(d.last_piv, m * sizeof(int32_t));
     ALLOC(d.tabu, n * (size_t)d.W * sizeof(uint32_t));
     ALLOC(d.row_cnt, n * sizeof(int32_t));
     ALLOC(d.col_cnt, n * sizeof(int32_t));
     ALLOC(d.log, (size_t)d.log_cap * 3 * sizeof(int32_t));
-    ALLOC(d.feas_ctr, 16);
+    ALLOC(d.partA, 64 * sizeof(PartA));
+    ALLOC(d.partB, 128 * sizeof(int2));
+    ALLOC(d.ctr, 64);
     ALLOC(d.st, sizeof(LpState));
     ALLOC(lp->xblock, xblock_bytes(d));
 #undef ALLOC
     XP_CUDA_OK(ctx, cudaMemset(d.st, 0, sizeof(LpState)));
-    XP_CUDA_OK(ctx, cudaMemset(d.feas_ctr, 0, 16));
-    d.sweep_ctr = d.feas_ctr + 1;
+    XP_CUDA_OK(ctx, cudaMemset(d.ctr, 0, 64));
+    XP_CUDA_OK(ctx, cudaMemset(d.last_piv, 0xff, m * sizeof(int32_t)));
     XP_CUDA_OK(ctx, cudaMemset(lp->xblock, 0, xblock_bytes(d)));
     d.xb[rank] = lp->xblock;
     lp->attached = G == 1;
     XP_CUDA_OK(ctx, cudaMallocHost((void **)&lp->h_st, sizeof(LpState)));
+    // Load every kernel of this path now: a lazy module load while another shard's
+    // kernel is spinning on a peer flag would wait for that kernel, i.e. forever.
+    cudaFuncAttributes fa;
+    XP_CUDA_OK(ctx, cudaFuncGetAttributes(&fa, k_pcol));
+    XP_CUDA_OK(ctx, cudaFuncGetAttributes(&fa, k_prow));
+    XP_CUDA_OK(ctx, cudaFuncGetAttributes(&fa, k_init));
+    XP_CUDA_OK(ctx, cudaFuncGetAttributes(&fa, k_feas_sol));
+    XP_CUDA_OK(ctx, cudaFuncGetAttributes(&fa, k_feas_rows));
+    XP_CUDA_OK(ctx, cudaFuncGetAttributes(&fa, k_feas_done));
+    XP_CUDA_OK(ctx, cudaFuncGetAttributes(&fa, k_checksum));
+    XP_CUDA_OK(ctx, preload_flush<1>());
+    XP_CUDA_OK(ctx, preload_flush<2>());
+    XP_CUDA_OK(ctx, preload_flush<4>());
+    XP_CUDA_OK(ctx, preload_flush<8>());
+    XP_CUDA_OK(ctx, preload_flush<12>());
+    XP_CUDA_OK(ctx, preload_flush<16>());
+    XP_CUDA_OK(ctx, preload_flush<24>());
+    XP_CUDA_OK(ctx, preload_flush<32>());
     *out = lp;
     return 0;
 }
@@ -1022,6 +1197,13 @@ extern "C" int xp_lp_f64_create_sharded(xp_ctx *ctx, int m, int C, int rank, int
                                         xp_lp_f64 **out)
 {
     return lp_create(ctx, m, C, rank, nranks, out);
+}
+
+extern "C" int xp_lp_f64_set_block(xp_lp_f64 *lp, int pivots_per_flush)
+{
+    if (!lp || pivots_per_flush < 0 || pivots_per_flush > KMAX) return XP_ERR_BAD_ARG;
+    lp->kblk = pivots_per_flush;
+    return 0;
 }
 
 extern "C" int xp_lp_f64_local_cols(const xp_lp_f64 *lp, int *col0, int *ncols)
@@ -1097,9 +1279,9 @@ extern "C" void xp_lp_f64_destroy(xp_lp_f64 *lp)
     cudaStreamSynchronize(lp->ctx->stream);
     for (int r = 0; r < MAXR; r++)
         if (lp->peer_map[r]) cudaIpcCloseMemHandle(lp->peer_map[r]);
-    void *ptrs[] = {d.tab,     d.tgtf,    d.prow,  d.fcol,     d.rhsbuf,  d.sol, lp->vc_diag,
-                    lp->vc_rhs, d.nvset,  d.bv2eq, d.eq2bv,    d.tabu,    d.row_cnt,
-                    d.col_cnt, d.log,     d.st,    d.feas_ctr, lp->xblock};
+    void *ptrs[] = {d.tab,   d.tgtf,     d.P,     d.rhsbuf, d.sol,     lp->vc_diag, lp->vc_rhs,
+                    d.nvset, d.bv2eq,    d.eq2bv, d.tabu,   d.row_cnt, d.col_cnt,   d.log,
+                    d.st,    d.last_piv, d.partA, d.partB,  d.ctr,     lp->xblock};
     for (void *p : ptrs) cudaFree(p);
     for (cudaEvent_t e : lp->evs) cudaEventDestroy(e);
     cudaFreeHost(lp->h_st);
@@ -1109,7 +1291,8 @@ extern "C" void xp_lp_f64_destroy(xp_lp_f64 *lp)
 static int lp_reset(xp_lp_f64 *lp)
 {
     xp_ctx *ctx = lp->ctx;
-    k_init<<<ctx->sm_count * 2, 256, 0, ctx->stream>>>(lp->d, 0u, 1);
+    const int k = lp->kblk > 0 ? lp->kblk : auto_block(lp->d);
+    k_init<<<ctx->sm_count * 2, 256, 0, ctx->stream>>>(lp->d, 0u, k, 1);
     ctx->launches++;
     XP_CUDA_OK(ctx, cudaGetLastError());
     return 0;
@@ -1207,27 +1390,25 @@ extern "C" int xp_lp_f64_solve(xp_lp_f64 *lp, uint32_t max_iter, int rule)
     }
     XP_CUDA_OK(ctx, cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream;
+    const int kblk = lp->kblk > 0 ? lp->kblk : auto_block(d);
     XP_CUDA_OK(ctx, cudaEventRecord(ctx->ev0, s));
-    k_init<<<1, 32, 0, s>>>(d, max_iter, 0);
+    k_init<<<1, 32, 0, s>>>(d, max_iter, kblk, 0);
     ctx->launches++;
-    if (lp->profile) {
-        XP_CUDA_OK(ctx, cudaMemcpyAsync(lp->h_st, d.st, sizeof(LpState), cudaMemcpyDeviceToHost, s));
-        XP_CUDA_OK(ctx, cudaStreamSynchronize(s));
-        lp->cnt_at_entry = lp->h_st->cnt;
-    }
-    // Each select+sweep pair is one simplex iteration; batches run without any
-    // host round trip, the host only polls the status word between batches.
-    // Every rank of a sharded LP sees the same status words, hence issues the
-    // same launches.
-    int batch = 8;
-    int n_prof = 0; // sweeps bracketed by events in this call
+    // One block = kblk x (k_pcol, k_prow) + k_flush, no host round trip inside;
+    // the host polls the status word between batches of blocks.  Every rank of a
+    // sharded LP sees the same status words, hence issues the same launches.
+    int blocks = 1;
+    int n_prof = 0; // flushes bracketed by events in this call
     for (;;) {
-        for (int b = 0; b < batch; b++) {
-            k_select<<<1, SEL_THREADS, 0, s>>>(d);
-            ctx->launches++;
+        for (int b = 0; b < blocks; b++) {
+            for (int k = 0; k < kblk; k++) {
+                k_pcol<<<d.gridA, TH, 0, s>>>(d);
+                k_prow<<<d.gridB, TH, 0, s>>>(d);
+            }
+            ctx->launches += 2 * kblk;
             const bool prof = lp->profile && n_prof < PROF_MAX_SWEEPS;
             if (prof) XP_CUDA_OK(ctx, cudaEventRecord(lp->evs[2 * n_prof], s));
-            sweep_launch(lp);
+            flush_launch(lp, kblk);
             if (prof) {
                 XP_CUDA_OK(ctx, cudaEventRecord(lp->evs[2 * n_prof + 1], s));
                 n_prof++;
@@ -1237,17 +1418,17 @@ extern "C" int xp_lp_f64_solve(xp_lp_f64 *lp, uint32_t max_iter, int rule)
         XP_CUDA_OK(ctx, cudaMemcpyAsync(lp->h_st, d.st, sizeof(LpState), cudaMemcpyDeviceToHost, s));
         XP_CUDA_OK(ctx, cudaStreamSynchronize(s));
         if (lp->h_st->status != XPI_RUNNING) break;
-        if (batch < 64) batch *= 2;
         unsigned long long left = (unsigned long long)max_iter - lp->h_st->cnt;
-        if ((unsigned long long)batch > left + 1) batch = (int)(left + 1);
+        int want = blocks < 8 ? blocks * 2 : 8;
+        unsigned long long need = left / kblk + 1; // the extra block reports TIME_OUT
+        blocks = (unsigned long long)want > need ? (int)need : want;
+        if (blocks < 1) blocks = 1;
     }
     if (lp->profile) {
-        // only the first (iterations done in this call) sweeps did real work
-        long long real = (long long)lp->h_st->cnt - (long long)lp->cnt_at_entry;
-        if (real > n_prof) real = n_prof;
-        for (long long k = 0; k < real; k++) {
+        for (int k = 0; k < n_prof; k++) {
             float ms = 0.f;
             XP_CUDA_OK(ctx, cudaEventElapsedTime(&ms, lp->evs[2 * k], lp->evs[2 * k + 1]));
+            if (ms < 0.004f) continue; // an empty launch (block still open / already terminal)
             lp->prof_sweep_ms += ms;
             lp->prof_sweeps++;
             if (k > 0) {
@@ -1382,6 +1563,7 @@ extern "C" int xp_six_slack_f64(xp_ctx *ctx, double *tableau, double *tgtf, int 
         if (rc) return rc;
         ctx->cached_lp = lp;
     }
+    lp->kblk = ctx->slack_block;
     rc = xp_lp_f64_upload(lp, tableau, tgtf, nvset, bvset, bv2eq, eq2bv, vc_diag, vc_rhs);
     if (rc) return rc;
     int st = xp_lp_f64_solve(lp, max_iter, rule);
@@ -1391,6 +1573,14 @@ extern "C" int xp_six_slack_f64(xp_ctx *ctx, double *tableau, double *tgtf, int 
         if (rc) st = rc;
     }
     return st;
+}
+
+// Block size used by xp_six_slack_f64 on this ctx (0 = automatic).
+extern "C" int xp_ctx_set_block(xp_ctx *ctx, int pivots_per_flush)
+{
+    if (!ctx || pivots_per_flush < 0 || pivots_per_flush > KMAX) return XP_ERR_BAD_ARG;
+    ctx->slack_block = pivots_per_flush;
+    return 0;
 }
 
 void xp_large_release_cached(xp_ctx *ctx)
