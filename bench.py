@@ -243,90 +243,115 @@ def run_ours(args):
         lp = sharded.ShardedLP(ctx, m, Ccols, rank, world, dist)
     else:
         lp = ctx.large_lp(m, Ccols)
-    lp.fill_synthetic(SEED)
-    lib.xp_lp_f64_profile(lp._h, 1)
-
-    done = 0
-
-    def step():
-        nonlocal done
-        st = lp.solve(done + P)
-        done += P
-        if st != xp.SIX_TIME_OUT:  # LP terminated: restart from a fresh instance
-            lp.fill_synthetic(SEED + done)
-            done = 0
-        return ctx.last_kernel_ms
-
-    for _ in range(args.warmup):
-        step()
-    lib.xp_lp_f64_profile(lp._h, 1)  # reset the per-launch accumulators
-    sampler = ClockSampler(local_rank)
-    barrier()
-    sampler.start()
-    launches0 = ctx.launches
-    t0 = time.perf_counter()
-    dev_ms = 0.0
-    for _ in range(args.steps):
-        dev_ms += step()
-    barrier()
-    wall_s = time.perf_counter() - t0
-    clocks = sampler.stop()
-    launches = ctx.launches - launches0
-    if world > 1:
-        t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_ms = float(t.item())
-    total_pivots = args.steps * P
-    value = total_pivots / (dev_ms * 1e-3)
-
-    n_sw, sw_ms, gap_ms = C.c_uint64(0), C.c_double(0), C.c_double(0)
-    lib.xp_lp_f64_profile_read(lp._h, C.byref(n_sw), C.byref(sw_ms), C.byref(gap_ms))
-    lib.xp_lp_f64_profile(lp._h, 0)
+    local_cols = lp.local_cols
     peak, peak_src = measured_peak_gbs()
-    local_cols = lp.local_cols if world > 1 else Ccols
-    alg_bytes = 2.0 * (m + 1) * local_cols * 8  # read+write of every entry
-    sweep_avg_ms = sw_ms.value / max(n_sw.value, 1)
-    achieved = alg_bytes / (sweep_avg_ms * 1e-3) / 1e9 if sweep_avg_ms > 0 else 0.0
+    B_pivot = 2.0 * (m + 1) * local_cols * 8  # read+write of every entry, per pivot
+
+    def timed_run(block, pivots, steps, warmup):
+        """`steps` steps of `pivots` simplex iterations each; device time = max over ranks."""
+        lp.set_block(block)
+        lp.fill_synthetic(SEED)
+        done = 0
+
+        def step():
+            nonlocal done
+            st = lp.solve(done + pivots)
+            done += pivots
+            if st != xp.SIX_TIME_OUT:  # LP terminated: restart from a fresh instance
+                lp.fill_synthetic(SEED + done)
+                done = 0
+            return ctx.last_kernel_ms
+        for _ in range(warmup):
+            step()
+        lib.xp_lp_f64_profile(lp._h, 1)
+        barrier()
+        l0 = ctx.launches
+        t0 = time.perf_counter()
+        dev_ms = 0.0
+        for _ in range(steps):
+            dev_ms += step()
+        barrier()
+        wall = time.perf_counter() - t0
+        launches = ctx.launches - l0
+        if world > 1:
+            t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dev_ms = float(t.item())
+        n_sw, sw_ms, gap_ms = C.c_uint64(0), C.c_double(0), C.c_double(0)
+        lib.xp_lp_f64_profile_read(lp._h, C.byref(n_sw), C.byref(sw_ms), C.byref(gap_ms))
+        lib.xp_lp_f64_profile(lp._h, 0)
+        return dict(dev_ms=dev_ms, wall=wall, launches=launches, pivots=steps * pivots,
+                    flushes=int(n_sw.value), flush_ms=sw_ms.value, gap_ms=gap_ms.value)
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    main = timed_run(args.block, P, args.steps, args.warmup)
+    clocks = sampler.stop()
+    value = main["pivots"] / (main["dev_ms"] * 1e-3)
+    k_eff = main["pivots"] / max(main["flushes"], 1)  # pivots applied per k_flush launch
+    flush_avg_ms = main["flush_ms"] / max(main["flushes"], 1)
+    moved = 2.0 * m * local_cols * 8  # one read + one write of the slice per launch
+    achieved = k_eff * B_pivot / (flush_avg_ms * 1e-3) / 1e9 if flush_avg_ms > 0 else 0.0
     traffic = None
-    prof = os.path.join(ROOT, "profiles", "r01_sweep_ncu_full.json")
+    prof = os.path.join(ROOT, "profiles", "r01_flush_ncu_full.json")
     if os.path.exists(prof) and world == 1:
         try:
             traffic = json.load(open(prof)).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
-    roofline = {"bound": "hbm", "kernel": "k_sweep (rank-1 update + next-column extraction)",
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "peak_source": peak_src, "traffic": traffic,
-                "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": sweep_avg_ms,
-                "launches_timed": int(n_sw.value),
-                "sweep_share_of_step": sw_ms.value / dev_ms if dev_ms > 0 else None,
-                "whole_pivot_frac_of_peak": value * alg_bytes / 1e9 / peak,
-                "whole_pivot_frac_of_8TBps": value * alg_bytes / 8e12}
+    roofline = {
+        "bound": "hbm", "kernel": "k_flush (rank-k tableau update, k pivots per pass)",
+        "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        "peak_source": peak_src, "traffic": traffic,
+        "algorithmic_bytes_per_launch": k_eff * B_pivot, "pivots_per_launch": k_eff,
+        "avg_launch_ms": flush_avg_ms, "launches_timed": main["flushes"],
+        "hbm_bytes_moved_per_launch": moved,
+        "hbm_moved_GBps": moved / (flush_avg_ms * 1e-3) / 1e9 if flush_avg_ms > 0 else None,
+        "hbm_moved_frac_of_peak": (moved / (flush_avg_ms * 1e-3) / 1e9 / peak) if flush_avg_ms > 0 else None,
+        "flush_share_of_step": main["flush_ms"] / main["dev_ms"] if main["dev_ms"] > 0 else None,
+        "note": "frac > 1 is expected: one launch applies k pivots to every entry in the "
+                "reference's rounding order, so the bytes the reference's schedule would move "
+                "(k x 2(m+1)C x 8) exceed the bytes this kernel moves (2 m C x 8); see DESIGN.md",
+        "whole_pivot_frac_of_peak": value * B_pivot / 1e9 / peak,
+        "whole_pivot_frac_of_8TBps": value * B_pivot / 8e12}
+
+    # the reference's own schedule (one tableau pass per pivot), same kernels with k = 1
+    r1 = timed_run(1, args.rank1_pivots, 3, 1)
+    r1_value = r1["pivots"] / (r1["dev_ms"] * 1e-3)
+    r1_sweep_ms = r1["flush_ms"] / max(r1["flushes"], 1)
+    rank1 = {"value": r1_value, "unit": "pivots/s", "pivots_per_launch": 1,
+             "avg_launch_ms": r1_sweep_ms,
+             "achieved": B_pivot / (r1_sweep_ms * 1e-3) / 1e9 if r1_sweep_ms > 0 else None,
+             "frac": (B_pivot / (r1_sweep_ms * 1e-3) / 1e9 / peak) if r1_sweep_ms > 0 else None,
+             "whole_pivot_frac_of_peak": r1_value * B_pivot / 1e9 / peak,
+             "whole_pivot_frac_of_8TBps": r1_value * B_pivot / 8e12}
 
     line = {
         "metric": "pivots/s", "value": value, "unit": "pivots/s", "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": main["dev_ms"] / args.steps,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
         "config": {"workload": f"c3: dense FP64 LP, tableau {m}x{Ccols}, {P} simplex iterations "
-                               "per step (reference pivot rule), HBM-resident"
+                               "per step (reference pivot rule, bit-identical state), HBM-resident"
                                + (f", column-sharded over {world} GPUs" if world > 1 else ""),
                    "l2": "inputs (1 GiB) larger than L2 (126 MB): no flush between iterations",
-                   "pivots_per_step": P},
-        "gpu_launches": int(launches), "wall_s": wall_s, "clocks": clocks, "roofline": roofline,
+                   "pivots_per_step": P, "pivots_per_tableau_pass": k_eff},
+        "gpu_launches": int(main["launches"]), "wall_s": main["wall"], "clocks": clocks,
+        "roofline": roofline, "rank1_schedule": rank1,
     }
 
     if world == 1:
-        # ---- e2e: the C-ABI call with pinned host buffers (H2D + K pivots + D2H per step)
+        # ---- e2e: the C-ABI call with pinned host buffers (H2D + P pivots + D2H per step)
         tab_bytes = m * Ccols * 8
         hp = C.c_void_p()
         ctx.check(lib.xp_host_alloc(ctx._h, C.c_size_t(tab_bytes), C.byref(hp)))
-        h_tab = np.ctypeslib.as_array(C.cast(hp, C.POINTER(C.c_double)), shape=(m, Ccols))
+        lp.set_block(args.block)
         lp.fill_synthetic(SEED)
         st0 = lp.download(want_tab=False)
         ctx.check(lib.xp_lp_f64_download(lp._h, hp, None, None, None, None, None, None, None, None,
                                          None, 0))
         lp.close()
+        ctx.set_block(args.block)
         tg, nv, bvs = st0["tgtf"].copy(), st0["nvset"].copy(), st0["bvset"].copy()
         b2e, e2b = st0["bv2eq"].copy(), st0["eq2bv"].copy()
         maxv, sol = np.zeros(1), np.zeros(Ccols)
@@ -387,11 +412,13 @@ def main():
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--pivots", type=int, default=25, help="simplex iterations per step")
+    ap.add_argument("--pivots", type=int, default=200, help="simplex iterations per step (SURVEY 8d: K = 200)")
+    ap.add_argument("--block", type=int, default=0, help="pivots per tableau pass (0 = automatic)")
+    ap.add_argument("--rank1-pivots", type=int, default=40)
     ap.add_argument("--m", type=int, default=M_ROWS)
     ap.add_argument("--n", type=int, default=N_VARS)
     ap.add_argument("--cpu-pivots", type=int, default=12)
-    ap.add_argument("--ref-pivots", type=int, default=2)
+    ap.add_argument("--ref-pivots", type=int, default=4)
     ap.add_argument("--port", action="store_true", help="reference arm: force the oracle port")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-batched", action="store_true")
