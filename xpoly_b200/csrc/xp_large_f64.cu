@@ -49,6 +49,7 @@
 // and exactly equivalent to the reference's byte-matrix scans.
 #include "xp_common.cuh"
 
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -204,21 +205,40 @@ __device__ __forceinline__ bool wait_words(const LpDev &d, size_t off, int first
 // ---------------------------------------------------------------------------
 // Replay of the pending updates (see the header comment).
 // ---------------------------------------------------------------------------
-// Entry (i, ql) now, at step t; pq[s] = P[s][ql].
+// Entry (i, ql) now, at step t; pq[s] = P[s][ql].  All loads are issued before the
+// dependent add chain starts (one memory round trip, not t).
 __device__ __forceinline__ double cur_in_col(const LpDev &d, int par, int t, int i, int ql,
                                              const double *pq)
 {
     const int s0 = d.last_piv[i];
-    double v = s0 >= 0 ? pq[s0] : d.tab[(size_t)i * d.Cl + ql];
-    for (int s = s0 + 1; s < t; s++) v = xp_add(v, xp_mul(ld_cg(Fptr(d, d.rank, par, s) + i), pq[s]));
+    const double a0 = d.tab[(size_t)i * d.Cl + ql];
+    const double *f0 = Fptr(d, d.rank, par, 0) + i;
+    double f[KMAX];
+#pragma unroll
+    for (int s = 0; s < KMAX; s++) f[s] = s < t ? ld_cg(f0 + (size_t)s * d.mpad) : 0.0;
+    double v = a0;
+#pragma unroll
+    for (int s = 0; s < KMAX; s++) {
+        if (s == s0) v = pq[s];
+        else if (s > s0 && s < t) v = xp_add(v, xp_mul(f[s], pq[s]));
+    }
     return v;
 }
 // Entry (p, jl) now, at step t; fp[s] = F[s][p], s0 = last_piv[p].
 __device__ __forceinline__ double cur_in_row(const LpDev &d, int t, int p, int s0, int jl,
                                              const double *fp)
 {
-    double v = s0 >= 0 ? d.P[(size_t)s0 * d.Cl + jl] : d.tab[(size_t)p * d.Cl + jl];
-    for (int s = s0 + 1; s < t; s++) v = xp_add(v, xp_mul(fp[s], d.P[(size_t)s * d.Cl + jl]));
+    const double a0 = d.tab[(size_t)p * d.Cl + jl];
+    const double *p0 = d.P + jl;
+    double pr[KMAX];
+#pragma unroll
+    for (int s = 0; s < KMAX; s++) pr[s] = s < t ? ld_cg(p0 + (size_t)s * d.Cl) : 0.0;
+    double v = a0;
+#pragma unroll
+    for (int s = 0; s < KMAX; s++) {
+        if (s == s0) v = pr[s];
+        else if (s > s0 && s < t) v = xp_add(v, xp_mul(fp[s], pr[s]));
+    }
     return v;
 }
 
@@ -504,6 +524,7 @@ __global__ void __launch_bounds__(TH) k_pcol(LpDev d)
         return;
     }
     const int t = st->t, par = st->blk & 1;
+    if (t >= st->kblk) return; // block full: k_flush comes first
     Seq x;
     x.xseq = st->xseq;
     x.xs = st->xs;
@@ -685,6 +706,381 @@ __global__ void __launch_bounds__(TH) k_prow(LpDev d)
 }
 
 // ---------------------------------------------------------------------------
+// k_panel: the fast path of k_pcol + k_prow for up to (kblk - t) consecutive
+// pivots in ONE persistent cooperative kernel (single GPU).  CTA c owns a fixed
+// range of rows (entering column, ratio test, constant column) and a fixed
+// range of columns (leaving row, objective row, pricing); two grid barriers per
+// pivot replace two kernel boundaries, every CTA reduces the per-CTA partial
+// results redundantly (deterministic, so all agree), and CTA 0 keeps the tabu
+// table / basis maps while the others already work on the next column.  Any
+// rare event (ratio test fails, no eligible candidate, optimum) ends the kernel
+// with the state in global memory; the k_pcol / k_prow pair that follows in the
+// stream handles that one pivot on the slow path, and the next k_panel resumes.
+// ---------------------------------------------------------------------------
+struct PanA { // per-CTA ratio-test result, both passes, with everything the pivot needs
+    double v1, rh1, a1, v2, rh2, a2;
+    int i1, bv1, s01, i2, bv2, s02;
+};
+struct PanB { // per-CTA pricing result
+    double c;
+    int cand, anypos;
+};
+struct RKey {
+    double v, rh, a;
+    int i, bv, s0;
+};
+__device__ __forceinline__ RKey rk_better(const RKey &x, const RKey &y)
+{
+    if (y.i < 0) return x;
+    if (x.i < 0) return y;
+    if (y.v < x.v || (y.v == x.v && y.i < x.i)) return y;
+    return x;
+}
+__device__ __forceinline__ RKey rk_shfl(const RKey &x, int o)
+{
+    RKey y;
+    y.v = __shfl_xor_sync(0xffffffffu, x.v, o);
+    y.rh = __shfl_xor_sync(0xffffffffu, x.rh, o);
+    y.a = __shfl_xor_sync(0xffffffffu, x.a, o);
+    y.i = __shfl_xor_sync(0xffffffffu, x.i, o);
+    y.bv = __shfl_xor_sync(0xffffffffu, x.bv, o);
+    y.s0 = __shfl_xor_sync(0xffffffffu, x.s0, o);
+    return y;
+}
+// block arg-min of two keys at once; result valid in every thread
+__device__ __forceinline__ void rk_block2(RKey &k1, RKey &k2, RKey *sh /* 2 x 9 */)
+{
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        k1 = rk_better(k1, rk_shfl(k1, o));
+        k2 = rk_better(k2, rk_shfl(k2, o));
+    }
+    __syncthreads();
+    if (lane == 0) {
+        sh[w] = k1;
+        sh[9 + w] = k2;
+    }
+    __syncthreads();
+    if (w == 0) {
+        RKey y1, y2;
+        y1.i = y2.i = -1;
+        y1.v = y2.v = y1.rh = y2.rh = y1.a = y2.a = 0.0;
+        y1.bv = y2.bv = y1.s0 = y2.s0 = 0;
+        if (lane < nw) {
+            y1 = sh[lane];
+            y2 = sh[9 + lane];
+        }
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {
+            y1 = rk_better(y1, rk_shfl(y1, o));
+            y2 = rk_better(y2, rk_shfl(y2, o));
+        }
+        if (lane == 0) {
+            sh[8] = y1;
+            sh[17] = y2;
+        }
+    }
+    __syncthreads();
+    k1 = sh[8];
+    k2 = sh[17];
+}
+
+__device__ __forceinline__ unsigned long long ld_acquire_gpu(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+// Returns false if the other CTAs did not arrive within SPIN_LIMIT (never on a
+// healthy device: the launch is cooperative, all CTAs are resident).
+__device__ __forceinline__ bool grid_barrier(unsigned long long *bar, unsigned long long target)
+{
+    __shared__ int s_ok;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(bar, 1ULL);
+        int ok = 1;
+        const unsigned long long t0 = clock64();
+        unsigned spins = 0;
+        while (ld_acquire_gpu(bar) < target) {
+            if ((++spins & 4095u) == 0 && clock64() - t0 > SPIN_LIMIT) {
+                ok = 0;
+                break;
+            }
+        }
+        s_ok = ok;
+    }
+    __syncthreads();
+    return s_ok != 0;
+}
+
+constexpr int PANEL_NBAR = 2 * KMAX + 2; // barrier arrivals per CTA and launch (padded on exit)
+
+__global__ void __launch_bounds__(TH, 1)
+k_panel(LpDev d, PanA *partA, PanB *partB, unsigned long long *bar, unsigned long long bar_base,
+        int rpc, int cpc, unsigned long long *dbg)
+{
+    extern __shared__ int s_dyn[]; // eq2bv and last_piv of the CTA's rows
+    __shared__ RKey s_rk[18];
+    __shared__ int shi[33];
+    __shared__ double s_c[33];
+    LpState *st = d.st;
+    const int tid = threadIdx.x, c = blockIdx.x, NB = gridDim.x;
+    const int n = d.n, m = d.m, Cl = d.Cl;
+    int nbar = 0;
+    int *s_e2b = s_dyn, *s_lp = s_dyn + rpc;
+    const int r_lo = min(m, c * rpc), r_hi = min(m, r_lo + rpc);
+    const int c_lo = min(Cl, c * cpc), c_hi = min(Cl, c_lo + cpc);
+
+    int t = st->t;
+    const int kblk = st->kblk, par = st->blk & 1;
+    unsigned cnt = st->cnt;
+    const unsigned max_iter = st->max_iter;
+    int q = st->q, zero_upto = st->zero_upto, anypos = st->anypos;
+    const bool go = st->status == XPI_RUNNING && !st->slow && !st->pivot_pending && q != INT_BIG;
+    double tg_rhs = st->tg_rhs;
+    unsigned n_log = st->n_log;
+    int n_touched = st->n_touched;
+    int slow_out = 0;
+    bool dirty = false;
+    if (go) {
+        for (int i = r_lo + tid; i < r_hi; i += TH) {
+            s_e2b[i - r_lo] = d.eq2bv[i];
+            s_lp[i - r_lo] = d.last_piv[i];
+        }
+        __syncthreads();
+    }
+    double cq = go && q < n ? ld_cg(d.tgtf + q) : 0.0; // single GPU: col0 == 0
+#define PANEL_T(k)                                                  \
+    if (dbg && c == 0 && tid == 0) {                                \
+        unsigned long long now__;                                   \
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now__));    \
+        dbg[k] += now__ - tprev;                                    \
+        tprev = now__;                                              \
+    }
+    unsigned long long tprev = 0;
+    if (dbg && c == 0 && tid == 0) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tprev));
+    while (go && t < kblk && cnt < max_iter) {
+        // ================= phase A: entering column, multipliers, ratio test =================
+        double pq[KMAX];
+#pragma unroll
+        for (int s = 0; s < KMAX; s++) pq[s] = s < t ? ld_cg(d.P + (size_t)s * Cl + q) : 0.0;
+        RKey b1, b2;
+        b1.i = b2.i = -1;
+        b1.v = b2.v = b1.rh = b2.rh = b1.a = b2.a = 0.0;
+        b1.bv = b2.bv = b1.s0 = b2.s0 = 0;
+        double *Ft = Fptr(d, 0, par, t);
+        for (int i = r_lo + tid; i < r_hi; i += TH) {
+            const int bv = s_e2b[i - r_lo], s0 = s_lp[i - r_lo];
+            const double a0 = d.tab[(size_t)i * Cl + q];
+            const double rh = d.rhsbuf[i];
+            const uint32_t tw = __ldcg(d.tabu + (size_t)q * d.W + (bv >> 5));
+            const int cc = __ldcg(d.col_cnt + bv);
+            const double *f0 = Fptr(d, 0, par, 0) + i;
+            double f[KMAX];
+#pragma unroll
+            for (int s = 0; s < KMAX; s++) f[s] = s < t ? ld_cg(f0 + (size_t)s * d.mpad) : 0.0;
+            double a = a0;
+#pragma unroll
+            for (int s = 0; s < KMAX; s++) {
+                if (s == s0) a = pq[s];
+                else if (s > s0 && s < t) a = xp_add(a, xp_mul(f[s], pq[s]));
+            }
+            __stcg(Ft + i, -a);
+            if (xp_feq(a, 0.0)) continue;          // neither pass takes a == 0 (tolerant)
+            if ((tw >> (bv & 31)) & 1u) continue;   // is_handle(q, bv), :589
+            if (cc >= n - 1) continue;              // !canBeBVCandidate, :596
+            RKey k;
+            k.v = xp_div(rh, a);
+            k.rh = rh;
+            k.a = a;
+            k.i = i;
+            k.bv = bv;
+            k.s0 = s0;
+            b2 = rk_better(b2, k);            // pass 2, :623-658
+            if (a > 0.0) b1 = rk_better(b1, k); // pass 1, :571-612
+        }
+        PANEL_T(0) // phase A loads + replay
+        rk_block2(b1, b2, s_rk);
+        if (tid == 0) {
+            PanA pa;
+            pa.v1 = b1.v, pa.rh1 = b1.rh, pa.a1 = b1.a, pa.i1 = b1.i, pa.bv1 = b1.bv, pa.s01 = b1.s0;
+            pa.v2 = b2.v, pa.rh2 = b2.rh, pa.a2 = b2.a, pa.i2 = b2.i, pa.bv2 = b2.bv, pa.s02 = b2.s0;
+            PanA *dst = partA + c;
+            __stcg(&dst->v1, pa.v1), __stcg(&dst->rh1, pa.rh1), __stcg(&dst->a1, pa.a1);
+            __stcg(&dst->v2, pa.v2), __stcg(&dst->rh2, pa.rh2), __stcg(&dst->a2, pa.a2);
+            __stcg(&dst->i1, pa.i1), __stcg(&dst->bv1, pa.bv1), __stcg(&dst->s01, pa.s01);
+            __stcg(&dst->i2, pa.i2), __stcg(&dst->bv2, pa.bv2), __stcg(&dst->s02, pa.s02);
+        }
+        PANEL_T(1) // block arg-min + partial store
+        nbar++;
+        if (!grid_barrier(bar, bar_base + (unsigned long long)nbar * NB)) {
+            if (tid == 0) st->status = XP_ERR_PEER;
+            return;
+        }
+        PANEL_T(2) // barrier 1
+        b1.i = b2.i = -1;
+        if (tid < NB) {
+            const PanA *src = partA + tid;
+            b1.v = __ldcg(&src->v1), b1.rh = __ldcg(&src->rh1), b1.a = __ldcg(&src->a1);
+            b1.i = __ldcg(&src->i1), b1.bv = __ldcg(&src->bv1), b1.s0 = __ldcg(&src->s01);
+            b2.v = __ldcg(&src->v2), b2.rh = __ldcg(&src->rh2), b2.a = __ldcg(&src->a2);
+            b2.i = __ldcg(&src->i2), b2.bv = __ldcg(&src->bv2), b2.s0 = __ldcg(&src->s02);
+        }
+        rk_block2(b1, b2, s_rk);
+        PANEL_T(3) // partial reduce
+        const RKey win = b1.i >= 0 ? b1 : b2;
+        if (win.i < 0) break; // ratio test failed: k_pcol redoes this column and takes the slow path
+        const int p = win.i, bv = win.bv, s0p = win.s0;
+        const double r = xp_div(1.0, win.a); // mulOfRow(eqnum, 1 / pivot), :1471
+        const bool r_one = xp_feq(r, 1.0), r_zero = xp_feq(r, 0.0);
+        const bool cq_zero = xp_feq(cq, 0.0), cq_one = xp_feq(cq, 1.0);
+        const double prow_rhs = xp_scale(win.rh, r, r_one, r_zero);
+        // ================= phase B: leaving row, objective row, constant column, pricing ====
+        double fp[KMAX];
+#pragma unroll
+        for (int s = 0; s < KMAX; s++) fp[s] = s < t ? ld_cg(Fptr(d, 0, par, s) + p) : 0.0;
+        int cand = INT_BIG, anyp = 0;
+        double ccand = 0.0;
+        double *Pt = d.P + (size_t)t * Cl;
+        for (int jl = c_lo + tid; jl < c_hi; jl += TH) {
+            const double a0 = d.tab[(size_t)p * Cl + jl];
+            const double tg0 = d.tgtf[jl];
+            const int nvraw = jl < n ? (int)__ldcg(d.nvset + jl) : 0;
+            const int rc = jl < n ? __ldcg(d.row_cnt + jl) : INT_BIG;
+            const double *p0 = d.P + jl;
+            double pr[KMAX];
+#pragma unroll
+            for (int s = 0; s < KMAX; s++) pr[s] = s < t ? ld_cg(p0 + (size_t)s * Cl) : 0.0;
+            double v = a0;
+#pragma unroll
+            for (int s = 0; s < KMAX; s++) {
+                if (s == s0p) v = pr[s];
+                else if (s > s0p && s < t) v = xp_add(v, xp_mul(fp[s], pr[s]));
+            }
+            const double xv = xp_scale(v, r, r_one, r_zero);
+            __stcg(Pt + jl, xv);
+            double tg = tg0;
+            if (jl < zero_upto && jl < n && !nvraw) tg = 0.0;     // zeroing owed by the scan (:1059)
+            double tt = xp_mul(xv, -1.0);                        // nvexp.mul(-1), :1496
+            if (jl >= n) tt = -tt;                               // constant column keeps its sign
+            tt = cq_zero ? 0.0 : (cq_one ? tt : xp_mul(tt, cq)); // nvexp.mul(tgtf[nv])
+            const double tn = xp_add(tt, tg);                    // tgtf.addRowToRow, :1501
+            d.tgtf[jl] = tn;
+            const int nvnew = jl == bv ? 1 : (jl == q ? 0 : nvraw); // basis after the swap
+            if (nvnew && tn > 0.0) { // pricing of the next iteration, :1054-1069
+                anyp = 1;
+                if (cand == INT_BIG && rc < n - 1) {
+                    cand = jl;
+                    ccand = tn;
+                }
+            }
+        }
+        for (int i = r_lo + tid; i < r_hi; i += TH) {
+            const double f = ld_cg(Ft + i);
+            d.rhsbuf[i] = i == p ? prow_rhs : xp_add(d.rhsbuf[i], xp_mul(f, prow_rhs));
+        }
+        PANEL_T(4) // phase B loads + replay + stores
+        if (p >= r_lo && p < r_hi && tid == 0) { // my row caches follow the swap
+            s_e2b[p - r_lo] = q;
+            s_lp[p - r_lo] = t;
+        }
+        {
+            const int mine = cand;
+            cand = xp_block_min_int(cand, shi);
+            anyp = __syncthreads_or(anyp);
+            if (mine == cand && cand != INT_BIG) s_c[32] = ccand; // unique owner of the minimum
+            __syncthreads();
+            if (tid == 0) {
+                PanB *dst = partB + c;
+                __stcg(&dst->c, cand != INT_BIG ? s_c[32] : 0.0);
+                __stcg(&dst->cand, cand);
+                __stcg(&dst->anypos, anyp);
+            }
+        }
+        PANEL_T(5) // block min + partial store
+        nbar++;
+        if (!grid_barrier(bar, bar_base + (unsigned long long)nbar * NB)) {
+            if (tid == 0) st->status = XP_ERR_PEER;
+            return;
+        }
+        PANEL_T(6) // barrier 2
+        {
+            int cd = INT_BIG, ap = 0;
+            double cv = 0.0;
+            if (tid < NB) {
+                const PanB *src = partB + tid;
+                cd = __ldcg(&src->cand);
+                ap = __ldcg(&src->anypos);
+                cv = __ldcg(&src->c);
+            }
+            const int mine = cd;
+            cd = xp_block_min_int(cd, shi);
+            ap = __syncthreads_or(ap);
+            if (mine == cd && cd != INT_BIG) s_c[32] = cv;
+            __syncthreads();
+            // ---- CTA 0 keeps the books of this pivot while the others move on ----
+            if (c == 0 && tid == 0) {
+                uint32_t *w = &d.tabu[(size_t)q * d.W + (bv >> 5)]; // genPair, :1156
+                const uint32_t bit = 1u << (bv & 31);
+                if (!(*w & bit)) {
+                    *w |= bit;
+                    d.row_cnt[q] += 1;
+                    d.col_cnt[bv] += 1;
+                }
+                if (n_log < d.log_cap) {
+                    d.log[3 * n_log] = q;
+                    d.log[3 * n_log + 1] = bv;
+                    d.log[3 * n_log + 2] = p;
+                }
+                n_log++;
+                d.nvset[q] = 0; // :1504-1510
+                d.nvset[bv] = 1;
+                d.eq2bv[p] = q;
+                d.bv2eq[q] = p;
+                d.bv2eq[bv] = -1;
+                d.last_piv[p] = t;
+                if (s0p < 0) st->touched[n_touched++] = p;
+                double tt = -xp_mul(prow_rhs, -1.0); // replica of the objective row's constant term
+                tt = cq_zero ? 0.0 : (cq_one ? tt : xp_mul(tt, cq));
+                tg_rhs = xp_add(tt, tg_rhs);
+            }
+            PANEL_T(7) // partial reduce + bookkeeping
+            if (dbg && c == 0 && tid == 0) dbg[15] += 1;
+            t++;
+            cnt++;
+            dirty = true;
+            q = cd;
+            anypos = ap;
+            cq = cd != INT_BIG ? s_c[32] : 0.0;
+            zero_upto = cd == INT_BIG ? n : cd;
+            __syncthreads();
+            if (cd == INT_BIG) { // no eligible candidate: the slow path re-prices (optimum / pair search)
+                slow_out = 1;
+                break;
+            }
+        }
+    }
+    if (c == 0 && tid == 0 && dirty) {
+        st->t = t;
+        st->cnt = cnt;
+        st->q = q;
+        st->anypos = anypos;
+        st->zero_upto = zero_upto;
+        st->slow = slow_out;
+        st->tg_rhs = tg_rhs;
+        st->n_log = n_log;
+        st->n_touched = n_touched;
+    }
+    if (tid == 0 && nbar < PANEL_NBAR) { // keep the barrier counter in step with the host's base
+        __threadfence();
+        atomicAdd(bar, (unsigned long long)(PANEL_NBAR - nbar));
+    }
+}
+
+// ---------------------------------------------------------------------------
 // k_flush: apply the t pending pivots to the tableau slice.
 // Each thread owns VEC adjacent columns and keeps P[0..KB)[cols] in registers;
 // the CTA walks `rows_per_cta` rows whose multipliers sit in shared memory.
@@ -784,6 +1180,183 @@ __global__ void __launch_bounds__(THREADS) k_flush(LpDev d, int rows_per_cta)
     __syncthreads();
     if (!s_flag) return;
     if (threadIdx.x == 0) {
+        d.ctr[2] = 0;
+        for (int k = 0; k < st->n_touched; k++) d.last_piv[st->touched[k]] = -1;
+        st->n_touched = 0;
+        st->t = 0;
+        st->blk += 1;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// k_flush_t: the same update with the operands of the rank-t recurrence in
+// shared memory (any t <= KMAX, no per-t register blocking): a CTA of THREADS
+// threads owns 2*THREADS adjacent columns, keeps P[0..t)[its columns] in shared
+// memory for its whole life, and walks its row group 64 rows at a time with the
+// rows' multipliers staged beside it; each thread carries a TR x 2 register
+// tile of tableau entries through the t steps (one 128-bit shared load of P and
+// TR/2 broadcast loads of F per step for 4*TR non-fused FP64 operations).
+// ---------------------------------------------------------------------------
+constexpr int FT_ROWS = 64; // rows staged per __syncthreads pair
+
+// THREADS = HALVES * LANES: LANES threads span a tile's 2*LANES columns, and the
+// HALVES thread groups take alternate TR-row tiles of the staged rows, sharing
+// the P tile (more warps per byte of shared memory).  Work units are
+// (column tile, block of FT_ROWS rows); every CTA takes one contiguous,
+// equally sized run of units, so the grid is exactly one resident wave, all
+// SMs finish together, and a CTA reloads its P tile at most once.  The
+// multipliers of unit u+1 and the tableau entries of the next tile are in
+// flight while the current tile runs its t steps.
+template <int TR, int LANES, int HALVES>
+__global__ void __launch_bounds__(LANES *HALVES) k_flush_t(LpDev d, int groups)
+{
+    extern __shared__ double sm[]; // sP[t][2*LANES] | sF[2][t][FT_ROWS] | s_lp[2][FT_ROWS]
+    __shared__ int s_flag;
+    constexpr int THREADS = LANES * HALVES, TC = 2 * LANES;
+    constexpr int TPB = FT_ROWS / (HALVES * TR); // tiles per unit and half
+    constexpr int FREG = (KMAX * FT_ROWS + THREADS - 1) / THREADS;
+    LpState *st = d.st;
+    const int t = st->t;
+    if (t == 0) return;
+    if (t < st->kblk && st->status == XPI_RUNNING) return; // block still open
+    const int par = st->blk & 1, Cl = d.Cl, m = d.m, tid = threadIdx.x;
+    const int lane = tid % LANES, half = tid / LANES;
+    double *sP = sm, *sF = sm + (size_t)t * TC;
+    int *s_lp = (int *)(sF + (size_t)2 * t * FT_ROWS);
+    const double *sPl = sP + 2 * lane;
+    const int nrb = (m + FT_ROWS - 1) / FT_ROWS;
+    const int ctiles = (Cl + TC - 1) / TC;
+    const long long units = (long long)ctiles * nrb;
+    int u0, u1;
+    if (groups > 0) { // HBM-bound regime: CTA = (column tile, row group); groups advance in step
+        const int ct = blockIdx.x % ctiles, g = blockIdx.x / ctiles;
+        const int bpg = (nrb + groups - 1) / groups;
+        u0 = ct * nrb + min(nrb, g * bpg);
+        u1 = ct * nrb + min(nrb, (g + 1) * bpg);
+    } else { // FP64-bound regime: equal contiguous runs, one resident wave, no idle SM
+        u0 = (int)(units * blockIdx.x / gridDim.x);
+        u1 = (int)(units * (blockIdx.x + 1) / gridDim.x);
+    }
+
+    auto load_P = [&](int ct) {
+        for (int e = tid; e < t * LANES; e += THREADS) {
+            const int s = e / LANES, l = e - s * LANES;
+            const int j = ct * TC + 2 * l;
+            double2 v = make_double2(0.0, 0.0);
+            if (j < Cl) v = *reinterpret_cast<const double2 *>(d.P + (size_t)s * Cl + j);
+            *reinterpret_cast<double2 *>(sP + (size_t)s * TC + 2 * l) = v;
+        }
+    };
+    // multipliers + pivot-row marks of unit u: global -> registers -> shared buffer (u & 1)
+    double freg[FREG];
+    int lpreg = -1;
+    auto fetch_F = [&](int u) {
+        const int rb = (u % nrb) * FT_ROWS;
+#pragma unroll
+        for (int k = 0; k < FREG; k++) {
+            const int e = tid + k * THREADS;
+            const int s = e / FT_ROWS, r = e - s * FT_ROWS;
+            freg[k] = (e < t * FT_ROWS && rb + r < m) ? ld_cg(Fptr(d, d.rank, par, s) + rb + r) : 0.0;
+        }
+        if (tid < FT_ROWS) lpreg = rb + tid < m ? d.last_piv[rb + tid] : -1;
+    };
+    auto store_F = [&](int u) {
+        double *dst = sF + (size_t)(u & 1) * t * FT_ROWS;
+#pragma unroll
+        for (int k = 0; k < FREG; k++) {
+            const int e = tid + k * THREADS;
+            if (e < t * FT_ROWS) dst[e] = freg[k];
+        }
+        if (tid < FT_ROWS) s_lp[(u & 1) * FT_ROWS + tid] = lpreg;
+    };
+    // tile k (0..TPB) of unit u: first row and first column of this thread
+    double2 nx[TR];
+    auto load_tile = [&](int u, int k) {
+        const int ct = u / nrb;
+        const int r = (u % nrb) * FT_ROWS + (k * HALVES + half) * TR;
+        const int j = ct * TC + 2 * lane;
+#pragma unroll
+        for (int w = 0; w < TR; w++)
+            nx[w] = (j < Cl && r + w < m) ? *reinterpret_cast<const double2 *>(d.tab + (size_t)(r + w) * Cl + j)
+                                          : make_double2(0.0, 0.0);
+    };
+    if (u0 < u1) {
+        load_P(u0 / nrb);
+        fetch_F(u0);
+        store_F(u0);
+        load_tile(u0, 0);
+    }
+    __syncthreads();
+    for (int u = u0; u < u1; u++) {
+        const int ct = u / nrb, rb = (u % nrb) * FT_ROWS;
+        const int j0 = ct * TC + 2 * lane;
+        const bool active = j0 < Cl; // Cl is even on this path
+        const double *sFu = sF + (size_t)(u & 1) * t * FT_ROWS;
+        const int *lpu = s_lp + (u & 1) * FT_ROWS;
+        const bool more = u + 1 < u1;
+        if (more) fetch_F(u + 1);
+        for (int k = 0; k < TPB; k++) {
+            double2 a[TR];
+#pragma unroll
+            for (int w = 0; w < TR; w++) a[w] = nx[w];
+            if (k + 1 < TPB) load_tile(u, k + 1);
+            else if (more) load_tile(u + 1, 0);
+            const int rc = (k * HALVES + half) * TR, row = rb + rc;
+            if (!active || row >= m) continue;
+            bool special = false;
+#pragma unroll
+            for (int w = 0; w < TR; w++) special |= (row + w < m) && lpu[rc + w] >= 0;
+            if (!special) {
+#pragma unroll 4
+                for (int s = 0; s < t; s++) {
+                    const double2 p2 = *reinterpret_cast<const double2 *>(sPl + (size_t)s * TC);
+                    const double *f = sFu + (size_t)s * FT_ROWS + rc;
+#pragma unroll
+                    for (int w = 0; w < TR; w += 2) {
+                        const double2 f2 = *reinterpret_cast<const double2 *>(f + w);
+                        a[w].x = xp_add(a[w].x, xp_mul(f2.x, p2.x));
+                        a[w].y = xp_add(a[w].y, xp_mul(f2.x, p2.y));
+                        a[w + 1].x = xp_add(a[w + 1].x, xp_mul(f2.y, p2.x));
+                        a[w + 1].y = xp_add(a[w + 1].y, xp_mul(f2.y, p2.y));
+                    }
+                }
+            } else { // a row of this tile was a pivot row at step s0: restart it from P[s0]
+#pragma unroll
+                for (int w = 0; w < TR; w++) {
+                    if (row + w >= m) continue;
+                    const int s0 = lpu[rc + w];
+                    double2 v = a[w];
+                    if (s0 >= 0) v = *reinterpret_cast<const double2 *>(sPl + (size_t)s0 * TC);
+                    for (int s = s0 + 1; s < t; s++) {
+                        const double2 p2 = *reinterpret_cast<const double2 *>(sPl + (size_t)s * TC);
+                        const double fs = sFu[(size_t)s * FT_ROWS + rc + w];
+                        v.x = xp_add(v.x, xp_mul(fs, p2.x));
+                        v.y = xp_add(v.y, xp_mul(fs, p2.y));
+                    }
+                    a[w] = v;
+                }
+            }
+#pragma unroll
+            for (int w = 0; w < TR; w++)
+                if (row + w < m) *reinterpret_cast<double2 *>(d.tab + (size_t)(row + w) * Cl + j0) = a[w];
+        }
+        if (more) {
+            store_F(u + 1); // the other buffer: nobody reads it during this unit
+            if ((u + 1) / nrb != ct) { // next unit starts a new column tile: swap the P tile
+                __syncthreads();
+                load_P((u + 1) / nrb);
+            }
+        }
+        __syncthreads();
+    }
+    // the last CTA closes the block
+    if (tid == 0) {
+        __threadfence();
+        s_flag = atomicAdd(&d.ctr[2], 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!s_flag) return;
+    if (tid == 0) {
         d.ctr[2] = 0;
         for (int k = 0; k < st->n_touched; k++) d.last_piv[st->touched[k]] = -1;
         st->n_touched = 0;
@@ -1053,6 +1626,14 @@ struct xp_lp_f64 {
     void *peer_map[MAXR] = {nullptr}; // IPC mappings to close
     bool attached = false;
     int kblk = 0; // 0: automatic
+    // persistent panel kernel (single GPU)
+    PanA *panA = nullptr;
+    PanB *panB = nullptr;
+    unsigned long long *bar = nullptr, bar_base = 0;
+    int panel_nb = 0, panel_rpc = 0, panel_cpc = 0;
+    bool use_panel = true;
+    int ft_min = 2, ft_balanced_min = 10, ft_smem_set = 0, ft_occ = 1, ft_occ_k = -1; // k_flush_t: smallest k that uses it, launch cache
+    unsigned long long *panel_dbg = nullptr; // XP_PANEL_DBG=1: per-phase ns accumulators (16 words)
     // optional per-launch timing of the flush kernel (CUDA events on the ctx stream)
     bool profile = false;
     std::vector<cudaEvent_t> evs;
@@ -1088,10 +1669,52 @@ static void flush_launch_kb(xp_ctx *ctx, const LpDev &d)
     ctx->launches++;
 }
 
-static void flush_launch(xp_lp_f64 *lp, int kblk)
+constexpr int FT_TR = 8, FT_LANES = 128, FT_HALVES = 2, FT_THREADS = FT_LANES * FT_HALVES;
+
+static size_t flush_t_smem(int kblk)
+{
+    return ((size_t)kblk * 2 * FT_LANES + (size_t)2 * kblk * FT_ROWS) * sizeof(double) + 2 * FT_ROWS * sizeof(int);
+}
+
+static int flush_t_launch(xp_lp_f64 *lp, int kblk)
 {
     xp_ctx *ctx = lp->ctx;
     const LpDev &d = lp->d;
+    const size_t smem = flush_t_smem(kblk);
+    if (lp->ft_smem_set < (int)smem) {
+        XP_CUDA_OK(ctx, cudaFuncSetAttribute(k_flush_t<FT_TR, FT_LANES, FT_HALVES>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)flush_t_smem(KMAX)));
+        lp->ft_smem_set = (int)flush_t_smem(KMAX);
+    }
+    if (lp->ft_occ_k != kblk) {
+        int occ = 1;
+        XP_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_flush_t<FT_TR, FT_LANES, FT_HALVES>,
+                                                                      FT_THREADS, smem));
+        lp->ft_occ = occ < 1 ? 1 : occ;
+        lp->ft_occ_k = kblk;
+    }
+    const int ctiles = (d.Cl + 2 * FT_LANES - 1) / (2 * FT_LANES);
+    const long long units = (long long)ctiles * ((d.m + FT_ROWS - 1) / FT_ROWS);
+    long long grid = (long long)lp->ft_occ * ctx->sm_count; // exactly one resident wave
+    if (grid > units) grid = units;
+    int groups = 0;
+    if (kblk < lp->ft_balanced_min) { // memory-bound: row groups that move through the rows together
+        groups = (int)(grid / ctiles);
+        const int nrb = (d.m + FT_ROWS - 1) / FT_ROWS;
+        if (groups < 1) groups = 1;
+        if (groups > nrb) groups = nrb;
+        grid = (long long)groups * ctiles;
+    }
+    k_flush_t<FT_TR, FT_LANES, FT_HALVES><<<(unsigned)grid, FT_THREADS, smem, ctx->stream>>>(d, groups);
+    ctx->launches++;
+    return 0;
+}
+
+static int flush_launch(xp_lp_f64 *lp, int kblk)
+{
+    xp_ctx *ctx = lp->ctx;
+    const LpDev &d = lp->d;
+    if ((d.Cl & 1) == 0 && kblk >= lp->ft_min) return flush_t_launch(lp, kblk);
     if (kblk <= 1) flush_launch_kb<1>(ctx, d);
     else if (kblk <= 2) flush_launch_kb<2>(ctx, d);
     else if (kblk <= 4) flush_launch_kb<4>(ctx, d);
@@ -1100,6 +1723,7 @@ static void flush_launch(xp_lp_f64 *lp, int kblk)
     else if (kblk <= 16) flush_launch_kb<16>(ctx, d);
     else if (kblk <= 24) flush_launch_kb<24>(ctx, d);
     else flush_launch_kb<32>(ctx, d);
+    return 0;
 }
 
 template <int KB>
@@ -1159,6 +1783,32 @@ static int lp_create(xp_ctx *ctx, int m, int C, int rank, int G, xp_lp_f64 **out
     ALLOC(d.st, sizeof(LpState));
     ALLOC(lp->xblock, xblock_bytes(d));
 #undef ALLOC
+    {
+        int span2 = d.Cl > m ? d.Cl : m;
+        int nb = (span2 + TH - 1) / TH;
+        const char *e = getenv("XP_PANEL_CTAS");
+        int cap = e ? atoi(e) : 64;
+        if (cap < 1) cap = 1;
+        if (cap > 128) cap = 128;
+        lp->panel_nb = nb < 1 ? 1 : (nb > cap ? cap : nb);
+        lp->panel_rpc = (m + lp->panel_nb - 1) / lp->panel_nb;
+        lp->panel_cpc = (d.Cl + lp->panel_nb - 1) / lp->panel_nb;
+        const char *fm = getenv("XP_FLUSH_T_MIN");
+        if (fm) lp->ft_min = atoi(fm);
+        const char *fb = getenv("XP_FLUSH_BALANCED_MIN");
+        if (fb) lp->ft_balanced_min = atoi(fb);
+        const char *u = getenv("XP_NO_PANEL");
+        lp->use_panel = G == 1 && !(u && atoi(u));
+        XP_CUDA_OK(ctx, cudaMalloc((void **)&lp->panA, 128 * sizeof(PanA)));
+        XP_CUDA_OK(ctx, cudaMalloc((void **)&lp->panB, 128 * sizeof(PanB)));
+        XP_CUDA_OK(ctx, cudaMalloc((void **)&lp->bar, 64));
+        XP_CUDA_OK(ctx, cudaMemset(lp->bar, 0, 64));
+        const char *dbg = getenv("XP_PANEL_DBG");
+        if (dbg && atoi(dbg)) {
+            XP_CUDA_OK(ctx, cudaMalloc((void **)&lp->panel_dbg, 128));
+            XP_CUDA_OK(ctx, cudaMemset(lp->panel_dbg, 0, 128));
+        }
+    }
     XP_CUDA_OK(ctx, cudaMemset(d.st, 0, sizeof(LpState)));
     XP_CUDA_OK(ctx, cudaMemset(d.ctr, 0, 64));
     XP_CUDA_OK(ctx, cudaMemset(d.last_piv, 0xff, m * sizeof(int32_t)));
@@ -1171,6 +1821,8 @@ static int lp_create(xp_ctx *ctx, int m, int C, int rank, int G, xp_lp_f64 **out
     cudaFuncAttributes fa;
     XP_CUDA_OK(ctx, cudaFuncGetAttributes(&fa, k_pcol));
     XP_CUDA_OK(ctx, cudaFuncGetAttributes(&fa, k_prow));
+    XP_CUDA_OK(ctx, cudaFuncGetAttributes(&fa, k_panel));
+    XP_CUDA_OK(ctx, cudaFuncGetAttributes(&fa, k_flush_t<FT_TR, FT_LANES, FT_HALVES>));
     XP_CUDA_OK(ctx, cudaFuncGetAttributes(&fa, k_init));
     XP_CUDA_OK(ctx, cudaFuncGetAttributes(&fa, k_feas_sol));
     XP_CUDA_OK(ctx, cudaFuncGetAttributes(&fa, k_feas_rows));
@@ -1283,6 +1935,20 @@ extern "C" void xp_lp_f64_destroy(xp_lp_f64 *lp)
                     d.nvset, d.bv2eq,    d.eq2bv, d.tabu,   d.row_cnt, d.col_cnt,   d.log,
                     d.st,    d.last_piv, d.partA, d.partB,  d.ctr,     lp->xblock};
     for (void *p : ptrs) cudaFree(p);
+    cudaFree(lp->panA);
+    cudaFree(lp->panB);
+    cudaFree(lp->bar);
+    if (lp->panel_dbg) {
+        unsigned long long h[16];
+        cudaMemcpy(h, lp->panel_dbg, 128, cudaMemcpyDeviceToHost);
+        if (h[15])
+            fprintf(stderr,
+                    "[xp panel] steps %llu: A %.2f  argminA %.2f  bar1 %.2f  redA %.2f  B %.2f  minB %.2f  "
+                    "bar2 %.2f  redB+book %.2f us/step\n",
+                    h[15], h[0] / 1e3 / h[15], h[1] / 1e3 / h[15], h[2] / 1e3 / h[15], h[3] / 1e3 / h[15],
+                    h[4] / 1e3 / h[15], h[5] / 1e3 / h[15], h[6] / 1e3 / h[15], h[7] / 1e3 / h[15]);
+        cudaFree(lp->panel_dbg);
+    }
     for (cudaEvent_t e : lp->evs) cudaEventDestroy(e);
     cudaFreeHost(lp->h_st);
     delete lp;
@@ -1378,6 +2044,21 @@ extern "C" int xp_lp_f64_fill_synthetic(xp_lp_f64 *lp, uint64_t seed)
     return lp_reset(lp);
 }
 
+static cudaError_t panel_launch(xp_lp_f64 *lp)
+{
+    LpDev d = lp->d;
+    PanA *pa = lp->panA;
+    PanB *pb = lp->panB;
+    unsigned long long *bar = lp->bar;
+    unsigned long long base = lp->bar_base;
+    int rpc = lp->panel_rpc, cpc = lp->panel_cpc;
+    unsigned long long *dbg = lp->panel_dbg;
+    void *args[] = {&d, &pa, &pb, &bar, &base, &rpc, &cpc, &dbg};
+    lp->bar_base += (unsigned long long)PANEL_NBAR * lp->panel_nb;
+    return cudaLaunchCooperativeKernel((void *)k_panel, dim3(lp->panel_nb), dim3(TH), args,
+                                       (size_t)2 * rpc * sizeof(int), lp->ctx->stream);
+}
+
 extern "C" int xp_lp_f64_solve(xp_lp_f64 *lp, uint32_t max_iter, int rule)
 {
     if (!lp) return XP_ERR_BAD_ARG;
@@ -1401,14 +2082,27 @@ extern "C" int xp_lp_f64_solve(xp_lp_f64 *lp, uint32_t max_iter, int rule)
     int n_prof = 0; // flushes bracketed by events in this call
     for (;;) {
         for (int b = 0; b < blocks; b++) {
-            for (int k = 0; k < kblk; k++) {
+            if (lp->use_panel) {
+                // fast path: all pivots of the block in one persistent kernel; the pair in
+                // the middle takes whatever single pivot needs the slow path
+                XP_CUDA_OK(ctx, panel_launch(lp));
                 k_pcol<<<d.gridA, TH, 0, s>>>(d);
                 k_prow<<<d.gridB, TH, 0, s>>>(d);
+                XP_CUDA_OK(ctx, panel_launch(lp));
+                ctx->launches += 4;
+            } else {
+                for (int k = 0; k < kblk; k++) {
+                    k_pcol<<<d.gridA, TH, 0, s>>>(d);
+                    k_prow<<<d.gridB, TH, 0, s>>>(d);
+                }
+                ctx->launches += 2 * kblk;
             }
-            ctx->launches += 2 * kblk;
             const bool prof = lp->profile && n_prof < PROF_MAX_SWEEPS;
             if (prof) XP_CUDA_OK(ctx, cudaEventRecord(lp->evs[2 * n_prof], s));
-            flush_launch(lp, kblk);
+            {
+                int frc = flush_launch(lp, kblk);
+                if (frc) return frc;
+            }
             if (prof) {
                 XP_CUDA_OK(ctx, cudaEventRecord(lp->evs[2 * n_prof + 1], s));
                 n_prof++;
