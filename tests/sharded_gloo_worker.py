@@ -114,7 +114,7 @@ def solve_sharded(sf, rank, world, max_iter):
         r1, r0 = feq(r, 1.0), feq(r, 0.0)
         c1, c0 = feq(cq, 1.0), feq(cq, 0.0)
         def sc(x):  # Matrix::mulOfRow short-circuits, matt.h:1358-1367
-            return x if r1 else (x * 0.0 if r0 else x * r)
+            return x if r1 else (np.zeros_like(x) if r0 else x * r)
         prow = sc(T[p].copy())
         prow_rhs = float(sc(np.float64(rhs[p])))
         f = -col[:m]

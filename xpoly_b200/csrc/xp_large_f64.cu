@@ -794,12 +794,14 @@ __device__ __forceinline__ unsigned long long ld_acquire_gpu(const unsigned long
 }
 // Returns false if the other CTAs did not arrive within SPIN_LIMIT (never on a
 // healthy device: the launch is cooperative, all CTAs are resident).
-__device__ __forceinline__ bool grid_barrier(unsigned long long *bar, unsigned long long target)
+__device__ __forceinline__ bool grid_barrier(unsigned long long *bar, unsigned long long target,
+                                             bool sys_fence = false)
 {
     __shared__ int s_ok;
     __syncthreads();
     if (threadIdx.x == 0) {
-        __threadfence();
+        if (sys_fence) __threadfence_system(); // this CTA wrote into peer GPUs
+        else __threadfence();
         atomicAdd(bar, 1ULL);
         int ok = 1;
         const unsigned long long t0 = clock64();
@@ -852,7 +854,10 @@ k_panel(LpDev d, PanA *partA, PanB *partB, unsigned long long *bar, unsigned lon
         }
         __syncthreads();
     }
-    double cq = go && q < n ? ld_cg(d.tgtf + q) : 0.0; // single GPU: col0 == 0
+    const int G = d.G, col0 = d.col0;
+    unsigned xseq = st->xseq, cseq = st->cseq;
+    // c_q: one GPU carries it from the pricing partials; sharded, it travels with the column
+    double cq = (go && G == 1 && q < n) ? ld_cg(d.tgtf + q) : 0.0;
 #define PANEL_T(k)                                                  \
     if (dbg && c == 0 && tid == 0) {                                \
         unsigned long long now__;                                   \
@@ -864,31 +869,61 @@ k_panel(LpDev d, PanA *partA, PanB *partB, unsigned long long *bar, unsigned lon
     if (dbg && c == 0 && tid == 0) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tprev));
     while (go && t < kblk && cnt < max_iter) {
         // ================= phase A: entering column, multipliers, ratio test =================
+        const int owner = owner_of(d, q);
+        const bool mine = owner == d.rank;
+        const int ql = q - col0;
+        cseq++;
+        if (!mine) { // the owner's k_panel pushes F[t] into my exchange block, then raises its flag
+            __shared__ int s_to;
+            if (tid == 0) {
+                const unsigned long long *w =
+                    (const unsigned long long *)(d.xb[d.rank] + offsetof(XHdr, colflag)) + owner;
+                const unsigned long long t0 = clock64();
+                unsigned spins = 0;
+                int ok = 1;
+                while (ld_acquire_sys(w) < cseq)
+                    if ((++spins & 1023u) == 0 && clock64() - t0 > SPIN_LIMIT) {
+                        ok = 0;
+                        break;
+                    }
+                s_to = ok;
+            }
+            __syncthreads();
+            if (!s_to) {
+                if (tid == 0) st->status = XP_ERR_PEER;
+                return;
+            }
+        }
         double pq[KMAX];
 #pragma unroll
-        for (int s = 0; s < KMAX; s++) pq[s] = s < t ? ld_cg(d.P + (size_t)s * Cl + q) : 0.0;
+        for (int s = 0; s < KMAX; s++) pq[s] = (mine && s < t) ? ld_cg(d.P + (size_t)s * Cl + ql) : 0.0;
         RKey b1, b2;
         b1.i = b2.i = -1;
         b1.v = b2.v = b1.rh = b2.rh = b1.a = b2.a = 0.0;
         b1.bv = b2.bv = b1.s0 = b2.s0 = 0;
-        double *Ft = Fptr(d, 0, par, t);
+        double *Ft = Fptr(d, d.rank, par, t);
         for (int i = r_lo + tid; i < r_hi; i += TH) {
             const int bv = s_e2b[i - r_lo], s0 = s_lp[i - r_lo];
-            const double a0 = d.tab[(size_t)i * Cl + q];
+            const double a0 = mine ? d.tab[(size_t)i * Cl + ql] : 0.0;
             const double rh = d.rhsbuf[i];
             const uint32_t tw = __ldcg(d.tabu + (size_t)q * d.W + (bv >> 5));
             const int cc = __ldcg(d.col_cnt + bv);
-            const double *f0 = Fptr(d, 0, par, 0) + i;
-            double f[KMAX];
+            double a;
+            if (mine) {
+                const double *f0 = Fptr(d, d.rank, par, 0) + i;
+                double f[KMAX];
 #pragma unroll
-            for (int s = 0; s < KMAX; s++) f[s] = s < t ? ld_cg(f0 + (size_t)s * d.mpad) : 0.0;
-            double a = a0;
+                for (int s = 0; s < KMAX; s++) f[s] = s < t ? ld_cg(f0 + (size_t)s * d.mpad) : 0.0;
+                a = a0;
 #pragma unroll
-            for (int s = 0; s < KMAX; s++) {
-                if (s == s0) a = pq[s];
-                else if (s > s0 && s < t) a = xp_add(a, xp_mul(f[s], pq[s]));
+                for (int s = 0; s < KMAX; s++) {
+                    if (s == s0) a = pq[s];
+                    else if (s > s0 && s < t) a = xp_add(a, xp_mul(f[s], pq[s]));
+                }
+                for (int r = 0; r < G; r++) __stcg(Fptr(d, r, par, t) + i, -a);
+            } else {
+                a = -ld_cg(Ft + i);
             }
-            __stcg(Ft + i, -a);
             if (xp_feq(a, 0.0)) continue;          // neither pass takes a == 0 (tolerant)
             if ((tw >> (bv & 31)) & 1u) continue;   // is_handle(q, bv), :589
             if (cc >= n - 1) continue;              // !canBeBVCandidate, :596
@@ -901,6 +936,10 @@ k_panel(LpDev d, PanA *partA, PanB *partB, unsigned long long *bar, unsigned lon
             k.s0 = s0;
             b2 = rk_better(b2, k);            // pass 2, :623-658
             if (a > 0.0) b1 = rk_better(b1, k); // pass 1, :571-612
+        }
+        if (G > 1 && mine && c == 0 && tid == 0) {
+            const double cqv = d.tgtf[ql];
+            for (int r = 0; r < G; r++) __stcg(Fptr(d, r, par, t) + m, cqv);
         }
         PANEL_T(0) // phase A loads + replay
         rk_block2(b1, b2, s_rk);
@@ -916,10 +955,13 @@ k_panel(LpDev d, PanA *partA, PanB *partB, unsigned long long *bar, unsigned lon
         }
         PANEL_T(1) // block arg-min + partial store
         nbar++;
-        if (!grid_barrier(bar, bar_base + (unsigned long long)nbar * NB)) {
+        if (!grid_barrier(bar, bar_base + (unsigned long long)nbar * NB, G > 1 && mine)) {
             if (tid == 0) st->status = XP_ERR_PEER;
             return;
         }
+        if (G > 1 && mine && c == 0 && tid < G && tid != d.rank) // every CTA's column chunk has landed
+            st_release_sys((unsigned long long *)(d.xb[tid] + offsetof(XHdr, colflag)) + d.rank, cseq);
+        if (G > 1) cq = ld_cg(Ft + m);
         PANEL_T(2) // barrier 1
         b1.i = b2.i = -1;
         if (tid < NB) {
@@ -946,10 +988,11 @@ k_panel(LpDev d, PanA *partA, PanB *partB, unsigned long long *bar, unsigned lon
         double ccand = 0.0;
         double *Pt = d.P + (size_t)t * Cl;
         for (int jl = c_lo + tid; jl < c_hi; jl += TH) {
+            const int g = col0 + jl; // global column index
             const double a0 = d.tab[(size_t)p * Cl + jl];
             const double tg0 = d.tgtf[jl];
-            const int nvraw = jl < n ? (int)__ldcg(d.nvset + jl) : 0;
-            const int rc = jl < n ? __ldcg(d.row_cnt + jl) : INT_BIG;
+            const int nvraw = g < n ? (int)__ldcg(d.nvset + g) : 0;
+            const int rc = g < n ? __ldcg(d.row_cnt + g) : INT_BIG;
             const double *p0 = d.P + jl;
             double pr[KMAX];
 #pragma unroll
@@ -963,17 +1006,17 @@ k_panel(LpDev d, PanA *partA, PanB *partB, unsigned long long *bar, unsigned lon
             const double xv = xp_scale(v, r, r_one, r_zero);
             __stcg(Pt + jl, xv);
             double tg = tg0;
-            if (jl < zero_upto && jl < n && !nvraw) tg = 0.0;     // zeroing owed by the scan (:1059)
+            if (g < zero_upto && g < n && !nvraw) tg = 0.0;      // zeroing owed by the scan (:1059)
             double tt = xp_mul(xv, -1.0);                        // nvexp.mul(-1), :1496
-            if (jl >= n) tt = -tt;                               // constant column keeps its sign
+            if (g >= n) tt = -tt;                                // constant column keeps its sign
             tt = cq_zero ? 0.0 : (cq_one ? tt : xp_mul(tt, cq)); // nvexp.mul(tgtf[nv])
             const double tn = xp_add(tt, tg);                    // tgtf.addRowToRow, :1501
             d.tgtf[jl] = tn;
-            const int nvnew = jl == bv ? 1 : (jl == q ? 0 : nvraw); // basis after the swap
+            const int nvnew = g == bv ? 1 : (g == q ? 0 : nvraw); // basis after the swap
             if (nvnew && tn > 0.0) { // pricing of the next iteration, :1054-1069
                 anyp = 1;
                 if (cand == INT_BIG && rc < n - 1) {
-                    cand = jl;
+                    cand = g;
                     ccand = tn;
                 }
             }
@@ -1016,11 +1059,32 @@ k_panel(LpDev d, PanA *partA, PanB *partB, unsigned long long *bar, unsigned lon
                 ap = __ldcg(&src->anypos);
                 cv = __ldcg(&src->c);
             }
-            const int mine = cd;
+            const int mycd = cd;
             cd = xp_block_min_int(cd, shi);
             ap = __syncthreads_or(ap);
-            if (mine == cd && cd != INT_BIG) s_c[32] = cv;
+            if (mycd == cd && cd != INT_BIG) s_c[32] = cv;
             __syncthreads();
+            if (G > 1) { // all-ranks arg-min: one 8-byte word per rank, lowest index wins
+                xseq++;
+                const size_t off = offsetof(XHdr, cand) + (size_t)(xseq & 1) * MAXR * 8;
+                if (c == 0 && tid < G)
+                    st_release_sys((unsigned long long *)(d.xb[tid] + off) + d.rank,
+                                   ((unsigned long long)xseq << 32) | ((unsigned long long)(ap ? 1u : 0u) << 31) |
+                                       (unsigned long long)(unsigned)cd);
+                const unsigned seq = xseq;
+                if (!wait_words(d, off, 0, G, [seq](unsigned long long v) { return (unsigned)(v >> 32) == seq; })) {
+                    if (tid == 0) st->status = XP_ERR_PEER;
+                    return;
+                }
+                const unsigned long long *wp = (const unsigned long long *)(d.xb[d.rank] + off);
+                cd = INT_BIG;
+                ap = 0;
+                for (int r = 0; r < G; r++) {
+                    const unsigned long long v = ld_acquire_sys(wp + r);
+                    cd = min(cd, (int)(v & 0x7fffffffu));
+                    ap |= (int)((v >> 31) & 1u);
+                }
+            }
             // ---- CTA 0 keeps the books of this pivot while the others move on ----
             if (c == 0 && tid == 0) {
                 uint32_t *w = &d.tabu[(size_t)q * d.W + (bv >> 5)]; // genPair, :1156
@@ -1054,7 +1118,7 @@ k_panel(LpDev d, PanA *partA, PanB *partB, unsigned long long *bar, unsigned lon
             dirty = true;
             q = cd;
             anypos = ap;
-            cq = cd != INT_BIG ? s_c[32] : 0.0;
+            if (G == 1) cq = cd != INT_BIG ? s_c[32] : 0.0;
             zero_upto = cd == INT_BIG ? n : cd;
             __syncthreads();
             if (cd == INT_BIG) { // no eligible candidate: the slow path re-prices (optimum / pair search)
@@ -1073,6 +1137,10 @@ k_panel(LpDev d, PanA *partA, PanB *partB, unsigned long long *bar, unsigned lon
         st->tg_rhs = tg_rhs;
         st->n_log = n_log;
         st->n_touched = n_touched;
+    }
+    if (c == 0 && tid == 0 && go) { // exchange counters advance even if no pivot completed
+        st->xseq = xseq;
+        st->cseq = cseq;
     }
     if (tid == 0 && nbar < PANEL_NBAR) { // keep the barrier counter in step with the host's base
         __threadfence();
@@ -1645,9 +1713,11 @@ constexpr int PROF_MAX_SWEEPS = 4096;
 
 static int auto_block(const LpDev &d)
 {
+    // measured on B200 (c3, 8192 x 16384): pivots/s keeps growing up to k = 32, where the
+    // flush (FP64-pipe bound, ~19 us per pivot) and the panel (~15 us per pivot) are comparable
     const long long cells = (long long)d.m * d.Cl;
-    if (cells >= (4LL << 20)) return 16;
-    if (cells >= (1LL << 18)) return 8;
+    if (cells >= (4LL << 20)) return 32;
+    if (cells >= (1LL << 18)) return 16;
     return 4;
 }
 
@@ -1798,7 +1868,7 @@ static int lp_create(xp_ctx *ctx, int m, int C, int rank, int G, xp_lp_f64 **out
         const char *fb = getenv("XP_FLUSH_BALANCED_MIN");
         if (fb) lp->ft_balanced_min = atoi(fb);
         const char *u = getenv("XP_NO_PANEL");
-        lp->use_panel = G == 1 && !(u && atoi(u));
+        lp->use_panel = !(u && atoi(u));
         XP_CUDA_OK(ctx, cudaMalloc((void **)&lp->panA, 128 * sizeof(PanA)));
         XP_CUDA_OK(ctx, cudaMalloc((void **)&lp->panB, 128 * sizeof(PanB)));
         XP_CUDA_OK(ctx, cudaMalloc((void **)&lp->bar, 64));
