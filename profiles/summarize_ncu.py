@@ -2,7 +2,10 @@
 """Summarise an `ncu --set full` report into the small JSON committed under
 profiles/ (the .ncu-rep itself stays in gpurun_out/, which is scratch).
 
-  python profiles/summarize_ncu.py gpurun_out/prof.ncu-rep profiles/out.json [kernel-substring]
+  python profiles/summarize_ncu.py gpurun_out/prof.ncu-rep profiles/out.json [kernel-substring] [min-us]
+
+Launches shorter than min-us (default 20) are dropped: the solver's kernel sequence is static, so
+some launches find nothing to do (block still open / LP already terminal) and return at once.
 """
 import csv
 import io
@@ -23,7 +26,9 @@ KEEP = ["dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__time_duration.sum
         "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
         "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
         "sm__inst_executed.sum", "smsp__inst_executed.sum", "sm__cycles_active.avg",
-        "lts__t_bytes.sum", "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"]
+        "lts__t_bytes.sum", "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
+        "smsp__issue_active.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active"]
 SCALE = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12,
          "ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}
 
@@ -55,6 +60,8 @@ def main():
                 d[k] = v
                 d[k + "__unit"] = u
         launches.append(d)
+    min_us = float(sys.argv[4]) if len(sys.argv) > 4 else 20.0
+    launches = [l for l in launches if l.get("gpu__time_duration.sum", 0.0) >= min_us]
     n = max(len(launches), 1)
     rd = sum(l.get("dram__bytes_read.sum", 0.0) for l in launches) / n
     wr = sum(l.get("dram__bytes_write.sum", 0.0) for l in launches) / n

@@ -437,7 +437,9 @@ __device__ inline int xpb_two_stage(XpB<typename Ops::E> &S, const XpBatchArgs &
 // Persistent CTAs pull LP indices from an atomic queue, so long-running LPs
 // (unbounded ones exit only after exhausting the tabu table) do not hold up
 // the rest of the grid.
-template <class Ops>
+// GWS = false keeps every state pointer in the shared address space at compile time
+// (LDS/STS instead of generic loads); GWS = true is the global-memory slab variant.
+template <class Ops, bool GWS>
 __device__ inline void xpb_kernel_body(const XpBatchArgs &A)
 {
     typedef typename Ops::E E;
@@ -445,7 +447,7 @@ __device__ inline void xpb_kernel_body(const XpBatchArgs &A)
     __shared__ int s_lp;
     XpB<E> S;
     long long *misc;
-    unsigned char *state = A.gws ? A.gws + (size_t)blockIdx.x * A.gws_stride : xpb_smem;
+    unsigned char *state = GWS ? A.gws + (size_t)blockIdx.x * A.gws_stride : xpb_smem;
     xpb_carve<E, typename Ops::Key>(S, state, A.maxm, A.maxn, &misc);
     Ops::bind(S, misc);
     for (;;) {

@@ -169,7 +169,13 @@ struct OpsF64 {
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS) k_batch_f64(XpBatchArgs A)
 {
-    xpb_kernel_body<OpsF64>(A);
+    xpb_kernel_body<OpsF64, false>(A);
+}
+
+// LPs beyond shared memory: same code, state slab in global memory
+__global__ void __launch_bounds__(1024) k_batch_f64_gws(XpBatchArgs A)
+{
+    xpb_kernel_body<OpsF64, true>(A);
 }
 
 int pick_threads(int maxm, int maxn)
@@ -195,7 +201,7 @@ int launch_f64(xp_ctx *ctx, XpBatchArgs &A)
         A.gws = (unsigned char *)ws;
         A.gws_stride = stride;
         XP_CUDA_OK(ctx, cudaMemsetAsync(A.queue, 0, sizeof(unsigned), ctx->stream));
-        k_batch_f64<1024><<<(unsigned)g, 1024, 0, ctx->stream>>>(A);
+        k_batch_f64_gws<<<(unsigned)g, 1024, 0, ctx->stream>>>(A);
         ctx->launches++;
         XP_CUDA_OK(ctx, cudaGetLastError());
         return 0;

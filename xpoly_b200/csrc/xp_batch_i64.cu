@@ -281,7 +281,13 @@ struct OpsI64 {
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS) k_batch_i64(XpBatchArgs A)
 {
-    xpb_kernel_body<OpsI64>(A);
+    xpb_kernel_body<OpsI64, false>(A);
+}
+
+// LPs beyond shared memory: same code, state slab in global memory
+__global__ void __launch_bounds__(1024) k_batch_i64_gws(XpBatchArgs A)
+{
+    xpb_kernel_body<OpsI64, true>(A);
 }
 
 int pick_threads_i64(int maxm, int maxn)
@@ -306,7 +312,7 @@ int launch_i64(xp_ctx *ctx, XpBatchArgs &A)
         A.gws = (unsigned char *)ws;
         A.gws_stride = stride;
         XP_CUDA_OK(ctx, cudaMemsetAsync(A.queue, 0, sizeof(unsigned), ctx->stream));
-        k_batch_i64<1024><<<(unsigned)g, 1024, 0, ctx->stream>>>(A);
+        k_batch_i64_gws<<<(unsigned)g, 1024, 0, ctx->stream>>>(A);
         ctx->launches++;
         XP_CUDA_OK(ctx, cudaGetLastError());
         return 0;

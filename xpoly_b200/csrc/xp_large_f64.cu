@@ -1694,6 +1694,7 @@ struct xp_lp_f64 {
     void *peer_map[MAXR] = {nullptr}; // IPC mappings to close
     bool attached = false;
     int kblk = 0; // 0: automatic
+    unsigned cnt_host = 0; // iteration count after the last solve (0 after an upload)
     // persistent panel kernel (single GPU)
     PanA *panA = nullptr;
     PanB *panB = nullptr;
@@ -2027,6 +2028,7 @@ extern "C" void xp_lp_f64_destroy(xp_lp_f64 *lp)
 static int lp_reset(xp_lp_f64 *lp)
 {
     xp_ctx *ctx = lp->ctx;
+    lp->cnt_host = 0;
     const int k = lp->kblk > 0 ? lp->kblk : auto_block(lp->d);
     k_init<<<ctx->sm_count * 2, 256, 0, ctx->stream>>>(lp->d, 0u, k, 1);
     ctx->launches++;
@@ -2141,7 +2143,14 @@ extern "C" int xp_lp_f64_solve(xp_lp_f64 *lp, uint32_t max_iter, int rule)
     }
     XP_CUDA_OK(ctx, cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream;
-    const int kblk = lp->kblk > 0 ? lp->kblk : auto_block(d);
+    int kblk = lp->kblk > 0 ? lp->kblk : auto_block(d);
+    if (lp->kblk == 0 && max_iter != XP_NO_ITER_LIMIT && max_iter > lp->cnt_host) {
+        // bounded run: equal blocks instead of full ones plus a short tail (same passes over
+        // the tableau, none of them nearly empty)
+        const unsigned left = max_iter - lp->cnt_host;
+        const unsigned nb = (left + kblk - 1) / kblk;
+        kblk = (int)((left + nb - 1) / nb);
+    }
     XP_CUDA_OK(ctx, cudaEventRecord(ctx->ev0, s));
     k_init<<<1, 32, 0, s>>>(d, max_iter, kblk, 0);
     ctx->launches++;
@@ -2213,6 +2222,7 @@ extern "C" int xp_lp_f64_solve(xp_lp_f64 *lp, uint32_t max_iter, int rule)
     XP_CUDA_OK(ctx, cudaStreamSynchronize(s));
     XP_CUDA_OK(ctx, cudaEventElapsedTime(&ctx->last_kernel_ms, ctx->ev0, ctx->ev1));
     if (lp->h_st->status == XP_ERR_PEER) ctx->err = "sharded LP: timed out waiting for a peer GPU";
+    lp->cnt_host = lp->h_st->cnt;
     return lp->h_st->status;
 }
 
