@@ -725,37 +725,13 @@ struct PanB { // per-CTA pricing result
     double c;
     int cand, anypos;
 };
-struct RKey {
-    double v, rh, a;
-    int i, bv, s0;
-};
-__device__ __forceinline__ RKey rk_better(const RKey &x, const RKey &y)
-{
-    if (y.i < 0) return x;
-    if (x.i < 0) return y;
-    if (y.v < x.v || (y.v == x.v && y.i < x.i)) return y;
-    return x;
-}
-__device__ __forceinline__ RKey rk_shfl(const RKey &x, int o)
-{
-    RKey y;
-    y.v = __shfl_xor_sync(0xffffffffu, x.v, o);
-    y.rh = __shfl_xor_sync(0xffffffffu, x.rh, o);
-    y.a = __shfl_xor_sync(0xffffffffu, x.a, o);
-    y.i = __shfl_xor_sync(0xffffffffu, x.i, o);
-    y.bv = __shfl_xor_sync(0xffffffffu, x.bv, o);
-    y.s0 = __shfl_xor_sync(0xffffffffu, x.s0, o);
-    return y;
-}
-// block arg-min of two keys at once; result valid in every thread
-__device__ __forceinline__ void rk_block2(RKey &k1, RKey &k2, RKey *sh /* 2 x 9 */)
+
+// block arg-min of two (value, row) keys at once; result valid in every thread
+__device__ __forceinline__ void argmin2_block(XpMinIdx &k1, XpMinIdx &k2, XpMinIdx *sh /* 2 x 9 */)
 {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        k1 = rk_better(k1, rk_shfl(k1, o));
-        k2 = rk_better(k2, rk_shfl(k2, o));
-    }
+    k1 = xp_warp_argmin(k1);
+    k2 = xp_warp_argmin(k2);
     __syncthreads();
     if (lane == 0) {
         sh[w] = k1;
@@ -763,19 +739,15 @@ __device__ __forceinline__ void rk_block2(RKey &k1, RKey &k2, RKey *sh /* 2 x 9 
     }
     __syncthreads();
     if (w == 0) {
-        RKey y1, y2;
+        XpMinIdx y1, y2;
         y1.i = y2.i = -1;
-        y1.v = y2.v = y1.rh = y2.rh = y1.a = y2.a = 0.0;
-        y1.bv = y2.bv = y1.s0 = y2.s0 = 0;
+        y1.v = y2.v = 0.0;
         if (lane < nw) {
             y1 = sh[lane];
             y2 = sh[9 + lane];
         }
-#pragma unroll
-        for (int o = 4; o > 0; o >>= 1) {
-            y1 = rk_better(y1, rk_shfl(y1, o));
-            y2 = rk_better(y2, rk_shfl(y2, o));
-        }
+        y1 = xp_warp_argmin(y1);
+        y2 = xp_warp_argmin(y2);
         if (lane == 0) {
             sh[8] = y1;
             sh[17] = y2;
@@ -820,19 +792,34 @@ __device__ __forceinline__ bool grid_barrier(unsigned long long *bar, unsigned l
 
 constexpr int PANEL_NBAR = 2 * KMAX + 2; // barrier arrivals per CTA and launch (padded on exit)
 
+__host__ __device__ inline size_t panel_smem_bytes(int rpc, int cpc)
+{
+    return (size_t)KMAX * ((size_t)rpc + cpc) * sizeof(double) + (size_t)2 * rpc * sizeof(int);
+}
+
+// CTA c owns rows [c*rpc, ..) and local columns [c*cpc, ..).  For its rows it keeps
+// eq2bv, last_piv and the multipliers F[0..t) of the open block in shared memory, for
+// its columns the pivot rows P[0..t): the replay of the pending updates runs out of
+// shared memory, and the only global reads on the critical path of a pivot are the
+// tableau column / row themselves and the per-CTA partial results.
 __global__ void __launch_bounds__(TH, 1)
 k_panel(LpDev d, PanA *partA, PanB *partB, unsigned long long *bar, unsigned long long bar_base,
         int rpc, int cpc, unsigned long long *dbg)
 {
-    extern __shared__ int s_dyn[]; // eq2bv and last_piv of the CTA's rows
-    __shared__ RKey s_rk[18];
+    extern __shared__ double s_dyn[]; // sF[KMAX][rpc] | sP[KMAX][cpc] | s_e2b[rpc] | s_lp[rpc]
+    __shared__ XpMinIdx s_mi[18];
     __shared__ int shi[33];
     __shared__ double s_c[33];
+    __shared__ double s_pq[KMAX], s_fp[KMAX];
+    __shared__ double s_wd[2]; // winner: rhs, pivot element
+    __shared__ int s_wi[2];    // winner: leaving variable, last_piv
+    __shared__ int s_to;
     LpState *st = d.st;
     const int tid = threadIdx.x, c = blockIdx.x, NB = gridDim.x;
-    const int n = d.n, m = d.m, Cl = d.Cl;
+    const int n = d.n, m = d.m, Cl = d.Cl, G = d.G, col0 = d.col0;
     int nbar = 0;
-    int *s_e2b = s_dyn, *s_lp = s_dyn + rpc;
+    double *sF = s_dyn, *sP = s_dyn + (size_t)KMAX * rpc;
+    int *s_e2b = (int *)(sP + (size_t)KMAX * cpc), *s_lp = s_e2b + rpc;
     const int r_lo = min(m, c * rpc), r_hi = min(m, r_lo + rpc);
     const int c_lo = min(Cl, c * cpc), c_hi = min(Cl, c_lo + cpc);
 
@@ -845,6 +832,7 @@ k_panel(LpDev d, PanA *partA, PanB *partB, unsigned long long *bar, unsigned lon
     double tg_rhs = st->tg_rhs;
     unsigned n_log = st->n_log;
     int n_touched = st->n_touched;
+    unsigned xseq = st->xseq, cseq = st->cseq;
     int slow_out = 0;
     bool dirty = false;
     if (go) {
@@ -852,10 +840,17 @@ k_panel(LpDev d, PanA *partA, PanB *partB, unsigned long long *bar, unsigned lon
             s_e2b[i - r_lo] = d.eq2bv[i];
             s_lp[i - r_lo] = d.last_piv[i];
         }
+        // resuming inside an open block: bring its factors into shared memory
+        for (int e = tid; e < t * (r_hi - r_lo); e += TH) {
+            const int s = e / (r_hi - r_lo), li = e - s * (r_hi - r_lo);
+            sF[(size_t)s * rpc + li] = ld_cg(Fptr(d, d.rank, par, s) + r_lo + li);
+        }
+        for (int e = tid; e < t * (c_hi - c_lo); e += TH) {
+            const int s = e / (c_hi - c_lo), lj = e - s * (c_hi - c_lo);
+            sP[(size_t)s * cpc + lj] = ld_cg(d.P + (size_t)s * Cl + c_lo + lj);
+        }
         __syncthreads();
     }
-    const int G = d.G, col0 = d.col0;
-    unsigned xseq = st->xseq, cseq = st->cseq;
     // c_q: one GPU carries it from the pricing partials; sharded, it travels with the column
     double cq = (go && G == 1 && q < n) ? ld_cg(d.tgtf + q) : 0.0;
 #define PANEL_T(k)                                                  \
@@ -873,85 +868,83 @@ k_panel(LpDev d, PanA *partA, PanB *partB, unsigned long long *bar, unsigned lon
         const bool mine = owner == d.rank;
         const int ql = q - col0;
         cseq++;
-        if (!mine) { // the owner's k_panel pushes F[t] into my exchange block, then raises its flag
-            __shared__ int s_to;
-            if (tid == 0) {
-                const unsigned long long *w =
-                    (const unsigned long long *)(d.xb[d.rank] + offsetof(XHdr, colflag)) + owner;
-                const unsigned long long t0 = clock64();
-                unsigned spins = 0;
-                int ok = 1;
-                while (ld_acquire_sys(w) < cseq)
-                    if ((++spins & 1023u) == 0 && clock64() - t0 > SPIN_LIMIT) {
-                        ok = 0;
-                        break;
-                    }
-                s_to = ok;
-            }
-            __syncthreads();
-            if (!s_to) {
-                if (tid == 0) st->status = XP_ERR_PEER;
-                return;
-            }
+        if (mine) {
+            if (tid < t) s_pq[tid] = ld_cg(d.P + (size_t)tid * Cl + ql);
+        } else if (tid == 0) { // the owner's k_panel pushes F[t] into my exchange block, then raises its flag
+            const unsigned long long *w =
+                (const unsigned long long *)(d.xb[d.rank] + offsetof(XHdr, colflag)) + owner;
+            const unsigned long long t0 = clock64();
+            unsigned spins = 0;
+            int ok = 1;
+            while (ld_acquire_sys(w) < cseq)
+                if ((++spins & 1023u) == 0 && clock64() - t0 > SPIN_LIMIT) {
+                    ok = 0;
+                    break;
+                }
+            s_to = ok;
         }
-        double pq[KMAX];
-#pragma unroll
-        for (int s = 0; s < KMAX; s++) pq[s] = (mine && s < t) ? ld_cg(d.P + (size_t)s * Cl + ql) : 0.0;
-        RKey b1, b2;
+        __syncthreads();
+        if (!mine && !s_to) {
+            if (tid == 0) st->status = XP_ERR_PEER;
+            return;
+        }
+        XpMinIdx b1, b2;
         b1.i = b2.i = -1;
-        b1.v = b2.v = b1.rh = b2.rh = b1.a = b2.a = 0.0;
-        b1.bv = b2.bv = b1.s0 = b2.s0 = 0;
+        b1.v = b2.v = 0.0;
+        double x1_rh = 0.0, x1_a = 0.0, x2_rh = 0.0, x2_a = 0.0; // extras of this thread's best rows
+        int x1_bv = 0, x1_s0 = 0, x2_bv = 0, x2_s0 = 0;
         double *Ft = Fptr(d, d.rank, par, t);
         for (int i = r_lo + tid; i < r_hi; i += TH) {
-            const int bv = s_e2b[i - r_lo], s0 = s_lp[i - r_lo];
-            const double a0 = mine ? d.tab[(size_t)i * Cl + ql] : 0.0;
+            const int li = i - r_lo;
+            const int bv = s_e2b[li], s0 = s_lp[li];
+            const double a0 = mine ? d.tab[(size_t)i * Cl + ql] : -ld_cg(Ft + i);
             const double rh = d.rhsbuf[i];
             const uint32_t tw = __ldcg(d.tabu + (size_t)q * d.W + (bv >> 5));
             const int cc = __ldcg(d.col_cnt + bv);
-            double a;
+            double a = a0;
             if (mine) {
-                const double *f0 = Fptr(d, d.rank, par, 0) + i;
-                double f[KMAX];
-#pragma unroll
-                for (int s = 0; s < KMAX; s++) f[s] = s < t ? ld_cg(f0 + (size_t)s * d.mpad) : 0.0;
-                a = a0;
-#pragma unroll
-                for (int s = 0; s < KMAX; s++) {
-                    if (s == s0) a = pq[s];
-                    else if (s > s0 && s < t) a = xp_add(a, xp_mul(f[s], pq[s]));
-                }
+                if (s0 >= 0) a = s_pq[s0];
+#pragma unroll 4
+                for (int s = s0 + 1; s < t; s++) a = xp_add(a, xp_mul(sF[(size_t)s * rpc + li], s_pq[s]));
                 for (int r = 0; r < G; r++) __stcg(Fptr(d, r, par, t) + i, -a);
-            } else {
-                a = -ld_cg(Ft + i);
             }
+            sF[(size_t)t * rpc + li] = -a;
             if (xp_feq(a, 0.0)) continue;          // neither pass takes a == 0 (tolerant)
             if ((tw >> (bv & 31)) & 1u) continue;   // is_handle(q, bv), :589
             if (cc >= n - 1) continue;              // !canBeBVCandidate, :596
-            RKey k;
+            XpMinIdx k;
             k.v = xp_div(rh, a);
-            k.rh = rh;
-            k.a = a;
             k.i = i;
-            k.bv = bv;
-            k.s0 = s0;
-            b2 = rk_better(b2, k);            // pass 2, :623-658
-            if (a > 0.0) b1 = rk_better(b1, k); // pass 1, :571-612
+            const XpMinIdx n2 = xp_better(b2, k); // pass 2, :623-658
+            if (n2.i == i) x2_rh = rh, x2_a = a, x2_bv = bv, x2_s0 = s0;
+            b2 = n2;
+            if (a > 0.0) { // pass 1, :571-612
+                const XpMinIdx n1 = xp_better(b1, k);
+                if (n1.i == i) x1_rh = rh, x1_a = a, x1_bv = bv, x1_s0 = s0;
+                b1 = n1;
+            }
         }
         if (G > 1 && mine && c == 0 && tid == 0) {
             const double cqv = d.tgtf[ql];
             for (int r = 0; r < G; r++) __stcg(Fptr(d, r, par, t) + m, cqv);
         }
         PANEL_T(0) // phase A loads + replay
-        rk_block2(b1, b2, s_rk);
-        if (tid == 0) {
-            PanA pa;
-            pa.v1 = b1.v, pa.rh1 = b1.rh, pa.a1 = b1.a, pa.i1 = b1.i, pa.bv1 = b1.bv, pa.s01 = b1.s0;
-            pa.v2 = b2.v, pa.rh2 = b2.rh, pa.a2 = b2.a, pa.i2 = b2.i, pa.bv2 = b2.bv, pa.s02 = b2.s0;
+        {
+            const int my1 = b1.i, my2 = b2.i;
+            argmin2_block(b1, b2, s_mi);
             PanA *dst = partA + c;
-            __stcg(&dst->v1, pa.v1), __stcg(&dst->rh1, pa.rh1), __stcg(&dst->a1, pa.a1);
-            __stcg(&dst->v2, pa.v2), __stcg(&dst->rh2, pa.rh2), __stcg(&dst->a2, pa.a2);
-            __stcg(&dst->i1, pa.i1), __stcg(&dst->bv1, pa.bv1), __stcg(&dst->s01, pa.s01);
-            __stcg(&dst->i2, pa.i2), __stcg(&dst->bv2, pa.bv2), __stcg(&dst->s02, pa.s02);
+            if (b1.i >= 0 && my1 == b1.i) { // the thread that owns the CTA's winner writes it out
+                __stcg(&dst->v1, b1.v), __stcg(&dst->rh1, x1_rh), __stcg(&dst->a1, x1_a);
+                __stcg(&dst->i1, b1.i), __stcg(&dst->bv1, x1_bv), __stcg(&dst->s01, x1_s0);
+            }
+            if (b2.i >= 0 && my2 == b2.i) {
+                __stcg(&dst->v2, b2.v), __stcg(&dst->rh2, x2_rh), __stcg(&dst->a2, x2_a);
+                __stcg(&dst->i2, b2.i), __stcg(&dst->bv2, x2_bv), __stcg(&dst->s02, x2_s0);
+            }
+            if (tid == 0) {
+                if (b1.i < 0) __stcg(&dst->i1, -1);
+                if (b2.i < 0) __stcg(&dst->i2, -1);
+            }
         }
         PANEL_T(1) // block arg-min + partial store
         nbar++;
@@ -963,47 +956,55 @@ k_panel(LpDev d, PanA *partA, PanB *partB, unsigned long long *bar, unsigned lon
             st_release_sys((unsigned long long *)(d.xb[tid] + offsetof(XHdr, colflag)) + d.rank, cseq);
         if (G > 1) cq = ld_cg(Ft + m);
         PANEL_T(2) // barrier 1
+        double w_rh1 = 0.0, w_a1 = 0.0, w_rh2 = 0.0, w_a2 = 0.0;
+        int w_bv1 = 0, w_s01 = 0, w_bv2 = 0, w_s02 = 0;
         b1.i = b2.i = -1;
+        b1.v = b2.v = 0.0;
         if (tid < NB) {
             const PanA *src = partA + tid;
-            b1.v = __ldcg(&src->v1), b1.rh = __ldcg(&src->rh1), b1.a = __ldcg(&src->a1);
-            b1.i = __ldcg(&src->i1), b1.bv = __ldcg(&src->bv1), b1.s0 = __ldcg(&src->s01);
-            b2.v = __ldcg(&src->v2), b2.rh = __ldcg(&src->rh2), b2.a = __ldcg(&src->a2);
-            b2.i = __ldcg(&src->i2), b2.bv = __ldcg(&src->bv2), b2.s0 = __ldcg(&src->s02);
+            b1.i = __ldcg(&src->i1), b2.i = __ldcg(&src->i2);
+            b1.v = __ldcg(&src->v1), w_rh1 = __ldcg(&src->rh1), w_a1 = __ldcg(&src->a1);
+            w_bv1 = __ldcg(&src->bv1), w_s01 = __ldcg(&src->s01);
+            b2.v = __ldcg(&src->v2), w_rh2 = __ldcg(&src->rh2), w_a2 = __ldcg(&src->a2);
+            w_bv2 = __ldcg(&src->bv2), w_s02 = __ldcg(&src->s02);
         }
-        rk_block2(b1, b2, s_rk);
+        {
+            const int my1 = b1.i, my2 = b2.i;
+            argmin2_block(b1, b2, s_mi);
+            if (b1.i >= 0) {
+                if (tid < NB && my1 == b1.i) s_wd[0] = w_rh1, s_wd[1] = w_a1, s_wi[0] = w_bv1, s_wi[1] = w_s01;
+            } else if (b2.i >= 0) {
+                if (tid < NB && my2 == b2.i) s_wd[0] = w_rh2, s_wd[1] = w_a2, s_wi[0] = w_bv2, s_wi[1] = w_s02;
+            }
+            __syncthreads();
+        }
         PANEL_T(3) // partial reduce
-        const RKey win = b1.i >= 0 ? b1 : b2;
-        if (win.i < 0) break; // ratio test failed: k_pcol redoes this column and takes the slow path
-        const int p = win.i, bv = win.bv, s0p = win.s0;
-        const double r = xp_div(1.0, win.a); // mulOfRow(eqnum, 1 / pivot), :1471
+        const int p = b1.i >= 0 ? b1.i : b2.i;
+        if (p < 0) break; // ratio test failed: k_pcol redoes this column and takes the slow path
+        const int bv = s_wi[0], s0p = s_wi[1];
+        const double r = xp_div(1.0, s_wd[1]); // mulOfRow(eqnum, 1 / pivot), :1471
         const bool r_one = xp_feq(r, 1.0), r_zero = xp_feq(r, 0.0);
         const bool cq_zero = xp_feq(cq, 0.0), cq_one = xp_feq(cq, 1.0);
-        const double prow_rhs = xp_scale(win.rh, r, r_one, r_zero);
+        const double prow_rhs = xp_scale(s_wd[0], r, r_one, r_zero);
         // ================= phase B: leaving row, objective row, constant column, pricing ====
-        double fp[KMAX];
-#pragma unroll
-        for (int s = 0; s < KMAX; s++) fp[s] = s < t ? ld_cg(Fptr(d, 0, par, s) + p) : 0.0;
+        if (tid < t) s_fp[tid] = ld_cg(Fptr(d, d.rank, par, tid) + p);
+        __syncthreads();
         int cand = INT_BIG, anyp = 0;
         double ccand = 0.0;
         double *Pt = d.P + (size_t)t * Cl;
         for (int jl = c_lo + tid; jl < c_hi; jl += TH) {
+            const int lj = jl - c_lo;
             const int g = col0 + jl; // global column index
             const double a0 = d.tab[(size_t)p * Cl + jl];
             const double tg0 = d.tgtf[jl];
             const int nvraw = g < n ? (int)__ldcg(d.nvset + g) : 0;
             const int rc = g < n ? __ldcg(d.row_cnt + g) : INT_BIG;
-            const double *p0 = d.P + jl;
-            double pr[KMAX];
-#pragma unroll
-            for (int s = 0; s < KMAX; s++) pr[s] = s < t ? ld_cg(p0 + (size_t)s * Cl) : 0.0;
             double v = a0;
-#pragma unroll
-            for (int s = 0; s < KMAX; s++) {
-                if (s == s0p) v = pr[s];
-                else if (s > s0p && s < t) v = xp_add(v, xp_mul(fp[s], pr[s]));
-            }
+            if (s0p >= 0) v = sP[(size_t)s0p * cpc + lj];
+#pragma unroll 4
+            for (int s = s0p + 1; s < t; s++) v = xp_add(v, xp_mul(s_fp[s], sP[(size_t)s * cpc + lj]));
             const double xv = xp_scale(v, r, r_one, r_zero);
+            sP[(size_t)t * cpc + lj] = xv;
             __stcg(Pt + jl, xv);
             double tg = tg0;
             if (g < zero_upto && g < n && !nvraw) tg = 0.0;      // zeroing owed by the scan (:1059)
@@ -1022,7 +1023,7 @@ k_panel(LpDev d, PanA *partA, PanB *partB, unsigned long long *bar, unsigned lon
             }
         }
         for (int i = r_lo + tid; i < r_hi; i += TH) {
-            const double f = ld_cg(Ft + i);
+            const double f = sF[(size_t)t * rpc + (i - r_lo)];
             d.rhsbuf[i] = i == p ? prow_rhs : xp_add(d.rhsbuf[i], xp_mul(f, prow_rhs));
         }
         PANEL_T(4) // phase B loads + replay + stores
@@ -1031,10 +1032,10 @@ k_panel(LpDev d, PanA *partA, PanB *partB, unsigned long long *bar, unsigned lon
             s_lp[p - r_lo] = t;
         }
         {
-            const int mine = cand;
+            const int mycand = cand;
             cand = xp_block_min_int(cand, shi);
             anyp = __syncthreads_or(anyp);
-            if (mine == cand && cand != INT_BIG) s_c[32] = ccand; // unique owner of the minimum
+            if (mycand == cand && cand != INT_BIG) s_c[32] = ccand; // unique owner of the minimum
             __syncthreads();
             if (tid == 0) {
                 PanB *dst = partB + c;
@@ -1870,6 +1871,18 @@ static int lp_create(xp_ctx *ctx, int m, int C, int rank, int G, xp_lp_f64 **out
         if (fb) lp->ft_balanced_min = atoi(fb);
         const char *u = getenv("XP_NO_PANEL");
         lp->use_panel = !(u && atoi(u));
+        // the panel kernel keeps the open block's factors of its rows / columns in shared
+        // memory; tableaux too large for that (or for one resident wave) use k_pcol / k_prow
+        while (lp->use_panel && panel_smem_bytes(lp->panel_rpc, lp->panel_cpc) > ctx->smem_optin - 4096 &&
+               lp->panel_nb < ctx->sm_count) {
+            lp->panel_nb = lp->panel_nb * 2 > ctx->sm_count ? ctx->sm_count : lp->panel_nb * 2;
+            lp->panel_rpc = (m + lp->panel_nb - 1) / lp->panel_nb;
+            lp->panel_cpc = (d.Cl + lp->panel_nb - 1) / lp->panel_nb;
+        }
+        if (panel_smem_bytes(lp->panel_rpc, lp->panel_cpc) > ctx->smem_optin - 4096) lp->use_panel = false;
+        if (lp->use_panel)
+            XP_CUDA_OK(ctx, cudaFuncSetAttribute(k_panel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 (int)ctx->smem_optin - 4096)); // one setting for every LP shape
         XP_CUDA_OK(ctx, cudaMalloc((void **)&lp->panA, 128 * sizeof(PanA)));
         XP_CUDA_OK(ctx, cudaMalloc((void **)&lp->panB, 128 * sizeof(PanB)));
         XP_CUDA_OK(ctx, cudaMalloc((void **)&lp->bar, 64));
@@ -2128,7 +2141,7 @@ static cudaError_t panel_launch(xp_lp_f64 *lp)
     void *args[] = {&d, &pa, &pb, &bar, &base, &rpc, &cpc, &dbg};
     lp->bar_base += (unsigned long long)PANEL_NBAR * lp->panel_nb;
     return cudaLaunchCooperativeKernel((void *)k_panel, dim3(lp->panel_nb), dim3(TH), args,
-                                       (size_t)2 * rpc * sizeof(int), lp->ctx->stream);
+                                       panel_smem_bytes(rpc, cpc), lp->ctx->stream);
 }
 
 extern "C" int xp_lp_f64_solve(xp_lp_f64 *lp, uint32_t max_iter, int rule)
