@@ -1883,8 +1883,8 @@ static int lp_create(xp_ctx *ctx, int m, int C, int rank, int G, xp_lp_f64 **out
         if (lp->use_panel)
             XP_CUDA_OK(ctx, cudaFuncSetAttribute(k_panel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                  (int)ctx->smem_optin - 4096)); // one setting for every LP shape
-        XP_CUDA_OK(ctx, cudaMalloc((void **)&lp->panA, 128 * sizeof(PanA)));
-        XP_CUDA_OK(ctx, cudaMalloc((void **)&lp->panB, 128 * sizeof(PanB)));
+        XP_CUDA_OK(ctx, cudaMalloc((void **)&lp->panA, 256 * sizeof(PanA)));
+        XP_CUDA_OK(ctx, cudaMalloc((void **)&lp->panB, 256 * sizeof(PanB)));
         XP_CUDA_OK(ctx, cudaMalloc((void **)&lp->bar, 64));
         XP_CUDA_OK(ctx, cudaMemset(lp->bar, 0, 64));
         const char *dbg = getenv("XP_PANEL_DBG");
