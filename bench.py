@@ -56,7 +56,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -148,8 +148,10 @@ def run_reference_arm(args):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1000.0 * P / value, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"c3: dense FP64 LP, tableau {args.m}x{C_cols}, "
-                               f"{P} simplex iterations per step from the slack basis"},
+        "config": {"workload": f"c3: dense FP64 LP, tableau {args.m}x{C_cols}, simplex iterations "
+                               "under the reference pivot rule from the slack basis",
+                   "pivots_per_step": P,
+                   "sample": f"bounded: {P} pivots per step (the reference needs ~0.8 s per pivot here)"},
         "cpu_baseline": {"value": value, "unit": "pivots/s", "cores": 1, "kind": kind,
                          "sample": f"{P} pivots of the same {args.m}x{C_cols} LP per step "
                                    "(solve loop timed inside the checker; reference set-up measured with max_iter=0 and subtracted)"},
@@ -210,6 +212,58 @@ def run_batched(ctx, xp, torch, dev):
                 "d2h_bytes_per_step": int(B * 12)},
         "status_matches_e2e": bool(np.array_equal(out["status"], st)),
     }
+
+
+def run_exact_and_bnb(ctx, xp):
+    """Config 4 (10k exact 24x48 LPs, fraction-free int64) and config 5 (knapsack-style B&B,
+    node relaxations batched on the GPU; the reference only solves this family up to ~50
+    variables) through the host-pointer C ABI."""
+    out = {}
+    r = np.random.RandomState(777)
+    B, m, n = 10_000, 24, 23
+    A = r.randint(0, 4, size=(B, m, n)) * (r.uniform(size=(B, m, n)) < 0.3)
+    leq = np.zeros((B, m, n + 1), dtype=np.int64)
+    leq[:, :, :n] = A
+    leq[:, :, n] = r.randint(0, 21, size=(B, m))
+    tg = np.zeros((B, n + 1), dtype=np.int64)
+    tg[:, :n] = r.randint(1, 6, size=(B, n))
+    ctx.two_stage_i64_batch(leq[:64], tg[:64])
+    ts = []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        res = ctx.two_stage_i64_batch(leq, tg)
+        ts.append(time.perf_counter() - t0)
+    st = res["status"]
+    out["exact"] = {"metric": "exact LPs/s", "workload": f"c4: {B} LPs, tableau {m}x{n + m + 1}, "
+                    "fraction-free int64 entries / 128-bit products, e2e through host pointers",
+                    "value": B / float(np.median(ts)), "unit": "LPs/s",
+                    "device_ms": ctx.last_kernel_ms, "device_LPs_per_s": B / (ctx.last_kernel_ms * 1e-3),
+                    "pivots_total": int(res["pivots"].astype(np.int64).sum()),
+                    "status_mix": {str(k): int((st == k).sum()) for k in np.unique(st)}}
+    # c5: 256 independent 40-item knapsacks (1 + n rows), general-integer B&B
+    T, nk = 256, 40
+    w = r.randint(5, 41, size=(T, nk))
+    pr = r.randint(5, 61, size=(T, nk))
+    L = np.zeros((T, nk + 1, nk + 1), dtype=np.int64)
+    L[:, 0, :nk] = w
+    L[:, 0, nk] = w.sum(axis=1) // 3
+    for j in range(nk):
+        L[:, 1 + j, j] = 1
+        L[:, 1 + j, nk] = 1
+    G = np.zeros((T, nk + 1), dtype=np.int64)
+    G[:, :nk] = pr
+    ctx.mip_solve_rat_batch(0, 0, L[:4], G[:4])
+    t0 = time.perf_counter()
+    mres = ctx.mip_solve_rat_batch(0, 0, L, G)
+    dt = time.perf_counter() - t0
+    nodes = int(mres["nodes"].astype(np.int64).sum())
+    ms = mres["status"]
+    out["bnb"] = {"metric": "B&B node LPs/s", "workload": f"c5: {T} knapsack MIPs of {nk} items "
+                  f"(tableau {nk + 1}x{2 * nk + 2} at the root), trees advanced in lockstep, node "
+                  "relaxations batched on the GPU, decisions replayed in the reference's DFS order",
+                  "value": nodes / dt, "unit": "node LPs/s", "trees_per_s": T / dt, "nodes_total": nodes,
+                  "status_mix": {str(k): int((ms == k).sum()) for k in np.unique(ms)}}
+    return out
 
 
 def run_ours(args):
@@ -331,9 +385,10 @@ def run_ours(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": main["dev_ms"] / args.steps,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": f"c3: dense FP64 LP, tableau {m}x{Ccols}, {P} simplex iterations "
-                               "per step (reference pivot rule, bit-identical state), HBM-resident"
-                               + (f", column-sharded over {world} GPUs" if world > 1 else ""),
+        "config": {"workload": f"c3: dense FP64 LP, tableau {m}x{Ccols}, simplex iterations "
+                               "under the reference pivot rule from the slack basis",
+                   "placement": "HBM-resident, bit-identical state"
+                                + (f", column-sharded over {world} GPUs" if world > 1 else ""),
                    "l2": "inputs (1 GiB) larger than L2 (126 MB): no flush between iterations",
                    "pivots_per_step": P, "pivots_per_tableau_pass": k_eff},
         "gpu_launches": int(main["launches"]), "wall_s": main["wall"], "clocks": clocks,
@@ -397,6 +452,7 @@ def run_ours(args):
         ctx.check(lib.xp_host_free(ctx._h, hp))
         if not args.no_batched:
             line["batched"] = run_batched(ctx, xp, torch, dev)
+            line.update(run_exact_and_bnb(ctx, xp))
     else:
         line["e2e"] = None
     if rank == 0:
@@ -409,7 +465,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--steps", type=int, default=32)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pivots", type=int, default=200, help="simplex iterations per step (SURVEY 8d: K = 200)")

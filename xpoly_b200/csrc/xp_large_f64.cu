@@ -1376,7 +1376,7 @@ __global__ void __launch_bounds__(LANES *HALVES) k_flush_t(LpDev d, int groups)
 #pragma unroll
             for (int w = 0; w < TR; w++) special |= (row + w < m) && lpu[rc + w] >= 0;
             if (!special) {
-#pragma unroll 4
+#pragma unroll 8
                 for (int s = 0; s < t; s++) {
                     const double2 p2 = *reinterpret_cast<const double2 *>(sPl + (size_t)s * TC);
                     const double *f = sFu + (size_t)s * FT_ROWS + rc;
