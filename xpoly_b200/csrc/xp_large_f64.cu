@@ -95,6 +95,12 @@ struct XHdr {
     unsigned long long arrive[MAXR];  // slow fetch: rank reached fetch #xs
     unsigned long long feas_in;       // feasibility chain: partial sums from rank-1 are in feas[]
     unsigned long long feas_res;      // (epoch << 2) | flags, broadcast by the last rank
+    // k_panel, sharded: the pivot the owner of the entering column decided (ratio test on
+    // its own copy of the column), by parity of the column event number
+    struct PivRec {
+        double a, rh, cq; // pivot element, constant term of the pivot row, c_q
+        int p, bv, s0, pad;
+    } piv[2];
 };
 constexpr size_t XHDR_BYTES = 1024;
 static_assert(sizeof(XHdr) <= XHDR_BYTES, "exchange header");
@@ -834,6 +840,7 @@ k_panel(LpDev d, PanA *partA, PanB *partB, unsigned long long *bar, unsigned lon
     int n_touched = st->n_touched;
     unsigned xseq = st->xseq, cseq = st->cseq;
     int slow_out = 0;
+    int q_prev = -1, bv_prev = -1; // the pivot whose basis swap CTA 0 may still be writing
     bool dirty = false;
     if (go) {
         for (int i = r_lo + tid; i < r_hi; i += TH) {
@@ -864,128 +871,140 @@ k_panel(LpDev d, PanA *partA, PanB *partB, unsigned long long *bar, unsigned lon
     if (dbg && c == 0 && tid == 0) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tprev));
     while (go && t < kblk && cnt < max_iter) {
         // ================= phase A: entering column, multipliers, ratio test =================
+        // Sharded: only the owner of column q runs it (its CTAs write the multipliers into
+        // every rank's F[t] on the way) and then hands the decision (p, pivot element, ...) to
+        // the peers together with the "column landed" flag; peers go straight to phase B.
         const int owner = owner_of(d, q);
         const bool mine = owner == d.rank;
         const int ql = q - col0;
         cseq++;
+        double *Ft = Fptr(d, d.rank, par, t);
+        int p, bv, s0p;
+        double piv_a, piv_rh;
         if (mine) {
             if (tid < t) s_pq[tid] = ld_cg(d.P + (size_t)tid * Cl + ql);
-        } else if (tid == 0) { // the owner's k_panel pushes F[t] into my exchange block, then raises its flag
-            const unsigned long long *w =
-                (const unsigned long long *)(d.xb[d.rank] + offsetof(XHdr, colflag)) + owner;
-            const unsigned long long t0 = clock64();
-            unsigned spins = 0;
-            int ok = 1;
-            while (ld_acquire_sys(w) < cseq)
-                if ((++spins & 1023u) == 0 && clock64() - t0 > SPIN_LIMIT) {
-                    ok = 0;
-                    break;
-                }
-            s_to = ok;
-        }
-        __syncthreads();
-        if (!mine && !s_to) {
-            if (tid == 0) st->status = XP_ERR_PEER;
-            return;
-        }
-        XpMinIdx b1, b2;
-        b1.i = b2.i = -1;
-        b1.v = b2.v = 0.0;
-        double x1_rh = 0.0, x1_a = 0.0, x2_rh = 0.0, x2_a = 0.0; // extras of this thread's best rows
-        int x1_bv = 0, x1_s0 = 0, x2_bv = 0, x2_s0 = 0;
-        double *Ft = Fptr(d, d.rank, par, t);
-        for (int i = r_lo + tid; i < r_hi; i += TH) {
-            const int li = i - r_lo;
-            const int bv = s_e2b[li], s0 = s_lp[li];
-            const double a0 = mine ? d.tab[(size_t)i * Cl + ql] : -ld_cg(Ft + i);
-            const double rh = d.rhsbuf[i];
-            const uint32_t tw = __ldcg(d.tabu + (size_t)q * d.W + (bv >> 5));
-            const int cc = __ldcg(d.col_cnt + bv);
-            double a = a0;
-            if (mine) {
+            __syncthreads();
+            XpMinIdx b1, b2;
+            b1.i = b2.i = -1;
+            b1.v = b2.v = 0.0;
+            double x1_rh = 0.0, x1_a = 0.0, x2_rh = 0.0, x2_a = 0.0; // extras of this thread's best rows
+            int x1_bv = 0, x1_s0 = 0, x2_bv = 0, x2_s0 = 0;
+            for (int i = r_lo + tid; i < r_hi; i += TH) {
+                const int li = i - r_lo;
+                const int rbv = s_e2b[li], s0 = s_lp[li];
+                const double a0 = d.tab[(size_t)i * Cl + ql];
+                const double rh = d.rhsbuf[i];
+                const uint32_t tw = __ldcg(d.tabu + (size_t)q * d.W + (rbv >> 5));
+                const int cc = __ldcg(d.col_cnt + rbv);
+                double a = a0;
                 if (s0 >= 0) a = s_pq[s0];
 #pragma unroll 4
                 for (int s = s0 + 1; s < t; s++) a = xp_add(a, xp_mul(sF[(size_t)s * rpc + li], s_pq[s]));
                 for (int r = 0; r < G; r++) __stcg(Fptr(d, r, par, t) + i, -a);
+                sF[(size_t)t * rpc + li] = -a;
+                if (xp_feq(a, 0.0)) continue;           // neither pass takes a == 0 (tolerant)
+                if ((tw >> (rbv & 31)) & 1u) continue;   // is_handle(q, bv), :589
+                if (cc >= n - 1) continue;               // !canBeBVCandidate, :596
+                XpMinIdx k;
+                k.v = xp_div(rh, a);
+                k.i = i;
+                const XpMinIdx n2 = xp_better(b2, k); // pass 2, :623-658
+                if (n2.i == i) x2_rh = rh, x2_a = a, x2_bv = rbv, x2_s0 = s0;
+                b2 = n2;
+                if (a > 0.0) { // pass 1, :571-612
+                    const XpMinIdx n1 = xp_better(b1, k);
+                    if (n1.i == i) x1_rh = rh, x1_a = a, x1_bv = rbv, x1_s0 = s0;
+                    b1 = n1;
+                }
             }
-            sF[(size_t)t * rpc + li] = -a;
-            if (xp_feq(a, 0.0)) continue;          // neither pass takes a == 0 (tolerant)
-            if ((tw >> (bv & 31)) & 1u) continue;   // is_handle(q, bv), :589
-            if (cc >= n - 1) continue;              // !canBeBVCandidate, :596
-            XpMinIdx k;
-            k.v = xp_div(rh, a);
-            k.i = i;
-            const XpMinIdx n2 = xp_better(b2, k); // pass 2, :623-658
-            if (n2.i == i) x2_rh = rh, x2_a = a, x2_bv = bv, x2_s0 = s0;
-            b2 = n2;
-            if (a > 0.0) { // pass 1, :571-612
-                const XpMinIdx n1 = xp_better(b1, k);
-                if (n1.i == i) x1_rh = rh, x1_a = a, x1_bv = bv, x1_s0 = s0;
-                b1 = n1;
+            PANEL_T(0) // phase A loads + replay
+            {
+                const int my1 = b1.i, my2 = b2.i;
+                argmin2_block(b1, b2, s_mi);
+                PanA *dst = partA + c;
+                if (b1.i >= 0 && my1 == b1.i) { // the thread that owns the CTA's winner writes it out
+                    __stcg(&dst->v1, b1.v), __stcg(&dst->rh1, x1_rh), __stcg(&dst->a1, x1_a);
+                    __stcg(&dst->i1, b1.i), __stcg(&dst->bv1, x1_bv), __stcg(&dst->s01, x1_s0);
+                }
+                if (b2.i >= 0 && my2 == b2.i) {
+                    __stcg(&dst->v2, b2.v), __stcg(&dst->rh2, x2_rh), __stcg(&dst->a2, x2_a);
+                    __stcg(&dst->i2, b2.i), __stcg(&dst->bv2, x2_bv), __stcg(&dst->s02, x2_s0);
+                }
+                if (tid == 0) {
+                    if (b1.i < 0) __stcg(&dst->i1, -1);
+                    if (b2.i < 0) __stcg(&dst->i2, -1);
+                }
             }
-        }
-        if (G > 1 && mine && c == 0 && tid == 0) {
-            const double cqv = d.tgtf[ql];
-            for (int r = 0; r < G; r++) __stcg(Fptr(d, r, par, t) + m, cqv);
-        }
-        PANEL_T(0) // phase A loads + replay
-        {
-            const int my1 = b1.i, my2 = b2.i;
-            argmin2_block(b1, b2, s_mi);
-            PanA *dst = partA + c;
-            if (b1.i >= 0 && my1 == b1.i) { // the thread that owns the CTA's winner writes it out
-                __stcg(&dst->v1, b1.v), __stcg(&dst->rh1, x1_rh), __stcg(&dst->a1, x1_a);
-                __stcg(&dst->i1, b1.i), __stcg(&dst->bv1, x1_bv), __stcg(&dst->s01, x1_s0);
+            PANEL_T(1) // block arg-min + partial store
+            nbar++;
+            if (!grid_barrier(bar, bar_base + (unsigned long long)nbar * NB, G > 1)) {
+                if (tid == 0) st->status = XP_ERR_PEER;
+                return;
             }
-            if (b2.i >= 0 && my2 == b2.i) {
-                __stcg(&dst->v2, b2.v), __stcg(&dst->rh2, x2_rh), __stcg(&dst->a2, x2_a);
-                __stcg(&dst->i2, b2.i), __stcg(&dst->bv2, x2_bv), __stcg(&dst->s02, x2_s0);
+            if (G > 1) cq = ld_cg(d.tgtf + ql);
+            PANEL_T(2) // barrier 1
+            double w_rh1 = 0.0, w_a1 = 0.0, w_rh2 = 0.0, w_a2 = 0.0;
+            int w_bv1 = 0, w_s01 = 0, w_bv2 = 0, w_s02 = 0;
+            b1.i = b2.i = -1;
+            b1.v = b2.v = 0.0;
+            if (tid < NB) {
+                const PanA *src = partA + tid;
+                b1.i = __ldcg(&src->i1), b2.i = __ldcg(&src->i2);
+                b1.v = __ldcg(&src->v1), w_rh1 = __ldcg(&src->rh1), w_a1 = __ldcg(&src->a1);
+                w_bv1 = __ldcg(&src->bv1), w_s01 = __ldcg(&src->s01);
+                b2.v = __ldcg(&src->v2), w_rh2 = __ldcg(&src->rh2), w_a2 = __ldcg(&src->a2);
+                w_bv2 = __ldcg(&src->bv2), w_s02 = __ldcg(&src->s02);
             }
+            {
+                const int my1 = b1.i, my2 = b2.i;
+                argmin2_block(b1, b2, s_mi);
+                if (b1.i >= 0) {
+                    if (tid < NB && my1 == b1.i) s_wd[0] = w_rh1, s_wd[1] = w_a1, s_wi[0] = w_bv1, s_wi[1] = w_s01;
+                } else if (b2.i >= 0) {
+                    if (tid < NB && my2 == b2.i) s_wd[0] = w_rh2, s_wd[1] = w_a2, s_wi[0] = w_bv2, s_wi[1] = w_s02;
+                }
+                __syncthreads();
+            }
+            PANEL_T(3) // partial reduce
+            p = b1.i >= 0 ? b1.i : b2.i;
+            bv = s_wi[0], s0p = s_wi[1];
+            piv_rh = s_wd[0], piv_a = s_wd[1];
+            if (G > 1 && c == 0 && tid < G && tid != d.rank) { // every column chunk landed (barrier): tell peer `tid`
+                XHdr::PivRec *dst = &((XHdr *)d.xb[tid])->piv[cseq & 1];
+                __stcg(&dst->a, piv_a), __stcg(&dst->rh, piv_rh), __stcg(&dst->cq, cq);
+                __stcg(&dst->p, p), __stcg(&dst->bv, bv), __stcg(&dst->s0, s0p);
+                __threadfence_system();
+                st_release_sys((unsigned long long *)(d.xb[tid] + offsetof(XHdr, colflag)) + d.rank, cseq);
+            }
+        } else {
             if (tid == 0) {
-                if (b1.i < 0) __stcg(&dst->i1, -1);
-                if (b2.i < 0) __stcg(&dst->i2, -1);
-            }
-        }
-        PANEL_T(1) // block arg-min + partial store
-        nbar++;
-        if (!grid_barrier(bar, bar_base + (unsigned long long)nbar * NB, G > 1 && mine)) {
-            if (tid == 0) st->status = XP_ERR_PEER;
-            return;
-        }
-        if (G > 1 && mine && c == 0 && tid < G && tid != d.rank) // every CTA's column chunk has landed
-            st_release_sys((unsigned long long *)(d.xb[tid] + offsetof(XHdr, colflag)) + d.rank, cseq);
-        if (G > 1) cq = ld_cg(Ft + m);
-        PANEL_T(2) // barrier 1
-        double w_rh1 = 0.0, w_a1 = 0.0, w_rh2 = 0.0, w_a2 = 0.0;
-        int w_bv1 = 0, w_s01 = 0, w_bv2 = 0, w_s02 = 0;
-        b1.i = b2.i = -1;
-        b1.v = b2.v = 0.0;
-        if (tid < NB) {
-            const PanA *src = partA + tid;
-            b1.i = __ldcg(&src->i1), b2.i = __ldcg(&src->i2);
-            b1.v = __ldcg(&src->v1), w_rh1 = __ldcg(&src->rh1), w_a1 = __ldcg(&src->a1);
-            w_bv1 = __ldcg(&src->bv1), w_s01 = __ldcg(&src->s01);
-            b2.v = __ldcg(&src->v2), w_rh2 = __ldcg(&src->rh2), w_a2 = __ldcg(&src->a2);
-            w_bv2 = __ldcg(&src->bv2), w_s02 = __ldcg(&src->s02);
-        }
-        {
-            const int my1 = b1.i, my2 = b2.i;
-            argmin2_block(b1, b2, s_mi);
-            if (b1.i >= 0) {
-                if (tid < NB && my1 == b1.i) s_wd[0] = w_rh1, s_wd[1] = w_a1, s_wi[0] = w_bv1, s_wi[1] = w_s01;
-            } else if (b2.i >= 0) {
-                if (tid < NB && my2 == b2.i) s_wd[0] = w_rh2, s_wd[1] = w_a2, s_wi[0] = w_bv2, s_wi[1] = w_s02;
+                const unsigned long long *w =
+                    (const unsigned long long *)(d.xb[d.rank] + offsetof(XHdr, colflag)) + owner;
+                const unsigned long long t0 = clock64();
+                unsigned spins = 0;
+                int ok = 1;
+                while (ld_acquire_sys(w) < cseq)
+                    if ((++spins & 1023u) == 0 && clock64() - t0 > SPIN_LIMIT) {
+                        ok = 0;
+                        break;
+                    }
+                s_to = ok;
             }
             __syncthreads();
+            if (!s_to) {
+                if (tid == 0) st->status = XP_ERR_PEER;
+                return;
+            }
+            const XHdr::PivRec *rec = &((const XHdr *)d.xb[d.rank])->piv[cseq & 1];
+            piv_a = ld_cg(&rec->a), piv_rh = ld_cg(&rec->rh), cq = ld_cg(&rec->cq);
+            p = __ldcg(&rec->p), bv = __ldcg(&rec->bv), s0p = __ldcg(&rec->s0);
+            PANEL_T(3)
         }
-        PANEL_T(3) // partial reduce
-        const int p = b1.i >= 0 ? b1.i : b2.i;
         if (p < 0) break; // ratio test failed: k_pcol redoes this column and takes the slow path
-        const int bv = s_wi[0], s0p = s_wi[1];
-        const double r = xp_div(1.0, s_wd[1]); // mulOfRow(eqnum, 1 / pivot), :1471
+        const double r = xp_div(1.0, piv_a); // mulOfRow(eqnum, 1 / pivot), :1471
         const bool r_one = xp_feq(r, 1.0), r_zero = xp_feq(r, 0.0);
         const bool cq_zero = xp_feq(cq, 0.0), cq_one = xp_feq(cq, 1.0);
-        const double prow_rhs = xp_scale(s_wd[0], r, r_one, r_zero);
+        const double prow_rhs = xp_scale(piv_rh, r, r_one, r_zero);
         // ================= phase B: leaving row, objective row, constant column, pricing ====
         if (tid < t) s_fp[tid] = ld_cg(Fptr(d, d.rank, par, tid) + p);
         __syncthreads();
@@ -997,7 +1016,9 @@ k_panel(LpDev d, PanA *partA, PanB *partB, unsigned long long *bar, unsigned lon
             const int g = col0 + jl; // global column index
             const double a0 = d.tab[(size_t)p * Cl + jl];
             const double tg0 = d.tgtf[jl];
-            const int nvraw = g < n ? (int)__ldcg(d.nvset + g) : 0;
+            int nvraw = g < n ? (int)__ldcg(d.nvset + g) : 0;
+            // CTA 0 may still be writing the previous pivot's swap: that one is applied by hand
+            nvraw = g == bv_prev ? 1 : (g == q_prev ? 0 : nvraw);
             const int rc = g < n ? __ldcg(d.row_cnt + g) : INT_BIG;
             double v = a0;
             if (s0p >= 0) v = sP[(size_t)s0p * cpc + lj];
@@ -1023,7 +1044,13 @@ k_panel(LpDev d, PanA *partA, PanB *partB, unsigned long long *bar, unsigned lon
             }
         }
         for (int i = r_lo + tid; i < r_hi; i += TH) {
-            const double f = sF[(size_t)t * rpc + (i - r_lo)];
+            double f;
+            if (mine) {
+                f = sF[(size_t)t * rpc + (i - r_lo)];
+            } else { // the owner wrote this step's multipliers into my F[t]
+                f = ld_cg(Ft + i);
+                sF[(size_t)t * rpc + (i - r_lo)] = f;
+            }
             d.rhsbuf[i] = i == p ? prow_rhs : xp_add(d.rhsbuf[i], xp_mul(f, prow_rhs));
         }
         PANEL_T(4) // phase B loads + replay + stores
@@ -1117,6 +1144,8 @@ k_panel(LpDev d, PanA *partA, PanB *partB, unsigned long long *bar, unsigned lon
             t++;
             cnt++;
             dirty = true;
+            q_prev = q;
+            bv_prev = bv;
             q = cd;
             anypos = ap;
             if (G == 1) cq = cd != INT_BIG ? s_c[32] : 0.0;
