@@ -51,6 +51,7 @@ struct XpB {
     int m, C, n, LD, W; // n = rhs_idx = C-1
     unsigned pivots;
     long long *misc;    // 8 spare 64-bit shared slots (exact path: D, overflow flag)
+    int togk, togi;     // which half of shk / shi the next single-barrier reduction uses
 };
 
 __host__ __device__ inline size_t xpb_align(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -156,15 +157,29 @@ __device__ inline void xpb_disable_nv(XpB<E> &S, int q)
     __syncthreads();
 }
 
+// Block reductions with ONE barrier: every warp leaves its result in one half of the scratch
+// array, all threads combine the (<= 16) warp results themselves, and consecutive reductions
+// alternate halves, so the barrier of the next one is what protects the slots from reuse.
+// (CTAs of more than 512 threads -- the global-memory slab variant -- take the 3-barrier form.)
+
 // Block arg-min over Ops::Key with the reference's "first strict minimum" rule.
 template <class Ops>
-__device__ inline typename Ops::Key xpb_block_best(typename Ops::Key x, void *shk)
+__device__ inline typename Ops::Key xpb_block_best(XpB<typename Ops::E> &S, typename Ops::Key x)
 {
     typedef typename Ops::Key K;
-    K *sh = (K *)shk;
+    K *sh = (K *)S.shk;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) x = Ops::better(x, Ops::shfl_xor(x, o));
+    if (nw <= 16) {
+        K *h = sh + (S.togk & 1) * 16;
+        S.togk++;
+        if (lane == 0) h[w] = x;
+        __syncthreads();
+        K y = h[0];
+        for (int k = 1; k < nw; k++) y = Ops::better(y, h[k]);
+        return y;
+    }
     __syncthreads();
     if (lane == 0) sh[w] = x;
     __syncthreads();
@@ -177,6 +192,40 @@ __device__ inline typename Ops::Key xpb_block_best(typename Ops::Key x, void *sh
     }
     __syncthreads();
     return sh[32];
+}
+
+// Block min of an int and OR of a flag at once.
+template <class E>
+__device__ inline int xpb_min_int_or(XpB<E> &S, int x, int &flag)
+{
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    x = xp_warp_min_int(x);
+    flag = __any_sync(0xffffffffu, flag);
+    if (nw <= 8) {
+        int *h = S.shi + (S.togi & 1) * 16;
+        S.togi++;
+        if (lane == 0) {
+            h[w] = x;
+            h[8 + w] = flag;
+        }
+        __syncthreads();
+        int y = h[0], f = h[8];
+        for (int k = 1; k < nw; k++) {
+            y = min(y, h[k]);
+            f |= h[8 + k];
+        }
+        flag = f;
+        return y;
+    }
+    x = xp_block_min_int(x, S.shi);
+    flag = __syncthreads_or(flag);
+    return x;
+}
+template <class E>
+__device__ inline int xpb_min_int(XpB<E> &S, int x)
+{
+    int f = 0;
+    return xpb_min_int_or(S, x, f);
 }
 
 // findPivotBV (lpsol.h:552-663).  Returns the pivot ROW or -1.
@@ -194,7 +243,7 @@ __device__ inline int xpb_ratio_test(XpB<typename Ops::E> &S, int q)
         if (S.col_cnt[bv] >= n - 1) continue;
         best = Ops::better(best, Ops::make_key(S.tab[i * S.LD + n], a, i));
     }
-    best = xpb_block_best<Ops>(best, S.shk);
+    best = xpb_block_best<Ops>(S, best);
     if (Ops::key_index(best) >= 0) return Ops::key_index(best);
     best = Ops::empty_key();
     for (int i = threadIdx.x; i < S.m; i += blockDim.x) { // pass 2, :623-658
@@ -205,7 +254,7 @@ __device__ inline int xpb_ratio_test(XpB<typename Ops::E> &S, int q)
         if (Ops::is_zero(a)) continue;
         best = Ops::better(best, Ops::make_key(S.tab[i * S.LD + n], a, i));
     }
-    best = xpb_block_best<Ops>(best, S.shk);
+    best = xpb_block_best<Ops>(S, best);
     return Ops::key_index(best);
 }
 
@@ -241,12 +290,10 @@ __device__ inline int xpb_solve_loop(XpB<typename Ops::E> &S, uint32_t max_iter,
                     if (best == XPB_BIG && S.row_cnt[j] < n - 1) best = j;
                 }
             }
-            best = xp_block_min_int(best, S.shi);
-            anypos = __syncthreads_or(anypos);
+            best = xpb_min_int_or(S, best, anypos);
             const int zlim = best == XPB_BIG ? n : best;
-            for (int j = tid; j < zlim; j += blockDim.x)
-                if (!S.nvset[j]) S.tgtf[j] = Ops::zero(); // :1059
-            __syncthreads();
+            for (int j = tid; j < zlim; j += blockDim.x) // only basic entries change and nobody reads
+                if (!S.nvset[j]) S.tgtf[j] = Ops::zero(); // those before the barriers of pivot(), :1059
             if (best == XPB_BIG) {
                 if (!anypos) { // optimal exit, :1089-1127
                     *iters = cnt;
@@ -268,7 +315,7 @@ __device__ inline int xpb_solve_loop(XpB<typename Ops::E> &S, uint32_t max_iter,
                                 break;
                             }
                         }
-                        cand = xp_block_min_int(cand, S.shi);
+                        cand = xpb_min_int(S, cand);
                         if (cand == XPB_BIG) break;
                         int r = xpb_ratio_test<Ops>(S, cand);
                         if (r >= 0) {
@@ -291,8 +338,7 @@ __device__ inline int xpb_solve_loop(XpB<typename Ops::E> &S, uint32_t max_iter,
             if (p >= 0) break;
             xpb_disable_nv(S, q); // :1146-1151
         }
-        const int bv = S.eq2bv[p];
-        __syncthreads();
+        const int bv = S.eq2bv[p]; // (the ratio test's barrier is behind every read of the table)
         if (tid == 0) { // genPair, :1156
             uint32_t *w = &S.tabu[q * S.W + (bv >> 5)];
             const uint32_t bit = 1u << (bv & 31);
@@ -380,7 +426,7 @@ __device__ inline int xpb_two_stage(XpB<typename Ops::E> &S, const XpBatchArgs &
                     cand = j;
                     break;
                 }
-            cand = xp_block_min_int(cand, S.shi);
+            cand = xpb_min_int(S, cand);
             if (cand == XPB_BIG) return XP_ERR_REFERENCE_UB; // reference ASSERTs (:937)
             rc = Ops::pivot(S, eqnum, cand);
             if (rc) return rc;
@@ -450,6 +496,7 @@ __device__ inline void xpb_kernel_body(const XpBatchArgs &A)
     unsigned char *state = GWS ? A.gws + (size_t)blockIdx.x * A.gws_stride : xpb_smem;
     xpb_carve<E, typename Ops::Key>(S, state, A.maxm, A.maxn, &misc);
     Ops::bind(S, misc);
+    S.togk = S.togi = 0;
     for (;;) {
         __syncthreads();
         if (threadIdx.x == 0) s_lp = (int)atomicAdd(A.queue, 1u);

@@ -5,6 +5,8 @@
 // semantics (flty.cpp:41-131) and operation order (lpsol.h:1455-1511).
 #include "xp_batch_core.cuh"
 
+#include <cstdlib>
+
 #include <cstring>
 
 namespace {
@@ -60,7 +62,7 @@ struct OpsF64 {
             k.i = i;
             best = xp_better(best, k);
         }
-        best = xpb_block_best<OpsF64>(best, S.shk);
+        best = xpb_block_best<OpsF64>(S, best);
         return best.i;
     }
 
@@ -167,7 +169,7 @@ struct OpsF64 {
 };
 
 template <int THREADS>
-__global__ void __launch_bounds__(THREADS) k_batch_f64(XpBatchArgs A)
+__global__ void __launch_bounds__(THREADS, (THREADS <= 128 ? 1024 / THREADS : 1)) k_batch_f64(XpBatchArgs A)
 {
     xpb_kernel_body<OpsF64, false>(A);
 }
@@ -180,6 +182,7 @@ __global__ void __launch_bounds__(1024) k_batch_f64_gws(XpBatchArgs A)
 
 int pick_threads(int maxm, int maxn)
 {
+    if (const char *e = getenv("XP_BATCH_THREADS")) return atoi(e); // tuning knob
     long long cells = (long long)maxm * (maxn + maxm + 2);
     if (cells <= 16 * 64) return 64;
     if (cells <= 16 * 256) return 128;

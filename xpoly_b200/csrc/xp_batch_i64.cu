@@ -139,7 +139,7 @@ struct OpsI64 {
             k.i = i;
             best = better(best, k);
         }
-        best = xpb_block_best<OpsI64>(best, S.shk);
+        best = xpb_block_best<OpsI64>(S, best);
         return best.i;
     }
 
@@ -279,7 +279,7 @@ struct OpsI64 {
 };
 
 template <int THREADS>
-__global__ void __launch_bounds__(THREADS) k_batch_i64(XpBatchArgs A)
+__global__ void __launch_bounds__(THREADS, (THREADS <= 128 ? 1024 / THREADS : 1)) k_batch_i64(XpBatchArgs A)
 {
     xpb_kernel_body<OpsI64, false>(A);
 }
