@@ -97,10 +97,7 @@ struct XHdr {
     unsigned long long feas_res;      // (epoch << 2) | flags, broadcast by the last rank
     // k_panel, sharded: the pivot the owner of the entering column decided (ratio test on
     // its own copy of the column), by parity of the column event number
-    struct PivRec {
-        double a, rh, cq; // pivot element, constant term of the pivot row, c_q
-        int p, bv, s0, pad;
-    } piv[2];
+    unsigned long long piv[2][9]; // a, rh, cq (2 words each), p, bv, s0: payload | tag << 32
 };
 constexpr size_t XHDR_BYTES = 1024;
 static_assert(sizeof(XHdr) <= XHDR_BYTES, "exchange header");
@@ -142,9 +139,14 @@ __host__ __device__ __forceinline__ size_t xoff_feas(const LpDev &d)
 {
     return XHDR_BYTES + ((size_t)(2 * KMAX) * d.mpad) * sizeof(double);
 }
+// k_panel, sharded: landing zone of the entering column, two tagged 8-byte words per row
+__host__ __device__ __forceinline__ size_t xoff_land(const LpDev &d, int par)
+{
+    return XHDR_BYTES + ((size_t)(2 * KMAX + 1 + 2 * par) * d.mpad) * sizeof(double);
+}
 __host__ __device__ __forceinline__ size_t xblock_bytes(const LpDev &d)
 {
-    return XHDR_BYTES + ((size_t)(2 * KMAX + 1) * d.mpad) * sizeof(double);
+    return XHDR_BYTES + ((size_t)(2 * KMAX + 5) * d.mpad) * sizeof(double);
 }
 __device__ __forceinline__ double *Fptr(const LpDev &d, int r, int par, int s)
 {
@@ -796,6 +798,52 @@ __device__ __forceinline__ bool grid_barrier(unsigned long long *bar, unsigned l
     return s_ok != 0;
 }
 
+// Tagged words between GPUs: 4 bytes of payload + the 4-byte number of the column event, so a
+// word is valid the moment its tag matches (8-byte stores are single-copy atomic) and neither
+// side needs a system-scope fence on the pivot path.
+__device__ __forceinline__ void ll_put(unsigned long long *w, unsigned tag, unsigned payload)
+{
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(w),
+                 "l"(((unsigned long long)tag << 32) | (unsigned long long)payload)
+                 : "memory");
+}
+__device__ __forceinline__ void ll_put_f64(unsigned long long *w, unsigned tag, double x)
+{
+    const unsigned long long b = (unsigned long long)__double_as_longlong(x);
+    ll_put(w, tag, (unsigned)b);
+    ll_put(w + 1, tag, (unsigned)(b >> 32));
+}
+// Polls two words until both carry `tag`; false on timeout.
+__device__ __forceinline__ bool ll_get_f64(const unsigned long long *w, unsigned tag, double &x)
+{
+    const unsigned long long t0 = clock64();
+    unsigned spins = 0;
+    for (;;) {
+        unsigned long long a, b;
+        asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(a) : "l"(w) : "memory");
+        asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(b) : "l"(w + 1) : "memory");
+        if ((unsigned)(a >> 32) == tag && (unsigned)(b >> 32) == tag) {
+            x = __longlong_as_double((long long)(((b & 0xffffffffULL) << 32) | (a & 0xffffffffULL)));
+            return true;
+        }
+        if ((++spins & 1023u) == 0 && clock64() - t0 > SPIN_LIMIT) return false;
+    }
+}
+__device__ __forceinline__ bool ll_get_u32(const unsigned long long *w, unsigned tag, unsigned &x)
+{
+    const unsigned long long t0 = clock64();
+    unsigned spins = 0;
+    for (;;) {
+        unsigned long long a;
+        asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(a) : "l"(w) : "memory");
+        if ((unsigned)(a >> 32) == tag) {
+            x = (unsigned)a;
+            return true;
+        }
+        if ((++spins & 1023u) == 0 && clock64() - t0 > SPIN_LIMIT) return false;
+    }
+}
+
 constexpr int PANEL_NBAR = 2 * KMAX + 2; // barrier arrivals per CTA and launch (padded on exit)
 
 __host__ __device__ inline size_t panel_smem_bytes(int rpc, int cpc)
@@ -819,7 +867,6 @@ k_panel(LpDev d, PanA *partA, PanB *partB, unsigned long long *bar, unsigned lon
     __shared__ double s_pq[KMAX], s_fp[KMAX];
     __shared__ double s_wd[2]; // winner: rhs, pivot element
     __shared__ int s_wi[2];    // winner: leaving variable, last_piv
-    __shared__ int s_to;
     LpState *st = d.st;
     const int tid = threadIdx.x, c = blockIdx.x, NB = gridDim.x;
     const int n = d.n, m = d.m, Cl = d.Cl, G = d.G, col0 = d.col0;
@@ -900,7 +947,10 @@ k_panel(LpDev d, PanA *partA, PanB *partB, unsigned long long *bar, unsigned lon
                 if (s0 >= 0) a = s_pq[s0];
 #pragma unroll 4
                 for (int s = s0 + 1; s < t; s++) a = xp_add(a, xp_mul(sF[(size_t)s * rpc + li], s_pq[s]));
-                for (int r = 0; r < G; r++) __stcg(Fptr(d, r, par, t) + i, -a);
+                __stcg(Ft + i, -a);
+                for (int r = 0; r < G; r++)
+                    if (r != d.rank)
+                        ll_put_f64((unsigned long long *)(d.xb[r] + xoff_land(d, cseq & 1)) + 2 * i, cseq, -a);
                 sF[(size_t)t * rpc + li] = -a;
                 if (xp_feq(a, 0.0)) continue;           // neither pass takes a == 0 (tolerant)
                 if ((tw >> (rbv & 31)) & 1u) continue;   // is_handle(q, bv), :589
@@ -937,7 +987,7 @@ k_panel(LpDev d, PanA *partA, PanB *partB, unsigned long long *bar, unsigned lon
             }
             PANEL_T(1) // block arg-min + partial store
             nbar++;
-            if (!grid_barrier(bar, bar_base + (unsigned long long)nbar * NB, G > 1)) {
+            if (!grid_barrier(bar, bar_base + (unsigned long long)nbar * NB)) {
                 if (tid == 0) st->status = XP_ERR_PEER;
                 return;
             }
@@ -969,35 +1019,35 @@ k_panel(LpDev d, PanA *partA, PanB *partB, unsigned long long *bar, unsigned lon
             p = b1.i >= 0 ? b1.i : b2.i;
             bv = s_wi[0], s0p = s_wi[1];
             piv_rh = s_wd[0], piv_a = s_wd[1];
-            if (G > 1 && c == 0 && tid < G && tid != d.rank) { // every column chunk landed (barrier): tell peer `tid`
-                XHdr::PivRec *dst = &((XHdr *)d.xb[tid])->piv[cseq & 1];
-                __stcg(&dst->a, piv_a), __stcg(&dst->rh, piv_rh), __stcg(&dst->cq, cq);
-                __stcg(&dst->p, p), __stcg(&dst->bv, bv), __stcg(&dst->s0, s0p);
-                __threadfence_system();
-                st_release_sys((unsigned long long *)(d.xb[tid] + offsetof(XHdr, colflag)) + d.rank, cseq);
+            if (G > 1 && c == 0 && tid < G && tid != d.rank) { // the decision, as tagged words, to peer `tid`
+                unsigned long long *dst = ((XHdr *)d.xb[tid])->piv[cseq & 1];
+                ll_put_f64(dst + 0, cseq, piv_a), ll_put_f64(dst + 2, cseq, piv_rh), ll_put_f64(dst + 4, cseq, cq);
+                ll_put(dst + 6, cseq, (unsigned)p), ll_put(dst + 7, cseq, (unsigned)bv);
+                ll_put(dst + 8, cseq, (unsigned)s0p);
             }
         } else {
-            if (tid == 0) {
-                const unsigned long long *w =
-                    (const unsigned long long *)(d.xb[d.rank] + offsetof(XHdr, colflag)) + owner;
-                const unsigned long long t0 = clock64();
-                unsigned spins = 0;
-                int ok = 1;
-                while (ld_acquire_sys(w) < cseq)
-                    if ((++spins & 1023u) == 0 && clock64() - t0 > SPIN_LIMIT) {
-                        ok = 0;
-                        break;
-                    }
-                s_to = ok;
+            // wait for the owner's decision (nine tagged words in my own exchange block)
+            __shared__ double s_rd[3];
+            __shared__ int s_ri[3];
+            int fail = 0;
+            if (tid < 6) {
+                const unsigned long long *src = ((const XHdr *)d.xb[d.rank])->piv[cseq & 1];
+                if (tid < 3) {
+                    double x = 0.0;
+                    fail = !ll_get_f64(src + 2 * tid, cseq, x);
+                    s_rd[tid] = x;
+                } else {
+                    unsigned x = 0;
+                    fail = !ll_get_u32(src + 3 + tid, cseq, x);
+                    s_ri[tid - 3] = (int)x;
+                }
             }
-            __syncthreads();
-            if (!s_to) {
+            if (__syncthreads_or(fail)) {
                 if (tid == 0) st->status = XP_ERR_PEER;
                 return;
             }
-            const XHdr::PivRec *rec = &((const XHdr *)d.xb[d.rank])->piv[cseq & 1];
-            piv_a = ld_cg(&rec->a), piv_rh = ld_cg(&rec->rh), cq = ld_cg(&rec->cq);
-            p = __ldcg(&rec->p), bv = __ldcg(&rec->bv), s0p = __ldcg(&rec->s0);
+            piv_a = s_rd[0], piv_rh = s_rd[1], cq = s_rd[2];
+            p = s_ri[0], bv = s_ri[1], s0p = s_ri[2];
             PANEL_T(3)
         }
         if (p < 0) break; // ratio test failed: k_pcol redoes this column and takes the slow path
@@ -1043,15 +1093,22 @@ k_panel(LpDev d, PanA *partA, PanB *partB, unsigned long long *bar, unsigned lon
                 }
             }
         }
+        int lost = 0;
         for (int i = r_lo + tid; i < r_hi; i += TH) {
-            double f;
+            double f = 0.0;
             if (mine) {
                 f = sF[(size_t)t * rpc + (i - r_lo)];
-            } else { // the owner wrote this step's multipliers into my F[t]
-                f = ld_cg(Ft + i);
+            } else { // the owner wrote this step's multipliers into my landing zone as tagged words
+                if (!ll_get_f64((const unsigned long long *)(d.xb[d.rank] + xoff_land(d, cseq & 1)) + 2 * i, cseq, f))
+                    lost = 1;
+                __stcg(Ft + i, f); // plain copy for the flush and for later replays
                 sF[(size_t)t * rpc + (i - r_lo)] = f;
             }
             d.rhsbuf[i] = i == p ? prow_rhs : xp_add(d.rhsbuf[i], xp_mul(f, prow_rhs));
+        }
+        if (G > 1 && __syncthreads_or(lost)) {
+            if (tid == 0) st->status = XP_ERR_PEER;
+            return;
         }
         PANEL_T(4) // phase B loads + replay + stores
         if (p >= r_lo && p < r_hi && tid == 0) { // my row caches follow the swap
@@ -1095,10 +1152,9 @@ k_panel(LpDev d, PanA *partA, PanB *partB, unsigned long long *bar, unsigned lon
             if (G > 1) { // all-ranks arg-min: one 8-byte word per rank, lowest index wins
                 xseq++;
                 const size_t off = offsetof(XHdr, cand) + (size_t)(xseq & 1) * MAXR * 8;
-                if (c == 0 && tid < G)
-                    st_release_sys((unsigned long long *)(d.xb[tid] + off) + d.rank,
-                                   ((unsigned long long)xseq << 32) | ((unsigned long long)(ap ? 1u : 0u) << 31) |
-                                       (unsigned long long)(unsigned)cd);
+                if (c == 0 && tid < G) // self-validating word: no fence
+                    ll_put((unsigned long long *)(d.xb[tid] + off) + d.rank, xseq,
+                           (ap ? 0x80000000u : 0u) | (unsigned)cd);
                 const unsigned seq = xseq;
                 if (!wait_words(d, off, 0, G, [seq](unsigned long long v) { return (unsigned)(v >> 32) == seq; })) {
                     if (tid == 0) st->status = XP_ERR_PEER;
