@@ -5,7 +5,7 @@
  * exact fraction-free integer twin of the Rational simplex.  The reference has
  * no FFI of its own (its API is C++ templates in src/com/lpsol.h); each entry
  * point below names the reference interface it replaces, and
- * xpoly_b200/host/xp_six.hpp wraps them with the reference's own signatures
+ * xpoly_b200/host/xp_six.hpp (compiled against the reference headers) wraps them with the reference's own signatures
  * (SIX<Mat,T>::maxm/minm/TwoStageMethod/set_param, MIP<Mat,T>::maxm/minm).
  * INTEGRATION.md shows the binding a maintainer adds.
  *

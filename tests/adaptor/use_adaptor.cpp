@@ -1,0 +1,56 @@
+// Compile/link check of xpoly_b200/host/xp_six.hpp against the reference's headers: the
+// reference's own example (example.cpp:54-93) through SIX<FloatMat,Float>::maxm and
+// Lineq::has_solution-style MIP calls, routed to libxpoly_b200.so.  Running it needs a GPU.
+#include "ltype.h"
+#include "comf.h"
+#include "strbuf.h"
+#include "smempool.h"
+#include "rational.h"
+#include "flty.h"
+#include "sstl.h"
+#include "matt.h"
+#include "bs.h"
+#include "sbs.h"
+#include "sgraph.h"
+#include "xmat.h"
+#include "linsys.h"
+#include "lpsol.h"
+#include "xp_six.hpp"
+
+using namespace xcom;
+
+int main()
+{
+    // max 2x1 - x2  s.t. 2x1 - x2 <= 2, x1 - 5x2 <= -4, x >= 0   (example.cpp:54-61)
+    FloatMat leq(2, 3), tgtf(1, 3), vc(2, 3), eq, sol;
+    double L[2][3] = {{2, -1, 2}, {1, -5, -4}};
+    for (int i = 0; i < 2; i++)
+        for (int j = 0; j < 3; j++) leq.set(i, j, Float(L[i][j]));
+    tgtf.set(0, 0, Float(2.0));
+    tgtf.set(0, 1, Float(-1.0));
+    tgtf.set(0, 2, Float(0.0));
+    vc.set(0, 0, Float(-1.0));
+    vc.set(1, 1, Float(-1.0));
+    SIX<FloatMat, Float> six;
+    Float maxv;
+    UINT st = six.maxm(maxv, sol, tgtf, vc, eq, leq);
+    printf("status %u max %.17g x = (%.17g, %.17g)\n", st, maxv.f(), sol.get(0, 0).f(), sol.get(0, 1).f());
+
+    RMat rleq(2, 3), rtg(1, 3), rvc(2, 3), req, rsol;
+    for (int i = 0; i < 2; i++)
+        for (int j = 0; j < 3; j++) rleq.set(i, j, Rational((int)L[i][j], 1));
+    rtg.set(0, 0, Rational(2, 1));
+    rtg.set(0, 1, Rational(-1, 1));
+    rtg.set(0, 2, Rational(0, 1));
+    rvc.set(0, 0, Rational(-1, 1));
+    rvc.set(1, 1, Rational(-1, 1));
+    SIX<RMat, Rational> rsix;
+    Rational rv;
+    UINT st2 = rsix.minm(rv, rsol, rtg, rvc, req, rleq);
+    printf("minm_rat status %u v %d/%d\n", st2, rv.num(), rv.den());
+    MIP<RMat, Rational> mip;
+    UINT st3 = mip.maxm(rv, rsol, rtg, rvc, req, rleq);
+    printf("mip_max_rat status %u v %d/%d x = (%d/%d, %d/%d)\n", st3, rv.num(), rv.den(), rsol.get(0, 0).num(),
+           rsol.get(0, 0).den(), rsol.get(0, 1).num(), rsol.get(0, 1).den());
+    return st == SIX_SUCC && maxv.f() == 2.0 ? 0 : 1;
+}

@@ -1,0 +1,158 @@
+// Adaptor for the reference tree: routes SIX<FloatMat,Float>, SIX<RMat,Rational> and
+// MIP<RMat,Rational> (maxm / minm) of stevenknown/xpoly to libxpoly_b200.so.
+//
+// Usage (in a translation unit of the reference, after its usual includes -- the order of
+// linsys.cpp:28-41 ending in "lpsol.h"):
+//     #include "xp_six.hpp"
+// The explicit specialisations below replace the generic template bodies of lpsol.h
+// (maxm :1992, minm :1661, MIP::maxm :2635, MIP::minm :2680) for these instantiations only;
+// every other member (set_param, reviseTargetFunc, TwoStageMethod, ...) stays the
+// reference's.  Link with -lxpoly_b200 -lcudart.  See INTEGRATION.md.
+//
+// This header needs the reference's headers and is therefore NOT compiled into the product
+// library; tests/test_adaptor_cpu.py compiles and links it where /root/reference exists.
+#pragma once
+
+#include <stdio.h>
+#include <stdlib.h>
+
+#include "xpoly_b200.h"
+
+namespace xcom {
+
+struct XpCtxHolder { // one context per host thread (the reference is single-threaded)
+    xp_ctx *ctx;
+    XpCtxHolder() : ctx(NULL)
+    {
+        if (xp_ctx_create(0, &ctx) != 0) {
+            fprintf(stderr, "xpoly_b200: %s\n", xp_last_error(ctx));
+            abort(); // no CPU fallback
+        }
+    }
+    ~XpCtxHolder() { xp_ctx_destroy(ctx); }
+};
+inline xp_ctx *xp_thread_ctx()
+{
+    static thread_local XpCtxHolder h;
+    return h.ctx;
+}
+
+template <class Mat> inline void *xp_raw(Mat const &m)
+{ // Matrix<T>::get_matrix() is non-const (matt.h:283); an empty matrix maps to NULL
+    Mat &mm = const_cast<Mat &>(m);
+    return mm.size() ? (void *)mm.get_matrix() : NULL;
+}
+
+inline UINT xp_status(int st)
+{
+    if (st < 0 && st != XP_ERR_REFERENCE_UB && st != XP_ERR_OVERFLOW) {
+        fprintf(stderr, "xpoly_b200: error %d: %s\n", st, xp_last_error(xp_thread_ctx()));
+        abort();
+    }
+    return (UINT)st; // SIX_SUCC .. SIX_TIME_OUT / IP_SUCC .. unchanged (lpsol.h:198-202, :2082-2085)
+}
+
+// ---------------------------------------------------------------- SIX<FloatMat,Float>
+template <>
+inline UINT SIX<FloatMat, Float>::maxm(OUT Float &maxv, OUT FloatMat &sol, FloatMat const &tgtf, IN FloatMat &vc,
+                                       FloatMat const &eq, FloatMat const &leq, INT rhs_idx)
+{
+    const int n = (int)tgtf.get_col_size() - 1; // the last column is the constant (lpsol.h:1516-1558)
+    ASSERT(rhs_idx == -1 || rhs_idx == n, ("unsupported rhs_idx"));
+    sol.reinit(1, n + 1); // lpsol.h:1880
+    double v = 0.0;
+    int st = xp_six_maxm_f64(xp_thread_ctx(), (int)leq.get_row_size(), n, (const double *)xp_raw(tgtf),
+                             (const double *)xp_raw(vc), (int)eq.get_row_size(), (const double *)xp_raw(eq),
+                             (const double *)xp_raw(leq), m_max_iter, &v, (double *)sol.get_matrix(), NULL);
+    maxv = Float(v);
+    return xp_status(st);
+}
+template <>
+inline UINT SIX<FloatMat, Float>::minm(OUT Float &minv, OUT FloatMat &sol, FloatMat const &tgtf, IN FloatMat &vc,
+                                       FloatMat const &eq, FloatMat const &leq, INT rhs_idx)
+{
+    const int n = (int)tgtf.get_col_size() - 1;
+    ASSERT(rhs_idx == -1 || rhs_idx == n, ("unsupported rhs_idx"));
+    sol.reinit(1, n + 1);
+    double v = 0.0;
+    int st = xp_six_minm_f64(xp_thread_ctx(), (int)leq.get_row_size(), n, (const double *)xp_raw(tgtf),
+                             (const double *)xp_raw(vc), (int)eq.get_row_size(), (const double *)xp_raw(eq),
+                             (const double *)xp_raw(leq), m_max_iter, &v, (double *)sol.get_matrix(), NULL);
+    minv = Float(v);
+    return xp_status(st);
+}
+
+// ---------------------------------------------------------------- SIX<RMat,Rational>
+// XP_ERR_OVERFLOW: the exact result does not fit int32/int32 -- the case in which the reference
+// would have silently replaced it by a 7-digit approximation (rational.cpp:189-226).
+template <>
+inline UINT SIX<RMat, Rational>::maxm(OUT Rational &maxv, OUT RMat &sol, RMat const &tgtf, IN RMat &vc,
+                                      RMat const &eq, RMat const &leq, INT rhs_idx)
+{
+    const int n = (int)tgtf.get_col_size() - 1;
+    ASSERT(rhs_idx == -1 || rhs_idx == n, ("unsupported rhs_idx"));
+    sol.reinit(1, n + 1);
+    xp_rat v = {0, 1};
+    int st = xp_six_maxm_rat(xp_thread_ctx(), (int)leq.get_row_size(), n, (const xp_rat *)xp_raw(tgtf),
+                             (const xp_rat *)xp_raw(vc), (int)eq.get_row_size(), (const xp_rat *)xp_raw(eq),
+                             (const xp_rat *)xp_raw(leq), m_max_iter, &v, (xp_rat *)sol.get_matrix(), NULL);
+    maxv = Rational(v.num, v.den);
+    return xp_status(st);
+}
+template <>
+inline UINT SIX<RMat, Rational>::minm(OUT Rational &minv, OUT RMat &sol, RMat const &tgtf, IN RMat &vc,
+                                      RMat const &eq, RMat const &leq, INT rhs_idx)
+{
+    const int n = (int)tgtf.get_col_size() - 1;
+    ASSERT(rhs_idx == -1 || rhs_idx == n, ("unsupported rhs_idx"));
+    sol.reinit(1, n + 1);
+    xp_rat v = {0, 1};
+    int st = xp_six_minm_rat(xp_thread_ctx(), (int)leq.get_row_size(), n, (const xp_rat *)xp_raw(tgtf),
+                             (const xp_rat *)xp_raw(vc), (int)eq.get_row_size(), (const xp_rat *)xp_raw(eq),
+                             (const xp_rat *)xp_raw(leq), m_max_iter, &v, (xp_rat *)sol.get_matrix(), NULL);
+    minv = Rational(v.num, v.den);
+    return xp_status(st);
+}
+
+// ---------------------------------------------------------------- MIP<RMat,Rational>
+// vc must be -I | 0 (MIP::verify, lpsol.h:2349-2358), which is what the C ABI assumes.
+template <>
+inline UINT MIP<RMat, Rational>::maxm(OUT Rational &maxv, OUT RMat &sol, RMat const &tgtf, IN RMat &vc,
+                                      RMat const &eq, RMat const &leq, bool is_bin, IN BMat *rational_indicator,
+                                      INT rhs_idx)
+{
+    ASSERT(rational_indicator == NULL, ("per-variable rational mask: use the reference path"));
+    const int n = (int)tgtf.get_col_size() - 1;
+    ASSERT(rhs_idx == -1 || rhs_idx == n, ("unsupported rhs_idx"));
+    (void)vc;
+    sol.reinit(1, n + 1);
+    xp_rat v = {0, 1};
+    int32_t nodes = 0;
+    int st = xp_mip_solve_rat(xp_thread_ctx(), /*is_min=*/0, is_bin ? 1 : 0, (int)leq.get_row_size(), n,
+                              (const xp_rat *)xp_raw(tgtf), (int)eq.get_row_size(), (const xp_rat *)xp_raw(eq),
+                              (const xp_rat *)xp_raw(leq), &v, (xp_rat *)sol.get_matrix(), &nodes);
+    maxv = Rational(v.num, v.den);
+    m_times = (UINT)nodes; // lpsol.h:2443
+    return xp_status(st);
+}
+template <>
+inline UINT MIP<RMat, Rational>::minm(OUT Rational &minv, OUT RMat &sol, RMat const &tgtf, IN RMat &vc,
+                                      RMat const &eq, RMat const &leq, bool is_bin, IN BMat *rational_indicator,
+                                      INT rhs_idx)
+{
+    ASSERT(rational_indicator == NULL, ("per-variable rational mask: use the reference path"));
+    const int n = (int)tgtf.get_col_size() - 1;
+    ASSERT(rhs_idx == -1 || rhs_idx == n, ("unsupported rhs_idx"));
+    (void)vc;
+    sol.reinit(1, n + 1);
+    xp_rat v = {0, 1};
+    int32_t nodes = 0;
+    int st = xp_mip_solve_rat(xp_thread_ctx(), /*is_min=*/1, is_bin ? 1 : 0, (int)leq.get_row_size(), n,
+                              (const xp_rat *)xp_raw(tgtf), (int)eq.get_row_size(), (const xp_rat *)xp_raw(eq),
+                              (const xp_rat *)xp_raw(leq), &v, (xp_rat *)sol.get_matrix(), &nodes);
+    minv = Rational(v.num, v.den);
+    m_times = (UINT)nodes;
+    return xp_status(st);
+}
+
+} // namespace xcom
