@@ -109,3 +109,31 @@ def test_empty_batch_and_beyond_shared_memory(ctx):
     assert out["status"].shape == (0,)
     lps = [H.gen_dense_lp(77, 130, 129), H.gen_mixed_lp(5, 130, 129, bneg=0.2)]
     run_uniform(ctx, lps, max_iter=60, tag="gmem-slab")
+
+
+def test_c2_full_batch_100k(ctx):
+    """BASELINE config 2 at its full size: 100 000 LPs of tableau 32 x 64 in one call.  Properties
+    that do not need the oracle on every LP: (a) an LP's result does not depend on where it sits
+    in the batch (reversed order gives the reversed results, bit for bit); (b) a ragged launch of
+    the same LPs agrees with the uniform one; (c) a random sample of 200 LPs equals the oracle."""
+    B, m, n = 100_000, 32, 31
+    r = np.random.RandomState(2024)
+    leq = r.uniform(0, 1, size=(B, m, n + 1))
+    leq[:, :, n] = 1.0 + leq[:, :, n] * n
+    tg = r.uniform(0, 1, size=(B, n + 1))
+    tg[:, n] = 0.0
+    a = ctx.two_stage_f64_batch(leq, tg)
+    b = ctx.two_stage_f64_batch(leq[::-1].copy(), tg[::-1].copy())
+    for k in ("status", "pivots", "eq2bv"):
+        assert np.array_equal(a[k], b[k][::-1]), k
+    for k in ("maxv", "slack_sol", "tgtf"):
+        assert np.array_equal(H.bits(a[k]), H.bits(b[k][::-1])), k
+    assert set(np.unique(a["status"])) <= {0, 1, 3}
+    idx = r.choice(B, size=200, replace=False)
+    rag = ctx.two_stage_f64_ragged([(leq[k], tg[k]) for k in idx[:64]])
+    for j, k in enumerate(idx[:64]):
+        assert rag["status"][j] == a["status"][k] and rag["pivots"][j] == a["pivots"][k]
+        assert np.array_equal(H.bits(rag["maxv"][j:j + 1]), H.bits(a["maxv"][k:k + 1]))
+    for k in idx:
+        o = H.two_stage("oracle", "f64", leq[k], tg[k], want_log=True)
+        check_lp(a, int(k), o, m, n, "c2-full")

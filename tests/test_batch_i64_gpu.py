@@ -110,3 +110,26 @@ def test_overflow_is_detected_not_wrapped(ctx):
     g = ctx.two_stage_i64_batch(leq, tg)
     assert (g["status"] == xp.ERR_OVERFLOW).any()
     assert set(np.unique(g["status"]).tolist()) <= {xp.ERR_OVERFLOW, 0, 1, 3}
+
+
+def test_c4_full_batch_10k(ctx):
+    """BASELINE config 4 at its full size: 10 000 exact LPs of tableau 24 x 48.  Order
+    independence over the whole batch, and a sample of 150 LPs against the oracle's Rational
+    solver (LPs where the reference fell into appro() are outside the parity set)."""
+    B, m, n = 10_000, 24, 23
+    r = np.random.RandomState(777)
+    A = r.randint(0, 4, size=(B, m, n)) * (r.uniform(size=(B, m, n)) < 0.3)
+    leq = np.zeros((B, m, n + 1), dtype=np.int64)
+    leq[:, :, :n] = A
+    leq[:, :, n] = r.randint(0, 21, size=(B, m))
+    tg = np.zeros((B, n + 1), dtype=np.int64)
+    tg[:, :n] = r.randint(1, 6, size=(B, n))
+    a = ctx.two_stage_i64_batch(leq, tg)
+    b = ctx.two_stage_i64_batch(leq[::-1].copy(), tg[::-1].copy())
+    for k in ("status", "pivots", "eq2bv", "maxv", "sol_num", "sol_den", "tgtf_num", "tgtf_den"):
+        assert np.array_equal(a[k], b[k][::-1]), k
+    assert (a["status"] == xp.ERR_OVERFLOW).sum() == 0
+    checked = 0
+    for k in r.choice(B, size=150, replace=False):
+        checked += check(a, int(k), oracle_exact(leq[k].astype(float), tg[k].astype(float)), m, n, "c4-full")
+    assert checked > 100

@@ -136,3 +136,41 @@ def test_linearity_property_full_size_sample(ctx):
         assert abs(col[r] - 1.0) < 1e-9
         assert np.abs(np.delete(col, r)).max() < 1e-9
     lp.close()
+
+
+def test_c3_full_size_properties_and_oracle_sample(ctx):
+    """BASELINE config 3 at its full size (8192 x 16384, 1 GiB): (a) the state after K pivots
+    does not depend on the block size -- k = 1 is the reference's own schedule of one tableau
+    pass per pivot, k = 32 applies 32 pivots per pass -- checked through the position-keyed
+    checksum of all 134 M doubles, the basis and the pivot sequence; (b) stopping and resuming
+    gives the same bits as running through; (c) pivot sequence, basis and objective constant
+    after a bounded sample equal the oracle's (the CPU needs ~0.15 s per pivot here)."""
+    from xpoly_b200.synth import dense_lp
+    m, n, K = 8192, 8191, 48
+    lp = ctx.large_lp(m, n + m + 1)
+    res = {}
+    for k in (1, 32, 7):
+        lp.set_block(k)
+        lp.fill_synthetic(20261017)
+        assert lp.solve(K) == xp.SIX_TIME_OUT
+        a = lp.download(want_tab=False, log_cap=K)
+        res[k] = (lp.checksum(), a["eq2bv"].copy(), a["log"].copy(), H.bits(a["tgtf"]).copy())
+    for k in (32, 7):
+        assert res[k][0] == res[1][0], ("checksum", k)
+        assert np.array_equal(res[k][1], res[1][1]) and np.array_equal(res[k][2], res[1][2])
+        assert np.array_equal(res[k][3], res[1][3])
+    lp.set_block(0)
+    lp.fill_synthetic(20261017)
+    for stop in (5, 17, K):
+        assert lp.solve(stop) == xp.SIX_TIME_OUT
+    assert lp.checksum() == res[1][0]
+    Ks = 10  # oracle sample
+    leq, tg = dense_lp(20261017, m, n)
+    o = H.slack_solve_oracle("f64", *xp.slack_form(leq, tg), max_iter=Ks, log_cap=Ks)
+    lp.fill_synthetic(20261017)
+    lp.solve(Ks)
+    a = lp.download(want_tab=False, log_cap=Ks)
+    assert np.array_equal(a["log"], o["log"])
+    assert np.array_equal(a["eq2bv"], o["eq2bv"])
+    assert np.array_equal(H.bits(a["tgtf"]), H.bits(o["tgtf"]))
+    lp.close()
