@@ -474,7 +474,7 @@ def main():
     ap.add_argument("--m", type=int, default=M_ROWS)
     ap.add_argument("--n", type=int, default=N_VARS)
     ap.add_argument("--cpu-pivots", type=int, default=12)
-    ap.add_argument("--ref-pivots", type=int, default=4)
+    ap.add_argument("--ref-pivots", type=int, default=3)
     ap.add_argument("--port", action="store_true", help="reference arm: force the oracle port")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-batched", action="store_true")
