@@ -44,10 +44,13 @@ def measured_peak_gbs():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    """nvidia-smi clocks / throttle reasons DURING the timed region.  The sampler is started
+    early (nvidia-smi needs a second or two before its first line), every line is stamped on
+    arrival, and `window(t0, t1)` summarises the lines that arrived inside the timed region."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index=0):
         self.index, self.proc, self.lines = index, None, []
@@ -56,7 +59,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                 "--format=csv,noheader,nounits", "-lms", "20"],
+                 "--format=csv,noheader,nounits", "-lms", "10"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -65,19 +68,30 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
+
+    def wait_ready(self, timeout=10.0):
+        t0 = time.perf_counter()
+        while self.proc and not self.lines and time.perf_counter() - t0 < timeout:
+            time.sleep(0.02)
 
     def stop(self):
         if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
+
+    def window(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0,
+                    "reasons": ["nvidia-smi unavailable"]}
         sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for ts, ln in list(self.lines):
+            if ts < t0 or ts > t1:
+                continue
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 7:
                 continue
@@ -86,7 +100,7 @@ class ClockSampler:
                 mx.append(float(f[1]))
             except ValueError:
                 continue
-            for nm, v in zip(names, f[3:7]):
+            for nm, v in zip(self.NAMES, f[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": float(np.median(sm)) if sm else None,
@@ -191,15 +205,27 @@ def run_batched(ctx, xp, torch, dev):
     dev_ms = float(np.median(ms))
     st = status.cpu().numpy()
     tot_piv = int(pivots.cpu().numpy().astype(np.int64).sum())
-    # end to end through the host-pointer C-ABI call (H2D of all LPs, D2H of results)
-    h_leq = leq.cpu().numpy()
-    h_tg = tg.cpu().numpy()
+    # end to end through the host-pointer C-ABI call (H2D of all LPs from PINNED host memory,
+    # D2H of results)
+    def pinned_like(t):
+        hp = C.c_void_p()
+        ctx.check(lib.xp_host_alloc(ctx._h, C.c_size_t(t.numel() * 8), C.byref(hp)))
+        a = np.ctypeslib.as_array(C.cast(hp, C.POINTER(C.c_double)), shape=tuple(t.shape))
+        a[...] = t.cpu().numpy()
+        return a, hp
+    h_leq, hp1 = pinned_like(leq)
+    h_tg, hp2 = pinned_like(tg)
     t_e2e = []
     for _ in range(3):
         t0 = time.perf_counter()
         out = ctx.two_stage_f64_batch(h_leq, h_tg, want=("status", "maxv"))
         t_e2e.append(time.perf_counter() - t0)
     e2e_s = float(np.median(t_e2e))
+    e2e_status = out["status"].copy()
+    h2d_bytes = int(h_leq.nbytes + h_tg.nbytes)
+    del h_leq, h_tg
+    ctx.check(lib.xp_host_free(ctx._h, hp1))
+    ctx.check(lib.xp_host_free(ctx._h, hp2))
     smem_bytes = tot_piv * 2.0 * (m + 1) * (n + m + 1) * 8
     return {
         "metric": "small LPs/s", "workload": f"c2: {B} LPs, tableau {m}x{n + m + 1}, FP64",
@@ -208,9 +234,11 @@ def run_batched(ctx, xp, torch, dev):
         "smem_algorithmic_GBps": smem_bytes / (dev_ms * 1e-3) / 1e9,
         "status_mix": {str(k): int((st == k).sum()) for k in np.unique(st)},
         "e2e": {"value": B / e2e_s, "unit": "LPs/s",
-                "h2d_bytes_per_step": int(h_leq.nbytes + h_tg.nbytes),
-                "d2h_bytes_per_step": int(B * 12)},
-        "status_matches_e2e": bool(np.array_equal(out["status"], st)),
+                "h2d_bytes_per_step": h2d_bytes,
+                "d2h_bytes_per_step": int(B * 12),
+                "api": "xp_six_two_stage_f64_batch (pinned host buffers; chunks uploaded while "
+                       "the previous chunk is being solved)"},
+        "status_matches_e2e": bool(np.array_equal(e2e_status, st)),
     }
 
 
@@ -287,6 +315,8 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     ctx = xp.Context(local_rank)
     lib = xp.lib()
     m, n = args.m, args.n
@@ -301,7 +331,7 @@ def run_ours(args):
     peak, peak_src = measured_peak_gbs()
     B_pivot = 2.0 * (m + 1) * local_cols * 8  # read+write of every entry, per pivot
 
-    def timed_run(block, pivots, steps, warmup):
+    def timed_run(block, pivots, steps, warmup, load_s=0.0):
         """`steps` steps of `pivots` simplex iterations each; device time = max over ranks."""
         lp.set_block(block)
         lp.fill_synthetic(SEED)
@@ -325,7 +355,8 @@ def run_ours(args):
         for _ in range(steps):
             dev_ms += step()
         barrier()
-        wall = time.perf_counter() - t0
+        t1 = time.perf_counter()
+        wall = t1 - t0
         launches = ctx.launches - l0
         if world > 1:
             t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
@@ -334,13 +365,27 @@ def run_ours(args):
         n_sw, sw_ms, gap_ms = C.c_uint64(0), C.c_double(0), C.c_double(0)
         lib.xp_lp_f64_profile_read(lp._h, C.byref(n_sw), C.byref(sw_ms), C.byref(gap_ms))
         lib.xp_lp_f64_profile(lp._h, 0)
+        # The timed region can be shorter than nvidia-smi's sampling period (8 GPUs: a few ms
+        # per step): keep the identical load running, untimed, until the clock sampler has had
+        # `load_s` seconds of it.  Every rank derives the same count from the reduced time.
+        extra = 0
+        if load_s > 0 and dev_ms > 0 and dev_ms * 1e-3 < load_s:
+            extra = int(np.ceil((load_s - dev_ms * 1e-3) / (dev_ms * 1e-3 / steps)))
+            for _ in range(extra):
+                step()
+            barrier()
+        t2 = time.perf_counter()
         return dict(dev_ms=dev_ms, wall=wall, launches=launches, pivots=steps * pivots,
-                    flushes=int(n_sw.value), flush_ms=sw_ms.value, gap_ms=gap_ms.value)
+                    flushes=int(n_sw.value), flush_ms=sw_ms.value, gap_ms=gap_ms.value,
+                    t0=t0, t1=t1, t2=t2, extra_steps=extra)
 
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    main = timed_run(args.block, P, args.steps, args.warmup)
-    clocks = sampler.stop()
+    sampler.wait_ready()
+    main = timed_run(args.block, P, args.steps, args.warmup, load_s=0.5)
+    sampler.stop()
+    clocks = sampler.window(main["t0"], main["t2"])
+    clocks["window"] = ("timed region" if main["extra_steps"] == 0 else
+                        f"timed region + {main['extra_steps']} untimed steps of the identical load "
+                        "(the timed region alone is shorter than the sampling period)")
     value = main["pivots"] / (main["dev_ms"] * 1e-3)
     k_eff = main["pivots"] / max(main["flushes"], 1)  # pivots applied per k_flush launch
     flush_avg_ms = main["flush_ms"] / max(main["flushes"], 1)
@@ -454,7 +499,63 @@ def run_ours(args):
             line["batched"] = run_batched(ctx, xp, torch, dev)
             line.update(run_exact_and_bnb(ctx, xp))
     else:
-        line["e2e"] = None
+        # ---- e2e at N GPUs: every rank moves ITS column slice of the host tableau through the
+        # C-ABI handle calls (upload of the full host arrays keeps the rank's slice, download
+        # writes the rank's columns back), pinned host buffers, all copies inside the timed
+        # region; wall clock between barriers, max over ranks.
+        tab_bytes = m * Ccols * 8
+        hp_in, hp_out = C.c_void_p(), C.c_void_p()
+        ctx.check(lib.xp_host_alloc(ctx._h, C.c_size_t(tab_bytes), C.byref(hp_in)))
+        ctx.check(lib.xp_host_alloc(ctx._h, C.c_size_t(tab_bytes), C.byref(hp_out)))
+        lp.set_block(args.block)
+        lp.fill_synthetic(SEED)
+        st0 = lp.download(want_tab=False)
+        ctx.check(lib.xp_lp_f64_download(lp._h, hp_in, None, None, None, None, None, None, None,
+                                         None, None, 0))
+        h_in = np.ctypeslib.as_array(C.cast(hp_in, C.POINTER(C.c_double)), shape=(m, Ccols))
+        # replicated inputs every rank needs whole: the constant column and the objective row
+        rhs = torch.from_numpy(np.ascontiguousarray(h_in[:, Ccols - 1])).to(dev)
+        dist.broadcast(rhs, src=world - 1)
+        h_in[:, Ccols - 1] = rhs.cpu().numpy()
+        tgt = torch.from_numpy(st0["tgtf"].copy()).to(dev)
+        dist.all_reduce(tgt)  # slices are disjoint, the rest of each rank's row is zero
+        tg0 = tgt.cpu().numpy()
+        nv0, b2e0, e2b0 = st0["nvset"].copy(), st0["bv2eq"].copy(), st0["eq2bv"].copy()
+        bvs0 = st0["bvset"].copy()
+        tg1, nv1, bvs1 = np.zeros(Ccols), np.zeros_like(nv0), np.zeros_like(bvs0)
+        b2e1, e2b1 = np.zeros_like(b2e0), np.zeros_like(e2b0)
+        maxv, sol = np.zeros(1), np.zeros(Ccols)
+        iters = np.zeros(1, dtype=np.uint32)
+        p = lambda a: a.ctypes.data_as(C.c_void_p)
+
+        def e2e_step():
+            barrier()
+            t0 = time.perf_counter()
+            ctx.check(lib.xp_lp_f64_upload(lp._h, hp_in, p(tg0), p(nv0), p(bvs0), p(b2e0), p(e2b0),
+                                           None, None))
+            st = ctx.check(lib.xp_lp_f64_solve(lp._h, C.c_uint32(P), 0))
+            ctx.check(lib.xp_lp_f64_download(lp._h, hp_out, p(tg1), p(nv1), p(bvs1), p(b2e1),
+                                             p(e2b1), p(maxv), p(sol), p(iters), None, 0))
+            barrier()
+            return time.perf_counter() - t0, int(iters[0]), st
+        e2e_step()
+        ts, its = [], 0
+        for _ in range(max(2, min(args.steps, 4))):
+            dt, it, _st = e2e_step()
+            ts.append(dt)
+            its += it
+        tt = torch.tensor([sum(ts)], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        small = Ccols * 8 + (Ccols - 1) * (1 + 4) + m * 4
+        line["e2e"] = {"value": its / float(tt.item()), "unit": "pivots/s",
+                       "h2d_bytes_per_step": int(tab_bytes + world * small + (world - 1) * m * 8),
+                       "d2h_bytes_per_step": int(tab_bytes + world * (small + Ccols * 8)),
+                       "ms_per_step": 1000.0 * float(tt.item()) / len(ts), "pivots_per_step": P,
+                       "api": "xp_lp_f64_upload + xp_lp_f64_solve + xp_lp_f64_download on the "
+                              "column-sharded handle (pinned host buffers, each rank moves its "
+                              "own column slice over its own PCIe link)"}
+        ctx.check(lib.xp_host_free(ctx._h, hp_in))
+        ctx.check(lib.xp_host_free(ctx._h, hp_out))
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -38,6 +38,15 @@ extern "C" void xp_ctx_destroy(xp_ctx *ctx)
         xp_large_release_cached(ctx);
         if (ctx->scratch) cudaFree(ctx->scratch);
         if (ctx->gws) cudaFree(ctx->gws);
+        if (ctx->pipe_copy) {
+            cudaStreamDestroy(ctx->pipe_copy);
+            cudaEventDestroy(ctx->pipe_begin);
+            for (int c = 0; c < XP_PIPE_MAX; c++) {
+                cudaStreamDestroy(ctx->pipe_stream[c]);
+                cudaEventDestroy(ctx->pipe_up[c]);
+                cudaEventDestroy(ctx->pipe_done[c]);
+            }
+        }
         cudaEventDestroy(ctx->ev0);
         cudaEventDestroy(ctx->ev1);
         cudaStreamDestroy(ctx->stream);
@@ -80,6 +89,19 @@ int xp_ctx_gws(xp_ctx *ctx, size_t bytes, void **out)
         ctx->gws_bytes = bytes;
     }
     *out = ctx->gws;
+    return 0;
+}
+
+int xp_ctx_pipe(xp_ctx *ctx)
+{
+    if (ctx->pipe_copy) return 0;
+    XP_CUDA_OK(ctx, cudaEventCreateWithFlags(&ctx->pipe_begin, cudaEventDisableTiming));
+    for (int c = 0; c < XP_PIPE_MAX; c++) {
+        XP_CUDA_OK(ctx, cudaStreamCreateWithFlags(&ctx->pipe_stream[c], cudaStreamNonBlocking));
+        XP_CUDA_OK(ctx, cudaEventCreateWithFlags(&ctx->pipe_up[c], cudaEventDisableTiming));
+        XP_CUDA_OK(ctx, cudaEventCreateWithFlags(&ctx->pipe_done[c], cudaEventDisableTiming));
+    }
+    XP_CUDA_OK(ctx, cudaStreamCreateWithFlags(&ctx->pipe_copy, cudaStreamNonBlocking)); // last: marks "ready"
     return 0;
 }
 

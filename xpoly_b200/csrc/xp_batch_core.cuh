@@ -604,50 +604,97 @@ inline int xpb_host_run(xp_ctx *ctx, const XpBatchHost &H, XpBatchLaunch launch)
     int32_t *d_st = H.status ? (int32_t *)take(B * 4) : nullptr;
     uint32_t *d_it = H.iters ? (uint32_t *)take(B * 4) : nullptr;
     uint32_t *d_pv = H.pivots ? (uint32_t *)take(B * 4) : nullptr;
-    XP_CUDA_OK(ctx, cudaMemcpyAsync(d_leq, H.leq, H.leq_len * 8, cudaMemcpyHostToDevice, s));
-    XP_CUDA_OK(ctx, cudaMemcpyAsync(d_tg, H.tgtf, H.tgtf_len * 8, cudaMemcpyHostToDevice, s));
-    XpBatchArgs A;
-    memset(&A, 0, sizeof A);
-    A.batch = H.batch;
-    A.m = H.m;
-    A.n = H.n;
-    A.ms = d_ms;
-    A.ns = d_ns;
-    A.leq_off = d_lo;
-    A.tgtf_off = d_to;
-    A.leq = d_leq;
-    A.tgtf = d_tg;
-    A.max_iter = H.max_iter;
-    A.ldo = H.ldo;
-    A.ldm = H.ldm;
-    A.status = d_st;
-    A.maxv = d_maxv;
-    A.slack_sol = d_sol;
-    A.slack_sol2 = d_sol2;
-    A.tgtf_out = d_tgo;
-    A.tgtf_out2 = d_tgo2;
-    A.eq2bv = d_e2b;
-    A.iters = d_it;
-    A.pivots = d_pv;
-    A.maxm = maxm;
-    A.maxn = maxn;
-    A.queue = queue;
-    XP_CUDA_OK(ctx, cudaEventRecord(ctx->ev0, s));
-    rc = launch(ctx, A);
-    if (rc) return rc;
-    XP_CUDA_OK(ctx, cudaEventRecord(ctx->ev1, s));
-#define XPB_D2H(dst, src, bytes) \
-    if (dst) XP_CUDA_OK(ctx, cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyDeviceToHost, s))
-    XPB_D2H(H.status, d_st, B * 4);
-    XPB_D2H(H.maxv, d_maxv, B * 8 * H.maxv_elems);
-    XPB_D2H(H.slack_sol, d_sol, B * ldo * 8);
-    XPB_D2H(H.slack_sol2, d_sol2, B * ldo * 8);
-    XPB_D2H(H.tgtf_out, d_tgo, B * ldo * 8);
-    XPB_D2H(H.tgtf_out2, d_tgo2, B * ldo * 8);
-    XPB_D2H(H.eq2bv, d_e2b, B * ldm * 4);
-    XPB_D2H(H.iters, d_it, B * 4);
-    XPB_D2H(H.pivots, d_pv, B * 4);
+    // Large uniform batches of small LPs are pipelined: the pool is cut into chunks, chunk c+1
+    // is uploaded (copy stream) while chunk c is being solved, and every chunk runs on its own
+    // stream so that the long tail of one chunk (unbounded LPs exit only after exhausting the
+    // tabu table) overlaps the next chunk's work.  Small or ragged batches: one chunk on the
+    // ctx stream.
+    const size_t in_bytes = (H.leq_len + H.tgtf_len) * 8;
+    int nc = 1;
+    if (!H.ms && in_bytes >= ((size_t)48 << 20) && (size_t)maxm * (maxn + maxm + 2) * 8 <= (64u << 10)) {
+        nc = (int)(in_bytes >> 26) + 1; // ~64 MB per chunk
+        if (nc > XP_PIPE_MAX) nc = XP_PIPE_MAX;
+        if ((size_t)nc > B / 1024) nc = (int)(B / 1024);
+        if (nc < 1) nc = 1;
+    }
+    if (nc > 1) {
+        rc = xp_ctx_pipe(ctx);
+        if (rc) return rc;
+        XP_CUDA_OK(ctx, cudaEventRecord(ctx->pipe_begin, s));
+        XP_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->pipe_copy, ctx->pipe_begin, 0));
+    }
+    const size_t per_leq = nc > 1 ? (size_t)H.m * (H.n + 1) : 0, per_tg = nc > 1 ? (size_t)H.n + 1 : 0;
+    for (int c = 0; c < nc; c++) {
+        const size_t k0 = B * c / nc, k1 = B * (c + 1) / nc, nb = k1 - k0;
+        cudaStream_t cs = nc > 1 ? ctx->pipe_stream[c] : s; // solve + download of this chunk
+        cudaStream_t up = nc > 1 ? ctx->pipe_copy : s;      // uploads, in chunk order
+        if (nc > 1) {
+            XP_CUDA_OK(ctx, cudaMemcpyAsync((char *)d_leq + k0 * per_leq * 8, (const char *)H.leq + k0 * per_leq * 8,
+                                            nb * per_leq * 8, cudaMemcpyHostToDevice, up));
+            XP_CUDA_OK(ctx, cudaMemcpyAsync((char *)d_tg + k0 * per_tg * 8, (const char *)H.tgtf + k0 * per_tg * 8,
+                                            nb * per_tg * 8, cudaMemcpyHostToDevice, up));
+            XP_CUDA_OK(ctx, cudaEventRecord(ctx->pipe_up[c], up));
+            XP_CUDA_OK(ctx, cudaStreamWaitEvent(cs, ctx->pipe_begin, 0));
+            XP_CUDA_OK(ctx, cudaStreamWaitEvent(cs, ctx->pipe_up[c], 0));
+        } else {
+            XP_CUDA_OK(ctx, cudaMemcpyAsync(d_leq, H.leq, H.leq_len * 8, cudaMemcpyHostToDevice, s));
+            XP_CUDA_OK(ctx, cudaMemcpyAsync(d_tg, H.tgtf, H.tgtf_len * 8, cudaMemcpyHostToDevice, s));
+        }
+        XpBatchArgs A;
+        memset(&A, 0, sizeof A);
+        A.batch = (int)nb;
+        A.m = H.m;
+        A.n = H.n;
+        A.ms = d_ms;
+        A.ns = d_ns;
+        A.leq_off = d_lo;
+        A.tgtf_off = d_to;
+        A.leq = (char *)d_leq + k0 * per_leq * 8;
+        A.tgtf = (char *)d_tg + k0 * per_tg * 8;
+        A.max_iter = H.max_iter;
+        A.ldo = H.ldo;
+        A.ldm = H.ldm;
+#define XPB_AT(ptr, stride) ((ptr) ? (void *)((char *)(ptr) + k0 * (size_t)(stride)) : nullptr)
+        A.status = (int32_t *)XPB_AT(d_st, 4);
+        A.maxv = XPB_AT(d_maxv, 8 * H.maxv_elems);
+        A.slack_sol = XPB_AT(d_sol, ldo * 8);
+        A.slack_sol2 = XPB_AT(d_sol2, ldo * 8);
+        A.tgtf_out = XPB_AT(d_tgo, ldo * 8);
+        A.tgtf_out2 = XPB_AT(d_tgo2, ldo * 8);
+        A.eq2bv = (int32_t *)XPB_AT(d_e2b, ldm * 4);
+        A.iters = (uint32_t *)XPB_AT(d_it, 4);
+        A.pivots = (uint32_t *)XPB_AT(d_pv, 4);
+        A.maxm = maxm;
+        A.maxn = maxn;
+        A.queue = queue + c; // one work-queue counter per chunk (chunks overlap)
+        if (c == 0) XP_CUDA_OK(ctx, cudaEventRecord(ctx->ev0, cs));
+        ctx->stream = cs; // the launcher issues on ctx->stream
+        rc = launch(ctx, A);
+        ctx->stream = s;
+        if (rc) return rc;
+        if (nc == 1) XP_CUDA_OK(ctx, cudaEventRecord(ctx->ev1, s));
+#define XPB_D2H(dst, src, stride)                                                               \
+    if (dst)                                                                                    \
+    XP_CUDA_OK(ctx, cudaMemcpyAsync((char *)(dst) + k0 * (size_t)(stride), XPB_AT(src, stride), \
+                                    nb * (size_t)(stride), cudaMemcpyDeviceToHost, cs))
+        XPB_D2H(H.status, d_st, 4);
+        XPB_D2H(H.maxv, d_maxv, 8 * H.maxv_elems);
+        XPB_D2H(H.slack_sol, d_sol, ldo * 8);
+        XPB_D2H(H.slack_sol2, d_sol2, ldo * 8);
+        XPB_D2H(H.tgtf_out, d_tgo, ldo * 8);
+        XPB_D2H(H.tgtf_out2, d_tgo2, ldo * 8);
+        XPB_D2H(H.eq2bv, d_e2b, ldm * 4);
+        XPB_D2H(H.iters, d_it, 4);
+        XPB_D2H(H.pivots, d_pv, 4);
 #undef XPB_D2H
+#undef XPB_AT
+        if (nc > 1) {
+            XP_CUDA_OK(ctx, cudaEventRecord(ctx->pipe_done[c], cs));
+            XP_CUDA_OK(ctx, cudaStreamWaitEvent(s, ctx->pipe_done[c], 0));
+        }
+    }
+    // pipelined: ev0 .. ev1 spans first kernel start .. last chunk complete
+    if (nc > 1) XP_CUDA_OK(ctx, cudaEventRecord(ctx->ev1, s));
     XP_CUDA_OK(ctx, cudaStreamSynchronize(s));
     XP_CUDA_OK(ctx, cudaEventElapsedTime(&ctx->last_kernel_ms, ctx->ev0, ctx->ev1));
     return 0;

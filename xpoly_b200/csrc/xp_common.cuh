@@ -15,6 +15,8 @@
 #define XPI_RUNNING (-1)
 #define XPI_OPT_PENDING (-2) /* no c_j > 0 left: feasibility check outstanding */
 
+#define XP_PIPE_MAX 16 /* chunks in flight of a pipelined batched host call */
+
 struct xp_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -32,6 +34,10 @@ struct xp_ctx {
     // global-memory state slabs of the batched kernels (LPs beyond shared memory)
     void *gws = nullptr;
     size_t gws_bytes = 0;
+    // upload/solve pipeline of the batched host-pointer entry points (xp_ctx_pipe)
+    cudaStream_t pipe_copy = nullptr;
+    cudaStream_t pipe_stream[XP_PIPE_MAX] = {};
+    cudaEvent_t pipe_begin = nullptr, pipe_up[XP_PIPE_MAX] = {}, pipe_done[XP_PIPE_MAX] = {};
 };
 
 #define XP_CUDA_OK(ctx, expr)                                                                  \
@@ -146,4 +152,5 @@ __device__ __forceinline__ int xp_block_min_int(int x, int *sh)
 // host-side helpers shared by the translation units
 int xp_ctx_scratch(xp_ctx *ctx, size_t bytes, void **out);
 int xp_ctx_gws(xp_ctx *ctx, size_t bytes, void **out);
+int xp_ctx_pipe(xp_ctx *ctx); // create the pipeline streams / events on first use
 void xp_large_release_cached(xp_ctx *ctx);
