@@ -673,6 +673,14 @@ inline int xpb_host_run(xp_ctx *ctx, const XpBatchHost &H, XpBatchLaunch launch)
         ctx->stream = s;
         if (rc) return rc;
         if (nc == 1) XP_CUDA_OK(ctx, cudaEventRecord(ctx->ev1, s));
+#undef XPB_AT
+    }
+    // Downloads are issued only after every chunk is queued: a D2H copy into pageable memory
+    // blocks the calling thread until it has completed.
+    for (int c = 0; c < nc; c++) {
+        const size_t k0 = B * c / nc, k1 = B * (c + 1) / nc, nb = k1 - k0;
+        cudaStream_t cs = nc > 1 ? ctx->pipe_stream[c] : s;
+#define XPB_AT(ptr, stride) ((ptr) ? (void *)((char *)(ptr) + k0 * (size_t)(stride)) : nullptr)
 #define XPB_D2H(dst, src, stride)                                                               \
     if (dst)                                                                                    \
     XP_CUDA_OK(ctx, cudaMemcpyAsync((char *)(dst) + k0 * (size_t)(stride), XPB_AT(src, stride), \
