@@ -137,3 +137,57 @@ def test_c2_full_batch_100k(ctx):
     for k in idx:
         o = H.two_stage("oracle", "f64", leq[k], tg[k], want_log=True)
         check_lp(a, int(k), o, m, n, "c2-full")
+
+
+def _ab(ctx, fn):
+    """Run fn() with the one-warp-per-LP register kernel (default for LPs of at most 32 rows /
+    64 variables) and again with the one-CTA-per-LP shared-memory kernel forced."""
+    import os
+    os.environ["XP_BATCH_WARP"] = "1"
+    a = fn()
+    os.environ["XP_BATCH_WARP"] = "0"
+    try:
+        b = fn()
+    finally:
+        os.environ.pop("XP_BATCH_WARP", None)
+    return a, b
+
+
+@pytest.mark.parametrize("m,n,bneg", [(32, 31, 0.0), (32, 31, 0.3), (24, 23, 0.3), (16, 40, 0.2),
+                                      (8, 55, 0.3), (8, 7, 0.3), (16, 15, 0.0), (5, 3, 0.5)])
+def test_warp_kernel_equals_cta_kernel(ctx, m, n, bneg):
+    """The register-resident warp kernel and the shared-memory CTA kernel are two schedules of
+    the same arithmetic: every output of a 4096-LP batch must agree bit for bit, for every
+    instantiation (rows 8/16/24/32, one or two column slots), with and without phase 1."""
+    B = 4096
+    r = np.random.RandomState(1000 * m + n)
+    leq = r.uniform(-1 if bneg else 0, 1, size=(B, m, n + 1))
+    leq[:, :, n] = np.where(r.uniform(size=(B, m)) < bneg, -1.0, 1.0) * (1.0 + r.uniform(size=(B, m)) * n)
+    tg = r.uniform(-0.2 if bneg else 0, 1, size=(B, n + 1))
+    tg[:, n] = 0.0
+    for K in (xp.NO_ITER_LIMIT, 5):
+        a, b = _ab(ctx, lambda: ctx.two_stage_f64_batch(leq, tg, K))
+        assert np.array_equal(a["status"], b["status"])
+        for k in ("pivots", "iters"):
+            assert np.array_equal(a[k], b[k]), k
+        ok = a["status"] != H.SIX_NO_PRI
+        assert np.array_equal(a["eq2bv"][ok], b["eq2bv"][ok])
+        for k in ("maxv", "slack_sol", "tgtf"):
+            assert np.array_equal(H.bits(a[k][ok]), H.bits(b[k][ok])), (k, K)
+
+
+def test_warp_kernel_ragged_equals_cta_kernel(ctx):
+    r = np.random.RandomState(11)
+    lps = []
+    for k in range(600):
+        m, n = int(r.randint(1, 33)), int(r.randint(1, 32))
+        if n + 1 + m > 64:
+            n = 63 - m
+        lps.append(H.gen_mixed_lp(4000 + k, m, n, bneg=0.2) if k % 2 else H.gen_dense_lp(4000 + k, m, n))
+    a, b = _ab(ctx, lambda: ctx.two_stage_f64_ragged(lps))
+    assert np.array_equal(a["status"], b["status"])
+    assert np.array_equal(a["pivots"], b["pivots"])
+    ok = a["status"] != H.SIX_NO_PRI
+    assert np.array_equal(a["eq2bv"][ok], b["eq2bv"][ok])
+    for k in ("maxv", "slack_sol", "tgtf"):
+        assert np.array_equal(H.bits(a[k][ok]), H.bits(b[k][ok])), k

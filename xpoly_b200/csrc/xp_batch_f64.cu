@@ -4,6 +4,7 @@
 // for the skeleton in xp_batch_core.cuh; bit-faithful to the reference's Float
 // semantics (flty.cpp:41-131) and operation order (lpsol.h:1455-1511).
 #include "xp_batch_core.cuh"
+#include "xp_batch_warp_f64.cuh"
 
 #include <cstdlib>
 
@@ -190,8 +191,39 @@ int pick_threads(int maxm, int maxn)
     return 512;
 }
 
+// Register-resident fast path: one warp per LP (xp_batch_warp_f64.cuh).
+template <int MR, int NS>
+int launch_warp(xp_ctx *ctx, XpBatchArgs &A)
+{
+    int occ = 1;
+    XP_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, xpw::k_warp_f64<MR, NS>,
+                                                                  32 * xpw::WARPS, 0));
+    if (occ < 1) occ = 1;
+    long long g = (long long)occ * ctx->sm_count;
+    const long long need = ((long long)A.batch + xpw::WARPS - 1) / xpw::WARPS;
+    if (g > need) g = need;
+    XP_CUDA_OK(ctx, cudaMemsetAsync(A.queue, 0, sizeof(unsigned), ctx->stream));
+    xpw::k_warp_f64<MR, NS><<<(unsigned)g, 32 * xpw::WARPS, 0, ctx->stream>>>(A);
+    ctx->launches++;
+    XP_CUDA_OK(ctx, cudaGetLastError());
+    return 0;
+}
+
+bool warp_path_enabled()
+{
+    const char *e = getenv("XP_BATCH_WARP"); // "0" forces the one-CTA-per-LP kernel (A/B tests)
+    return !(e && e[0] == '0');
+}
+
 int launch_f64(xp_ctx *ctx, XpBatchArgs &A)
 {
+    if (A.maxm <= 32 && A.maxn + 1 + A.maxm <= 64 && warp_path_enabled()) {
+        const bool one = A.maxn + 1 + A.maxm <= 32;
+        if (A.maxm <= 8) return one ? launch_warp<8, 1>(ctx, A) : launch_warp<8, 2>(ctx, A);
+        if (A.maxm <= 16) return one ? launch_warp<16, 1>(ctx, A) : launch_warp<16, 2>(ctx, A);
+        if (A.maxm <= 24) return launch_warp<24, 2>(ctx, A);
+        return launch_warp<32, 2>(ctx, A);
+    }
     const size_t smem = xpb_smem_bytes(A.maxm, A.maxn, sizeof(double), sizeof(XpMinIdx));
     if (smem > ctx->smem_optin) {
         // Same kernel, state slab in global memory: one 1024-thread CTA per LP.
