@@ -177,11 +177,45 @@ def run_reference_arm(args):
 
 
 # ---------------------------------------------------------------- GPU side
-def run_batched(ctx, xp, torch, dev):
-    """Config 2: 100k LPs of tableau 32x64, one CTA per LP."""
-    B, m, n = BATCH_LPS, BATCH_M, BATCH_N
+def ctx_sm_count(torch, dev):
+    return torch.cuda.get_device_properties(dev).multi_processor_count
+
+
+def sm_clock_hz(torch, dev):
+    """Max SM clock (MEASURED_PEAKS.json if present, else the device property)."""
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(p))["sm_max_mhz"]) * 1e6
+    except Exception:
+        return torch.cuda.get_device_properties(dev).clock_rate * 1e3
+
+
+def run_batched(ctx, xp, torch, dev, with_cpu=True, rank=0, world=1, dist=None):
+    """Config 2: 100k LPs of tableau 32x64, one warp per LP.  With N ranks the batch is split
+    N ways (independent units, no collective: SURVEY 8e); times are the max over ranks."""
+    Btot, m, n = BATCH_LPS, BATCH_M, BATCH_N
+    B = Btot * (rank + 1) // world - Btot * rank // world
+
+    def sync_max(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sync_sum(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t)
+        return float(t.item())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
     g = torch.Generator(device=dev)
-    g.manual_seed(SEED)
+    g.manual_seed(SEED + rank)
     leq = torch.rand((B, m, n + 1), dtype=torch.float64, device=dev, generator=g)
     leq[:, :, n] = 1.0 + leq[:, :, n] * n
     tg = torch.rand((B, n + 1), dtype=torch.float64, device=dev, generator=g)
@@ -201,10 +235,13 @@ def run_batched(ctx, xp, torch, dev):
         return ctx.last_kernel_ms
     for _ in range(3):
         once()
-    ms = [once() for _ in range(5)]
+    ms = []
+    for _ in range(5):
+        barrier()
+        ms.append(sync_max(once()))
     dev_ms = float(np.median(ms))
     st = status.cpu().numpy()
-    tot_piv = int(pivots.cpu().numpy().astype(np.int64).sum())
+    tot_piv = int(sync_sum(float(pivots.cpu().numpy().astype(np.int64).sum())))
     # end to end through the host-pointer C-ABI call (H2D of all LPs from PINNED host memory,
     # D2H of results)
     def pinned_like(t):
@@ -217,28 +254,64 @@ def run_batched(ctx, xp, torch, dev):
     h_tg, hp2 = pinned_like(tg)
     t_e2e = []
     for _ in range(3):
+        barrier()
         t0 = time.perf_counter()
         out = ctx.two_stage_f64_batch(h_leq, h_tg, want=("status", "maxv"))
-        t_e2e.append(time.perf_counter() - t0)
+        t_e2e.append(sync_max(time.perf_counter() - t0))
     e2e_s = float(np.median(t_e2e))
     e2e_status = out["status"].copy()
-    h2d_bytes = int(h_leq.nbytes + h_tg.nbytes)
+    h2d_bytes = int(sync_sum(float(h_leq.nbytes + h_tg.nbytes)))
+    cpu = None
+    if with_cpu and world == 1:
+        # CPU baseline beside it: the oracle port's TwoStageMethod on a bounded
+        # sample of the same LPs, one LP after the other per thread, on 1 core and on all cores.
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import harness as H
+        o = H.oracle()
+        o.xo_two_stage_f64_many.restype = C.c_double
+        T = max(1, min(64, len(os.sched_getaffinity(0))))
+        S1, ST = min(B, 4000), min(B, 4000 * T)
+        cst = np.zeros(ST, dtype=np.int32)
+
+        def cpu_run(lo, hi):
+            vp = lambda a: a.ctypes.data_as(C.c_void_p)
+            return o.xo_two_stage_f64_many(hi - lo, m, n, vp(h_leq[lo:hi]), vp(h_tg[lo:hi]), vp(cst[lo:hi]))
+        t1 = cpu_run(0, S1)
+        t0 = time.perf_counter()
+        th = [threading.Thread(target=cpu_run, args=(ST * i // T, ST * (i + 1) // T)) for i in range(T)]
+        [t.start() for t in th]
+        [t.join() for t in th]
+        tT = time.perf_counter() - t0
+        cpu = {"value": ST / tT, "unit": "LPs/s", "cores": T, "kind": "port",
+               "sample": f"the first {ST} of the {B} LPs, {T} host threads each looping over its "
+                         "slice (the reference solves one LP per call)",
+               "one_core": {"value": S1 / t1, "sample": f"the first {S1} LPs"},
+               "status_matches_gpu": bool(np.array_equal(cst, e2e_status[:ST]))}
     del h_leq, h_tg
     ctx.check(lib.xp_host_free(ctx._h, hp1))
     ctx.check(lib.xp_host_free(ctx._h, hp2))
-    smem_bytes = tot_piv * 2.0 * (m + 1) * (n + m + 1) * 8
+    # roofline of this path: the FP64 pipe.  One pivot is (m+1) x C non-fused multiply + add
+    # pairs (lpsol.h:1481-1501); the pipe issues 64 FP64 lanes per clock per SM.
+    fp64_ops = tot_piv * 2.0 * (m + 1) * (n + m + 1)
+    fp64_peak = ctx_sm_count(torch, dev) * 64 * sm_clock_hz(torch, dev)
     return {
-        "metric": "small LPs/s", "workload": f"c2: {B} LPs, tableau {m}x{n + m + 1}, FP64",
-        "value": B / (dev_ms * 1e-3), "unit": "LPs/s", "ms": dev_ms,
+        "metric": "small LPs/s", "workload": f"c2: {Btot} LPs, tableau {m}x{n + m + 1}, FP64"
+                                             + (f", split over {world} GPUs" if world > 1 else ""),
+        "value": Btot / (dev_ms * 1e-3), "unit": "LPs/s", "ms": dev_ms, "scaling": "strong",
         "pivots_total": tot_piv, "pivots_per_s": tot_piv / (dev_ms * 1e-3),
-        "smem_algorithmic_GBps": smem_bytes / (dev_ms * 1e-3) / 1e9,
-        "status_mix": {str(k): int((st == k).sum()) for k in np.unique(st)},
-        "e2e": {"value": B / e2e_s, "unit": "LPs/s",
+        "kernel": "k_warp_f64<32,2>: one warp per LP, tableau in registers",
+        "roofline": {"bound": "fp64 pipe (non-fused mul + add, 64 lanes/clk/SM)",
+                     "achieved": fp64_ops / (dev_ms * 1e-3) / 1e12, "peak": world * fp64_peak / 1e12,
+                     "unit": "Tops/s", "frac": fp64_ops / (dev_ms * 1e-3) / (world * fp64_peak),
+                     "algorithmic_ops_per_pivot": 2 * (m + 1) * (n + m + 1)},
+        "status_mix_rank0": {str(k): int((st == k).sum()) for k in np.unique(st)},
+        "e2e": {"value": Btot / e2e_s, "unit": "LPs/s",
                 "h2d_bytes_per_step": h2d_bytes,
-                "d2h_bytes_per_step": int(B * 12),
+                "d2h_bytes_per_step": int(Btot * 12),
                 "api": "xp_six_two_stage_f64_batch (pinned host buffers; chunks uploaded while "
                        "the previous chunk is being solved)"},
         "status_matches_e2e": bool(np.array_equal(e2e_status, st)),
+        "cpu_baseline": cpu,
     }
 
 
@@ -496,7 +569,7 @@ def run_ours(args):
                 "basis_after_sample_matches_gpu": same}
         ctx.check(lib.xp_host_free(ctx._h, hp))
         if not args.no_batched:
-            line["batched"] = run_batched(ctx, xp, torch, dev)
+            line["batched"] = run_batched(ctx, xp, torch, dev, with_cpu=not args.no_cpu)
             line.update(run_exact_and_bnb(ctx, xp))
     else:
         # ---- e2e at N GPUs: every rank moves ITS column slice of the host tableau through the
@@ -556,6 +629,12 @@ def run_ours(args):
                               "own column slice over its own PCIe link)"}
         ctx.check(lib.xp_host_free(ctx._h, hp_in))
         ctx.check(lib.xp_host_free(ctx._h, hp_out))
+        barrier()
+        lp.close()
+        barrier()
+        if not args.no_batched:
+            line["batched"] = run_batched(ctx, xp, torch, dev, with_cpu=False, rank=rank,
+                                          world=world, dist=dist)
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:

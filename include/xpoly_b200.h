@@ -269,6 +269,20 @@ int xp_mip_solve_rat_batch(xp_ctx *ctx, int is_min, int is_bin, int batch, int m
  * result[k] = 1 / 0. */
 int xp_has_solution_rat_batch(xp_ctx *ctx, int batch, int m, int n, const xp_rat *leq,
                               int is_int_sol, int is_unique_sol, int32_t *result);
+/* The same for the shape the real producer emits (DepPolyMgr::buildDepPoly,
+ * poly.cpp:1166-1195: one query per reference pair and loop depth): system b has
+ * ns[b] variables, ms[b] inequality rows at leq_pool + leq_off[b] and ks[b]
+ * equality rows at eq_pool + eq_off[b] (offsets in xp_rat elements, rows of
+ * ns[b]+1 entries; ks / eq_* may be NULL).  All max problems of the batch go to
+ * the GPU together, then the min problems of the systems still undecided, and
+ * B&B trees advance in lockstep.  result[b] = 1 / 0, or XP_ERR_REFERENCE_UB for a
+ * system on which the reference itself has undefined behaviour (equalities
+ * without inequalities, linsys.cpp:851-854; convertEq2Ineq, lpsol.h:1232); the
+ * other systems are still answered. */
+int xp_has_solution_rat_ragged(xp_ctx *ctx, int batch, const int32_t *ns, const int32_t *ms,
+                               const int64_t *leq_off, const xp_rat *leq_pool, const int32_t *ks,
+                               const int64_t *eq_off, const xp_rat *eq_pool, int is_int_sol,
+                               int is_unique_sol, int32_t *result);
 
 #ifdef __cplusplus
 }

@@ -481,3 +481,29 @@ int xo_has_solution_rat(int m, int n, const xo_rat *leq, int k, const xo_rat *eq
     mat_free_rat(&Tg);
     return res;
 }
+
+/* bench.py's CPU baseline for the batched configuration: TwoStageMethod on `batch` LPs of one
+ * shape, one after the other (the reference has no batching; callers loop).  Re-entrant, so
+ * the bench can run one call per host thread on disjoint slices.  Returns seconds spent. */
+double xo_two_stage_f64_many(int batch, int m, int n, const double *leq, const double *tgtf,
+                             int32_t *status)
+{
+    int cap = n + m + 2;
+    double *tab = (double *)malloc((size_t)m * cap * sizeof(double));
+    double *otg = (double *)malloc((size_t)cap * sizeof(double));
+    double *ssol = (double *)malloc((size_t)cap * sizeof(double));
+    int32_t *eq2bv = (int32_t *)malloc((size_t)m * sizeof(int32_t));
+    int32_t *bv2eq = (int32_t *)malloc((size_t)cap * sizeof(int32_t));
+    uint8_t *nv = (uint8_t *)malloc((size_t)cap), *bv = (uint8_t *)malloc((size_t)cap);
+    double t0 = xo_now();
+    for (int k = 0; k < batch; k++) {
+        int dims[4];
+        double maxv;
+        status[k] = xo_two_stage_f64(m, n, leq + (size_t)k * m * (n + 1), tgtf + (size_t)k * (n + 1),
+                                     0xFFFFFFFFu, dims, tab, otg, eq2bv, bv2eq, nv, bv, &maxv, ssol,
+                                     NULL, 0, NULL);
+    }
+    double dt = xo_now() - t0;
+    free(tab); free(otg); free(ssol); free(eq2bv); free(bv2eq); free(nv); free(bv);
+    return dt;
+}

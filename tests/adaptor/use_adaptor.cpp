@@ -52,5 +52,22 @@ int main()
     UINT st3 = mip.maxm(rv, rsol, rtg, rvc, req, rleq);
     printf("mip_max_rat status %u v %d/%d x = (%d/%d, %d/%d)\n", st3, rv.num(), rv.den(), rsol.get(0, 0).num(),
            rsol.get(0, 0).den(), rsol.get(0, 1).num(), rsol.get(0, 1).den());
+    // Lineq::has_solution's dependence queries, collected and answered at once
+    static const int QA[6][3] = {{-1, 0, -1}, {1, 0, 10}, {0, -1, -1}, {0, 1, 10}, {1, -1, 1}, {-1, 1, -1}};
+    static const int QB[5][3] = {{-1, 0, -1}, {1, 0, 10}, {0, -1, -1}, {0, 1, 10}, {1, -1, -20}};
+    static const int QC[6][3] = {{-1, 0, -1}, {1, 0, 10}, {0, -1, -1}, {0, 1, 10}, {2, -2, 1}, {-2, 2, -1}};
+    RMat qa(6, 3), qb(5, 3), qc(6, 3), qe;
+    for (int i = 0; i < 6; i++)
+        for (int j = 0; j < 3; j++) {
+            qa.set(i, j, Rational(QA[i][j], 1));
+            qc.set(i, j, Rational(QC[i][j], 1));
+            if (i < 5) qb.set(i, j, Rational(QB[i][j], 1));
+        }
+    XpHasSolutionBatch hb;
+    hb.add(qa, qe, 2);
+    hb.add(qb, qe, 2);
+    hb.add(qc, qe, 2);
+    hb.run(true, true);
+    printf("has_solution %d %d %d\n", (int)hb.get(0), (int)hb.get(1), (int)hb.get(2));
     return st == SIX_SUCC && maxv.f() == 2.0 ? 0 : 1;
 }

@@ -28,7 +28,8 @@ def test_adaptor_compiles_and_links():
     assert r.returncode == 0, r.stderr[-4000:]
     # the specialisations really replaced the template bodies: the binary imports the C ABI
     syms = subprocess.run(["nm", "-D", "--undefined-only", exe], capture_output=True, text=True).stdout
-    for s in ("xp_six_maxm_f64", "xp_six_minm_rat", "xp_mip_solve_rat", "xp_ctx_create"):
+    for s in ("xp_six_maxm_f64", "xp_six_minm_rat", "xp_mip_solve_rat", "xp_has_solution_rat_ragged",
+              "xp_ctx_create"):
         assert s in syms, s
     # what the UNMODIFIED reference answers for the same three calls (the GPU test compares)
     import numpy as np
@@ -42,4 +43,9 @@ def test_adaptor_compiles_and_links():
              "minm_rat status %d v %d/%d" % (b["status"], b["v"][0], b["v"][1]),
              "mip_max_rat status %d v %d/%d x = (%d/%d, %d/%d)" % (c["status"], c["v"][0], c["v"][1],
                                                                   *c["sol"][0], *c["sol"][1])]
+    qa = [[-1, 0, -1], [1, 0, 10], [0, -1, -1], [0, 1, 10], [1, -1, 1], [-1, 1, -1]]
+    qb = [[-1, 0, -1], [1, 0, 10], [0, -1, -1], [0, 1, 10], [1, -1, -20]]
+    qc = [[-1, 0, -1], [1, 0, 10], [0, -1, -1], [0, 1, 10], [2, -2, 1], [-2, 2, -1]]
+    hs = [H.has_solution("ref", H.to_rat(np.array(q, dtype=np.int64))) for q in (qa, qb, qc)]
+    lines.append("has_solution %d %d %d" % tuple(hs))
     open(os.path.join(ROOT, "oracle", "_ref", "use_adaptor.expected"), "w").write("\n".join(lines) + "\n")

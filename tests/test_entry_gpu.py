@@ -225,3 +225,45 @@ def test_has_solution_dependence_queries(ctx):
     res2 = ctx.has_solution_batch(np.stack(lps).astype(np.int64), is_int=False, is_unique=False)
     for k, l in enumerate(lps):
         assert res2[k] == H.has_solution("oracle", H.to_rat(l), is_int=False, is_unique=False), k
+
+
+def test_has_solution_ragged_with_equalities(ctx):
+    """The producer's shape (poly.cpp:1166-1195): systems of different sizes, inequalities plus
+    equalities, answered in one call; each against the oracle's Lineq::has_solution.  Systems on
+    which the reference has undefined behaviour come back as XP_ERR_REFERENCE_UB."""
+    r = np.random.RandomState(42)
+    systems = []
+    for k in range(160):
+        n = int(r.randint(2, 6))
+        m = int(r.randint(2, 9))
+        leq = np.zeros((m, n + 1), dtype=np.int64)
+        leq[:, :n] = r.randint(-2, 4, size=(m, n)) * (r.uniform(size=(m, n)) < 0.7)
+        leq[:, n] = r.randint(0, 25, size=m)
+        eq = None
+        if k % 3 == 0:
+            ke = int(r.randint(1, 3))
+            eq = np.zeros((ke, n + 1), dtype=np.int64)
+            eq[:, :n] = r.randint(-2, 3, size=(ke, n))
+            eq[:, n] = r.randint(0, 10, size=ke)
+        systems.append((leq, eq))
+    systems.append(None)
+    for is_int, is_unique in ((True, True), (False, False)):
+        res = ctx.has_solution_ragged(systems[:-1], is_int=is_int, is_unique=is_unique)
+        n_ub = 0
+        for k, (leq, eq) in enumerate(systems[:-1]):
+            o = H.has_solution("oracle", H.to_rat(leq), None if eq is None else H.to_rat(eq),
+                               is_int=is_int, is_unique=is_unique)
+            if res[k] < 0:
+                assert res[k] == xp.ERR_REFERENCE_UB and eq is not None, (k, res[k])
+                n_ub += 1
+                continue
+            assert res[k] == o, (k, res[k], o, is_int)
+        assert n_ub < 40
+    # the uniform entry point is the ragged one with equal shapes
+    lps = [H.gen_int_lp(k, 6, 4, alo=-1, ahi=4, density=0.8, blo=1, bhi=25)[0] for k in range(50)]
+    a = ctx.has_solution_batch(np.stack(lps).astype(np.int64))
+    b = ctx.has_solution_ragged([(l.astype(np.int64), None) for l in lps])
+    assert np.array_equal(a, b)
+    # equalities without inequalities: the reference writes a 1 x 0 objective (linsys.cpp:851)
+    e = np.array([[1, -1, 0]], dtype=np.int64)
+    assert ctx.has_solution_ragged([(None, e)]).tolist() == [xp.ERR_REFERENCE_UB]

@@ -442,6 +442,39 @@ def _has_solution_batch(self, leq, is_int=True, is_unique=True):
     return res
 
 
+def _has_solution_ragged(self, systems, is_int=True, is_unique=True):
+    """systems: list of (leq or None, eq or None), integer or (…, 2) int32 rational arrays with
+    n+1 columns each.  Returns int32 results (1 / 0 / negative per-system code)."""
+    B = len(systems)
+    ns = np.zeros(B, dtype=np.int32)
+    ms = np.zeros(B, dtype=np.int32)
+    ks = np.zeros(B, dtype=np.int32)
+    lo = np.zeros(B, dtype=np.int64)
+    eo = np.zeros(B, dtype=np.int64)
+    lp, ep = [], []
+    ll = el = 0
+    for b, (leq, eq) in enumerate(systems):
+        leq = None if leq is None or len(leq) == 0 else _rat(leq)
+        eq = None if eq is None or len(eq) == 0 else _rat(eq)
+        ns[b] = (leq if leq is not None else eq).shape[1] - 1
+        if leq is not None:
+            ms[b], lo[b] = leq.shape[0], ll
+            lp.append(leq.reshape(-1, 2))
+            ll += leq.shape[0] * leq.shape[1]
+        if eq is not None:
+            ks[b], eo[b] = eq.shape[0], el
+            ep.append(eq.reshape(-1, 2))
+            el += eq.shape[0] * eq.shape[1]
+    lpool = np.ascontiguousarray(np.concatenate(lp)) if lp else np.zeros((1, 2), dtype=np.int32)
+    epool = np.ascontiguousarray(np.concatenate(ep)) if ep else np.zeros((1, 2), dtype=np.int32)
+    res = np.zeros(B, dtype=np.int32)
+    self.check(lib().xp_has_solution_rat_ragged(self._h, B, _p(ns), _p(ms), _p(lo), _p(lpool),
+                                                _p(ks), _p(eo), _p(epool), int(is_int),
+                                                int(is_unique), _p(res)))
+    return res
+
+
+Context.has_solution_ragged = _has_solution_ragged
 Context.six_solve = _six_solve
 Context.six_solve_batch = _six_solve_batch
 Context.mip_solve = _mip_solve

@@ -698,58 +698,119 @@ extern "C" int xp_mip_solve_rat_batch(xp_ctx *ctx, int is_min, int is_bin, int b
 }
 
 // ---- Lineq::has_solution (linsys.cpp:830-906), batched ----
-extern "C" int xp_has_solution_rat_batch(xp_ctx *ctx, int batch, int m, int n, const xp_rat *leq,
-                                         int is_int_sol, int is_unique_sol, int32_t *result)
+namespace {
+
+// Systems Ls[b] (leq, may be empty) / Es[b] (eq, may be empty) over ns[b] variables, vc = -I.
+// result[b] = 1 / 0, or a negative code for a system on which the reference itself would run
+// into undefined behaviour (the other systems are still answered).
+int has_solution_core(xp_ctx *ctx, const std::vector<Mat<Q>> &Ls, const std::vector<Mat<Q>> &Es,
+                      const std::vector<int> &ns, int is_int_sol, int is_unique_sol, int32_t *result)
 {
-    XP_ENTRY_GUARD(ctx);
-    if (batch < 0 || m < 1 || n < 1 || !leq || !result) return XP_ERR_BAD_ARG;
-    std::vector<Mat<Q>> Ls(batch), Ts(batch);
-    const Mat<Q> V = default_vc<Q>(n), E;
+    const int batch = (int)Ls.size();
+    std::vector<Mat<Q>> Ts(batch), Vs(batch);
+    std::vector<int> pending;
     for (int b = 0; b < batch; b++) {
-        Ls[b] = mat_q(m, n + 1, leq + (size_t)b * m * (n + 1));
-        Ts[b] = Mat<Q>(1, n + 1); // all-ones objective, reviseTargetFunc (lpsol.h:2052-2074)
-        for (int j = 0; j < n; j++)
-            if (!Ls[b].col_all_eq(j, Q::zero())) Ts[b].at(0, j) = Q::from_int(1);
         result[b] = 0;
+        if (Ls[b].empty() && Es[b].empty()) continue; // linsys.cpp:845-847
+        if (Ls[b].empty()) { // tgtf(1, leq.get_col_size()) is 1 x 0 and is then written, :851-854
+            result[b] = XP_ERR_REFERENCE_UB;
+            continue;
+        }
+        const int n = ns[b];
+        Vs[b] = default_vc<Q>(n);
+        Ts[b] = Mat<Q>(1, n + 1); // all-ones objective, reviseTargetFunc (lpsol.h:2052-2074)
+        for (int j = 0; j < n; j++) {
+            bool nz = !Ls[b].col_all_eq(j, Q::zero());
+            if (!Es[b].empty() && !Es[b].col_all_eq(j, Q::zero())) nz = true;
+            if (nz) Ts[b].at(0, j) = Q::from_int(1);
+        }
+        pending.push_back(b);
     }
-    std::vector<int> pending(batch);
-    for (int b = 0; b < batch; b++) pending[b] = b;
     for (int pass = 0; pass < 2 && !pending.empty(); pass++) { // max first, then min
         const bool is_min = pass == 1;
-        std::vector<int> st(pending.size());
+        std::vector<int> st(pending.size(), 0);
         if (is_int_sol) {
             std::vector<MipTree<Q>> trees(pending.size());
-            for (size_t k = 0; k < pending.size(); k++)
-                trees[k].start(Ts[pending[k]], V, E, Ls[pending[k]], !is_min, false);
+            for (size_t k = 0; k < pending.size(); k++) {
+                const int b = pending[k];
+                trees[k].start(Ts[b], Vs[b], Es[b], Ls[b], !is_min, false);
+            }
             int rc = run_trees<Q>(ctx, trees);
             if (rc) return rc;
             for (size_t k = 0; k < pending.size(); k++) st[k] = trees[k].ret_status;
         } else {
             std::vector<SixJob<Q>> jobs(pending.size());
             std::vector<const Mat<Q> *> l, t;
+            std::vector<size_t> live;
             for (size_t k = 0; k < pending.size(); k++) {
-                int e = jobs[k].prepare(is_min, Ts[pending[k]], V, E, Ls[pending[k]]);
-                if (e) return e;
+                const int b = pending[k];
+                int e = jobs[k].prepare(is_min, Ts[b], Vs[b], Es[b], Ls[b]);
+                if (e) {
+                    st[k] = e < 0 ? e : XP_ERR_BAD_ARG;
+                    continue;
+                }
+                live.push_back(k);
                 l.push_back(&jobs[k].lp_leq);
                 t.push_back(&jobs[k].lp_tgtf);
             }
             std::vector<ResQ> R;
             int rc = two_stage_many_q(ctx, l, t, XP_NO_ITER_LIMIT, R);
             if (rc) return rc;
-            for (size_t k = 0; k < pending.size(); k++) {
+            for (size_t i = 0; i < live.size(); i++) {
                 Q::T val;
-                std::vector<Q::T> s;
-                st[k] = jobs[k].finish(R[k], val, s);
+                std::vector<Q::T> sv;
+                st[live[i]] = jobs[live[i]].finish(R[i], val, sv);
             }
         }
         std::vector<int> next;
         for (size_t k = 0; k < pending.size(); k++) {
-            if (st[k] < 0) return st[k];
+            const int b = pending[k];
+            if (st[k] < 0) result[b] = st[k];
             // IP_SUCC == SIX_SUCC == 0 and IP_UNBOUND == SIX_UNBOUND == 1
-            if (st[k] == 0 || (!is_unique_sol && st[k] == 1)) result[pending[k]] = 1;
-            else next.push_back(pending[k]);
+            else if (st[k] == 0 || (!is_unique_sol && st[k] == 1)) result[b] = 1;
+            else next.push_back(b);
         }
         pending.swap(next);
     }
     return 0;
+}
+
+} // namespace
+
+extern "C" int xp_has_solution_rat_batch(xp_ctx *ctx, int batch, int m, int n, const xp_rat *leq,
+                                         int is_int_sol, int is_unique_sol, int32_t *result)
+{
+    XP_ENTRY_GUARD(ctx);
+    if (batch < 0 || m < 1 || n < 1 || !leq || !result) return XP_ERR_BAD_ARG;
+    std::vector<Mat<Q>> Ls(batch), Es(batch);
+    std::vector<int> ns(batch, n);
+    for (int b = 0; b < batch; b++) Ls[b] = mat_q(m, n + 1, leq + (size_t)b * m * (n + 1));
+    int rc = has_solution_core(ctx, Ls, Es, ns, is_int_sol, is_unique_sol, result);
+    if (rc) return rc;
+    for (int b = 0; b < batch; b++)
+        if (result[b] < 0) return result[b]; // uniform API: any failing system fails the call
+    return 0;
+}
+
+// The real caller shape (DepPolyMgr::buildDepPoly, poly.cpp:1166-1195: one query per
+// reference pair and loop depth): systems of different sizes, inequalities and equalities.
+extern "C" int xp_has_solution_rat_ragged(xp_ctx *ctx, int batch, const int32_t *ns,
+                                          const int32_t *ms, const int64_t *leq_off,
+                                          const xp_rat *leq_pool, const int32_t *ks,
+                                          const int64_t *eq_off, const xp_rat *eq_pool,
+                                          int is_int_sol, int is_unique_sol, int32_t *result)
+{
+    XP_ENTRY_GUARD(ctx);
+    if (batch < 0 || !ns || !ms || !result) return XP_ERR_BAD_ARG;
+    std::vector<Mat<Q>> Ls(batch), Es(batch);
+    std::vector<int> nv(batch);
+    for (int b = 0; b < batch; b++) {
+        const int n = ns[b], m = ms[b], k = ks ? ks[b] : 0;
+        if (n < 1 || m < 0 || k < 0) return XP_ERR_BAD_ARG;
+        if ((m > 0 && (!leq_off || !leq_pool)) || (k > 0 && (!eq_off || !eq_pool))) return XP_ERR_BAD_ARG;
+        nv[b] = n;
+        if (m > 0) Ls[b] = mat_q(m, n + 1, leq_pool + leq_off[b]);
+        if (k > 0) Es[b] = mat_q(k, n + 1, eq_pool + eq_off[b]);
+    }
+    return has_solution_core(ctx, Ls, Es, nv, is_int_sol, is_unique_sol, result);
 }

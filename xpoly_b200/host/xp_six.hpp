@@ -16,6 +16,8 @@
 #include <stdio.h>
 #include <stdlib.h>
 
+#include <vector>
+
 #include "xpoly_b200.h"
 
 namespace xcom {
@@ -154,5 +156,60 @@ inline UINT MIP<RMat, Rational>::minm(OUT Rational &minv, OUT RMat &sol, RMat co
     m_times = (UINT)nodes;
     return xp_status(st);
 }
+
+// ---------------------------------------------------------------- Lineq::has_solution, batched
+// The producer side (DepPolyMgr::buildDepPoly, poly.cpp:1166-1195) asks one has_solution
+// question per reference pair and loop depth, each synchronously (linsys.cpp:830-906).  This
+// collector keeps the call shape -- add() takes exactly has_solution's arguments -- and answers
+// all collected systems with one xp_has_solution_rat_ragged call.  vc must be the default -I | 0
+// (what every caller in the reference passes).
+class XpHasSolutionBatch {
+    std::vector<int32_t> m_ns, m_ms, m_ks, m_res;
+    std::vector<int64_t> m_lo, m_eo;
+    std::vector<xp_rat> m_lp, m_ep;
+    static void append(std::vector<xp_rat> &pool, RMat const &m)
+    {
+        const xp_rat *p = (const xp_rat *)xp_raw(m);
+        if (p) pool.insert(pool.end(), p, p + (size_t)m.get_row_size() * m.get_col_size());
+    }
+
+public:
+    // Returns the index of the query.
+    UINT add(RMat const &leq, RMat const &eq, UINT rhs_idx)
+    {
+        ASSERT0(leq.size() == 0 || leq.get_col_size() == rhs_idx + 1);
+        ASSERT0(eq.size() == 0 || eq.get_col_size() == rhs_idx + 1);
+        m_ns.push_back((int32_t)rhs_idx);
+        m_ms.push_back((int32_t)(leq.size() ? leq.get_row_size() : 0));
+        m_ks.push_back((int32_t)(eq.size() ? eq.get_row_size() : 0));
+        m_lo.push_back((int64_t)m_lp.size());
+        m_eo.push_back((int64_t)m_ep.size());
+        append(m_lp, leq);
+        append(m_ep, eq);
+        return (UINT)m_ns.size() - 1;
+    }
+    UINT size() const { return (UINT)m_ns.size(); }
+    // Answers every collected query (is_int_sol / is_unique_sol as in linsys.cpp:830).
+    void run(bool is_int_sol, bool is_unique_sol)
+    {
+        m_res.assign(m_ns.size(), 0);
+        if (m_ns.empty()) return;
+        xp_rat dummy = {0, 1};
+        int st = xp_has_solution_rat_ragged(xp_thread_ctx(), (int)m_ns.size(), m_ns.data(), m_ms.data(),
+                                            m_lo.data(), m_lp.empty() ? &dummy : m_lp.data(), m_ks.data(),
+                                            m_eo.data(), m_ep.empty() ? &dummy : m_ep.data(),
+                                            is_int_sol ? 1 : 0, is_unique_sol ? 1 : 0, m_res.data());
+        xp_status(st);
+    }
+    // has_solution's answer for query i; a system on which the reference has undefined
+    // behaviour (XP_ERR_REFERENCE_UB) reads as "no solution found".
+    bool get(UINT i) const { return m_res[i] == 1; }
+    INT raw(UINT i) const { return m_res[i]; }
+    void clean()
+    {
+        m_ns.clear(); m_ms.clear(); m_ks.clear(); m_res.clear();
+        m_lo.clear(); m_eo.clear(); m_lp.clear(); m_ep.clear();
+    }
+};
 
 } // namespace xcom
