@@ -190,6 +190,17 @@ int xp_six_two_stage_f64_ragged(xp_ctx *ctx, int batch, const int32_t *ms, const
                                 double *tgtf_out, int32_t *eq2bv, uint32_t *iters,
                                 uint32_t *pivots);
 
+/* One FP64 LP of any size on the HBM-resident path, same contract as one entry of
+ * the batch above (slack_sol / tgtf_out: n+m+1 entries, eq2bv: m).  Phase 1
+ * (constructBasicFeasibleSolution, lpsol.h:838-988: auxiliary column, forced first
+ * pivot, auxiliary solve, pivoting xa out, objective restoration, column deletion)
+ * runs on the device: the only bulk transfer is the upload of leq.  *status
+ * receives the SIX status; the return value is 0 or a negative error. */
+int xp_six_two_stage_f64_large(xp_ctx *ctx, int m, int n, const double *leq, const double *tgtf,
+                               uint32_t max_iter, int rule, int32_t *status, double *maxv,
+                               double *slack_sol, double *tgtf_out, int32_t *eq2bv,
+                               uint32_t *iters, uint32_t *pivots);
+
 /* ------------------------- TwoStageMethod level: batched exact (fraction-free)
  * The exact twin of SIX<RMat,Rational>::TwoStageMethod: integer tableau N with
  * one common denominator D per LP (a_ij = N_ij / D), int64 entries, 128-bit

@@ -174,3 +174,39 @@ def test_c3_full_size_properties_and_oracle_sample(ctx):
     assert np.array_equal(a["eq2bv"], o["eq2bv"])
     assert np.array_equal(H.bits(a["tgtf"]), H.bits(o["tgtf"]))
     lp.close()
+
+
+def _check_two_stage(ctx, leq, tg, K, tag):
+    g = ctx.two_stage_f64_large(leq, tg, K)
+    o = H.two_stage("oracle", "f64", leq, tg, K, want_log=True)
+    m, n = leq.shape[0], leq.shape[1] - 1
+    assert g["status"] == o["status"], (tag, g["status"], o["status"])
+    assert g["pivots"] == len(o["log"]), (tag, "pivots", g["pivots"], len(o["log"]))
+    if o["status"] == H.SIX_NO_PRI:
+        return g
+    Cc = n + m + 1
+    assert o["cols"] == Cc
+    assert np.array_equal(g["eq2bv"], o["eq2bv"]), (tag, "eq2bv")
+    assert np.array_equal(H.bits(g["tgtf"]), H.bits(o["tgtf"])), (tag, "tgtf")
+    assert np.array_equal(H.bits(g["maxv"]), H.bits(o["maxv"])), (tag, "maxv")
+    assert np.array_equal(H.bits(g["slack_sol"]), H.bits(o["slack_sol"])), (tag, "sol")
+    return g
+
+
+@pytest.mark.parametrize("m,n", [(3, 2), (40, 30), (130, 129), (150, 260), (300, 200)])
+def test_two_stage_large_phase1_on_device(ctx, m, n):
+    """TwoStageMethod on the HBM-resident path with constructBasicFeasibleSolution on the device
+    (auxiliary column, forced first pivot, auxiliary solve, xa pivot-out, objective restoration,
+    column deletion): bit for bit against the oracle, with and without phase 1, bounded and not."""
+    seen = set()
+    for k in range(6):
+        leq, tg = H.gen_mixed_lp(31 * m + k, m, n, bneg=0.3 if k % 2 == 0 else 0.0)
+        for K in ((H.NO_LIMIT, 7) if m <= 150 else (60,)):
+            g = _check_two_stage(ctx, leq, tg, K, ("mixed", m, n, k, K))
+            seen.add(g["status"])
+    leq, tg = H.gen_dense_lp(5 * m, m, n)  # b > 0, c > 0: no auxiliary LP
+    _check_two_stage(ctx, leq, tg, 40, ("dense", m, n))
+    tg2 = -np.abs(tg)  # no positive cost: auxiliary LP although b > 0 (:1803)
+    tg2[n] = 0.0
+    _check_two_stage(ctx, leq, tg2, 40, ("nopos", m, n))
+    assert len(seen) >= 1

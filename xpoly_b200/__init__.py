@@ -298,6 +298,25 @@ def _two_stage_f64_ragged(self, lps, max_iter=NO_ITER_LIMIT):
     return out
 
 
+def _two_stage_f64_large(self, leq, tgtf, max_iter=NO_ITER_LIMIT):
+    """SIX::TwoStageMethod for one LP on the HBM-resident path (phase 1 on the device)."""
+    leq, tgtf = _f64(leq), _f64(tgtf)
+    m, n = leq.shape[0], leq.shape[1] - 1
+    Cc = n + m + 1
+    st = C.c_int32(0)
+    out = dict(maxv=np.zeros(1), slack_sol=np.zeros(Cc), tgtf=np.zeros(Cc),
+               eq2bv=np.zeros(m, dtype=np.int32), iters=np.zeros(1, dtype=np.uint32),
+               pivots=np.zeros(1, dtype=np.uint32))
+    self.check(lib().xp_six_two_stage_f64_large(
+        self._h, m, n, _p(leq), _p(tgtf), C.c_uint32(max_iter), RULE_REFERENCE, C.byref(st),
+        _p(out["maxv"]), _p(out["slack_sol"]), _p(out["tgtf"]), _p(out["eq2bv"]), _p(out["iters"]),
+        _p(out["pivots"])))
+    out["status"] = st.value
+    out["iters"], out["pivots"] = int(out["iters"][0]), int(out["pivots"][0])
+    return out
+
+
+Context.two_stage_f64_large = _two_stage_f64_large
 Context.two_stage_f64_batch = _two_stage_f64_batch
 Context.two_stage_f64_ragged = _two_stage_f64_ragged
 

@@ -3,7 +3,8 @@
 // normalize, dual, calcFinalSolution, B&B bookkeeping) is xp_host_six.hpp; every
 // TwoStageMethod (slack form, phase 1, solveSlackForm) runs on the GPU:
 //   - LPs that fit shared memory go to the one-CTA-per-LP kernels, many per launch;
-//   - larger FP64 LPs go to the HBM-resident path (host-mediated phase 1).
+//   - larger FP64 LPs go to the HBM-resident path (xp_six_two_stage_f64_large, phase 1 on
+//     the device too).
 // There is no CPU solve path in here.
 #include "xp_batch_core.cuh"
 
@@ -23,163 +24,22 @@ bool fits_smem(const xp_ctx *ctx, int m, int n, size_t key_bytes)
     return xpb_smem_bytes(m, n, 8, key_bytes) <= ctx->smem_optin;
 }
 
-// SIX::pivot (lpsol.h:1455-1511) on the host, FP64, used only by the
-// host-mediated phase 1 of LPs too large for shared memory (two pivots per solve).
-void host_pivot(std::vector<double> &tab, std::vector<double> &tg, int m, int C, int rhs, int p,
-                int q, std::vector<uint8_t> &nvset, std::vector<int32_t> &bv2eq,
-                std::vector<int32_t> &eq2bv)
-{
-    const int bv = eq2bv[p];
-    double *rowp = &tab[(size_t)p * C];
-    const double r = 1.0 / rowp[q];
-    if (!F64::eq(r, 1.0)) {
-        const bool z = F64::eq(r, 0.0);
-        for (int j = 0; j < C; j++) rowp[j] = z ? 0.0 : rowp[j] * r;
-    }
-    const double cq = tg[q];
-    for (int i = 0; i < m; i++) {
-        if (i == p) continue;
-        double *row = &tab[(size_t)i * C];
-        const double f = -row[q];
-        for (int j = 0; j < C; j++) {
-            const double v = f * rowp[j];
-            row[j] = row[j] + v;
-        }
-    }
-    const bool cz = F64::eq(cq, 0.0), c1 = F64::eq(cq, 1.0);
-    for (int j = 0; j < C; j++) {
-        double t = rowp[j] * -1.0;
-        if (j >= rhs) t = -t;
-        t = cz ? 0.0 : (c1 ? t : t * cq);
-        tg[j] = t + tg[j];
-    }
-    nvset[q] = 0;
-    nvset[bv] = 1;
-    eq2bv[p] = q;
-    bv2eq[q] = p;
-    bv2eq[bv] = -1;
-}
-
-// TwoStageMethod (lpsol.h:1906-1930) for one FP64 LP on the HBM-resident path.
+// TwoStageMethod (lpsol.h:1906-1930) for one FP64 LP on the HBM-resident path; phase 1
+// (constructBasicFeasibleSolution, :838-988) runs on the device as well.
 int two_stage_large_f64(xp_ctx *ctx, const Mat<F64> &leq, const Mat<F64> &tg, uint32_t max_iter,
                         ResF &R)
 {
-    const int m = leq.r, n = leq.c - 1;
-    bool pos = false, bneg = false;
-    for (int j = 0; j < n; j++) pos |= tg.at(0, j) > 0.0;
-    for (int i = 0; i < m; i++) bneg |= leq.at(i, n) < 0.0;
-    const bool aux = !pos || bneg; // stage1, :1794-1803
-    const int Cm = n + m + 1;
+    const int m = leq.r, n = leq.c - 1, Cm = n + m + 1;
     R.slack_sol.assign(Cm, 0.0);
     R.tgtf.assign(Cm, 0.0);
     R.eq2bv.assign(m, 0);
     R.maxv = 0.0;
-    xp_lp_f64 *lp = nullptr;
-    int rc;
-    if (!aux) {
-        rc = xp_lp_f64_create(ctx, m, Cm, &lp);
-        if (rc) return rc;
-        rc = xp_lp_f64_upload_leq(lp, leq.a.data(), tg.a.data(), n);
-        int st = rc ? rc : xp_lp_f64_solve(lp, max_iter, XP_RULE_REFERENCE);
-        if (st >= 0)
-            rc = xp_lp_f64_download(lp, nullptr, R.tgtf.data(), nullptr, nullptr, nullptr,
-                                    R.eq2bv.data(), &R.maxv, R.slack_sol.data(), nullptr, nullptr, 0);
-        xp_lp_f64_destroy(lp);
-        R.status = (st >= 0 && rc) ? rc : st;
-        return 0;
-    }
-    // ---- constructBasicFeasibleSolution, lpsol.h:838-988, host-mediated ----
-    const int xa = n, s0 = n + 1, rhs = n + 1 + m, C = rhs + 1;
-    std::vector<double> tab((size_t)m * C, 0.0), tgt(C, 0.0), sol(C, 0.0);
-    std::vector<uint8_t> nvset(rhs, 0), bvset(rhs, 0);
-    std::vector<int32_t> bv2eq(rhs, -1), eq2bv(m, 0);
-    for (int i = 0; i < m; i++) {
-        for (int j = 0; j < n; j++) tab[(size_t)i * C + j] = leq.at(i, j);
-        tab[(size_t)i * C + xa] = -1.0;
-        tab[(size_t)i * C + s0 + i] = 1.0;
-        tab[(size_t)i * C + rhs] = leq.at(i, n);
-        eq2bv[i] = s0 + i;
-        bv2eq[s0 + i] = i;
-    }
-    for (int j = 0; j < s0; j++) nvset[j] = 1;
-    tgt[xa] = -1.0;
-    int prow = 0; // row of the first minimum constant term, :894-904
-    for (int i = 1; i < m; i++)
-        if (tab[(size_t)prow * C + rhs] > tab[(size_t)i * C + rhs]) prow = i;
-    host_pivot(tab, tgt, m, C, rhs, prow, xa, nvset, bv2eq, eq2bv);
-    for (int j = 0; j < rhs; j++) bvset[j] = !nvset[j];
-    double maxv = 0.0;
-    uint32_t iters = 0;
-    int st = xp_six_slack_f64(ctx, tab.data(), tgt.data(), m, C, nvset.data(), bvset.data(),
-                              bv2eq.data(), eq2bv.data(), nullptr, nullptr, max_iter,
-                              XP_RULE_REFERENCE, &maxv, sol.data(), &iters, nullptr, 0);
-    if (st < 0) return st;
-    if (st != XP_SIX_SUCC || !F64::eq(maxv, 0.0)) { // :912-922
-        R.status = XP_SIX_NO_PRI_FEASIBLE_SOL;
-        return 0;
-    }
-    if (!nvset[xa]) { // :924-941
-        const int eqnum = bv2eq[xa];
-        int cand = -1;
-        for (int j = 0; j < rhs; j++)
-            if (nvset[j] && !F64::eq(tab[(size_t)eqnum * C + j], 0.0)) {
-                cand = j;
-                break;
-            }
-        if (cand < 0) {
-            R.status = XP_ERR_REFERENCE_UB;
-            return 0;
-        }
-        host_pivot(tab, tgt, m, C, rhs, eqnum, cand, nvset, bv2eq, eq2bv);
-    }
-    // restore the original objective by substitution, :944-953 (FloatMat::substit)
-    for (int j = 0; j < C; j++) tgt[j] = j < n ? tg.at(0, j) : (j == rhs ? tg.at(0, n) : 0.0);
-    for (int i = 0; i < rhs; i++) {
-        const double ci = tgt[i];
-        if (F64::eq(ci, 0.0) || nvset[i]) continue;
-        const double *ex = &tab[(size_t)bv2eq[i] * C];
-        const double ev = ex[i];
-        const bool skip = F64::eq(ev, 0.0);
-        double s = -1.0;
-        if (!F64::eq(ci, ev)) s = (-ci) / ev;
-        const bool sz = F64::eq(s, 0.0), s1 = F64::eq(s, 1.0);
-        for (int j = 0; j < C; j++) {
-            double tj = tgt[j];
-            if (j >= rhs) tj = tj * -1.0;
-            if (!skip) {
-                double x = sz ? 0.0 : (s1 ? ex[j] : ex[j] * s);
-                tj = x + tj;
-            }
-            if (j >= rhs) tj = tj * -1.0;
-            tgt[j] = tj;
-        }
-    }
-    // drop column xa, re-index the maps, :956-986
-    std::vector<double> tab2((size_t)m * Cm), tg2(Cm);
-    for (int i = 0; i < m; i++)
-        for (int j = 0, k = 0; j < C; j++)
-            if (j != xa) tab2[(size_t)i * Cm + k++] = tab[(size_t)i * C + j];
-    std::vector<uint8_t> nv2(Cm - 1), bvs2(Cm - 1);
-    std::vector<int32_t> b2e2(Cm - 1);
-    for (int j = 0, k = 0; j < C; j++)
-        if (j != xa) {
-            tg2[k] = tgt[j];
-            if (j < rhs) {
-                nv2[k] = nvset[j];
-                bvs2[k] = !nvset[j];
-                b2e2[k] = bv2eq[j];
-            }
-            k++;
-        }
-    for (int i = 0; i < m; i++)
-        if (eq2bv[i] > xa) eq2bv[i]--;
-    st = xp_six_slack_f64(ctx, tab2.data(), tg2.data(), m, Cm, nv2.data(), bvs2.data(), b2e2.data(),
-                          eq2bv.data(), nullptr, nullptr, max_iter, XP_RULE_REFERENCE, &R.maxv,
-                          R.slack_sol.data(), &iters, nullptr, 0);
-    if (st < 0) return st;
+    int32_t st = 0;
+    int rc = xp_six_two_stage_f64_large(ctx, m, n, leq.a.data(), tg.a.data(), max_iter, XP_RULE_REFERENCE,
+                                        &st, &R.maxv, R.slack_sol.data(), R.tgtf.data(), R.eq2bv.data(),
+                                        nullptr, nullptr);
+    if (rc) return rc;
     R.status = st;
-    R.tgtf = tg2;
-    R.eq2bv = eq2bv;
     return 0;
 }
 

@@ -2460,3 +2460,318 @@ void xp_large_release_cached(xp_ctx *ctx)
     if (ctx->cached_lp) xp_lp_f64_destroy((xp_lp_f64 *)ctx->cached_lp);
     ctx->cached_lp = nullptr;
 }
+
+// ---------------------------------------------------------------------------
+// TwoStageMethod on the HBM-resident path with phase 1 ON THE DEVICE
+// (SURVEY 8f3): constructBasicFeasibleSolution (lpsol.h:838-988) -- auxiliary
+// column, forced first pivot, aux solve, pivoting xa out, objective restoration
+// by substitution, column deletion -- without the tableau ever visiting the
+// host: the only upload is the caller's leq (half the slack form), the only
+// downloads are O(C) vectors.  Single GPU (the sharded path takes slack forms).
+// ---------------------------------------------------------------------------
+namespace {
+
+// [A | -1 | I | b], objective -xa, identity basis (lpsol.h:860-875, :1405-1433); d.C = n+m+2.
+__global__ void k_aux_form(LpDev d, const double *leq, int n)
+{
+    const int m = d.m, C = d.C, s0 = n + 1;
+    const size_t total = (size_t)m * C;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+         e += (size_t)gridDim.x * blockDim.x) {
+        const int i = (int)(e / C), j = (int)(e % C);
+        double v;
+        if (j < n) v = leq[(size_t)i * (n + 1) + j];
+        else if (j == n) v = -1.0;
+        else if (j < C - 1) v = (j - s0 == i) ? 1.0 : 0.0;
+        else v = leq[(size_t)i * (n + 1) + n];
+        d.tab[e] = v;
+    }
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < C; j += gridDim.x * blockDim.x) {
+        d.tgtf[j] = j == n ? -1.0 : 0.0;
+        if (j < C - 1) {
+            d.nvset[j] = j < s0;
+            d.bv2eq[j] = j < s0 ? -1 : j - s0;
+        }
+        if (j < m) {
+            d.eq2bv[j] = s0 + j;
+            d.rhsbuf[j] = leq[(size_t)j * (n + 1) + n];
+        }
+        if (j == 0) d.st->tg_rhs = 0.0;
+    }
+}
+
+// SIX::pivot (lpsol.h:1455-1511) at a GIVEN (p, q), first half: the scaled pivot row into
+// P[0][.], the multipliers -a[i][q] into F[0][0][.], the objective row and the basis maps.
+// One CTA: the scalars it reads (a[p][q], c_q, eq2bv[p]) are overwritten by it.
+__global__ void __launch_bounds__(1024) k_xpiv_prepare(LpDev d, int p, int q)
+{
+    __shared__ double s_pv, s_cq;
+    __shared__ int s_bv;
+    const int tid = threadIdx.x, C = d.C, n = d.n, m = d.m;
+    if (tid == 0) {
+        s_pv = d.tab[(size_t)p * C + q];
+        s_cq = d.tgtf[q];
+        s_bv = d.eq2bv[p];
+    }
+    __syncthreads();
+    const double cq = s_cq;
+    const double r = xp_div(1.0, s_pv);
+    const bool r_one = xp_feq(r, 1.0), r_zero = xp_feq(r, 0.0);
+    const bool cq_zero = xp_feq(cq, 0.0), cq_one = xp_feq(cq, 1.0);
+    double *F = Fptr(d, 0, 0, 0);
+    for (int i = tid; i < m; i += blockDim.x) F[i] = i == p ? 0.0 : -d.tab[(size_t)i * C + q]; // :1485
+    const double *rowp = d.tab + (size_t)p * C;
+    for (int j = tid; j < C; j += blockDim.x) {
+        const double x = xp_scale(rowp[j], r, r_one, r_zero); // :1471
+        d.P[j] = x;
+        double t = xp_mul(x, -1.0); // objective row, :1496-1501
+        if (j >= n) t = -t;
+        t = cq_zero ? 0.0 : (cq_one ? t : xp_mul(t, cq));
+        const double c = xp_add(t, d.tgtf[j]);
+        d.tgtf[j] = c;
+        if (j == n) d.st->tg_rhs = c;
+    }
+    if (tid == 0) { // :1504-1510
+        const int bv = s_bv;
+        d.nvset[q] = 0;
+        d.nvset[bv] = 1;
+        d.eq2bv[p] = q;
+        d.bv2eq[q] = p;
+        d.bv2eq[bv] = -1;
+    }
+}
+
+// ... second half: the rank-1 elimination over the whole tableau (:1481-1490), row p := P[0].
+__global__ void k_xpiv_apply(LpDev d, int p)
+{
+    const int C = d.C;
+    const double *F = Fptr(d, 0, 0, 0);
+    const size_t total = (size_t)d.m * C;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+         e += (size_t)gridDim.x * blockDim.x) {
+        const int i = (int)(e / C), j = (int)(e % C);
+        const double x = d.P[j];
+        d.tab[e] = i == p ? x : xp_add(d.tab[e], xp_mul(F[i], x));
+    }
+}
+
+// lpsol.h:944-953 with FloatMat::substit (xmat.cpp:1491-1520), is_eq = false: the original
+// objective with every basic variable substituted by its row, one variable after the other
+// (each step reads coefficients the previous ones produced).  One CTA.
+__global__ void __launch_bounds__(1024) k_restore_objective(LpDev d, const double *tg, int n_orig)
+{
+    __shared__ int s_list[1024];
+    __shared__ int s_cnt;
+    const int tid = threadIdx.x, C = d.C, rhs = d.n;
+    for (int j = tid; j < C; j += blockDim.x)
+        d.tgtf[j] = j < n_orig ? tg[j] : (j == rhs ? tg[n_orig] : 0.0);
+    __syncthreads();
+    for (int i0 = 0; i0 < rhs; i0 += 1024) {
+        // basic variables of this chunk, ascending
+        if (tid == 0) s_cnt = 0;
+        __syncthreads();
+        const int i = i0 + tid;
+        const bool basic = i < rhs && !d.nvset[i];
+        const unsigned bal = __ballot_sync(0xffffffffu, basic);
+        __shared__ int s_woff[33];
+        if ((tid & 31) == 0) s_woff[tid >> 5] = __popc(bal);
+        __syncthreads();
+        if (tid == 0) {
+            int acc = 0;
+            for (int w = 0; w < 32; w++) {
+                const int c = s_woff[w];
+                s_woff[w] = acc;
+                acc += c;
+            }
+            s_cnt = acc;
+        }
+        __syncthreads();
+        if (basic) s_list[s_woff[tid >> 5] + __popc(bal & ((1u << (tid & 31)) - 1u))] = i;
+        __syncthreads();
+        const int cnt = s_cnt;
+        for (int k = 0; k < cnt; k++) {
+            const int v = s_list[k];
+            const double ci = d.tgtf[v];
+            if (xp_feq(ci, 0.0)) continue; // uniform: every thread reads the same word
+            const double *ex = d.tab + (size_t)d.bv2eq[v] * C;
+            const double ev = ex[v];
+            const bool skip = xp_feq(ev, 0.0);
+            double s = -1.0;
+            if (!xp_feq(ci, ev)) s = xp_div(-ci, ev);
+            const bool s_zero = xp_feq(s, 0.0), s_one = xp_feq(s, 1.0);
+            __syncthreads(); // everybody has read c_v
+            for (int j = tid; j < C; j += blockDim.x) {
+                double tj = d.tgtf[j];
+                if (j >= rhs) tj = xp_mul(tj, -1.0);
+                if (!skip) {
+                    const double x = s_zero ? 0.0 : (s_one ? ex[j] : xp_mul(ex[j], s));
+                    tj = xp_add(x, tj);
+                }
+                if (j >= rhs) tj = xp_mul(tj, -1.0);
+                d.tgtf[j] = tj;
+            }
+            __syncthreads();
+        }
+        __syncthreads();
+    }
+    if (tid == 0) d.st->tg_rhs = d.tgtf[rhs];
+}
+
+// Drop column xa of `a` into `b` (b.C = a.C - 1) and re-index the maps (lpsol.h:956-986).
+__global__ void k_drop_column(LpDev a, LpDev b, int xa)
+{
+    const int m = a.m, Ca = a.C, Cb = b.C;
+    const size_t total = (size_t)m * Cb;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+         e += (size_t)gridDim.x * blockDim.x) {
+        const int i = (int)(e / Cb), k = (int)(e % Cb);
+        b.tab[e] = a.tab[(size_t)i * Ca + (k < xa ? k : k + 1)];
+    }
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < Cb; k += gridDim.x * blockDim.x) {
+        const int j = k < xa ? k : k + 1;
+        b.tgtf[k] = a.tgtf[j];
+        if (k < Cb - 1) {
+            b.nvset[k] = a.nvset[j];
+            b.bv2eq[k] = a.bv2eq[j];
+        }
+        if (k < m) {
+            const int bv = a.eq2bv[k];
+            b.eq2bv[k] = bv > xa ? bv - 1 : bv;
+            b.rhsbuf[k] = a.rhsbuf[k];
+        }
+        if (k == 0) b.st->tg_rhs = a.st->tg_rhs;
+    }
+}
+
+int xpiv_at(xp_lp_f64 *lp, int p, int q)
+{
+    xp_ctx *ctx = lp->ctx;
+    cudaStream_t s = ctx->stream;
+    k_xpiv_prepare<<<1, 1024, 0, s>>>(lp->d, p, q);
+    k_xpiv_apply<<<ctx->sm_count * 8, 256, 0, s>>>(lp->d, p);
+    k_rhs_from_tab<<<(lp->d.m + 255) / 256, 256, 0, s>>>(lp->d);
+    ctx->launches += 3;
+    XP_CUDA_OK(ctx, cudaGetLastError());
+    return 0;
+}
+
+struct LpGuard { // destroys the handle on every exit path
+    xp_lp_f64 *lp = nullptr;
+    ~LpGuard()
+    {
+        if (lp) xp_lp_f64_destroy(lp);
+    }
+};
+
+} // namespace
+
+extern "C" int xp_six_two_stage_f64_large(xp_ctx *ctx, int m, int n, const double *leq,
+                                          const double *tgtf, uint32_t max_iter, int rule,
+                                          int32_t *status, double *maxv, double *slack_sol,
+                                          double *tgtf_out, int32_t *eq2bv, uint32_t *iters,
+                                          uint32_t *pivots)
+{
+    if (!ctx || m < 1 || n < 1 || !leq || !tgtf || !status) return XP_ERR_BAD_ARG;
+    if (rule != XP_RULE_REFERENCE) return XP_ERR_BAD_ARG;
+    XP_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    const int Cm = n + m + 1;
+    // stage1 decision on the caller's arrays, :1794-1803
+    bool pos = false, bneg = false;
+    for (int j = 0; j < n; j++) pos |= tgtf[j] > 0.0;
+    int prow = 0; // row of the first minimum constant term, :894-904
+    for (int i = 0; i < m; i++) {
+        const double b = leq[(size_t)i * (n + 1) + n];
+        bneg |= b < 0.0;
+        if (leq[(size_t)prow * (n + 1) + n] > b) prow = i;
+    }
+    const bool aux = !pos || bneg;
+    if (maxv) *maxv = 0.0;
+    if (iters) *iters = 0;
+    if (pivots) *pivots = 0;
+    // the caller's LP in device scratch (the only bulk upload of the call)
+    void *scr = nullptr;
+    const size_t in_elems = (size_t)m * (n + 1) + (n + 1);
+    int rc = xp_ctx_scratch(ctx, in_elems * sizeof(double), &scr);
+    if (rc) return rc;
+    double *d_leq = (double *)scr, *d_tg = d_leq + (size_t)m * (n + 1);
+    XP_CUDA_OK(ctx, cudaMemcpyAsync(d_leq, leq, (size_t)m * (n + 1) * sizeof(double), cudaMemcpyHostToDevice, s));
+    XP_CUDA_OK(ctx, cudaMemcpyAsync(d_tg, tgtf, (n + 1) * sizeof(double), cudaMemcpyHostToDevice, s));
+    unsigned n_piv = 0;
+    LpGuard A, M;
+    rc = xp_lp_f64_create(ctx, m, Cm, &M.lp);
+    if (rc) return rc;
+    M.lp->kblk = ctx->slack_block;
+    if (!aux) {
+        k_slack_form<<<ctx->sm_count * 4, 256, 0, s>>>(M.lp->d, d_leq, d_tg, n);
+        ctx->launches++;
+        M.lp->d.vc_diag = M.lp->d.vc_rhs = nullptr;
+        XP_CUDA_OK(ctx, cudaGetLastError());
+    } else {
+        const int xa = n, Ca = Cm + 1;
+        rc = xp_lp_f64_create(ctx, m, Ca, &A.lp);
+        if (rc) return rc;
+        A.lp->kblk = ctx->slack_block;
+        k_aux_form<<<ctx->sm_count * 4, 256, 0, s>>>(A.lp->d, d_leq, n);
+        ctx->launches++;
+        A.lp->d.vc_diag = A.lp->d.vc_rhs = nullptr;
+        rc = xpiv_at(A.lp, prow, xa); // forced first pivot, :892-908
+        if (rc) return rc;
+        n_piv++;
+        rc = lp_reset(A.lp);
+        if (rc) return rc;
+        int st = xp_lp_f64_solve(A.lp, max_iter, rule);
+        if (st < 0) return st;
+        n_piv += A.lp->h_st->cnt;
+        if (pivots) *pivots = n_piv;
+        if (st != XP_SIX_SUCC || !xp_feq(A.lp->h_st->maxv, 0.0)) { // :912-922
+            *status = XP_SIX_NO_PRI_FEASIBLE_SOL;
+            return 0;
+        }
+        // xa still basic: pivot it out on the first non-basic column with a non-zero entry in
+        // its row, :924-941 (one row and the basis flags come to the host: O(C) bytes)
+        std::vector<uint8_t> nv(Ca - 1);
+        std::vector<int32_t> b2e(Ca - 1);
+        XP_CUDA_OK(ctx, cudaMemcpyAsync(nv.data(), A.lp->d.nvset, Ca - 1, cudaMemcpyDeviceToHost, s));
+        XP_CUDA_OK(ctx, cudaMemcpyAsync(b2e.data(), A.lp->d.bv2eq, (Ca - 1) * sizeof(int32_t),
+                                        cudaMemcpyDeviceToHost, s));
+        XP_CUDA_OK(ctx, cudaStreamSynchronize(s));
+        if (!nv[xa]) {
+            const int eqnum = b2e[xa];
+            std::vector<double> row(Ca);
+            XP_CUDA_OK(ctx, cudaMemcpyAsync(row.data(), A.lp->d.tab + (size_t)eqnum * Ca, Ca * sizeof(double),
+                                            cudaMemcpyDeviceToHost, s));
+            XP_CUDA_OK(ctx, cudaStreamSynchronize(s));
+            int cand = -1;
+            for (int j = 0; j < Ca - 1; j++)
+                if (nv[j] && !xp_feq(row[j], 0.0)) {
+                    cand = j;
+                    break;
+                }
+            if (cand < 0) { // reference ASSERTs (:937)
+                *status = XP_ERR_REFERENCE_UB;
+                return 0;
+            }
+            rc = xpiv_at(A.lp, eqnum, cand);
+            if (rc) return rc;
+            n_piv++;
+        }
+        k_restore_objective<<<1, 1024, 0, s>>>(A.lp->d, d_tg, n); // :944-953
+        k_drop_column<<<ctx->sm_count * 4, 256, 0, s>>>(A.lp->d, M.lp->d, xa); // :956-986
+        ctx->launches += 2;
+        M.lp->d.vc_diag = M.lp->d.vc_rhs = nullptr;
+        XP_CUDA_OK(ctx, cudaGetLastError());
+    }
+    rc = lp_reset(M.lp);
+    if (rc) return rc;
+    int st = xp_lp_f64_solve(M.lp, max_iter, rule);
+    if (st < 0) return st;
+    uint32_t it = 0;
+    rc = xp_lp_f64_download(M.lp, nullptr, tgtf_out, nullptr, nullptr, nullptr, eq2bv, maxv, slack_sol, &it,
+                            nullptr, 0);
+    if (rc) return rc;
+    if (iters) *iters = it;
+    if (pivots) *pivots = n_piv + it;
+    *status = st;
+    return 0;
+}
