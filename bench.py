@@ -272,10 +272,12 @@ def run_batched(ctx, xp, torch, dev, with_cpu=True, rank=0, world=1, dist=None):
         T = max(1, min(64, len(os.sched_getaffinity(0))))
         S1, ST = min(B, 4000), min(B, 4000 * T)
         cst = np.zeros(ST, dtype=np.int32)
+        cmx = np.zeros(ST)
 
         def cpu_run(lo, hi):
             vp = lambda a: a.ctypes.data_as(C.c_void_p)
-            return o.xo_two_stage_f64_many(hi - lo, m, n, vp(h_leq[lo:hi]), vp(h_tg[lo:hi]), vp(cst[lo:hi]))
+            return o.xo_two_stage_f64_many(hi - lo, m, n, vp(h_leq[lo:hi]), vp(h_tg[lo:hi]),
+                                           vp(cst[lo:hi]), vp(cmx[lo:hi]))
         t1 = cpu_run(0, S1)
         t0 = time.perf_counter()
         th = [threading.Thread(target=cpu_run, args=(ST * i // T, ST * (i + 1) // T)) for i in range(T)]
@@ -286,7 +288,9 @@ def run_batched(ctx, xp, torch, dev, with_cpu=True, rank=0, world=1, dist=None):
                "sample": f"the first {ST} of the {B} LPs, {T} host threads each looping over its "
                          "slice (the reference solves one LP per call)",
                "one_core": {"value": S1 / t1, "sample": f"the first {S1} LPs"},
-               "status_matches_gpu": bool(np.array_equal(cst, e2e_status[:ST]))}
+               "status_matches_gpu": bool(np.array_equal(cst, e2e_status[:ST])),
+               "objective_bits_match_gpu": bool(np.array_equal(cmx.view(np.uint64),
+                                                               out["maxv"][:ST].view(np.uint64)))}
     del h_leq, h_tg
     ctx.check(lib.xp_host_free(ctx._h, hp1))
     ctx.check(lib.xp_host_free(ctx._h, hp2))

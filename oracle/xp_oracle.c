@@ -486,7 +486,7 @@ int xo_has_solution_rat(int m, int n, const xo_rat *leq, int k, const xo_rat *eq
  * shape, one after the other (the reference has no batching; callers loop).  Re-entrant, so
  * the bench can run one call per host thread on disjoint slices.  Returns seconds spent. */
 double xo_two_stage_f64_many(int batch, int m, int n, const double *leq, const double *tgtf,
-                             int32_t *status)
+                             int32_t *status, double *maxv_out)
 {
     int cap = n + m + 2;
     double *tab = (double *)malloc((size_t)m * cap * sizeof(double));
@@ -502,6 +502,7 @@ double xo_two_stage_f64_many(int batch, int m, int n, const double *leq, const d
         status[k] = xo_two_stage_f64(m, n, leq + (size_t)k * m * (n + 1), tgtf + (size_t)k * (n + 1),
                                      0xFFFFFFFFu, dims, tab, otg, eq2bv, bv2eq, nv, bv, &maxv, ssol,
                                      NULL, 0, NULL);
+        if (maxv_out) maxv_out[k] = status[k] == XO_SIX_SUCC ? maxv : 0.0;
     }
     double dt = xo_now() - t0;
     free(tab); free(otg); free(ssol); free(eq2bv); free(bv2eq); free(nv); free(bv);

@@ -102,7 +102,7 @@ int xo_has_solution_rat(int m, int n, const xo_rat *leq, int k, const xo_rat *eq
 double xo_last_solve_seconds(void);
 /* TwoStageMethod on `batch` FP64 LPs of one shape in a loop; returns the seconds spent. */
 double xo_two_stage_f64_many(int batch, int m, int n, const double *leq, const double *tgtf,
-                             int32_t *status);
+                             int32_t *status, double *maxv_out /* optional: maxv on SUCC, else 0 */);
 
 /* std::mt19937_64 + uniform_real_distribution<double>(0,1) stream (libstdc++). */
 void xo_mt64_uniform(uint64_t seed, size_t count, double *out);

@@ -201,7 +201,7 @@ def test_two_stage_large_phase1_on_device(ctx, m, n):
     seen = set()
     for k in range(6):
         leq, tg = H.gen_mixed_lp(31 * m + k, m, n, bneg=0.3 if k % 2 == 0 else 0.0)
-        for K in ((H.NO_LIMIT, 7) if m <= 150 else (60,)):
+        for K in ((H.NO_LIMIT, 7) if m <= 130 else (60, 400)):
             g = _check_two_stage(ctx, leq, tg, K, ("mixed", m, n, k, K))
             seen.add(g["status"])
     leq, tg = H.gen_dense_lp(5 * m, m, n)  # b > 0, c > 0: no auxiliary LP
