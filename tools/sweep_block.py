@@ -16,9 +16,9 @@ lp = ctx.large_lp(m, Cc)
 for k in [int(x) for x in os.environ.get("KS", "1,2,4,8,12,16,24,32").split(",")]:
     lp.set_block(k)
     lp.fill_synthetic(20261017)
-    lp.solve(k * 2)          # warm-up
+    lp.solve(max(k, 1) * 2)          # warm-up
     lib.xp_lp_f64_profile(lp._h, 1)
-    done = k * 2
+    done = max(k, 1) * 2
     ms = 0.0
     reps = 3
     for _ in range(reps):
@@ -31,6 +31,6 @@ for k in [int(x) for x in os.environ.get("KS", "1,2,4,8,12,16,24,32").split(",")
     piv = reps * P
     print(f"k={k:2d} status={st} {piv / (ms * 1e-3):9.1f} pivots/s  {ms * 1e3 / piv:7.2f} us/pivot  "
           f"flush avg {sw.value / max(nsw.value, 1) * 1e3:7.1f} us x{nsw.value}  "
-          f"panel+gaps {gap.value * 1e3 / max(nsw.value - reps, 1) / k:6.2f} us/pivot", flush=True)
+          f"panel+gaps {gap.value * 1e3 / max(nsw.value - reps, 1) / max(k, 1):6.2f} us/pivot", flush=True)
 lp.close()
 ctx.close()

@@ -67,6 +67,7 @@ struct LpState {
     unsigned max_iter;
     int t;     // pivots pending in the open block (rows of P / F in use)
     int kblk;  // block size
+    int kadapt; // > 0: bounded run, block sizes chosen per block with this upper bound
     int blk;   // blocks flushed so far (parity selects the F buffer)
     int q;     // entering column of the next step (INT_BIG: none)
     int anypos;
@@ -179,6 +180,23 @@ __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned l
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 __device__ __forceinline__ double ld_cg(const double *p) { return __ldcg(p); }
+
+// Size of the next block of a bounded run (max_iter known): as few passes over the tableau as
+// the upper bound allows, sizes in multiples of 8 (the flush kernel's unrolled step count) and
+// none of them nearly empty, e.g. 200 pivots -> 32 32 32 32 24 24 24.  A pure function of
+// replicated state, so every rank of a sharded LP picks the same size.
+__device__ __forceinline__ void next_block(LpState *st)
+{
+    const int kmax = st->kadapt;
+    if (kmax <= 0 || st->max_iter == XP_NO_ITER_LIMIT || st->cnt >= st->max_iter) return;
+    const unsigned left = st->max_iter - st->cnt;
+    const unsigned nb = (left + kmax - 1) / kmax;
+    unsigned k = (left + nb - 1) / nb;
+    if (k >= 16) k = (k + 7) & ~7u;
+    if (k > (unsigned)kmax) k = kmax;
+    if (k > left) k = left;
+    st->kblk = k < 1 ? 1 : (int)k;
+}
 
 // Threads 0..G-1 each write `w` to the word at byte offset `off` of rank t's
 // block.  Callers __syncthreads() first when the word guards data.
@@ -1339,6 +1357,7 @@ __global__ void __launch_bounds__(THREADS) k_flush(LpDev d, int rows_per_cta)
         st->n_touched = 0;
         st->t = 0;
         st->blk += 1;
+        next_block(st);
     }
 }
 
@@ -1516,6 +1535,7 @@ __global__ void __launch_bounds__(LANES *HALVES) k_flush_t(LpDev d, int groups)
         st->n_touched = 0;
         st->t = 0;
         st->blk += 1;
+        next_block(st);
     }
 }
 
@@ -1657,11 +1677,16 @@ __global__ void k_init(LpDev d, unsigned max_iter, int kblk, int fresh)
             st->maxv = 0.0; // :1027
             st->status = XPI_RUNNING;
             st->kblk = kblk > 0 ? kblk : 1;
+            st->kadapt = 0;
         } else {
             if (st->status == XP_SIX_TIME_OUT && st->cnt < max_iter) st->status = XPI_RUNNING; // resume
-            if (kblk > 0 && st->t == 0) st->kblk = kblk;
+            if (kblk != 0 && st->t == 0) { // kblk < 0: adaptive with upper bound -kblk
+                st->kblk = kblk > 0 ? kblk : -kblk;
+                st->kadapt = kblk > 0 ? 0 : -kblk;
+            }
         }
         st->max_iter = max_iter;
+        if (!fresh && st->t == 0) next_block(st);
     }
 }
 
@@ -2241,16 +2266,11 @@ extern "C" int xp_lp_f64_solve(xp_lp_f64 *lp, uint32_t max_iter, int rule)
     }
     XP_CUDA_OK(ctx, cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream;
-    int kblk = lp->kblk > 0 ? lp->kblk : auto_block(d);
-    if (lp->kblk == 0 && max_iter != XP_NO_ITER_LIMIT && max_iter > lp->cnt_host) {
-        // bounded run: equal blocks instead of full ones plus a short tail (same passes over
-        // the tableau, none of them nearly empty)
-        const unsigned left = max_iter - lp->cnt_host;
-        const unsigned nb = (left + kblk - 1) / kblk;
-        kblk = (int)((left + nb - 1) / nb);
-    }
+    const int kblk = lp->kblk > 0 ? lp->kblk : auto_block(d); // upper bound of every block
+    // bounded run with automatic blocking: the device picks each block's size (next_block)
+    const bool adaptive = lp->kblk == 0 && max_iter != XP_NO_ITER_LIMIT && max_iter > lp->cnt_host;
     XP_CUDA_OK(ctx, cudaEventRecord(ctx->ev0, s));
-    k_init<<<1, 32, 0, s>>>(d, max_iter, kblk, 0);
+    k_init<<<1, 32, 0, s>>>(d, max_iter, adaptive ? -kblk : kblk, 0);
     ctx->launches++;
     // One block = kblk x (k_pcol, k_prow) + k_flush, no host round trip inside;
     // the host polls the status word between batches of blocks.  Every rank of a
@@ -2299,7 +2319,7 @@ extern "C" int xp_lp_f64_solve(xp_lp_f64 *lp, uint32_t max_iter, int rule)
         for (int k = 0; k < n_prof; k++) {
             float ms = 0.f;
             XP_CUDA_OK(ctx, cudaEventElapsedTime(&ms, lp->evs[2 * k], lp->evs[2 * k + 1]));
-            if (ms < 0.004f) continue; // an empty launch (block still open / already terminal)
+            if (ms < 0.020f) continue; // an empty launch (block still open / already terminal)
             lp->prof_sweep_ms += ms;
             lp->prof_sweeps++;
             if (k > 0) {
