@@ -133,3 +133,34 @@ def test_c4_full_batch_10k(ctx):
     for k in r.choice(B, size=150, replace=False):
         checked += check(a, int(k), oracle_exact(leq[k].astype(float), tg[k].astype(float)), m, n, "c4-full")
     assert checked > 100
+
+
+@pytest.mark.parametrize("m,n,neg", [(24, 23, False), (24, 23, True), (32, 31, False), (16, 40, True),
+                                     (8, 55, True), (7, 4, True), (16, 15, True), (3, 2, True)])
+def test_warp_kernel_equals_cta_kernel_exact(ctx, m, n, neg):
+    """The register-resident warp kernel and the shared-memory CTA kernel of the exact path are
+    two schedules of the same integer arithmetic: every output of a 4096-LP batch agrees, for
+    every instantiation, with and without phase 1, overflow flags included."""
+    import os
+    B = 4096
+    r = np.random.RandomState(77 * m + n)
+    A = r.randint(-2 if neg else 0, 4, size=(B, m, n)) * (r.uniform(size=(B, m, n)) < 0.35)
+    leq = np.zeros((B, m, n + 1), dtype=np.int64)
+    leq[:, :, :n] = A
+    leq[:, :, n] = r.randint(-5 if neg else 0, 21, size=(B, m))
+    tg = np.zeros((B, n + 1), dtype=np.int64)
+    tg[:, :n] = r.randint(-1 if neg else 1, 6, size=(B, n))
+    for K in (xp.NO_ITER_LIMIT, 6):
+        os.environ["XP_BATCH_WARP"] = "2"  # force the warp kernel for every shape that fits
+        a = ctx.two_stage_i64_batch(leq, tg, K)
+        os.environ["XP_BATCH_WARP"] = "0"
+        try:
+            b = ctx.two_stage_i64_batch(leq, tg, K)
+        finally:
+            os.environ.pop("XP_BATCH_WARP", None)
+        assert np.array_equal(a["status"], b["status"]), (K, np.flatnonzero(a["status"] != b["status"])[:5])
+        assert np.array_equal(a["pivots"], b["pivots"])
+        assert np.array_equal(a["iters"], b["iters"])
+        ok = (a["status"] >= 0) & (a["status"] != H.SIX_NO_PRI)
+        for k in ("eq2bv", "maxv", "sol_num", "sol_den", "tgtf_num", "tgtf_den"):
+            assert np.array_equal(a[k][ok], b[k][ok]), (k, K)

@@ -21,6 +21,9 @@
 // chain per pivot, by one thread), so the per-element cost is two 64x64->128
 // products, a 128-bit subtract, a funnel shift and one 64-bit multiply.
 #include "xp_batch_core.cuh"
+#include "xp_batch_warp_i64.cuh"
+
+#include <cstdlib>
 
 namespace {
 
@@ -298,8 +301,40 @@ int pick_threads_i64(int maxm, int maxn)
     return 256;
 }
 
+// Register-resident fast path: one warp per LP (xp_batch_warp_i64.cuh).
+template <int MR, int NS>
+int launch_warp_i64(xp_ctx *ctx, XpBatchArgs &A)
+{
+    int occ = 1;
+    XP_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, xpwi::k_warp_i64<MR, NS>,
+                                                                  32 * xpwi::WARPS, 0));
+    if (occ < 1) occ = 1;
+    long long g = (long long)occ * ctx->sm_count;
+    const long long need = ((long long)A.batch + xpwi::WARPS - 1) / xpwi::WARPS;
+    if (g > need) g = need;
+    XP_CUDA_OK(ctx, cudaMemsetAsync(A.queue, 0, sizeof(unsigned), ctx->stream));
+    xpwi::k_warp_i64<MR, NS><<<(unsigned)g, 32 * xpwi::WARPS, 0, ctx->stream>>>(A);
+    ctx->launches++;
+    XP_CUDA_OK(ctx, cudaGetLastError());
+    return 0;
+}
+
 int launch_i64(xp_ctx *ctx, XpBatchArgs &A)
 {
+    // Measured on B200: with 128-bit products the register kernel only pays while a lane's share
+    // of the tableau leaves room for four warps per scheduler -- dependence-feasibility systems
+    // (~7 x 11: 1.4x the CTA kernel); at 24 x 48 it runs at 255 registers with spills and loses
+    // (100 000 LPs: 126 ms against 72 ms), so larger shapes stay on the one-CTA-per-LP kernel.
+    const char *we = getenv("XP_BATCH_WARP"); // "0" forces the CTA kernel, "2" the warp kernel (A/B tests)
+    const bool fits = A.maxm <= 32 && A.maxn + 1 + A.maxm <= 64;
+    const bool one = A.maxn + 1 + A.maxm <= 32;
+    const bool pays = A.maxm <= 8 || (A.maxm <= 16 && one);
+    if (fits && !(we && we[0] == '0') && (pays || (we && we[0] == '2'))) {
+        if (A.maxm <= 8) return one ? launch_warp_i64<8, 1>(ctx, A) : launch_warp_i64<8, 2>(ctx, A);
+        if (A.maxm <= 16) return one ? launch_warp_i64<16, 1>(ctx, A) : launch_warp_i64<16, 2>(ctx, A);
+        if (A.maxm <= 24) return launch_warp_i64<24, 2>(ctx, A);
+        return launch_warp_i64<32, 2>(ctx, A);
+    }
     const size_t smem = xpb_smem_bytes(A.maxm, A.maxn, sizeof(i64), sizeof(KeyI64));
     if (smem > ctx->smem_optin) {
         // Same kernel, state slab in global memory: one 1024-thread CTA per LP.

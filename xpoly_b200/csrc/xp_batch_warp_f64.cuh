@@ -102,6 +102,7 @@ struct LP {
     unsigned pivots;
     int lane;
     double *sc;            // this warp's scratch line (32 doubles, shared memory)
+    static constexpr int kNS = NS;
 };
 
 // M(s) for slot 0 and, with two slots, slot 1
@@ -196,18 +197,20 @@ __device__ __forceinline__ void set_row(LP<MR, NS> &W, int p, double r0, double 
 }
 
 // newPPT (lpsol.h:390-399)
-template <int MR, int NS>
-__device__ __forceinline__ void tabu_reset(LP<MR, NS> &W)
+template <class L>
+__device__ __forceinline__ void tabu_reset(L &W)
 {
+    constexpr int NS = L::kNS;
     W.t0 = W.t1 = 0ull;
     W.rc0 = W.rc1 = W.cc0 = W.cc1 = 0;
     const u64 all = (0 >= W.n - 1) ? low_mask(W.n) : 0ull;
     W.rowfull = all;
     W.colfull = all;
 }
-template <int MR, int NS>
-__device__ __forceinline__ void tabu_masks(LP<MR, NS> &W)
+template <class L>
+__device__ __forceinline__ void tabu_masks(L &W)
 {
+    constexpr int NS = L::kNS;
     const int lim = W.n - 1, j0 = W.lane, j1 = 32 + W.lane;
     W.rowfull = colmask<NS>(j0 < W.n && W.rc0 >= lim, j1 < W.n && W.rc1 >= lim);
     W.colfull = colmask<NS>(j0 < W.n && W.cc0 >= lim, j1 < W.n && W.cc1 >= lim);
@@ -215,9 +218,10 @@ __device__ __forceinline__ void tabu_masks(LP<MR, NS> &W)
 // PivotPairTab::genPair (lpsol.h:100), counters kept as in the CTA kernel.  The counters only
 // grow between resets, so the two "full" masks are updated in place: one shuffle carries
 // (newly set, row now full) from the owner of q, one ballot the column flag of bv's owner.
-template <int MR, int NS>
-__device__ __forceinline__ void tabu_gen_pair(LP<MR, NS> &W, int q, int bv)
+template <class L>
+__device__ __forceinline__ void tabu_gen_pair(L &W, int q, int bv)
 {
+    constexpr int NS = L::kNS;
     const int lim = W.n - 1;
     int info = 0; // bit 0: pair newly set, bit 1: row q full now
     if (W.lane == (q & 31)) {
@@ -253,9 +257,10 @@ __device__ __forceinline__ void tabu_gen_pair(LP<MR, NS> &W, int q, int bv)
     }
 }
 // PivotPairTab::disableNV (lpsol.h:114-121)
-template <int MR, int NS>
-__device__ __forceinline__ void tabu_disable_nv(LP<MR, NS> &W, int q)
+template <class L>
+__device__ __forceinline__ void tabu_disable_nv(L &W, int q)
 {
+    constexpr int NS = L::kNS;
     const u64 want = low_mask(W.n) & ~(1ull << q);
     u64 add = 0ull;
     if (W.lane == (q & 31)) {
