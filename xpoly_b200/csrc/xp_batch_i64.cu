@@ -295,6 +295,7 @@ __global__ void __launch_bounds__(1024) k_batch_i64_gws(XpBatchArgs A)
 
 int pick_threads_i64(int maxm, int maxn)
 {
+    if (const char *e = getenv("XP_BATCH_THREADS_I64")) return atoi(e); // tuning knob
     long long cells = (long long)maxm * (maxn + maxm + 2);
     if (cells <= 16 * 64) return 64;
     if (cells <= 16 * 256) return 128;
