@@ -37,6 +37,20 @@ def run_uniform(ctx, lps, max_iter=H.NO_LIMIT, tag=None):
     return g
 
 
+def _ab(ctx, fn):
+    """Run fn() with the one-warp-per-LP register kernel (default for LPs of at most 32 rows /
+    64 variables) and again with the one-CTA-per-LP shared-memory kernel forced."""
+    import os
+    os.environ["XP_BATCH_WARP"] = "1"
+    a = fn()
+    os.environ["XP_BATCH_WARP"] = "0"
+    try:
+        b = fn()
+    finally:
+        os.environ.pop("XP_BATCH_WARP", None)
+    return a, b
+
+
 def test_c2_shape_dense_32x64(ctx):
     """Config 2 shape (tableau 32x64), SURVEY 8(d) distribution: status mix SUCC /
     OPTIMAL_IS_INFEASIBLE / UNBOUND must match per LP."""
@@ -124,6 +138,13 @@ def test_c2_full_batch_100k(ctx):
     tg[:, n] = 0.0
     a = ctx.two_stage_f64_batch(leq, tg)
     b = ctx.two_stage_f64_batch(leq[::-1].copy(), tg[::-1].copy())
+    # (d) the shared-memory CTA kernel, forced, gives the same bits on all 100 000 LPs as the
+    # register-resident warp kernel that serves this shape by default
+    _, cta = _ab(ctx, lambda: ctx.two_stage_f64_batch(leq, tg))
+    for k in ("status", "pivots", "iters", "eq2bv"):
+        assert np.array_equal(a[k], cta[k]), ("warp vs cta", k)
+    for k in ("maxv", "slack_sol", "tgtf"):
+        assert np.array_equal(H.bits(a[k]), H.bits(cta[k])), ("warp vs cta", k)
     for k in ("status", "pivots", "eq2bv"):
         assert np.array_equal(a[k], b[k][::-1]), k
     for k in ("maxv", "slack_sol", "tgtf"):
@@ -137,20 +158,6 @@ def test_c2_full_batch_100k(ctx):
     for k in idx:
         o = H.two_stage("oracle", "f64", leq[k], tg[k], want_log=True)
         check_lp(a, int(k), o, m, n, "c2-full")
-
-
-def _ab(ctx, fn):
-    """Run fn() with the one-warp-per-LP register kernel (default for LPs of at most 32 rows /
-    64 variables) and again with the one-CTA-per-LP shared-memory kernel forced."""
-    import os
-    os.environ["XP_BATCH_WARP"] = "1"
-    a = fn()
-    os.environ["XP_BATCH_WARP"] = "0"
-    try:
-        b = fn()
-    finally:
-        os.environ.pop("XP_BATCH_WARP", None)
-    return a, b
 
 
 @pytest.mark.parametrize("m,n,bneg", [(32, 31, 0.0), (32, 31, 0.3), (24, 23, 0.3), (16, 40, 0.2),
