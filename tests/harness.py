@@ -182,7 +182,8 @@ def two_stage(which, kind, leq, tgtf, max_iter=NO_LIMIT, want_log=False):
 
 def mip_solve(which, kind, is_min, is_bin, leq, tgtf, eq=None):
     lib, pre = _lib_and_prefix(which)
-    m, n1 = leq.shape[0], leq.shape[1]
+    m = 0 if leq is None else leq.shape[0]
+    n1 = (leq if leq is not None else eq).shape[1]
     n = n1 - 1
     k = 0 if eq is None else eq.shape[0]
     if kind == "f64":
@@ -191,7 +192,7 @@ def mip_solve(which, kind, is_min, is_bin, leq, tgtf, eq=None):
     else:
         v = np.zeros(2, dtype=np.int32)
         sol = np.zeros((n1, 2), dtype=np.int32)
-    args = [int(is_min), int(is_bin), m, n, P(np.ascontiguousarray(leq)),
+    args = [int(is_min), int(is_bin), m, n, P(None if leq is None else np.ascontiguousarray(leq)),
             P(np.ascontiguousarray(tgtf)), k, P(None if eq is None else np.ascontiguousarray(eq)),
             P(v), P(sol)]
     nodes = C.c_int(0)

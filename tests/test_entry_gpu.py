@@ -267,3 +267,35 @@ def test_has_solution_ragged_with_equalities(ctx):
     # equalities without inequalities: the reference writes a 1 x 0 objective (linsys.cpp:851)
     e = np.array([[1, -1, 0]], dtype=np.int64)
     assert ctx.has_solution_ragged([(None, e)]).tolist() == [xp.ERR_REFERENCE_UB]
+
+
+def fea_schedule_system(r):
+    """The MIP PolyTran::FeaSchedule builds (poly.cpp:5094-5133): equalities only (Farkas
+    identities over u- and lambda-multipliers), all variables >= 0, objective = sum of the u's."""
+    nu, nl, ke = int(r.randint(2, 5)), int(r.randint(3, 7)), int(r.randint(2, 5))
+    n = nu + nl
+    eq = np.zeros((ke, n + 1), dtype=np.int64)
+    eq[:, :n] = r.randint(-2, 3, size=(ke, n))
+    eq[:, n] = r.randint(0, 6, size=ke)
+    tg = np.zeros(n + 1, dtype=np.int64)
+    tg[:nu] = 1
+    return eq, tg
+
+
+def test_fea_schedule_shape_mip(ctx):
+    """maxm, then minm when that fails (poly.cpp:5126-5133), on equality-only
+    integer programs, against the oracle: status, value, solution, node count."""
+    r = np.random.RandomState(5)
+    seen = set()
+    for k in range(60):
+        eq, tg = fea_schedule_system(r)
+        for is_min in (0, 1):
+            g = ctx.mip_solve("rat", is_min, 0, None, tg, eq=eq)
+            o = H.mip_solve("oracle", "rat", is_min, 0, None, H.to_rat(tg), eq=H.to_rat(eq))
+            same_rat(g, o, ("fea", k, is_min))
+            if o["status"] >= 0:
+                assert g["nodes"] == o["nodes"], (k, is_min)
+            seen.add(o["status"])
+            if o["status"] == 0:
+                break
+    assert {0, 1, 2} <= seen

@@ -95,3 +95,51 @@ def test_equalities_including_reference_bug_path():
         b = H.six_solve("ref", "f64", 0, leq, tg, None, E)
         assert a["status"] == b["status"] and eqv("f64", a["v"], b["v"])
     assert n_ub > 0
+
+
+def test_fea_schedule_shape_mip_and_has_solution_with_equalities():
+    """The two callers of section 8(f): PolyTran::FeaSchedule's equality-only integer programs
+    (poly.cpp:5094-5133: maxm, then minm) and Lineq::has_solution on systems with equalities."""
+    r = np.random.RandomState(5)
+    for k in range(40):
+        nu, nl, ke = int(r.randint(2, 5)), int(r.randint(3, 7)), int(r.randint(2, 5))
+        n = nu + nl
+        eq = np.zeros((ke, n + 1), dtype=np.int64)
+        eq[:, :n] = r.randint(-2, 3, size=(ke, n))
+        eq[:, n] = r.randint(0, 6, size=ke)
+        tg = np.zeros(n + 1, dtype=np.int64)
+        tg[:nu] = 1
+        for is_min in (0, 1):
+            a = H.mip_solve("oracle", "rat", is_min, 0, None, H.to_rat(tg), eq=H.to_rat(eq))
+            if a["status"] < 0:
+                continue  # the reference has undefined behaviour here
+            b = H.mip_solve("ref", "rat", is_min, 0, None, H.to_rat(tg), eq=H.to_rat(eq))
+            assert a["status"] == b["status"], (k, is_min)
+            if a["status"] == 0:
+                assert np.array_equal(a["v"], b["v"]) and np.array_equal(a["sol"], b["sol"])
+    checked = 0
+    for k in range(120):
+        n, m = int(r.randint(2, 5)), int(r.randint(2, 7))
+        leq = np.zeros((m, n + 1), dtype=np.int64)
+        leq[:, :n] = r.randint(-2, 4, size=(m, n))
+        leq[:, n] = r.randint(0, 20, size=m)
+        eq = np.zeros((1, n + 1), dtype=np.int64)
+        eq[:, :n] = r.randint(-2, 3, size=(1, n))
+        eq[:, n] = r.randint(0, 8)
+        # has_solution = MIP max, then MIP min, on the all-ones objective restricted to the columns
+        # that occur (reviseTargetFunc).  Where one of them walks into convertEq2Ineq's
+        # out-of-bounds read (lpsol.h:1232, possible at any B&B node) the reference's answer is
+        # whatever the heap held; the oracle reports XO_ERR_REFERENCE_UB and the case is skipped.
+        tg = np.zeros(n + 1, dtype=np.int64)
+        tg[:n] = ((leq[:, :n] != 0).any(axis=0) | (eq[:, :n] != 0).any(axis=0)).astype(np.int64)
+        amax = H.mip_solve("oracle", "rat", 0, 0, H.to_rat(leq), H.to_rat(tg), eq=H.to_rat(eq))
+        if amax["status"] < 0:
+            continue
+        if amax["status"] != 0:
+            amin = H.mip_solve("oracle", "rat", 1, 0, H.to_rat(leq), H.to_rat(tg), eq=H.to_rat(eq))
+            if amin["status"] < 0:
+                continue
+        checked += 1
+        assert H.has_solution("oracle", H.to_rat(leq), H.to_rat(eq)) == \
+            H.has_solution("ref", H.to_rat(leq), H.to_rat(eq)), k
+    assert checked >= 15
