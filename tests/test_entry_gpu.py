@@ -292,9 +292,11 @@ def test_fea_schedule_shape_mip(ctx):
         for is_min in (0, 1):
             g = ctx.mip_solve("rat", is_min, 0, None, tg, eq=eq)
             o = H.mip_solve("oracle", "rat", is_min, 0, None, H.to_rat(tg), eq=H.to_rat(eq))
+            if o["status"] < 0:  # the reference has undefined behaviour here: only the code is defined
+                assert g["status"] == o["status"], (k, is_min, g["status"], o["status"])
+                continue
             same_rat(g, o, ("fea", k, is_min))
-            if o["status"] >= 0:
-                assert g["nodes"] == o["nodes"], (k, is_min)
+            assert g["nodes"] == o["nodes"], (k, is_min)
             seen.add(o["status"])
             if o["status"] == 0:
                 break
