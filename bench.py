@@ -388,6 +388,33 @@ def run_exact_and_bnb(ctx, xp):
                   "relaxations batched on the GPU, decisions replayed in the reference's DFS order",
                   "value": nodes / dt, "unit": "node LPs/s", "trees_per_s": T / dt, "nodes_total": nodes,
                   "status_mix": {str(k): int((ms == k).sum()) for k in np.unique(ms)}}
+    # 8(f1/f2): Lineq::has_solution over a dependence-graph build's worth of queries (systems of
+    # different sizes, integer solutions wanted), one ragged call; the oracle port beside it
+    Q = 20_000
+    systems = []
+    for k in range(Q):
+        nq, mq = int(r.randint(2, 6)), int(r.randint(3, 10))
+        sysm = np.zeros((mq, nq + 1), dtype=np.int64)
+        sysm[:, :nq] = r.randint(-2, 4, size=(mq, nq)) * (r.uniform(size=(mq, nq)) < 0.7)
+        sysm[:, nq] = r.randint(0, 25, size=mq)
+        systems.append((sysm, None))
+    ctx.has_solution_ragged(systems[:64])
+    t0 = time.perf_counter()
+    res = ctx.has_solution_ragged(systems)
+    dt = time.perf_counter() - t0
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import harness as H
+    S = 300
+    t0 = time.perf_counter()
+    cpu = [H.has_solution("oracle", H.to_rat(systems[k][0])) for k in range(S)]
+    dtc = time.perf_counter() - t0
+    out["has_solution"] = {"metric": "dependence queries/s", "workload": f"{Q} Lineq::has_solution systems, "
+                           "2-5 variables x 3-9 inequalities, integer solutions (max then min MIP, B&B trees "
+                           "in lockstep), one xp_has_solution_rat_ragged call from host memory",
+                           "value": Q / dt, "unit": "queries/s", "feasible": int((res == 1).sum()),
+                           "cpu_baseline": {"value": S / dtc, "unit": "queries/s", "cores": 1, "kind": "port",
+                                            "sample": f"the first {S} systems",
+                                            "answers_match_gpu": bool(np.array_equal(np.array(cpu), res[:S]))}}
     return out
 
 
@@ -510,6 +537,15 @@ def run_ours(args):
                 "(k x 2(m+1)C x 8) exceed the bytes this kernel moves (2 m C x 8); see DESIGN.md",
         "whole_pivot_frac_of_peak": value * B_pivot / 1e9 / peak,
         "whole_pivot_frac_of_8TBps": value * B_pivot / 8e12}
+    # what actually limits this launch at k >= ~23: the FP64 pipe (mul and add not fused, as the
+    # reference's rounding order demands): 2 m C operations per pivot, 64 lanes/clk/SM
+    # (tools/fp64_peak.cu measures 18.5 T lanes/s on B200)
+    fp64_peak = ctx_sm_count(torch, dev) * 64 * sm_clock_hz(torch, dev)
+    fp64_ops = k_eff * 2.0 * m * local_cols
+    roofline["limiter_at_this_k"] = {
+        "bound": "fp64 pipe (non-fused mul + add)", "unit": "Tops/s", "peak": fp64_peak / 1e12,
+        "achieved": fp64_ops / (flush_avg_ms * 1e-3) / 1e12 if flush_avg_ms > 0 else None,
+        "frac": fp64_ops / (flush_avg_ms * 1e-3) / fp64_peak if flush_avg_ms > 0 else None}
 
     # the reference's own schedule (one tableau pass per pivot), same kernels with k = 1
     r1 = timed_run(1, args.rank1_pivots, 3, 1)
