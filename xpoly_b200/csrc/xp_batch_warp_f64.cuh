@@ -200,7 +200,6 @@ __device__ __forceinline__ void set_row(LP<MR, NS> &W, int p, double r0, double 
 template <class L>
 __device__ __forceinline__ void tabu_reset(L &W)
 {
-    constexpr int NS = L::kNS;
     W.t0 = W.t1 = 0ull;
     W.rc0 = W.rc1 = W.cc0 = W.cc1 = 0;
     const u64 all = (0 >= W.n - 1) ? low_mask(W.n) : 0ull;

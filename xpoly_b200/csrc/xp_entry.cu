@@ -10,6 +10,8 @@
 
 #include "../host/xp_host_six.hpp"
 
+#include <atomic>
+#include <thread>
 #include <vector>
 
 using namespace xph;
@@ -22,6 +24,44 @@ typedef TwoStageResult<F64> ResF;
 bool fits_smem(const xp_ctx *ctx, int m, int n, size_t key_bytes)
 {
     return xpb_smem_bytes(m, n, 8, key_bytes) <= ctx->smem_optin;
+}
+
+// Host-side loops over independent items (trees of a B&B batch, LPs of a ragged launch):
+// run f(i) for i in [0, n) on the host's cores once the batch is large enough to pay for the
+// threads.  The exact policy's overflow flag is thread-local and sticky, so every item carries
+// its own copy (ovf[i], in/out): an item never sees another item's overflow, whatever thread
+// it ran on -- the result does not depend on the schedule.
+template <class P, class F>
+void for_items(size_t n, std::vector<char> &ovf, F f)
+{
+    auto one = [&](size_t i) {
+        P::overflow() = ovf[i] != 0;
+        f(i);
+        ovf[i] = P::overflow();
+    };
+    unsigned T = std::thread::hardware_concurrency();
+    if (T > 16) T = 16;
+    const bool keep = P::overflow();
+    if (n < 1024 || T < 2) {
+        for (size_t i = 0; i < n; i++) one(i);
+        P::overflow() = keep;
+        return;
+    }
+    std::atomic<size_t> next(0);
+    const size_t chunk = 128;
+    auto work = [&]() {
+        for (;;) {
+            const size_t b = next.fetch_add(chunk);
+            if (b >= n) break;
+            const size_t e = b + chunk < n ? b + chunk : n;
+            for (size_t i = b; i < e; i++) one(i);
+        }
+    };
+    std::vector<std::thread> th;
+    for (unsigned t = 1; t < T; t++) th.emplace_back(work);
+    work();
+    for (auto &x : th) x.join();
+    P::overflow() = keep;
 }
 
 // TwoStageMethod (lpsol.h:1906-1930) for one FP64 LP on the HBM-resident path; phase 1
@@ -175,7 +215,8 @@ int two_stage_group_q(xp_ctx *ctx, const std::vector<const Mat<Q> *> &leqs,
         ldm = std::max(ldm, L.r);
     }
     std::vector<int64_t> lp(ll), tp(tl);
-    for (int s = 0; s < S; s++) {
+    std::vector<char> iovf(S, 0);
+    for_items<Q>((size_t)S, iovf, [&](size_t s) {
         const Mat<Q> &L = *leqs[live[s]], &T = *tgs[live[s]];
         std::vector<long long> &sc = scale[live[s]];
         sc.assign(L.r + 1, 1);
@@ -199,7 +240,7 @@ int two_stage_group_q(xp_ctx *ctx, const std::vector<const Mat<Q> *> &leqs,
             tp[to[s] + j] = (int64_t)v;
         }
         if (ovf) out[live[s]].status = XP_ERR_OVERFLOW;
-    }
+    });
     std::vector<int64_t> maxv((size_t)S * 2), sn((size_t)S * ldo), sd((size_t)S * ldo),
         tn((size_t)S * ldo), td((size_t)S * ldo);
     std::vector<int32_t> status(S), e2b((size_t)S * ldm);
@@ -208,9 +249,9 @@ int two_stage_group_q(xp_ctx *ctx, const std::vector<const Mat<Q> *> &leqs,
                                          ldo, ldm, status.data(), maxv.data(), sn.data(), sd.data(),
                                          tn.data(), td.data(), e2b.data(), nullptr, nullptr);
     if (rc) return rc;
-    for (int s = 0; s < S; s++) {
+    for_items<Q>((size_t)S, iovf, [&](size_t s) {
         ResQ &R = out[live[s]];
-        if (R.status == XP_ERR_OVERFLOW) continue; // input scaling already overflowed
+        if (R.status == XP_ERR_OVERFLOW) return; // input scaling already overflowed
         const int m = ms[s], n = ns[s], Cm = m + n + 1;
         const std::vector<long long> &sc = scale[live[s]];
         const Q::T k0 = Q::from_int(sc[m]);
@@ -230,7 +271,8 @@ int two_stage_group_q(xp_ctx *ctx, const std::vector<const Mat<Q> *> &leqs,
             R.tgtf[j] = Q::div(tv, k0);
         }
         R.eq2bv.assign(e2b.begin() + (size_t)s * ldm, e2b.begin() + (size_t)s * ldm + m);
-    }
+        if (Q::overflow()) R.status = XP_ERR_OVERFLOW; // a scaled-back value left int64
+    });
     return 0;
 }
 
@@ -299,40 +341,54 @@ int solve_one(xp_ctx *ctx, bool is_min, const Mat<P> &tg, const Mat<P> &vc, cons
 template <class P>
 int run_trees(xp_ctx *ctx, std::vector<MipTree<P>> &trees)
 {
+    const size_t NT = trees.size();
+    std::vector<char> tovf(NT, 0); // per-tree overflow state of the exact policy
+    std::vector<SixJob<P>> slot(NT);
+    std::vector<char> has(NT);
     for (;;) {
-        std::vector<int> act;
-        std::vector<SixJob<P>> jobs;
-        for (int t = 0; t < (int)trees.size(); t++) {
-            if (trees[t].done) continue;
+        // host preparation of every live tree's next node LP (normalize, dual), in parallel
+        for_items<P>(NT, tovf, [&](size_t t) {
+            has[t] = 0;
             for (;;) { // node LPs whose host preparation already fails are fed back at once
-                if (trees[t].done) break;
+                if (trees[t].done) return;
                 const typename MipTree<P>::Frame &f = trees[t].top();
                 SixJob<P> job;
                 int st = job.prepare(!trees[t].is_max, trees[t].tgtf, trees[t].vc, f.eq, f.leq);
                 if (st == 0) {
-                    act.push_back(t);
-                    jobs.push_back(std::move(job));
-                    break;
+                    slot[t] = std::move(job);
+                    has[t] = 1;
+                    return;
                 }
                 trees[t].feed(st, P::zero(), std::vector<typename P::T>());
             }
-        }
-        if (act.empty()) return 0;
+        });
+        std::vector<int> act;
+        for (size_t t = 0; t < NT; t++)
+            if (has[t]) act.push_back((int)t);
+        if (act.empty()) break;
         std::vector<const Mat<P> *> l, tg;
-        for (auto &j : jobs) {
-            l.push_back(&j.lp_leq);
-            tg.push_back(&j.lp_tgtf);
+        for (int t : act) {
+            l.push_back(&slot[t].lp_leq);
+            tg.push_back(&slot[t].lp_tgtf);
         }
         std::vector<TwoStageResult<P>> R;
         int rc = Many<P>::run(ctx, l, tg, 10000u, R); // six.set_param(m_indent, 10000), :2441
         if (rc) return rc;
-        for (size_t k = 0; k < act.size(); k++) {
+        // final solution of every node LP and the tree's accept / prune decision, in parallel
+        // (trees are independent; within a tree the order is the reference's DFS order)
+        std::vector<char> aovf(act.size());
+        for (size_t k = 0; k < act.size(); k++) aovf[k] = tovf[act[k]];
+        for_items<P>(act.size(), aovf, [&](size_t k) {
             typename P::T v;
             std::vector<typename P::T> sol;
-            int st = jobs[k].finish(R[k], v, sol);
+            int st = slot[act[k]].finish(R[k], v, sol);
             trees[act[k]].feed(st, v, sol);
-        }
+        });
+        for (size_t k = 0; k < act.size(); k++) tovf[act[k]] = aovf[k];
     }
+    for (size_t t = 0; t < NT; t++)
+        if (tovf[t]) P::overflow() = true;
+    return 0;
 }
 
 int mip_status(int st) { return st; }

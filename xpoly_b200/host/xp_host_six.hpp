@@ -32,6 +32,11 @@ constexpr double kEps = 0.00000000000000001; // INFINITESIMAL, flty.h:46
 // ------------------------------------------------------------------ F64 policy
 struct F64 {
     typedef double T;
+    static bool &overflow() // FP64 never overflows into an error; kept for a uniform interface
+    {
+        static thread_local bool f = false;
+        return f;
+    }
     static T zero() { return 0.0; }
     static T from_int(long long i) { return (double)i; }
     static T add(T a, T b) { return a + b; }
