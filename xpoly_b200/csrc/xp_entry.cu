@@ -11,6 +11,9 @@
 #include "../host/xp_host_six.hpp"
 
 #include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -26,11 +29,83 @@ bool fits_smem(const xp_ctx *ctx, int m, int n, size_t key_bytes)
     return xpb_smem_bytes(m, n, 8, key_bytes) <= ctx->smem_optin;
 }
 
-// Host-side loops over independent items (trees of a B&B batch, LPs of a ragged launch):
-// run f(i) for i in [0, n) on the host's cores once the batch is large enough to pay for the
-// threads.  The exact policy's overflow flag is thread-local and sticky, so every item carries
-// its own copy (ovf[i], in/out): an item never sees another item's overflow, whatever thread
-// it ran on -- the result does not depend on the schedule.
+// Host-side loops over independent items (trees of a B&B batch, LPs of a ragged launch) run
+// on a small pool of worker threads (created on first use, parked on a condition variable in
+// between: a B&B batch calls this four times per wave, far too often to spawn threads).
+class HostPool {
+    std::vector<std::thread> th_;
+    std::mutex m_, busy_;
+    std::condition_variable cv_, done_;
+    std::function<void()> job_;
+    unsigned long long gen_ = 0;
+    int pending_ = 0;
+    bool stop_ = false;
+
+public:
+    explicit HostPool(unsigned n)
+    {
+        for (unsigned t = 0; t < n; t++)
+            th_.emplace_back([this]() {
+                unsigned long long seen = 0;
+                for (;;) {
+                    std::function<void()> j;
+                    {
+                        std::unique_lock<std::mutex> l(m_);
+                        cv_.wait(l, [&]() { return stop_ || gen_ != seen; });
+                        if (stop_) return;
+                        seen = gen_;
+                        j = job_;
+                    }
+                    j();
+                    {
+                        std::lock_guard<std::mutex> l(m_);
+                        if (--pending_ == 0) done_.notify_one();
+                    }
+                }
+            });
+    }
+    ~HostPool()
+    {
+        {
+            std::lock_guard<std::mutex> l(m_);
+            stop_ = true;
+        }
+        cv_.notify_all();
+        for (auto &t : th_) t.join();
+    }
+    unsigned workers() const { return (unsigned)th_.size(); }
+    // Runs f on every worker and on the caller; false if the pool is in use by another host
+    // thread (the caller then runs f alone).
+    bool run(const std::function<void()> &f)
+    {
+        if (th_.empty() || !busy_.try_lock()) return false;
+        {
+            std::lock_guard<std::mutex> l(m_);
+            job_ = f;
+            pending_ = (int)th_.size();
+            gen_++;
+        }
+        cv_.notify_all();
+        f();
+        {
+            std::unique_lock<std::mutex> l(m_);
+            done_.wait(l, [&]() { return pending_ == 0; });
+        }
+        busy_.unlock();
+        return true;
+    }
+};
+HostPool &host_pool()
+{
+    unsigned T = std::thread::hardware_concurrency();
+    if (T > 16) T = 16;
+    static HostPool p(T > 1 ? T - 1 : 0);
+    return p;
+}
+
+// run f(i) for i in [0, n).  The exact policy's overflow flag is thread-local and sticky, so
+// every item carries its own copy (ovf[i], in/out): an item never sees another item's
+// overflow, whatever thread it ran on -- the result does not depend on the schedule.
 template <class P, class F>
 void for_items(size_t n, std::vector<char> &ovf, F f)
 {
@@ -39,28 +114,27 @@ void for_items(size_t n, std::vector<char> &ovf, F f)
         f(i);
         ovf[i] = P::overflow();
     };
-    unsigned T = std::thread::hardware_concurrency();
-    if (T > 16) T = 16;
     const bool keep = P::overflow();
-    if (n < 1024 || T < 2) {
-        for (size_t i = 0; i < n; i++) one(i);
-        P::overflow() = keep;
-        return;
+    bool done = false;
+    if (n >= 64) {
+        HostPool &pool = host_pool();
+        std::atomic<size_t> next(0);
+        size_t chunk = n / (8 * (pool.workers() + 1));
+        if (chunk < 1) chunk = 1;
+        if (chunk > 128) chunk = 128;
+        done = pool.run([&]() {
+            const bool mine = P::overflow();
+            for (;;) {
+                const size_t b = next.fetch_add(chunk);
+                if (b >= n) break;
+                const size_t e = b + chunk < n ? b + chunk : n;
+                for (size_t i = b; i < e; i++) one(i);
+            }
+            P::overflow() = mine;
+        });
     }
-    std::atomic<size_t> next(0);
-    const size_t chunk = 128;
-    auto work = [&]() {
-        for (;;) {
-            const size_t b = next.fetch_add(chunk);
-            if (b >= n) break;
-            const size_t e = b + chunk < n ? b + chunk : n;
-            for (size_t i = b; i < e; i++) one(i);
-        }
-    };
-    std::vector<std::thread> th;
-    for (unsigned t = 1; t < T; t++) th.emplace_back(work);
-    work();
-    for (auto &x : th) x.join();
+    if (!done)
+        for (size_t i = 0; i < n; i++) one(i);
     P::overflow() = keep;
 }
 
