@@ -210,3 +210,33 @@ def test_two_stage_large_phase1_on_device(ctx, m, n):
     tg2[n] = 0.0
     _check_two_stage(ctx, leq, tg2, 40, ("nopos", m, n))
     assert len(seen) >= 1
+
+
+def lower_bound_lp(seed, m, n, nneg):
+    """A feasible LP that needs phase 1 and passes it: the dense family plus `nneg` lower bounds
+    -x_j <= -l_j (negative constant terms), so the auxiliary LP reaches 0, xa is pivoted out (or
+    already non-basic), the objective is restored by substitution and column xa is dropped."""
+    r = np.random.RandomState(seed)
+    leq = np.zeros((m + nneg, n + 1))
+    leq[:m, :n] = r.uniform(0, 1, size=(m, n))
+    leq[:m, n] = 1 + r.uniform(0, 1, size=m) * n
+    for t in range(nneg):
+        leq[m + t, t] = -1.0
+        leq[m + t, n] = -0.01 * (t + 1)
+    tg = np.zeros(n + 1)
+    tg[:n] = r.uniform(0, 1, size=n)
+    return leq, tg
+
+
+@pytest.mark.parametrize("m,n,nneg", [(20, 15, 2), (100, 80, 3), (200, 150, 3), (300, 400, 4)])
+def test_two_stage_large_phase1_succeeds(ctx, m, n, nneg):
+    """The whole of constructBasicFeasibleSolution on the device with a successful phase 1 (the
+    mixed-sign family above mostly ends in SIX_NO_PRI_FEASIBLE_SOL before the objective is
+    restored): statuses past phase 1, every output bit for bit against the oracle."""
+    seen = set()
+    for s in range(5):
+        leq, tg = lower_bound_lp(s, m, n, nneg)
+        for K in ((H.NO_LIMIT, 9) if m <= 20 else (400,)):
+            g = _check_two_stage(ctx, leq, tg, K, ("lb", m, n, s, K))
+            seen.add(g["status"])
+    assert H.SIX_NO_PRI not in seen and len(seen) >= 1
