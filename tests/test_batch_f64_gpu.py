@@ -198,3 +198,38 @@ def test_warp_kernel_ragged_equals_cta_kernel(ctx):
     assert np.array_equal(a["eq2bv"][ok], b["eq2bv"][ok])
     for k in ("maxv", "slack_sol", "tgtf"):
         assert np.array_equal(H.bits(a[k][ok]), H.bits(b[k][ok])), k
+
+
+def lower_bound_lp(seed, m, n, nneg, integer=False):
+    """Feasible LPs that need phase 1 and pass it (dense family + lower bounds -x_j <= -l_j)."""
+    r = np.random.RandomState(seed)
+    leq = np.zeros((m + nneg, n + 1))
+    if integer:
+        leq[:m, :n] = r.randint(0, 4, size=(m, n)) * (r.uniform(size=(m, n)) < 0.5)
+        leq[:m, n] = r.randint(8, 30, size=m)
+    else:
+        leq[:m, :n] = r.uniform(0, 1, size=(m, n))
+        leq[:m, n] = 1 + r.uniform(0, 1, size=m) * n
+    for t in range(nneg):
+        leq[m + t, t] = -1.0
+        leq[m + t, n] = -1.0 if integer else -0.01 * (t + 1)
+    tg = np.zeros(n + 1)
+    tg[:n] = r.randint(1, 6, size=n) if integer else r.uniform(0, 1, size=n)
+    return leq, tg
+
+
+@pytest.mark.parametrize("m,n,nneg", [(5, 4, 1), (20, 15, 2), (28, 30, 3)])
+def test_phase1_succeeds_objective_restored(ctx, m, n, nneg):
+    """Phase 1 that succeeds -- aux optimum 0, xa pivoted out, objective restored by
+    substitution, column xa dropped, main solve -- on the register-resident warp kernel and,
+    forced, on the CTA kernel, against the oracle."""
+    lps = [lower_bound_lp(s, m, n, nneg) for s in range(120)]
+    import os
+    for force in ("1", "0"):
+        os.environ["XP_BATCH_WARP"] = force
+        try:
+            g = run_uniform(ctx, lps, tag=("lb", m, n, force))
+            run_uniform(ctx, lps[:40], max_iter=6, tag=("lbK", m, n, force))
+        finally:
+            os.environ.pop("XP_BATCH_WARP", None)
+        assert H.SIX_NO_PRI not in set(g["status"].tolist())

@@ -164,3 +164,20 @@ def test_warp_kernel_equals_cta_kernel_exact(ctx, m, n, neg):
         ok = (a["status"] >= 0) & (a["status"] != H.SIX_NO_PRI)
         for k in ("eq2bv", "maxv", "sol_num", "sol_den", "tgtf_num", "tgtf_den"):
             assert np.array_equal(a[k][ok], b[k][ok]), (k, K)
+
+
+@pytest.mark.parametrize("m,n,nneg", [(5, 4, 1), (6, 8, 2), (20, 15, 2)])
+def test_phase1_succeeds_exact(ctx, m, n, nneg):
+    """Exact path, phase 1 that succeeds (objective restored, column xa dropped, main solve): the
+    warp kernel (forced for every shape) and the CTA kernel against the Rational oracle."""
+    import os
+    from test_batch_f64_gpu import lower_bound_lp
+    lps = [tuple(a.astype(np.int64) for a in lower_bound_lp(s, m, n, nneg, integer=True)) for s in range(100)]
+    for force in ("2", "0"):
+        os.environ["XP_BATCH_WARP"] = force
+        try:
+            g, checked = run(ctx, lps, tag=("lb-exact", m, n, force))
+        finally:
+            os.environ.pop("XP_BATCH_WARP", None)
+        assert checked >= 50
+        assert (g["status"] != H.SIX_NO_PRI).sum() >= 50
