@@ -118,7 +118,7 @@ def test_equalities_and_free_variables(ctx):
 
 def test_large_lp_through_entry_goes_to_hbm_path(ctx):
     """An LP too large for shared memory is routed to the HBM-resident path,
-    including the host-mediated phase 1 (negative right-hand sides)."""
+    including phase 1 on the device (negative right-hand sides)."""
     leq, tg = H.gen_dense_lp(3, 150, 149)
     same_f64(ctx.six_solve("f64", 0, leq, tg), H.six_solve("oracle", "f64", 0, leq, tg), "large")
     leq2 = leq.copy()
@@ -126,6 +126,13 @@ def test_large_lp_through_entry_goes_to_hbm_path(ctx):
     leq2[::7, :-1] *= -1.0
     same_f64(ctx.six_solve("f64", 0, leq2, tg, max_iter=60),
              H.six_solve("oracle", "f64", 0, leq2, tg, max_iter=60), "large-phase1")
+    # phase 1 that succeeds (lower bounds), through maxm and -- on the explicit dual -- minm
+    from test_large_f64_gpu import lower_bound_lp
+    for s in range(3):
+        l3, t3 = lower_bound_lp(s, 140, 120, 3)
+        for is_min in (0, 1):
+            same_f64(ctx.six_solve("f64", is_min, l3, t3, max_iter=300),
+                     H.six_solve("oracle", "f64", is_min, l3, t3, max_iter=300), ("large-lb", s, is_min))
 
 
 def test_batched_entry_f64_and_rat(ctx):
