@@ -21,6 +21,7 @@
 // chain per pivot, by one thread), so the per-element cost is two 64x64->128
 // products, a 128-bit subtract, a funnel shift and one 64-bit multiply.
 #include "xp_batch_core.cuh"
+#include "xp_exact_arith.cuh"
 #include "xp_batch_warp_i64.cuh"
 
 #include <cstdlib>
@@ -39,37 +40,9 @@ struct KeyI64 {
 // misc slots (shared): [0] D, [1] overflow flag, [2] inverse of D's odd part, [3] tz(D)
 enum { M_D = 0, M_OVF = 1, M_INV = 2, M_TZ = 3 };
 
-__device__ __forceinline__ u64 inv_odd64(u64 d)
-{ // d odd: Newton iteration for d^-1 mod 2^64
-    u64 x = (d * 3) ^ 2; // 5 correct bits
-    x *= 2 - d * x;
-    x *= 2 - d * x;
-    x *= 2 - d * x;
-    x *= 2 - d * x;
-    return x;
-}
-
-// (a*b - c*d) / D exactly, or flag overflow if the quotient leaves int64.
-__device__ __forceinline__ i64 ff_div(i128 x, u64 D, u64 inv, int tz, int &ovf)
-{
-    const bool neg = x < 0;
-    unsigned __int128 ax = neg ? (unsigned __int128)(-x) : (unsigned __int128)x;
-    if ((u64)(ax >> 63) >= D) ovf = 1; // |x| >= D * 2^63  <=>  |q| >= 2^63
-    u64 lo = (u64)(ax >> tz);          // low 64 bits of |x| / 2^tz (exact)
-    u64 q = lo * inv;                  // exact quotient mod 2^64
-    return neg ? -(i64)q : (i64)q;
-}
-
-__device__ __forceinline__ i64 gcd64(i64 a, i64 b)
-{
-    u64 x = a < 0 ? (u64)(-a) : (u64)a, y = b < 0 ? (u64)(-b) : (u64)b;
-    while (y) {
-        u64 t = x % y;
-        x = y;
-        y = t;
-    }
-    return (i64)x;
-}
+using xpx::ff_div;
+using xpx::gcd64;
+using xpx::inv_odd64;
 
 struct OpsI64 {
     typedef i64 E;
@@ -153,8 +126,8 @@ struct OpsI64 {
         const int bv = S.eq2bv[p];
         const i64 P = S.tab[p * LD + q];
         const i64 cq = S.tgtf[q];
-        const u64 D = (u64)S.misc[M_D], inv = (u64)S.misc[M_INV];
-        const int tz = (int)S.misc[M_TZ];
+        xpx::Div dv;
+        dv.set((u64)S.misc[M_D], (u64)S.misc[M_INV], (int)S.misc[M_TZ]);
         const i64 aP = P < 0 ? -P : P;
         const bool sneg = P < 0;
         __syncthreads();
@@ -164,14 +137,14 @@ struct OpsI64 {
                 S.fcol[i] = sneg ? -f : f; // s * N_iq
             }
         __syncthreads();
-        int ovf = 0;
+        bool ovf = false;
         const i64 *rowp = S.tab + p * LD;
         const i64 scq = sneg ? -cq : cq;
         for (int j = tid; j < C; j += blockDim.x) { // objective row
             i128 x = (i128)S.tgtf[j] * aP;
             i128 y = (i128)scq * rowp[j];
             x = j >= n ? x + y : x - y;
-            S.tgtf[j] = ff_div(x, D, inv, tz, ovf);
+            S.tgtf[j] = ff_div(x, dv, ovf);
         }
         for (int i = w; i < m; i += nw) { // integer-preserving elimination
             if (i == p) continue;
@@ -179,7 +152,7 @@ struct OpsI64 {
             i64 *row = S.tab + i * LD;
             for (int j = lane; j < C; j += 32) {
                 i128 x = (i128)row[j] * aP - (i128)f * rowp[j];
-                row[j] = ff_div(x, D, inv, tz, ovf);
+                row[j] = ff_div(x, dv, ovf);
             }
         }
         __syncthreads();
@@ -193,8 +166,7 @@ struct OpsI64 {
             S.misc[M_INV] = (i64)inv_odd64((u64)aP >> t);
         }
         S.pivots++;
-        ovf = __syncthreads_or(ovf);
-        return ovf ? XP_ERR_OVERFLOW : 0;
+        return __syncthreads_or(ovf ? 1 : 0) ? XP_ERR_OVERFLOW : 0;
     }
 
     // Optimal exit.  In exact arithmetic the row-sum half of is_feasible

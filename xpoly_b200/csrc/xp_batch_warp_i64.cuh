@@ -18,6 +18,7 @@
 #pragma once
 
 #include "xp_batch_warp_f64.cuh"
+#include "xp_exact_arith.cuh"
 
 #ifdef __CUDACC__
 
@@ -41,8 +42,7 @@ struct LP {
     i64 sol0, sol1;     // slack solution numerators (over D), own columns
     i64 cr;             // objective constant numerator (uniform)
     i64 b;              // constant column, row `lane`
-    u64 D, inv;         // common denominator, inverse of its odd part mod 2^64 (uniform)
-    int tz;             // trailing zeros of D
+    xpx::Div dv;        // common denominator D and the constants of the division by it (uniform)
     int e2b;
     int b2e0, b2e1;
     u64 t0, t1;
@@ -63,35 +63,8 @@ __device__ __forceinline__ i64 at_col(i64 x0, i64 x1, int j)
     return shfl_i64(pick<NS>(x0, x1, j >> 5), j & 31);
 }
 
-__device__ __forceinline__ u64 inv_odd64(u64 d)
-{ // d odd: Newton iteration for d^-1 mod 2^64
-    u64 x = (d * 3) ^ 2;
-    x *= 2 - d * x;
-    x *= 2 - d * x;
-    x *= 2 - d * x;
-    x *= 2 - d * x;
-    return x;
-}
-// x / D exactly (x is a multiple of D), or flag overflow if the quotient leaves int64.
-__device__ __forceinline__ i64 ff_div(i128 x, u64 D, u64 inv, int tz, bool &ovf)
-{
-    const bool neg = x < 0;
-    unsigned __int128 ax = neg ? (unsigned __int128)(-x) : (unsigned __int128)x;
-    if ((u64)(ax >> 63) >= D) ovf = true; // |x| >= D * 2^63  <=>  |q| >= 2^63
-    const u64 lo = (u64)(ax >> tz);
-    const u64 q = lo * inv;
-    return neg ? -(i64)q : (i64)q;
-}
-__device__ __forceinline__ i64 gcd64(i64 a, i64 b)
-{
-    u64 x = a < 0 ? (u64)(-a) : (u64)a, y = b < 0 ? (u64)(-b) : (u64)b;
-    while (y) {
-        u64 t = x % y;
-        x = y;
-        y = t;
-    }
-    return (i64)x;
-}
+using xpx::ff_div;
+using xpx::gcd64;
 
 template <int MR, int NS>
 __device__ __forceinline__ void col_to_scratch(LP<MR, NS> &W, int q)
@@ -208,8 +181,7 @@ __device__ __forceinline__ int pivot(LP<MR, NS> &W, int p, int q, bool have_col)
     const i64 P = W.sc[p];
     const i64 aql = lane < MR ? W.sc[lane] : 0;
     const i64 cq = at_col<NS>(W.c0, W.c1, q);
-    const u64 D = W.D, inv = W.inv;
-    const int tz = W.tz;
+    const xpx::Div dv = W.dv;
     const i64 aP = P < 0 ? -P : P;
     const bool sneg = P < 0;
     const i64 scq = sneg ? -cq : cq;
@@ -218,30 +190,28 @@ __device__ __forceinline__ int pivot(LP<MR, NS> &W, int p, int q, bool have_col)
     const i64 rhsp = shfl_i64(W.b, p);
     bool ovf = false;
     // objective row: Nt_j <- (Nt_j*|P| - s*Nt_q*N_pj) / D, constant with + (:1496-1501)
-    W.c0 = ff_div((i128)W.c0 * aP - (i128)scq * rp0, D, inv, tz, ovf);
-    if (NS == 2) W.c1 = ff_div((i128)W.c1 * aP - (i128)scq * rp1, D, inv, tz, ovf);
-    W.cr = ff_div((i128)W.cr * aP + (i128)scq * rhsp, D, inv, tz, ovf);
+    W.c0 = ff_div((i128)W.c0 * aP - (i128)scq * rp0, dv, ovf);
+    if (NS == 2) W.c1 = ff_div((i128)W.c1 * aP - (i128)scq * rp1, dv, ovf);
+    W.cr = ff_div((i128)W.cr * aP + (i128)scq * rhsp, dv, ovf);
 #pragma unroll
     for (int i = 0; i < MR; i += 2) { // N_ij <- (N_ij*|P| - s*N_iq*N_pj) / D; row p comes out as 0 and is set below
         const longlong2 f2 = *reinterpret_cast<const longlong2 *>(W.sc + i);
         const i64 f0 = sneg ? -f2.x : f2.x, f1 = sneg ? -f2.y : f2.y;
-        W.a0[i] = ff_div((i128)W.a0[i] * aP - (i128)f0 * rp0, D, inv, tz, ovf);
-        W.a0[i + 1] = ff_div((i128)W.a0[i + 1] * aP - (i128)f1 * rp0, D, inv, tz, ovf);
+        W.a0[i] = ff_div((i128)W.a0[i] * aP - (i128)f0 * rp0, dv, ovf);
+        W.a0[i + 1] = ff_div((i128)W.a0[i + 1] * aP - (i128)f1 * rp0, dv, ovf);
         if (NS == 2) {
-            W.a1[i] = ff_div((i128)W.a1[i] * aP - (i128)f0 * rp1, D, inv, tz, ovf);
-            W.a1[i + 1] = ff_div((i128)W.a1[i + 1] * aP - (i128)f1 * rp1, D, inv, tz, ovf);
+            W.a1[i] = ff_div((i128)W.a1[i] * aP - (i128)f0 * rp1, dv, ovf);
+            W.a1[i + 1] = ff_div((i128)W.a1[i + 1] * aP - (i128)f1 * rp1, dv, ovf);
         }
         asm volatile("" ::: "memory"); // keep the multiplier loads with their rows (register pressure)
     }
     {
         const i64 fl = sneg ? -aql : aql;
-        const i64 nb = ff_div((i128)W.b * aP - (i128)fl * rhsp, D, inv, tz, ovf);
+        const i64 nb = ff_div((i128)W.b * aP - (i128)fl * rhsp, dv, ovf);
         W.b = (lane == p) ? (sneg ? -rhsp : rhsp) : nb;
     }
     set_row(W, p, sneg ? -rp0 : rp0, sneg ? -rp1 : rp1); // row p: N_pj <- s*N_pj
-    W.D = (u64)aP;
-    W.tz = __ffsll(aP) - 1;
-    W.inv = inv_odd64((u64)aP >> W.tz);
+    W.dv.set((u64)aP);
     W.nvm = (W.nvm & ~(1ull << q)) | (1ull << bv);
     if (lane == p) W.e2b = q;
     if (lane == q) W.b2e0 = p;
@@ -344,7 +314,7 @@ template <int MR, int NS>
 __device__ __forceinline__ int restore_objective(LP<MR, NS> &W, const i64 *tg, int n_orig)
 {
     const int lane = W.lane;
-    const i64 D = (i64)W.D;
+    const i64 D = (i64)W.dv.D;
     i128 acc0 = lane < n_orig ? (i128)tg[lane] * D : (i128)0;
     i128 acc1 = (NS == 2 && 32 + lane < n_orig) ? (i128)tg[32 + lane] * D : (i128)0;
     i128 accr = (i128)tg[n_orig] * D;
@@ -398,9 +368,7 @@ __device__ __forceinline__ int two_stage(LP<MR, NS> &W, const XpBatchArgs &A, co
     W.m = m;
     W.n = s0 + m;
     W.pivots = 0;
-    W.D = 1;
-    W.inv = 1;
-    W.tz = 0;
+    W.dv.set(1ull);
 #pragma unroll
     for (int i = 0; i < MR; i++) {
 #define XPW_LOAD(s)                                                    \
@@ -490,7 +458,7 @@ template <int MR, int NS>
 __device__ __forceinline__ void write_out(const LP<MR, NS> &W, const XpBatchArgs &A, int k, int st, uint32_t iters)
 {
     const int lane = W.lane, n = W.n;
-    const i64 D = (i64)W.D;
+    const i64 D = (i64)W.dv.D;
     if (lane == 0) {
         if (A.maxv) put_frac(st == XP_SIX_SUCC ? W.cr : 0, D, (i64 *)A.maxv + 2 * (size_t)k, (i64 *)A.maxv + 2 * (size_t)k + 1);
         if (A.status) A.status[k] = st;
