@@ -899,7 +899,10 @@ k_panel(LpDev d, PanA *partA, PanB *partB, unsigned long long *bar, unsigned lon
     unsigned cnt = st->cnt;
     const unsigned max_iter = st->max_iter;
     int q = st->q, zero_upto = st->zero_upto, anypos = st->anypos;
-    const bool go = st->status == XPI_RUNNING && !st->slow && !st->pivot_pending && q != INT_BIG;
+    // (a launch that finds the block already full, or the iteration budget spent, must not pay
+    // for bringing the open block's factors into shared memory)
+    const bool go = st->status == XPI_RUNNING && !st->slow && !st->pivot_pending && q != INT_BIG &&
+                    t < kblk && cnt < max_iter;
     double tg_rhs = st->tg_rhs;
     unsigned n_log = st->n_log;
     int n_touched = st->n_touched;
