@@ -161,8 +161,10 @@ int xp_lp_f64_peer_attach_local(xp_lp_f64 *lp, xp_lp_f64 *const *all /* nranks, 
 /* ------------------------------------------ TwoStageMethod level: batched FP64
  * Replaces SIX<FloatMat,Float>::TwoStageMethod (lpsol.h:1906-1930: stage1,
  * slack, constructBasicFeasibleSolution, solveSlackForm) for a batch of
- * independent normalised LPs (x >= 0, no equalities), one CTA per LP with the
- * tableau in shared memory.
+ * independent normalised LPs (x >= 0, no equalities): one warp per LP with the
+ * tableau in registers (up to 32 rows x 64 variables), one CTA per LP with the
+ * tableau in shared memory beyond that.  Large uniform batches are uploaded in
+ * chunks while earlier chunks are being solved.
  *
  * Uniform batch: every LP has leq m x (n+1) at leq + k*m*(n+1) and tgtf 1 x (n+1)
  * at tgtf + k*(n+1).  Outputs per LP k (any may be NULL): status[k];
