@@ -101,6 +101,70 @@ def main():
     Cc = [[-1, 0, -1], [1, 0, 10], [0, -1, -1], [0, 1, 10], [2, -2, 1], [-2, 2, -1]]
     out["has_solution_A6"] = {nm: int(H.has_solution("ref", H.to_rat(np.array(M, dtype=float))))
                               for nm, M in (("A", A), ("B", B), ("C", Cc))}
+    # --- phase 1 that SUCCEEDS (lower bounds -x_j <= -l_j): aux optimum 0, xa pivoted out,
+    #     objective restored by substitution, column xa dropped, main solve
+    ok1 = []
+    for k in range(24):
+        m, n, nneg = [(5, 4, 1), (12, 9, 2), (20, 15, 2)][k % 3]
+        r0 = np.random.RandomState(500 + k)
+        leq = np.zeros((m + nneg, n + 1))
+        leq[:m, :n] = r0.uniform(0, 1, size=(m, n))
+        leq[:m, n] = 1 + r0.uniform(0, 1, size=m) * n
+        for t in range(nneg):
+            leq[m + t, t] = -1.0
+            leq[m + t, n] = -0.01 * (t + 1)
+        tg = np.zeros(n + 1)
+        tg[:n] = r0.uniform(0, 1, size=n)
+        r = H.two_stage("ref", "f64", leq, tg)
+        assert r["status"] != 2
+        ok1.append(dict(leq=hx(leq), tgtf=hx(tg), m=m + nneg, n=n, status=r["status"],
+                        eq2bv=r["eq2bv"].tolist(), maxv=hx(r["maxv"]), tgtf_out=hx(r["tgtf"]),
+                        slack_sol=hx(r["slack_sol"])))
+    out["two_stage_f64_phase1_ok"] = ok1
+    # --- PolyTran::FeaSchedule's MIP shape (poly.cpp:5094-5133): equalities only, objective =
+    #     sum of the first nu variables, maxm then minm
+    fea = []
+    r0 = np.random.RandomState(5)
+    for k in range(40):
+        nu, nl, ke = int(r0.randint(2, 5)), int(r0.randint(3, 7)), int(r0.randint(2, 5))
+        n = nu + nl
+        eq = np.zeros((ke, n + 1), dtype=np.int64)
+        eq[:, :n] = r0.randint(-2, 3, size=(ke, n))
+        eq[:, n] = r0.randint(0, 6, size=ke)
+        tg = np.zeros(n + 1, dtype=np.int64)
+        tg[:nu] = 1
+        d = dict(eq=eq.tolist(), tgtf=tg.tolist())
+        for nm, is_min in (("max", 0), ("min", 1)):
+            if H.mip_solve("oracle", "rat", is_min, 0, None, H.to_rat(tg), eq=H.to_rat(eq))["status"] < 0:
+                d[nm] = None  # the reference has undefined behaviour here (lpsol.h:1232)
+                continue
+            r = H.mip_solve("ref", "rat", is_min, 0, None, H.to_rat(tg), eq=H.to_rat(eq))
+            d[nm] = dict(status=r["status"], v=r["v"].tolist(),
+                         sol=r["sol"].tolist() if r["status"] == 0 else None)
+        fea.append(d)
+    out["fea_schedule_mip"] = fea
+    # --- Lineq::has_solution with equalities, on systems free of the reference's UB
+    hse = []
+    r0 = np.random.RandomState(77)
+    for k in range(150):
+        n, m = int(r0.randint(2, 5)), int(r0.randint(2, 7))
+        leq = np.zeros((m, n + 1), dtype=np.int64)
+        leq[:, :n] = r0.randint(-2, 4, size=(m, n))
+        leq[:, n] = r0.randint(0, 20, size=m)
+        eq = np.zeros((1, n + 1), dtype=np.int64)
+        eq[:, :n] = r0.randint(-2, 3, size=(1, n))
+        eq[:, n] = r0.randint(0, 8)
+        tg = np.zeros(n + 1, dtype=np.int64)
+        tg[:n] = ((leq[:, :n] != 0).any(axis=0) | (eq[:, :n] != 0).any(axis=0)).astype(np.int64)
+        amax = H.mip_solve("oracle", "rat", 0, 0, H.to_rat(leq), H.to_rat(tg), eq=H.to_rat(eq))
+        if amax["status"] < 0:
+            continue
+        if amax["status"] != 0 and \
+                H.mip_solve("oracle", "rat", 1, 0, H.to_rat(leq), H.to_rat(tg), eq=H.to_rat(eq))["status"] < 0:
+            continue
+        hse.append(dict(leq=leq.tolist(), eq=eq.tolist(),
+                        result=int(H.has_solution("ref", H.to_rat(leq), H.to_rat(eq)))))
+    out["has_solution_eq"] = hse
     json.dump(out, open(os.path.join(HERE, "reference_vectors.json"), "w"), indent=0)
     print("wrote reference_vectors.json:", {k: (len(v) if isinstance(v, list) else "obj")
                                             for k, v in out.items()})

@@ -308,3 +308,37 @@ def test_fea_schedule_shape_mip(ctx):
             if o["status"] == 0:
                 break
     assert {0, 1, 2} <= seen
+
+
+def test_golden_reference_answers_for_the_8f_callers(ctx):
+    """tests/golden (written by the unmodified reference): TwoStageMethod with a successful
+    phase 1 on both FP64 paths, FeaSchedule-shape MIPs, has_solution with equalities."""
+    import json, os
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_vectors.json")))
+    unhex = lambda xs: np.array([float.fromhex(x) for x in xs], dtype=np.float64)
+    for k, d in enumerate(gold["two_stage_f64_phase1_ok"]):
+        leq = unhex(d["leq"]).reshape(d["m"], d["n"] + 1)
+        tg = unhex(d["tgtf"])
+        b = ctx.two_stage_f64_batch(leq[None], tg[None])
+        g = ctx.two_stage_f64_large(leq, tg)
+        Cc = d["m"] + d["n"] + 1
+        for nm, st, e2b, mv, tgo, ss in (("batched", b["status"][0], b["eq2bv"][0], b["maxv"][0:1], b["tgtf"][0], b["slack_sol"][0]),
+                                         ("large", g["status"], g["eq2bv"], g["maxv"], g["tgtf"], g["slack_sol"])):
+            assert st == d["status"], (k, nm)
+            assert e2b[:d["m"]].tolist() == d["eq2bv"], (k, nm)
+            assert np.array_equal(H.bits(mv), H.bits(unhex(d["maxv"]))), (k, nm)
+            assert np.array_equal(H.bits(tgo[:Cc]), H.bits(unhex(d["tgtf_out"]))), (k, nm)
+            assert np.array_equal(H.bits(ss[:Cc]), H.bits(unhex(d["slack_sol"]))), (k, nm)
+    for k, d in enumerate(gold["fea_schedule_mip"]):
+        eq, tg = np.array(d["eq"], dtype=np.int64), np.array(d["tgtf"], dtype=np.int64)
+        for nm, is_min in (("max", 0), ("min", 1)):
+            g = ctx.mip_solve("rat", is_min, 0, None, tg, eq=eq)
+            if d[nm] is None:
+                assert g["status"] == xp.ERR_REFERENCE_UB, (k, nm)
+                continue
+            assert g["status"] == d[nm]["status"], (k, nm)
+            if g["status"] == 0:
+                assert g["v"].tolist() == d[nm]["v"] and g["sol"].tolist() == d[nm]["sol"], (k, nm)
+    systems = [(np.array(d["leq"], dtype=np.int64), np.array(d["eq"], dtype=np.int64)) for d in gold["has_solution_eq"]]
+    res = ctx.has_solution_ragged(systems)
+    assert res.tolist() == [d["result"] for d in gold["has_solution_eq"]]

@@ -116,3 +116,33 @@ def test_edge_cases():
             assert b["status"] == r["status"]
             if r["status"] != 2:
                 assert np.array_equal(H.bits(b["tab"]), H.bits(r["tab"]))
+
+
+def test_phase1_success_family():
+    """TwoStageMethod where phase 1 succeeds (objective restored, column xa dropped)."""
+    for k, d in enumerate(GOLD["two_stage_f64_phase1_ok"]):
+        leq = unhex(d["leq"]).reshape(d["m"], d["n"] + 1)
+        tg = unhex(d["tgtf"])
+        r = H.two_stage("oracle", "f64", leq, tg)
+        assert r["status"] == d["status"], k
+        assert r["eq2bv"].tolist() == d["eq2bv"], k
+        for a, b in (("maxv", "maxv"), ("tgtf", "tgtf_out"), ("slack_sol", "slack_sol")):
+            assert np.array_equal(H.bits(r[a]), H.bits(unhex(d[b]))), (k, a)
+
+
+def test_fea_schedule_and_has_solution_with_equalities():
+    """The callers of SURVEY 8(f): FeaSchedule's equality-only MIPs and has_solution with
+    equalities, as the unmodified reference answered them."""
+    for k, d in enumerate(GOLD["fea_schedule_mip"]):
+        eq, tg = np.array(d["eq"], dtype=np.int64), np.array(d["tgtf"], dtype=np.int64)
+        for nm, is_min in (("max", 0), ("min", 1)):
+            r = H.mip_solve("oracle", "rat", is_min, 0, None, H.to_rat(tg), eq=H.to_rat(eq))
+            if d[nm] is None:
+                assert r["status"] < 0, (k, nm)
+                continue
+            assert r["status"] == d[nm]["status"], (k, nm)
+            if r["status"] == 0:
+                assert r["v"].tolist() == d[nm]["v"] and r["sol"].tolist() == d[nm]["sol"], (k, nm)
+    for k, d in enumerate(GOLD["has_solution_eq"]):
+        leq, eq = np.array(d["leq"], dtype=np.int64), np.array(d["eq"], dtype=np.int64)
+        assert H.has_solution("oracle", H.to_rat(leq), H.to_rat(eq)) == d["result"], k
