@@ -2279,6 +2279,11 @@ extern "C" int xp_lp_f64_solve(xp_lp_f64 *lp, uint32_t max_iter, int rule)
     // the host polls the status word between batches of blocks.  Every rank of a
     // sharded LP sees the same status words, hence issues the same launches.
     int blocks = 1;
+    if (max_iter != XP_NO_ITER_LIMIT && max_iter > lp->cnt_host) {
+        // bounded run: the number of blocks is known, issue them without polling in between
+        const unsigned long long need = ((unsigned long long)max_iter - lp->cnt_host + kblk - 1) / kblk + 1;
+        blocks = need > 8 ? 8 : (int)need;
+    }
     int n_prof = 0; // flushes bracketed by events in this call
     for (;;) {
         for (int b = 0; b < blocks; b++) {
