@@ -1383,6 +1383,19 @@ constexpr int FT_ROWS = 64; // rows staged per __syncthreads pair
 // SMs finish together, and a CTA reloads its P tile at most once.  The
 // multipliers of unit u+1 and the tableau entries of the next tile are in
 // flight while the current tile runs its t steps.
+__device__ __forceinline__ void cp_async_cg16(void *smem, const void *g, int src_bytes)
+{ // 16-byte asynchronous copy global -> shared (L2 only); bytes beyond src_bytes are zero-filled
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sa), "l"(g), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_ca4(void *smem, const void *g)
+{
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 template <int TR, int LANES, int HALVES>
 __global__ void __launch_bounds__(LANES *HALVES) k_flush_t(LpDev d, int groups)
 {
@@ -1390,7 +1403,6 @@ __global__ void __launch_bounds__(LANES *HALVES) k_flush_t(LpDev d, int groups)
     __shared__ int s_flag;
     constexpr int THREADS = LANES * HALVES, TC = 2 * LANES;
     constexpr int TPB = FT_ROWS / (HALVES * TR); // tiles per unit and half
-    constexpr int FREG = (KMAX * FT_ROWS + THREADS - 1) / THREADS;
     LpState *st = d.st;
     const int t = st->t;
     if (t == 0) return;
@@ -1423,27 +1435,23 @@ __global__ void __launch_bounds__(LANES *HALVES) k_flush_t(LpDev d, int groups)
             *reinterpret_cast<double2 *>(sP + (size_t)s * TC + 2 * l) = v;
         }
     };
-    // multipliers + pivot-row marks of unit u: global -> registers -> shared buffer (u & 1)
-    double freg[FREG];
-    int lpreg = -1;
-    auto fetch_F = [&](int u) {
+    // multipliers + pivot-row marks of unit u: global -> shared buffer (u & 1) with cp.async, no
+    // registers in between (the copy of unit u+1 is in flight while unit u is being computed)
+    auto copy_F = [&](int u) {
         const int rb = (u % nrb) * FT_ROWS;
-#pragma unroll
-        for (int k = 0; k < FREG; k++) {
-            const int e = tid + k * THREADS;
-            const int s = e / FT_ROWS, r = e - s * FT_ROWS;
-            freg[k] = (e < t * FT_ROWS && rb + r < m) ? ld_cg(Fptr(d, d.rank, par, s) + rb + r) : 0.0;
-        }
-        if (tid < FT_ROWS) lpreg = rb + tid < m ? d.last_piv[rb + tid] : -1;
-    };
-    auto store_F = [&](int u) {
         double *dst = sF + (size_t)(u & 1) * t * FT_ROWS;
-#pragma unroll
-        for (int k = 0; k < FREG; k++) {
-            const int e = tid + k * THREADS;
-            if (e < t * FT_ROWS) dst[e] = freg[k];
+        for (int e = tid; e < t * (FT_ROWS / 2); e += THREADS) {
+            const int s = e / (FT_ROWS / 2), r = 2 * (e - s * (FT_ROWS / 2));
+            const double *row = Fptr(d, d.rank, par, s);
+            const int left = m - (rb + r); // rows of this pair that exist: >= 2, 1 or <= 0 (zero fill)
+            cp_async_cg16(dst + (size_t)s * FT_ROWS + r, row + (left > 0 ? rb + r : 0), left >= 2 ? 16 : (left == 1 ? 8 : 0));
         }
-        if (tid < FT_ROWS) s_lp[(u & 1) * FT_ROWS + tid] = lpreg;
+        if (tid < FT_ROWS) {
+            int *lp = s_lp + (u & 1) * FT_ROWS + tid;
+            if (rb + tid < m) cp_async_ca4(lp, d.last_piv + rb + tid);
+            else *lp = -1;
+        }
+        cp_async_commit();
     };
     // tile k (0..TPB) of unit u: first row and first column of this thread
     double2 nx[TR];
@@ -1458,10 +1466,10 @@ __global__ void __launch_bounds__(LANES *HALVES) k_flush_t(LpDev d, int groups)
     };
     if (u0 < u1) {
         load_P(u0 / nrb);
-        fetch_F(u0);
-        store_F(u0);
+        copy_F(u0);
         load_tile(u0, 0);
     }
+    cp_async_wait_all();
     __syncthreads();
     for (int u = u0; u < u1; u++) {
         const int ct = u / nrb, rb = (u % nrb) * FT_ROWS;
@@ -1470,7 +1478,7 @@ __global__ void __launch_bounds__(LANES *HALVES) k_flush_t(LpDev d, int groups)
         const double *sFu = sF + (size_t)(u & 1) * t * FT_ROWS;
         const int *lpu = s_lp + (u & 1) * FT_ROWS;
         const bool more = u + 1 < u1;
-        if (more) fetch_F(u + 1);
+        if (more) copy_F(u + 1); // the other buffer: nobody reads it during this unit
         for (int k = 0; k < TPB; k++) {
             double2 a[TR];
 #pragma unroll
@@ -1516,13 +1524,11 @@ __global__ void __launch_bounds__(LANES *HALVES) k_flush_t(LpDev d, int groups)
             for (int w = 0; w < TR; w++)
                 if (row + w < m) *reinterpret_cast<double2 *>(d.tab + (size_t)(row + w) * Cl + j0) = a[w];
         }
-        if (more) {
-            store_F(u + 1); // the other buffer: nobody reads it during this unit
-            if ((u + 1) / nrb != ct) { // next unit starts a new column tile: swap the P tile
-                __syncthreads();
-                load_P((u + 1) / nrb);
-            }
+        if (more && (u + 1) / nrb != ct) { // next unit starts a new column tile: swap the P tile
+            __syncthreads();
+            load_P((u + 1) / nrb);
         }
+        cp_async_wait_all();
         __syncthreads();
     }
     // the last CTA closes the block
