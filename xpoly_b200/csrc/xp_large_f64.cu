@@ -1463,8 +1463,7 @@ __global__ void __launch_bounds__(LANES *HALVES) k_flush_t(LpDev d, int groups)
     // nobody can be more than one unit ahead of the slowest warp (the copies of unit lu+1 are
     // issued at the start of unit lu, and unit lu+1 only opens once all 256 threads have done so),
     // so the buffer being refilled -- last read two units ago -- is free.
-    auto copy_F = [&](int u, int b) {
-        const int rb = (u % nrb) * FT_ROWS;
+    auto copy_F = [&](int rb, int b) { // rb: first row of the unit
         double *dst = sF + (size_t)b * t * FT_ROWS;
         for (int e = tid; e < t * (FT_ROWS / 2); e += THREADS) {
             const int s = e / (FT_ROWS / 2), r = 2 * (e - s * (FT_ROWS / 2));
@@ -1478,9 +1477,8 @@ __global__ void __launch_bounds__(LANES *HALVES) k_flush_t(LpDev d, int groups)
     };
     // tile k (0..TPB) of unit u: first row and first column of this thread
     double2 nx[TR];
-    auto load_tile = [&](int u, int k) {
-        const int ct = u / nrb;
-        const int r = (u % nrb) * FT_ROWS + (k * HALVES + half) * TR;
+    auto load_tile = [&](int ct, int rb, int k) { // column tile, first row of the unit, tile in the unit
+        const int r = rb + (k * HALVES + half) * TR;
         const int j = ct * TC + 2 * lane;
 #pragma unroll
         for (int w = 0; w < TR; w++)
@@ -1496,15 +1494,20 @@ __global__ void __launch_bounds__(LANES *HALVES) k_flush_t(LpDev d, int groups)
     // Memory-bound passes (few steps per unit) keep the plain scheme -- wait for the copies,
     // block barrier per unit -- which measures 5 % faster there; compute-bound ones drop it.
     const bool mb = t >= 12;
+    int ct = u0 < u1 ? u0 / nrb : 0, rb = u0 < u1 ? (u0 % nrb) * FT_ROWS : 0; // advanced without divisions
     if (u0 < u1) {
-        load_P(u0 / nrb);
-        copy_F(u0, 0);
-        load_tile(u0, 0);
+        load_P(ct);
+        copy_F(rb, 0);
+        load_tile(ct, rb, 0);
     }
     if (!mb) cp_async_wait_all();
     __syncthreads(); // the P tile (plain stores)
     for (int u = u0; u < u1; u++) {
-        const int ct = u / nrb, rb = (u % nrb) * FT_ROWS;
+        int ct1 = ct, rb1 = rb + FT_ROWS; // the next unit
+        if (rb1 >= nrb * FT_ROWS) {
+            ct1 = ct + 1;
+            rb1 = 0;
+        }
         const int j0 = ct * TC + 2 * lane;
         const bool active = j0 < Cl; // Cl is even on this path
         const int lu = u - u0, buf = lu % 3;
@@ -1512,18 +1515,24 @@ __global__ void __launch_bounds__(LANES *HALVES) k_flush_t(LpDev d, int groups)
         const int *lpu = s_lp + buf * FT_ROWS;
         const bool more = u + 1 < u1;
         if (mb) mbar_wait(&s_mbar[buf], (unsigned)(lu / 3) & 1u); // this unit's multipliers have landed
-        if (more) copy_F(u + 1, (lu + 1) % 3);
+        if (more) copy_F(rb1, (lu + 1) % 3);
         for (int k = 0; k < TPB; k++) {
             double2 a[TR];
 #pragma unroll
             for (int w = 0; w < TR; w++) a[w] = nx[w];
-            if (k + 1 < TPB) load_tile(u, k + 1);
-            else if (more) load_tile(u + 1, 0);
+            if (k + 1 < TPB) load_tile(ct, rb, k + 1);
+            else if (more) load_tile(ct1, rb1, 0);
             const int rc = (k * HALVES + half) * TR, row = rb + rc;
             if (!active || row >= m) continue;
+            // marks are -1 (not a pivot row of this block) or the step: any >= 0 <=> AND >= 0
             bool special = false;
+            if (TR == 8) {
+                const int4 l0 = *reinterpret_cast<const int4 *>(lpu + rc), l1 = *reinterpret_cast<const int4 *>(lpu + rc + 4);
+                special = (l0.x & l0.y & l0.z & l0.w & l1.x & l1.y & l1.z & l1.w) >= 0;
+            } else {
 #pragma unroll
-            for (int w = 0; w < TR; w++) special |= (row + w < m) && lpu[rc + w] >= 0;
+                for (int w = 0; w < TR; w++) special |= (row + w < m) && lpu[rc + w] >= 0;
+            }
             if (!special) {
 #pragma unroll 8
                 for (int s = 0; s < t; s++) {
@@ -1558,15 +1567,17 @@ __global__ void __launch_bounds__(LANES *HALVES) k_flush_t(LpDev d, int groups)
             for (int w = 0; w < TR; w++)
                 if (row + w < m) *reinterpret_cast<double2 *>(d.tab + (size_t)(row + w) * Cl + j0) = a[w];
         }
-        if (more && (u + 1) / nrb != ct) { // next unit starts a new column tile: swap the P tile
+        if (more && ct1 != ct) { // next unit starts a new column tile: swap the P tile
             __syncthreads();
-            load_P((u + 1) / nrb);
+            load_P(ct1);
             __syncthreads();
         }
         if (!mb) {
             cp_async_wait_all();
             __syncthreads();
         }
+        ct = ct1;
+        rb = rb1;
     }
     // the last CTA closes the block
     if (tid == 0) {
