@@ -1418,9 +1418,9 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *b, unsigned parity
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 template <int TR, int LANES, int HALVES>
-__global__ void __launch_bounds__(LANES *HALVES) k_flush_t(LpDev d, int groups)
+__global__ void __launch_bounds__(LANES *HALVES) k_flush_t(LpDev d, int groups, int nbuf)
 {
-    extern __shared__ double sm[]; // sP[t][2*LANES] | sF[3][t][FT_ROWS] | s_lp[3][FT_ROWS]
+    extern __shared__ double sm[]; // sP[t][2*LANES] | sF[nbuf][t][FT_ROWS] | s_lp[nbuf][FT_ROWS], nbuf = 3 (or 2)
     __shared__ int s_flag;
     __shared__ unsigned long long s_mbar[3]; // "multipliers of unit lu have landed", lu % 3
     constexpr int THREADS = LANES * HALVES, TC = 2 * LANES;
@@ -1432,7 +1432,7 @@ __global__ void __launch_bounds__(LANES *HALVES) k_flush_t(LpDev d, int groups)
     const int par = st->blk & 1, Cl = d.Cl, m = d.m, tid = threadIdx.x;
     const int lane = tid % LANES, half = tid / LANES;
     double *sP = sm, *sF = sm + (size_t)t * TC;
-    int *s_lp = (int *)(sF + (size_t)3 * t * FT_ROWS);
+    int *s_lp = (int *)(sF + (size_t)nbuf * t * FT_ROWS);
     const double *sPl = sP + 2 * lane;
     const int nrb = (m + FT_ROWS - 1) / FT_ROWS;
     const int ctiles = (Cl + TC - 1) / TC;
@@ -1493,7 +1493,7 @@ __global__ void __launch_bounds__(LANES *HALVES) k_flush_t(LpDev d, int groups)
     __syncthreads();
     // Memory-bound passes (few steps per unit) keep the plain scheme -- wait for the copies,
     // block barrier per unit -- which measures 5 % faster there; compute-bound ones drop it.
-    const bool mb = t >= 12;
+    const bool mb = t >= 12 && nbuf == 3; // (two buffers: the host found no room for three at two CTAs per SM)
     int ct = u0 < u1 ? u0 / nrb : 0, rb = u0 < u1 ? (u0 % nrb) * FT_ROWS : 0; // advanced without divisions
     if (u0 < u1) {
         load_P(ct);
@@ -1510,12 +1510,12 @@ __global__ void __launch_bounds__(LANES *HALVES) k_flush_t(LpDev d, int groups)
         }
         const int j0 = ct * TC + 2 * lane;
         const bool active = j0 < Cl; // Cl is even on this path
-        const int lu = u - u0, buf = lu % 3;
+        const int lu = u - u0, buf = lu % nbuf;
         const double *sFu = sF + (size_t)buf * t * FT_ROWS;
         const int *lpu = s_lp + buf * FT_ROWS;
         const bool more = u + 1 < u1;
         if (mb) mbar_wait(&s_mbar[buf], (unsigned)(lu / 3) & 1u); // this unit's multipliers have landed
-        if (more) copy_F(rb1, (lu + 1) % 3);
+        if (more) copy_F(rb1, (lu + 1) % nbuf);
         for (int k = 0; k < TPB; k++) {
             double2 a[TR];
 #pragma unroll
@@ -1869,7 +1869,7 @@ struct xp_lp_f64 {
     unsigned long long *bar = nullptr, bar_base = 0;
     int panel_nb = 0, panel_rpc = 0, panel_cpc = 0;
     bool use_panel = true;
-    int ft_min = 2, ft_balanced_min = 10, ft_smem_set = 0, ft_occ = 1, ft_occ_k = -1; // k_flush_t: smallest k that uses it, launch cache
+    int ft_min = 2, ft_balanced_min = 10, ft_smem_set = 0, ft_occ = 1, ft_occ_k = -1, ft_nbuf = 3; // k_flush_t: smallest k that uses it, launch cache
     unsigned long long *panel_dbg = nullptr; // XP_PANEL_DBG=1: per-phase ns accumulators (16 words)
     // optional per-launch timing of the flush kernel (CUDA events on the ctx stream)
     bool profile = false;
@@ -1910,16 +1910,16 @@ static void flush_launch_kb(xp_ctx *ctx, const LpDev &d)
 
 constexpr int FT_TR = 8, FT_LANES = 128, FT_HALVES = 2, FT_THREADS = FT_LANES * FT_HALVES;
 
-static size_t flush_t_smem(int kblk)
+static size_t flush_t_smem(int kblk, int nbuf = 3)
 {
-    return ((size_t)kblk * 2 * FT_LANES + (size_t)3 * kblk * FT_ROWS) * sizeof(double) + 3 * FT_ROWS * sizeof(int);
+    return ((size_t)kblk * 2 * FT_LANES + (size_t)nbuf * kblk * FT_ROWS) * sizeof(double) + nbuf * FT_ROWS * sizeof(int);
 }
 
 static int flush_t_launch(xp_lp_f64 *lp, int kblk)
 {
     xp_ctx *ctx = lp->ctx;
     const LpDev &d = lp->d;
-    const size_t smem = flush_t_smem(kblk);
+    size_t smem = flush_t_smem(kblk);
     if (lp->ft_smem_set < (int)smem) {
         XP_CUDA_OK(ctx, cudaFuncSetAttribute(k_flush_t<FT_TR, FT_LANES, FT_HALVES>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)flush_t_smem(KMAX)));
@@ -1929,9 +1929,21 @@ static int flush_t_launch(xp_lp_f64 *lp, int kblk)
         int occ = 1;
         XP_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_flush_t<FT_TR, FT_LANES, FT_HALVES>,
                                                                       FT_THREADS, smem));
+        lp->ft_nbuf = 3;
+        const char *fb = getenv("XP_FLUSH_NBUF"); // "2" forces the two-buffer fallback (tests)
+        if (occ < 2 || (fb && fb[0] == '2')) { // three multiplier buffers cost the second CTA per SM here: fall back to two
+            int occ2 = 1;
+            XP_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, k_flush_t<FT_TR, FT_LANES, FT_HALVES>,
+                                                                          FT_THREADS, flush_t_smem(kblk, 2)));
+            if (occ2 > occ || (fb && fb[0] == '2')) {
+                occ = occ2;
+                lp->ft_nbuf = 2;
+            }
+        }
         lp->ft_occ = occ < 1 ? 1 : occ;
         lp->ft_occ_k = kblk;
     }
+    smem = flush_t_smem(kblk, lp->ft_nbuf);
     const int ctiles = (d.Cl + 2 * FT_LANES - 1) / (2 * FT_LANES);
     const long long units = (long long)ctiles * ((d.m + FT_ROWS - 1) / FT_ROWS);
     long long grid = (long long)lp->ft_occ * ctx->sm_count; // exactly one resident wave
@@ -1944,7 +1956,7 @@ static int flush_t_launch(xp_lp_f64 *lp, int kblk)
         if (groups > nrb) groups = nrb;
         grid = (long long)groups * ctiles;
     }
-    k_flush_t<FT_TR, FT_LANES, FT_HALVES><<<(unsigned)grid, FT_THREADS, smem, ctx->stream>>>(d, groups);
+    k_flush_t<FT_TR, FT_LANES, FT_HALVES><<<(unsigned)grid, FT_THREADS, smem, ctx->stream>>>(d, groups, lp->ft_nbuf);
     ctx->launches++;
     return 0;
 }
