@@ -234,8 +234,12 @@ int xp_six_two_stage_i64_ragged(xp_ctx *ctx, int batch, const int32_t *ms, const
  * split), [explicit dual for min], TwoStageMethod on the GPU, calcFinalSolution.
  * tgtf 1 x (n+1); vc n x (n+1) or NULL (= -I | 0); eq k x (n+1) (k may be 0);
  * leq m x (n+1).  sol: n+1 entries, written on XP_SIX_SUCC.  eq2bv_out
- * (optional, capacity m + 2k): the final basis, which the reference only
- * exposes through TwoStageMethod.
+ * (optional): the final basis of the LP that was solved, which the reference
+ * only exposes through TwoStageMethod.  Capacity: m + 2k entries for maxm (the
+ * normalised primal: every equality becomes two inequalities); 2n entries for
+ * minm, which solves the explicit dual (lpsol.h:1585-1655: one row per
+ * normalised variable, n plus at most n free-variable splits).  Never more than
+ * that is written; entries past the solved LP's row count are left untouched.
  */
 int xp_six_maxm_f64(xp_ctx *ctx, int m, int n, const double *tgtf, const double *vc, int k,
                     const double *eq, const double *leq, uint32_t max_iter, double *maxv,
@@ -291,10 +295,14 @@ int xp_has_solution_rat_batch(xp_ctx *ctx, int batch, int m, int n, const xp_rat
  * B&B trees advance in lockstep.  result[b] = 1 / 0, or XP_ERR_REFERENCE_UB for a
  * system on which the reference itself has undefined behaviour (equalities
  * without inequalities, linsys.cpp:851-854; convertEq2Ineq, lpsol.h:1232); the
- * other systems are still answered. */
+ * other systems are still answered.  A system that does not lie inside its pool
+ * (negative offset, offset + rows*(n+1) > pool length) fails the call with
+ * XP_ERR_BAD_ARG before anything is read. */
 int xp_has_solution_rat_ragged(xp_ctx *ctx, int batch, const int32_t *ns, const int32_t *ms,
-                               const int64_t *leq_off, const xp_rat *leq_pool, const int32_t *ks,
-                               const int64_t *eq_off, const xp_rat *eq_pool, int is_int_sol,
+                               const int64_t *leq_off, const xp_rat *leq_pool,
+                               size_t leq_pool_len /* xp_rat elements */, const int32_t *ks,
+                               const int64_t *eq_off, const xp_rat *eq_pool,
+                               size_t eq_pool_len /* xp_rat elements */, int is_int_sol,
                                int is_unique_sol, int32_t *result);
 
 #ifdef __cplusplus

@@ -313,6 +313,31 @@ void xo_mt64_uniform(uint64_t seed, size_t count, double *out)
     }
 }
 
+
+/* Position-keyed 64-bit checksum of an FP64 matrix: sum over (i, j) of
+ * mix64(bits(a[i][j]) ^ mix64(i * C + j)) mod 2^64, splitmix64 finaliser.  The same key
+ * function as the product's xp_lp_f64_checksum (k_checksum), restated here so a test can
+ * compare the device tableau with the oracle's at sizes where downloading 1 GiB per
+ * checkpoint would dominate (K in {1, 10, 50, 200} at c3). */
+static uint64_t xo_mix64(uint64_t z)
+{
+    z += 0x9E3779B97F4A7C15ULL;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+uint64_t xo_checksum_f64(const double *a, int rows, int cols)
+{
+    uint64_t s = 0;
+    for (int i = 0; i < rows; i++)
+        for (int j = 0; j < cols; j++) {
+            uint64_t b;
+            memcpy(&b, &a[(size_t)i * cols + j], 8);
+            s += xo_mix64(b ^ xo_mix64((uint64_t)((size_t)i * cols + j)));
+        }
+    return s;
+}
+
 static double g_xo_last_seconds = 0.0;
 double xo_last_solve_seconds(void) { return g_xo_last_seconds; }
 static double xo_now(void)

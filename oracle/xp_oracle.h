@@ -104,6 +104,9 @@ double xo_last_solve_seconds(void);
 double xo_two_stage_f64_many(int batch, int m, int n, const double *leq, const double *tgtf,
                              int32_t *status, double *maxv_out /* optional: maxv on SUCC, else 0 */);
 
+/* Position-keyed checksum of an FP64 matrix (same key function as xp_lp_f64_checksum). */
+uint64_t xo_checksum_f64(const double *a, int rows, int cols);
+
 /* std::mt19937_64 + uniform_real_distribution<double>(0,1) stream (libstdc++). */
 void xo_mt64_uniform(uint64_t seed, size_t count, double *out);
 

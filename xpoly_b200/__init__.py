@@ -400,11 +400,17 @@ def _six_solve(self, kind, is_min, leq, tgtf, vc=None, eq=None, max_iter=NO_ITER
     m = 0 if leq is None else leq.shape[0]
     k = 0 if eq is None else eq.shape[0]
     sol = np.zeros((n + 1,) + tgtf.shape[1:], dtype=tgtf.dtype)
-    e2b = np.zeros(m + 2 * k + n + 2, dtype=np.int32)
+    # exactly the documented capacity (m + 2k for maxm, 2n for minm) plus a canary word the
+    # library must never touch
+    cap = 2 * n if is_min else m + 2 * k
+    e2b = np.full(cap + 1, -1, dtype=np.int32)
+    e2b[cap] = 0x5AFE5AFE
     fn = getattr(lib(), f"xp_six_{'minm' if is_min else 'maxm'}_{kind}")
     st = self.check(fn(self._h, m, n, _p(tgtf), _p(vc), k, _p(eq), _p(leq), C.c_uint32(max_iter),
                        _p(v), _p(sol), _p(e2b)))
-    return dict(status=st, v=v, sol=sol, eq2bv=e2b)
+    if e2b[cap] != 0x5AFE5AFE:
+        raise RuntimeError("xp_six_*: eq2bv_out written past its documented capacity")
+    return dict(status=st, v=v, sol=sol, eq2bv=e2b[:cap])
 
 
 def _six_solve_batch(self, kind, is_min, leq, tgtf, max_iter=NO_ITER_LIMIT):
@@ -488,8 +494,9 @@ def _has_solution_ragged(self, systems, is_int=True, is_unique=True):
     epool = np.ascontiguousarray(np.concatenate(ep)) if ep else np.zeros((1, 2), dtype=np.int32)
     res = np.zeros(B, dtype=np.int32)
     self.check(lib().xp_has_solution_rat_ragged(self._h, B, _p(ns), _p(ms), _p(lo), _p(lpool),
-                                                _p(ks), _p(eo), _p(epool), int(is_int),
-                                                int(is_unique), _p(res)))
+                                                C.c_size_t(ll), _p(ks), _p(eo), _p(epool),
+                                                C.c_size_t(el), int(is_int), int(is_unique),
+                                                _p(res)))
     return res
 
 

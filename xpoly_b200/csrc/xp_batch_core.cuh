@@ -561,6 +561,10 @@ inline int xpb_host_run(xp_ctx *ctx, const XpBatchHost &H, XpBatchLaunch launch)
             maxm = H.ms[k] > maxm ? H.ms[k] : maxm;
             maxn = H.ns[k] > maxn ? H.ns[k] : maxn;
             if (H.ms[k] + H.ns[k] + 1 > H.ldo) return XP_ERR_BAD_ARG;
+            // every LP must lie inside the pools (offsets and lengths in elements)
+            if (!H.leq_off || !H.tgtf_off || H.leq_off[k] < 0 || H.tgtf_off[k] < 0) return XP_ERR_BAD_ARG;
+            if ((size_t)H.leq_off[k] + (size_t)H.ms[k] * (H.ns[k] + 1) > H.leq_len) return XP_ERR_BAD_ARG;
+            if ((size_t)H.tgtf_off[k] + (size_t)H.ns[k] + 1 > H.tgtf_len) return XP_ERR_BAD_ARG;
         }
         if (H.ldm < maxm) return XP_ERR_BAD_ARG;
     }

@@ -475,6 +475,17 @@ int mip_status(int st) { return st; }
     XP_CUDA_OK(ctx, cudaSetDevice((ctx)->device)); \
     Q::overflow() = false;
 
+// eq2bv_out holds the basis of the LP that was actually solved: the normalised primal
+// (m + 2k rows) for maxm, its explicit dual (one row per normalised variable: n plus the
+// free-variable splits, at most 2n) for minm.  The documented capacities (m + 2k / 2n,
+// include/xpoly_b200.h) bound the copy; entries past the solved LP's row count are untouched.
+static void copy_basis(const std::vector<int32_t> &e2b, bool is_min, int m, int n, int k, int32_t *out)
+{
+    if (!out) return;
+    const size_t cap = is_min ? (size_t)2 * n : (size_t)m + 2 * (size_t)k;
+    std::copy(e2b.begin(), e2b.begin() + (e2b.size() < cap ? e2b.size() : cap), out);
+}
+
 static int six_f64(xp_ctx *ctx, bool is_min, int m, int n, const double *tgtf, const double *vc,
                    int k, const double *eq, const double *leq, uint32_t max_iter, double *v,
                    double *sol, int32_t *eq2bv_out)
@@ -487,7 +498,7 @@ static int six_f64(xp_ctx *ctx, bool is_min, int m, int n, const double *tgtf, c
     std::vector<int32_t> e2b;
     int st = solve_one<F64>(ctx, is_min, T, V, E, L, max_iter, *v, s, &e2b);
     if (st == XP_SIX_SUCC && sol) std::copy(s.begin(), s.begin() + n + 1, sol);
-    if (eq2bv_out) std::copy(e2b.begin(), e2b.end(), eq2bv_out);
+    copy_basis(e2b, is_min, m, n, k, eq2bv_out);
     return st;
 }
 
@@ -523,7 +534,7 @@ static int six_rat(xp_ctx *ctx, bool is_min, int m, int n, const xp_rat *tgtf, c
         for (int j = 0; j <= n && sol; j++) ok &= to_rat(s[j], &sol[j]);
         if (!ok) return XP_ERR_OVERFLOW;
     }
-    if (eq2bv_out) std::copy(e2b.begin(), e2b.end(), eq2bv_out);
+    copy_basis(e2b, is_min, m, n, k, eq2bv_out);
     return st;
 }
 
@@ -786,8 +797,9 @@ extern "C" int xp_has_solution_rat_batch(xp_ctx *ctx, int batch, int m, int n, c
 // reference pair and loop depth): systems of different sizes, inequalities and equalities.
 extern "C" int xp_has_solution_rat_ragged(xp_ctx *ctx, int batch, const int32_t *ns,
                                           const int32_t *ms, const int64_t *leq_off,
-                                          const xp_rat *leq_pool, const int32_t *ks,
-                                          const int64_t *eq_off, const xp_rat *eq_pool,
+                                          const xp_rat *leq_pool, size_t leq_pool_len,
+                                          const int32_t *ks, const int64_t *eq_off,
+                                          const xp_rat *eq_pool, size_t eq_pool_len,
                                           int is_int_sol, int is_unique_sol, int32_t *result)
 {
     XP_ENTRY_GUARD(ctx);
@@ -798,6 +810,9 @@ extern "C" int xp_has_solution_rat_ragged(xp_ctx *ctx, int batch, const int32_t 
         const int n = ns[b], m = ms[b], k = ks ? ks[b] : 0;
         if (n < 1 || m < 0 || k < 0) return XP_ERR_BAD_ARG;
         if ((m > 0 && (!leq_off || !leq_pool)) || (k > 0 && (!eq_off || !eq_pool))) return XP_ERR_BAD_ARG;
+        // every system must lie inside its pool (offsets and lengths in xp_rat elements)
+        if (m > 0 && (leq_off[b] < 0 || (size_t)leq_off[b] + (size_t)m * (n + 1) > leq_pool_len)) return XP_ERR_BAD_ARG;
+        if (k > 0 && (eq_off[b] < 0 || (size_t)eq_off[b] + (size_t)k * (n + 1) > eq_pool_len)) return XP_ERR_BAD_ARG;
         nv[b] = n;
         if (m > 0) Ls[b] = mat_q(m, n + 1, leq_pool + leq_off[b]);
         if (k > 0) Es[b] = mat_q(k, n + 1, eq_pool + eq_off[b]);

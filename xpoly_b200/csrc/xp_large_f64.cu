@@ -1880,6 +1880,8 @@ struct xp_lp_f64 {
 
 constexpr int PROF_MAX_SWEEPS = 4096;
 
+extern "C" void xp_lp_f64_destroy(xp_lp_f64 *lp);
+
 static int auto_block(const LpDev &d)
 {
     // measured on B200 (c3, 8192 x 16384): pivots/s keeps growing up to k = 32, where the
@@ -1986,6 +1988,8 @@ static cudaError_t preload_flush()
     return cudaFuncGetAttributes(&fa, k_flush<KB, (KB <= 16 ? 2 : 1), 256, (KB <= 4 ? 8 : 4)>);
 }
 
+static int lp_create_fill(xp_ctx *ctx, int m, int C, int rank, int G, xp_lp_f64 *lp);
+
 static int lp_create(xp_ctx *ctx, int m, int C, int rank, int G, xp_lp_f64 **out)
 {
     if (!ctx || !out || m < 1 || C < 2 || G < 1 || G > MAXR || rank < 0 || rank >= G)
@@ -1994,8 +1998,22 @@ static int lp_create(xp_ctx *ctx, int m, int C, int rank, int G, xp_lp_f64 **out
     XP_CUDA_OK(ctx, cudaSetDevice(ctx->device));
     xp_lp_f64 *lp = new xp_lp_f64();
     lp->ctx = ctx;
+    memset(&lp->d, 0, sizeof lp->d);
+    const int rc = lp_create_fill(ctx, m, C, rank, G, lp);
+    if (rc) { // e.g. out of memory half way: give back what was allocated (destroy takes nulls)
+        const std::string why = ctx->err;
+        xp_lp_f64_destroy(lp);
+        cudaGetLastError();
+        ctx->err = why;
+        return rc;
+    }
+    *out = lp;
+    return 0;
+}
+
+static int lp_create_fill(xp_ctx *ctx, int m, int C, int rank, int G, xp_lp_f64 *lp)
+{
     LpDev &d = lp->d;
-    memset(&d, 0, sizeof d);
     d.m = m;
     d.C = C;
     d.n = C - 1;
@@ -2099,7 +2117,6 @@ static int lp_create(xp_ctx *ctx, int m, int C, int rank, int G, xp_lp_f64 **out
     XP_CUDA_OK(ctx, preload_flush<16>());
     XP_CUDA_OK(ctx, preload_flush<24>());
     XP_CUDA_OK(ctx, preload_flush<32>());
-    *out = lp;
     return 0;
 }
 

@@ -167,6 +167,7 @@ class XpHasSolutionBatch {
     std::vector<int32_t> m_ns, m_ms, m_ks, m_res;
     std::vector<int64_t> m_lo, m_eo;
     std::vector<xp_rat> m_lp, m_ep;
+    UINT m_failed = 0;
     static void append(std::vector<xp_rat> &pool, RMat const &m)
     {
         const xp_rat *p = (const xp_rat *)xp_raw(m);
@@ -196,15 +197,23 @@ public:
         if (m_ns.empty()) return;
         xp_rat dummy = {0, 1};
         int st = xp_has_solution_rat_ragged(xp_thread_ctx(), (int)m_ns.size(), m_ns.data(), m_ms.data(),
-                                            m_lo.data(), m_lp.empty() ? &dummy : m_lp.data(), m_ks.data(),
-                                            m_eo.data(), m_ep.empty() ? &dummy : m_ep.data(),
-                                            is_int_sol ? 1 : 0, is_unique_sol ? 1 : 0, m_res.data());
+                                            m_lo.data(), m_lp.empty() ? &dummy : m_lp.data(), m_lp.size(),
+                                            m_ks.data(), m_eo.data(), m_ep.empty() ? &dummy : m_ep.data(),
+                                            m_ep.size(), is_int_sol ? 1 : 0, is_unique_sol ? 1 : 0,
+                                            m_res.data());
         xp_status(st);
+        m_failed = 0;
+        for (size_t i = 0; i < m_res.size(); i++) m_failed += m_res[i] < 0;
     }
-    // has_solution's answer for query i; a system on which the reference has undefined
-    // behaviour (XP_ERR_REFERENCE_UB) reads as "no solution found".
-    bool get(UINT i) const { return m_res[i] == 1; }
+    // has_solution's answer for query i.  A query the solver could not decide (negative code:
+    // XP_ERR_OVERFLOW past int64, XP_ERR_REFERENCE_UB where the reference itself has undefined
+    // behaviour, XP_ERR_BAD_ARG) answers TRUE: in the producer (DepPoly::is_empty,
+    // poly.cpp:530-573) "no solution" drops the dependence, so an undecided system must stay a
+    // dependence -- the conservative direction for a compiler.  failed() / raw(i) tell a caller
+    // which answers were defaulted, e.g. to re-ask the synchronous Lineq::has_solution.
+    bool get(UINT i) const { return m_res[i] != 0; }
     INT raw(UINT i) const { return m_res[i]; }
+    UINT failed() const { return m_failed; }
     void clean()
     {
         m_ns.clear(); m_ms.clear(); m_ks.clear(); m_res.clear();
