@@ -127,6 +127,18 @@ int xp_lp_f64_download(xp_lp_f64 *lp, double *tableau, double *tgtf, uint8_t *nv
 #define XP_MAX_BLOCK 32
 int xp_lp_f64_set_block(xp_lp_f64 *lp, int pivots_per_flush);
 int xp_ctx_set_block(xp_ctx *ctx, int pivots_per_flush); /* for xp_six_slack_f64 */
+/* Pricing window of the panel kernel.  The reference enters the LOWEST-index column
+ * with c_j > 0 (lpsol.h:1054-1069); while that column lies among the first `width`
+ * columns, the decision chain of a pivot (entering column, ratio test, leaving row,
+ * pricing) is run by one 16-CTA cluster that carries the objective row and the pivot
+ * rows for that window only, and everything to its right is brought up to date once per
+ * block.  Same operations per entry in the same order, hence the same bits; a pricing
+ * scan that leaves the window falls back to the full-width kernels for that pivot.
+ * width: 0 = automatic (on for large LPs), < 0 = off, > 0 = forced.  Every rank of a
+ * sharded LP must make the same call; takes effect at the next solve. */
+int xp_lp_f64_set_window(xp_lp_f64 *lp, int width);
+int xp_lp_f64_window(const xp_lp_f64 *lp); /* width in use (0 = off) */
+int xp_ctx_set_window(xp_ctx *ctx, int width); /* for xp_six_slack_f64 / xp_six_two_stage_f64_large */
 /* Per-launch timing of the tableau-update kernel (k_flush) with CUDA events on
  * the ctx stream (bench.py's roofline leg).  sweep_ms sums the launches that did
  * real work since enable; gap_ms the time between consecutive ones (the panel

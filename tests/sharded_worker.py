@@ -18,14 +18,20 @@ from xpoly_b200 import sharded  # noqa: E402
 
 def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
-    local = int(os.environ.get("LOCAL_RANK", rank))
+    one_gpu = bool(os.environ.get("XP_TEST_ONE_GPU"))
+    # one-GPU mode: every process opens the SAME device; the exchange blocks still travel as
+    # real cudaIpc handles between processes (kernels of different processes are time-sliced,
+    # so every cross-rank wait costs a context switch: small cases only)
+    local = 0 if one_gpu else int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(local)
     dist.init_process_group("gloo")
     ctx = xp.Context(local)
-    cases = [("dense", 7001, 24, 23, H.NO_LIMIT), ("dense", 7002, 64, 63, H.NO_LIMIT),
-             ("mixed", 3, 10, 9, H.NO_LIMIT), ("mixed", 1, 12, 30, H.NO_LIMIT),
-             ("dense", 4242, 256, 255, 40)]
-    for kind, seed, m, n, K in cases:
+    cases = [("dense", 7001, 24, 23, H.NO_LIMIT, 0), ("dense", 7002, 64, 63, H.NO_LIMIT, 1 << 20),
+             ("mixed", 3, 10, 9, H.NO_LIMIT, 0), ("mixed", 1, 12, 30, H.NO_LIMIT, 4),
+             ("dense", 4242, 256, 255, 40, 0), ("dense", 4242, 256, 255, 70, 1 << 20)]
+    if one_gpu:
+        cases = [("dense", 7001, 24, 23, 12, -1), ("dense", 7002, 40, 39, 40, 1 << 20), ("mixed", 3, 10, 9, 30, 3)]
+    for kind, seed, m, n, K, window in cases:
         if kind == "dense":
             leq, tg = H.gen_dense_lp(seed, m, n)
         else:
@@ -33,6 +39,7 @@ def main():
             leq[:, n] = np.abs(leq[:, n])
         sf = xp.slack_form(leq, tg)
         lp = sharded.ShardedLP(ctx, m, sf[0].shape[1], rank, world, dist)
+        lp.set_window(window)  # > 0: rank 0 decides runs of pivots alone (k_wpanel), peers replay
         lp.upload(*sf)
         st = lp.solve(K)
         g = lp.download(log_cap=1 << 16)

@@ -23,17 +23,65 @@ def assert_same_state(g, o, tag):
 BLOCKS = (0, 1, 3, 32)  # pivots per tableau pass: automatic, the reference's schedule, odd, maximum
 
 
-def run_both(ctx, leq, tgtf, max_iter=H.NO_LIMIT, tag=None, blocks=BLOCKS):
+def run_both(ctx, leq, tgtf, max_iter=H.NO_LIMIT, tag=None, blocks=BLOCKS, windows=(0,)):
     sf = xp.slack_form(leq, tgtf)
     o = H.slack_solve_oracle("f64", *sf, max_iter=max_iter)
     try:
-        for k in blocks:
-            ctx.set_block(k)
-            g = ctx.six_slack_f64(*sf, max_iter=max_iter, log_cap=1 << 16)
-            assert_same_state(g, o, (tag, "block", k))
+        for w in windows:
+            ctx.set_window(w)
+            for k in blocks:
+                ctx.set_block(k)
+                g = ctx.six_slack_f64(*sf, max_iter=max_iter, log_cap=1 << 16)
+                assert_same_state(g, o, (tag, "block", k, "window", w))
     finally:
         ctx.set_block(0)
+        ctx.set_window(0)
     return g
+
+
+# pricing windows: off, one column (every scan leaves it), a few columns (scans leave it now and
+# then: the full-width kernels take those pivots), the whole tableau
+WINDOWS = (-1, 1, 6, 1 << 20)
+
+
+@pytest.mark.parametrize("m,n", [(6, 5), (16, 15), (33, 20), (7, 40), (40, 64), (130, 129)])
+def test_windowed_panel_dense(ctx, m, n):
+    """k_wpanel + k_prow_bulk (one 16-CTA cluster decides inside the pricing window, the columns
+    outside follow once per block) leave the oracle's bits: whole tableau, objective row, basis,
+    pivot sequence -- for windows that never, sometimes and always contain the entering column."""
+    for seed in range(4):
+        leq, tg = H.gen_dense_lp(8100 + seed, m, n)
+        run_both(ctx, leq, tg, tag=("wdense", m, n, seed), blocks=(0, 1, 5, 32), windows=WINDOWS)
+
+
+@pytest.mark.parametrize("m,n", [(6, 5), (10, 9), (16, 15), (12, 30)])
+def test_windowed_panel_mixed_sign(ctx, m, n):
+    """Ratio test failing inside the windowed kernel (-> disableNV on the slow path), its pass 2
+    (negative pivots) and tabu exhaustion, with the window forced on."""
+    seen = set()
+    for seed in range(8):
+        leq, tg = H.gen_mixed_lp(100 + seed, m, n)
+        leq[:, n] = np.abs(leq[:, n])
+        seen.add(run_both(ctx, leq, tg, tag=("wmixed", m, n, seed), blocks=(0, 32), windows=(3, 1 << 20))["status"])
+    assert 1 in seen
+
+
+def test_windowed_panel_bounded_and_resume(ctx):
+    """max_iter stops inside a windowed block; resuming continues it (factors reloaded)."""
+    leq, tg = H.gen_dense_lp(8200, 96, 95)
+    sf = xp.slack_form(leq, tg)
+    for w in (8, 1 << 20):
+        lp = ctx.large_lp(*sf[0].shape)
+        lp.set_window(w)
+        assert lp.window == min(w, sf[0].shape[1])
+        lp.set_block(32)
+        lp.upload(*sf)
+        for K in (3, 10, 45, 46, 120):
+            st = lp.solve(K)
+            g = lp.download(log_cap=1 << 16)
+            g["status"] = st
+            assert_same_state(g, H.slack_solve_oracle("f64", *sf, max_iter=K), ("wresume", w, K))
+        lp.close()
 
 
 @pytest.mark.parametrize("m,n", [(2, 2), (6, 5), (8, 7), (10, 9), (16, 15), (33, 20), (7, 40)])
@@ -164,7 +212,7 @@ def test_c3_full_size_properties_and_oracle_sample(ctx):
     for stop in (5, 17, K):
         assert lp.solve(stop) == xp.SIX_TIME_OUT
     assert lp.checksum() == res[1][0]
-    Ks = 10  # oracle sample
+    Ks = 10  # live oracle sample
     leq, tg = dense_lp(20261017, m, n)
     o = H.slack_solve_oracle("f64", *xp.slack_form(leq, tg), max_iter=Ks, log_cap=Ks)
     lp.fill_synthetic(20261017)
@@ -173,6 +221,40 @@ def test_c3_full_size_properties_and_oracle_sample(ctx):
     assert np.array_equal(a["log"], o["log"])
     assert np.array_equal(a["eq2bv"], o["eq2bv"])
     assert np.array_equal(H.bits(a["tgtf"]), H.bits(o["tgtf"]))
+    lp.close()
+
+
+def test_c3_full_size_checkpoints_vs_reference(ctx):
+    """the 8192 x 16384 LP after K = 1, 10, 50, 200 pivots against the CPU side --
+    position-keyed checksum of all 134 M tableau doubles, of the objective row, the basis and the
+    whole pivot sequence.  tests/golden/c3_checkpoints.json holds what the oracle port AND the
+    unmodified reference (TwoStageMethod, set_param(0, K)) computed for this seed
+    (tools/c3_checkpoints.py; the two agree); the windowed and the full-width panel, blocked and
+    unblocked, must all land on the same bits."""
+    import json
+    import os
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "c3_checkpoints.json")))
+    m, n = gold["m"], gold["n"]
+    assert (m, n) == (8192, 8191) and gold["seed"] == 20261017
+    for K in ("1", "10", "50", "200"):  # the fixture itself: reference == port
+        for f in ("status", "tab", "tgtf", "eq2bv_sum"):
+            assert gold["reference"][K][f] == gold["oracle"][K][f], (K, f)
+    lp = ctx.large_lp(m, n + m + 1)
+    wts = np.arange(1, m + 1, dtype=np.int64)
+    for window, block in ((0, 0), (-1, 0), (0, 7)):
+        lp.set_window(window)
+        lp.set_block(block)
+        lp.fill_synthetic(gold["seed"])
+        assert (lp.window > 0) == (window == 0)
+        for K in (1, 10, 50, 200):
+            assert lp.solve(K) == xp.SIX_TIME_OUT
+            ref = gold["reference"][str(K)]
+            a = lp.download(want_tab=False, log_cap=K)
+            ct, cg = lp.checksum()
+            assert ct == ref["tab"], ("tableau checksum", window, block, K)
+            assert cg == ref["tgtf"], ("objective checksum", window, block, K)
+            assert int(a["eq2bv"].astype(np.int64).dot(wts)) == ref["eq2bv_sum"], ("basis", window, block, K)
+            assert np.array_equal(a["log"], np.array(gold["oracle"]["200"]["log"])[:K]), ("pivot sequence", K)
     lp.close()
 
 

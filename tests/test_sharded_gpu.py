@@ -22,7 +22,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def solve_sharded_inproc(G, sf, max_iters, device=0, block=0):
+def solve_sharded_inproc(G, sf, max_iters, device=0, block=0, window=0):
     """Returns one merged result dict per entry of max_iters (successive resumes)."""
     tab, tg = sf[0], sf[1]
     m, Cc = tab.shape
@@ -31,6 +31,7 @@ def solve_sharded_inproc(G, sf, max_iters, device=0, block=0):
     for lp in lps:
         lp.peer_attach_local(lps)
         lp.set_block(block)
+        lp.set_window(window)
         lp.upload(*sf)
     outs = []
     for K in max_iters:
@@ -102,6 +103,29 @@ def test_inproc_dense_to_termination(G):
     assert seen <= {0, 1, 3}
 
 
+@pytest.mark.parametrize("G", [2, 3, 4])
+@pytest.mark.parametrize("window", [2, 1 << 20])
+def test_inproc_windowed_leader(G, window):
+    """Windowed panel on a sharded LP: rank 0 decides runs of pivots alone (its slice holds the
+    window) and hands records + multiplier columns to the peers, which replay the replicated
+    state; scans that leave the window go through the per-pivot exchange kernels."""
+    for seed, (m, n) in enumerate([(16, 15), (24, 23), (33, 20), (40, 64)]):
+        leq, tg = H.gen_dense_lp(7100 + seed, m, n)
+        sf = xp.slack_form(leq, tg)
+        g = solve_sharded_inproc(G, sf, [H.NO_LIMIT], block=(0, 32, 5, 1)[seed % 4], window=window)[0]
+        assert_same_state(g, H.slack_solve_oracle("f64", *sf), ("wshard", G, window, m, n))
+    leq, tg = H.gen_mixed_lp(5, 12, 30)
+    leq[:, 30] = np.abs(leq[:, 30])
+    sf = xp.slack_form(leq, tg)
+    g = solve_sharded_inproc(G, sf, [H.NO_LIMIT], block=32, window=window)[0]
+    assert_same_state(g, H.slack_solve_oracle("f64", *sf), ("wshard-mixed", G, window))
+    leq, tg = H.gen_dense_lp(4243, 96, 95)
+    sf = xp.slack_form(leq, tg)
+    outs = solve_sharded_inproc(G, sf, [7, 40, 41], block=16, window=window)
+    for K, g in zip((7, 40, 41), outs):
+        assert_same_state(g, H.slack_solve_oracle("f64", *sf, max_iter=K), ("wshard-resume", G, window, K))
+
+
 @pytest.mark.parametrize("G", [2, 4])
 def test_inproc_mixed_sign_slow_paths(G):
     """disableNV retries, the pass-2 ratio test and the findPivotNVandBVPair search
@@ -145,5 +169,19 @@ def test_multiprocess_ipc(world):
            "--master-addr", "127.0.0.1", "--master-port", str(port),
            os.path.join(ROOT, "tests", "sharded_worker.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "SHARDED_WORKER_OK" in r.stdout
+
+
+def test_multiprocess_ipc_one_gpu():
+    """The CUDA-IPC path on a single-GPU box: two PROCESSES, both on cuda:0, exchange-block handles
+    all-gathered between them and opened with cudaIpcOpenMemHandle -- the same code path as one
+    process per GPU, minus NVLink.  Every rank compares its slice and the replicated state with the
+    oracle bit for bit (full-width exchange kernels and the windowed leader)."""
+    env = dict(os.environ, XP_TEST_ONE_GPU="1")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+           "--master-addr", "127.0.0.1", "--master-port", "29649",
+           os.path.join(ROOT, "tests", "sharded_worker.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=420, env=env)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "SHARDED_WORKER_OK" in r.stdout

@@ -132,6 +132,10 @@ class Context:
         """Pivots per pass over the tableau for six_slack_f64 (0 = automatic)."""
         self.check(lib().xp_ctx_set_block(self._h, int(k)))
 
+    def set_window(self, w):
+        """Pricing window for six_slack_f64 / two_stage_f64_large: 0 automatic, < 0 off, > 0 forced."""
+        self.check(lib().xp_ctx_set_window(self._h, int(w)))
+
     def large_lp(self, m, Cc, rank=0, nranks=1):
         return LargeLP(self, m, Cc, rank, nranks)
 
@@ -153,6 +157,14 @@ class LargeLP:
 
     def set_block(self, k):
         self.ctx.check(lib().xp_lp_f64_set_block(self._h, int(k)))
+
+    def set_window(self, w):
+        """Pricing window of the panel kernel: 0 automatic, < 0 off, > 0 forced width."""
+        self.ctx.check(lib().xp_lp_f64_set_window(self._h, int(w)))
+
+    @property
+    def window(self):
+        return int(lib().xp_lp_f64_window(self._h))
 
     def peer_handle(self):
         buf = np.zeros(PEER_HANDLE_BYTES, dtype=np.uint8)

@@ -49,9 +49,13 @@
 // and exactly equivalent to the reference's byte-matrix scans.
 #include "xp_common.cuh"
 
+#include <cooperative_groups.h>
+
 #include <cstdlib>
 #include <cstring>
 #include <vector>
+
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -81,6 +85,9 @@ struct LpState {
     unsigned xs;   // slow-path column fetches so far
     unsigned cseq; // entering columns published so far
     unsigned fe;   // feasibility-chain epoch
+    unsigned wseq; // windowed-panel launches that did work so far (never reset: flag words only grow)
+    int wb_t0;      // first pivot of the open block whose deferred columns k_prow_bulk still owes
+    int wb_pending; // k_wpanel made pivots [wb_t0, t): their P rows / objective entries beyond the window are due
     int n_touched;
     int touched[KMAX]; // rows with last_piv >= 0
     double r, cq, prow_rhs;
@@ -99,6 +106,11 @@ struct XHdr {
     // k_panel, sharded: the pivot the owner of the entering column decided (ratio test on
     // its own copy of the column), by parity of the column event number
     unsigned long long piv[2][9]; // a, rh, cq (2 words each), p, bv, s0: payload | tag << 32
+    // windowed panel (k_wpanel), sharded: rank 0 decides a whole run of pivots alone and hands
+    // the peers its exit state + one record per pivot (xoff_rec) + the multiplier columns
+    unsigned long long wflag;       // leader -> peer: number of the windowed launch whose results are in place
+    unsigned long long wack[MAXR];  // peer -> leader: last windowed launch the peer has consumed
+    int wexit[8];                   // leader -> peer: t, q, anypos, zero_upto, slow, status
 };
 constexpr size_t XHDR_BYTES = 1024;
 static_assert(sizeof(XHdr) <= XHDR_BYTES, "exchange header");
@@ -116,6 +128,7 @@ struct LpDev {
     int col0, Cl; // first local column, local width (row stride of tab and P)
     int mpad;     // doubles per F row (m+1 padded)
     int gridA, gridB;
+    int w, wrpc, wwpc; // windowed panel: window = global columns [0, w) (0: off), rows / window columns per CTA
     double *tab, *tgtf, *P, *rhsbuf, *sol;
     const double *vc_diag, *vc_rhs; // may be null
     uint8_t *nvset;
@@ -145,9 +158,18 @@ __host__ __device__ __forceinline__ size_t xoff_land(const LpDev &d, int par)
 {
     return XHDR_BYTES + ((size_t)(2 * KMAX + 1 + 2 * par) * d.mpad) * sizeof(double);
 }
+// k_wpanel: one record per pivot of the open block, by block parity
+struct WRec {
+    double r, cq, prow_rhs; // 1 / pivot element, c_q, scaled constant term of the pivot row
+    int p, q, bv, s0p;      // pivot row, entering / leaving variable, last_piv[p] before this pivot
+};
+__host__ __device__ __forceinline__ size_t xoff_rec(const LpDev &d, int par)
+{
+    return XHDR_BYTES + ((size_t)(2 * KMAX + 5) * d.mpad) * sizeof(double) + (size_t)par * KMAX * sizeof(WRec);
+}
 __host__ __device__ __forceinline__ size_t xblock_bytes(const LpDev &d)
 {
-    return XHDR_BYTES + ((size_t)(2 * KMAX + 5) * d.mpad) * sizeof(double);
+    return XHDR_BYTES + ((size_t)(2 * KMAX + 5) * d.mpad) * sizeof(double) + (size_t)2 * KMAX * sizeof(WRec);
 }
 __device__ __forceinline__ double *Fptr(const LpDev &d, int r, int par, int s)
 {
@@ -1255,6 +1277,8 @@ k_panel(LpDev d, PanA *partA, PanB *partB, unsigned long long *bar, unsigned lon
     }
 }
 
+#include "xp_large_wpanel.cuh"
+
 // ---------------------------------------------------------------------------
 // k_flush: apply the t pending pivots to the tableau slice.
 // Each thread owns VEC adjacent columns and keeps P[0..KB)[cols] in registers;
@@ -1871,6 +1895,9 @@ struct xp_lp_f64 {
     bool use_panel = true;
     int ft_min = 2, ft_balanced_min = 10, ft_smem_set = 0, ft_occ = 1, ft_occ_k = -1, ft_nbuf = 3; // k_flush_t: smallest k that uses it, launch cache
     unsigned long long *panel_dbg = nullptr; // XP_PANEL_DBG=1: per-phase ns accumulators (16 words)
+    unsigned long long *wpanel_dbg = nullptr; // the same for the windowed panel
+    int window = 0;  // requested window: 0 automatic, < 0 off, > 0 forced width (xp_lp_f64_set_window)
+    bool wpanel_ready = false; // kernel attributes set
     // optional per-launch timing of the flush kernel (CUDA events on the ctx stream)
     bool profile = false;
     std::vector<cudaEvent_t> evs;
@@ -1989,6 +2016,7 @@ static cudaError_t preload_flush()
 }
 
 static int lp_create_fill(xp_ctx *ctx, int m, int C, int rank, int G, xp_lp_f64 *lp);
+static int window_config(xp_lp_f64 *lp);
 
 static int lp_create(xp_ctx *ctx, int m, int C, int rank, int G, xp_lp_f64 **out)
 {
@@ -2088,7 +2116,11 @@ static int lp_create_fill(xp_ctx *ctx, int m, int C, int rank, int G, xp_lp_f64 
         if (dbg && atoi(dbg)) {
             XP_CUDA_OK(ctx, cudaMalloc((void **)&lp->panel_dbg, 128));
             XP_CUDA_OK(ctx, cudaMemset(lp->panel_dbg, 0, 128));
+            XP_CUDA_OK(ctx, cudaMalloc((void **)&lp->wpanel_dbg, 128));
+            XP_CUDA_OK(ctx, cudaMemset(lp->wpanel_dbg, 0, 128));
         }
+        const int wrc = window_config(lp);
+        if (wrc) return wrc;
     }
     XP_CUDA_OK(ctx, cudaMemset(d.st, 0, sizeof(LpState)));
     XP_CUDA_OK(ctx, cudaMemset(d.ctr, 0, 64));
@@ -2103,6 +2135,9 @@ static int lp_create_fill(xp_ctx *ctx, int m, int C, int rank, int G, xp_lp_f64 
     XP_CUDA_OK(ctx, cudaFuncGetAttributes(&fa, k_pcol));
     XP_CUDA_OK(ctx, cudaFuncGetAttributes(&fa, k_prow));
     XP_CUDA_OK(ctx, cudaFuncGetAttributes(&fa, k_panel));
+    XP_CUDA_OK(ctx, cudaFuncGetAttributes(&fa, k_wpanel));
+    XP_CUDA_OK(ctx, cudaFuncGetAttributes(&fa, k_wpanel_peer));
+    XP_CUDA_OK(ctx, cudaFuncGetAttributes(&fa, k_prow_bulk));
     XP_CUDA_OK(ctx, cudaFuncGetAttributes(&fa, k_flush_t<FT_TR, FT_LANES, FT_HALVES>));
     XP_CUDA_OK(ctx, cudaFuncGetAttributes(&fa, k_init));
     XP_CUDA_OK(ctx, cudaFuncGetAttributes(&fa, k_feas_sol));
@@ -2137,6 +2172,15 @@ extern "C" int xp_lp_f64_set_block(xp_lp_f64 *lp, int pivots_per_flush)
     lp->kblk = pivots_per_flush;
     return 0;
 }
+
+extern "C" int xp_lp_f64_set_window(xp_lp_f64 *lp, int width)
+{
+    if (!lp) return XP_ERR_BAD_ARG;
+    lp->window = width;
+    return window_config(lp);
+}
+
+extern "C" int xp_lp_f64_window(const xp_lp_f64 *lp) { return lp ? lp->d.w : 0; }
 
 extern "C" int xp_lp_f64_local_cols(const xp_lp_f64 *lp, int *col0, int *ncols)
 {
@@ -2228,6 +2272,14 @@ extern "C" void xp_lp_f64_destroy(xp_lp_f64 *lp)
                     h[15], h[0] / 1e3 / h[15], h[1] / 1e3 / h[15], h[2] / 1e3 / h[15], h[3] / 1e3 / h[15],
                     h[4] / 1e3 / h[15], h[5] / 1e3 / h[15], h[6] / 1e3 / h[15], h[7] / 1e3 / h[15]);
         cudaFree(lp->panel_dbg);
+    }
+    if (lp->wpanel_dbg) {
+        unsigned long long h[16];
+        cudaMemcpy(h, lp->wpanel_dbg, 128, cudaMemcpyDeviceToHost);
+        if (h[15])
+            fprintf(stderr, "[xp wpanel] steps %llu (window %d): A %.2f  exchA %.2f  B %.2f  exchB %.2f us/step\n",
+                    h[15], lp->d.w, h[0] / 1e3 / h[15], h[1] / 1e3 / h[15], h[2] / 1e3 / h[15], h[3] / 1e3 / h[15]);
+        cudaFree(lp->wpanel_dbg);
     }
     for (cudaEvent_t e : lp->evs) cudaEventDestroy(e);
     cudaFreeHost(lp->h_st);
@@ -2325,6 +2377,100 @@ extern "C" int xp_lp_f64_fill_synthetic(xp_lp_f64 *lp, uint64_t seed)
     return lp_reset(lp);
 }
 
+// Windowed panel: window width and the cluster's row / column split (see xp_large_wpanel.cuh).
+// A pure function of (m, C, G, requested width), so every rank of a sharded LP agrees.
+static int window_config(xp_lp_f64 *lp)
+{
+    xp_ctx *ctx = lp->ctx;
+    LpDev &d = lp->d;
+    d.w = d.wrpc = d.wwpc = 0;
+    int want = lp->window;
+    if (const char *e = getenv("XP_WINDOW"))
+        if (want == 0) want = atoi(e);
+    if (want < 0 || !lp->use_panel) return 0;
+    const int Cl0 = d.G > 1 ? shard_lo(d.C, d.G, 1) : d.C; // rank 0's slice holds the window
+    const int rpc = (d.m + WNC - 1) / WNC;
+    if (rpc > WTH * WRPT) return 0;
+    int w;
+    if (want > 0) {
+        w = want < Cl0 ? want : Cl0;
+    } else { // automatic: large LPs only (small ones are launch-bound either way)
+        if (d.m < 2048 || Cl0 < 2048) return 0;
+        w = Cl0 < 4096 ? (Cl0 & ~15) : 4096;
+    }
+    int wpc = (w + WNC - 1) / WNC;
+    while (wpc > 1 && (wpc > WTH || wpanel_smem_bytes(rpc, wpc) + 8192 > ctx->smem_optin)) wpc--;
+    if (wpc > WTH || wpanel_smem_bytes(rpc, wpc) + 8192 > ctx->smem_optin) return 0;
+    if (wpc * WNC < w) w = wpc * WNC;
+    if (!lp->wpanel_ready) {
+        XP_CUDA_OK(ctx, cudaFuncSetAttribute(k_wpanel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        XP_CUDA_OK(ctx, cudaFuncSetAttribute(k_wpanel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)ctx->smem_optin - 8192));
+        XP_CUDA_OK(ctx, cudaFuncSetAttribute(k_prow_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)(2 * KMAX * WB_TH * sizeof(double))));
+        lp->wpanel_ready = true;
+    }
+    if (d.rank == 0) { // can the device hold one such cluster at all?
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(WNC);
+        cfg.blockDim = dim3(WTHB);
+        cfg.dynamicSmemBytes = wpanel_smem_bytes(rpc, wpc);
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = WNC;
+        at[0].val.clusterDim.y = at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        int nc = 0;
+        cudaError_t e = cudaOccupancyMaxActiveClusters(&nc, k_wpanel, &cfg);
+        if (e != cudaSuccess || nc < 1) {
+            cudaGetLastError();
+            if (d.G > 1) { // the peers cannot know: a sharded LP needs the same answer everywhere
+                ctx->err = "windowed panel: a 16-CTA cluster does not fit this device (set XP_WINDOW=-1 on every rank)";
+                return XP_ERR_CUDA;
+            }
+            return 0;
+        }
+    }
+    d.w = w;
+    d.wrpc = rpc;
+    d.wwpc = wpc;
+    return 0;
+}
+
+static cudaError_t wpanel_launch(xp_lp_f64 *lp)
+{
+    const LpDev &d = lp->d;
+    cudaStream_t s = lp->ctx->stream;
+    lp->ctx->launches += 2;
+    cudaError_t e;
+    if (d.rank == 0) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(WNC);
+        cfg.blockDim = dim3(WTHB);
+        cfg.dynamicSmemBytes = wpanel_smem_bytes(d.wrpc, d.wwpc);
+        cfg.stream = s;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = WNC;
+        at[0].val.clusterDim.y = at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        e = cudaLaunchKernelEx(&cfg, k_wpanel, d, lp->wpanel_dbg);
+    } else {
+        k_wpanel_peer<<<1, 32, 0, s>>>(d);
+        e = cudaGetLastError();
+    }
+    if (e != cudaSuccess) return e;
+    // the columns the window left out (and, on peers, the replicated bookkeeping)
+    const int jl0 = d.w - d.col0 > 0 ? d.w - d.col0 : 0;
+    int grid = (d.Cl - jl0 + WB_TH - 1) / WB_TH;
+    if (grid < 1) grid = 1;
+    if (grid > 2 * lp->ctx->sm_count) grid = 2 * lp->ctx->sm_count;
+    k_prow_bulk<<<grid, WB_TH, 2 * KMAX * WB_TH * sizeof(double), s>>>(d);
+    return cudaGetLastError();
+}
+
 static cudaError_t panel_launch(xp_lp_f64 *lp)
 {
     LpDev d = lp->d;
@@ -2370,7 +2516,18 @@ extern "C" int xp_lp_f64_solve(xp_lp_f64 *lp, uint32_t max_iter, int rule)
     int n_prof = 0; // flushes bracketed by events in this call
     for (;;) {
         for (int b = 0; b < blocks; b++) {
-            if (lp->use_panel) {
+            if (lp->use_panel && d.w > 0) {
+                // windowed fast path (one cluster decides the whole block inside the window, the
+                // deferred columns follow in bulk); the pair in the middle takes whatever single
+                // pivot needs the slow path or lies outside the window; the full-width panel
+                // finishes a block the window cannot
+                XP_CUDA_OK(ctx, wpanel_launch(lp));
+                k_pcol<<<d.gridA, TH, 0, s>>>(d);
+                k_prow<<<d.gridB, TH, 0, s>>>(d);
+                XP_CUDA_OK(ctx, wpanel_launch(lp));
+                XP_CUDA_OK(ctx, panel_launch(lp));
+                ctx->launches += 3;
+            } else if (lp->use_panel) {
                 // fast path: all pivots of the block in one persistent kernel; the pair in
                 // the middle takes whatever single pivot needs the slow path
                 XP_CUDA_OK(ctx, panel_launch(lp));
@@ -2547,6 +2704,10 @@ extern "C" int xp_six_slack_f64(xp_ctx *ctx, double *tableau, double *tgtf, int 
         ctx->cached_lp = lp;
     }
     lp->kblk = ctx->slack_block;
+    if (lp->window != ctx->slack_window) {
+        rc = xp_lp_f64_set_window(lp, ctx->slack_window);
+        if (rc) return rc;
+    }
     rc = xp_lp_f64_upload(lp, tableau, tgtf, nvset, bvset, bv2eq, eq2bv, vc_diag, vc_rhs);
     if (rc) return rc;
     int st = xp_lp_f64_solve(lp, max_iter, rule);
@@ -2563,6 +2724,15 @@ extern "C" int xp_ctx_set_block(xp_ctx *ctx, int pivots_per_flush)
 {
     if (!ctx || pivots_per_flush < 0 || pivots_per_flush > KMAX) return XP_ERR_BAD_ARG;
     ctx->slack_block = pivots_per_flush;
+    return 0;
+}
+
+// Pricing window used by xp_six_slack_f64 / xp_six_two_stage_f64_large on this ctx
+// (see xp_lp_f64_set_window).
+extern "C" int xp_ctx_set_window(xp_ctx *ctx, int width)
+{
+    if (!ctx) return XP_ERR_BAD_ARG;
+    ctx->slack_window = width;
     return 0;
 }
 
@@ -2813,6 +2983,10 @@ extern "C" int xp_six_two_stage_f64_large(xp_ctx *ctx, int m, int n, const doubl
     rc = xp_lp_f64_create(ctx, m, Cm, &M.lp);
     if (rc) return rc;
     M.lp->kblk = ctx->slack_block;
+    if (ctx->slack_window != 0) {
+        rc = xp_lp_f64_set_window(M.lp, ctx->slack_window);
+        if (rc) return rc;
+    }
     if (!aux) {
         k_slack_form<<<ctx->sm_count * 4, 256, 0, s>>>(M.lp->d, d_leq, d_tg, n);
         ctx->launches++;
@@ -2823,6 +2997,10 @@ extern "C" int xp_six_two_stage_f64_large(xp_ctx *ctx, int m, int n, const doubl
         rc = xp_lp_f64_create(ctx, m, Ca, &A.lp);
         if (rc) return rc;
         A.lp->kblk = ctx->slack_block;
+        if (ctx->slack_window != 0) {
+            rc = xp_lp_f64_set_window(A.lp, ctx->slack_window);
+            if (rc) return rc;
+        }
         k_aux_form<<<ctx->sm_count * 4, 256, 0, s>>>(A.lp->d, d_leq, n);
         ctx->launches++;
         A.lp->d.vc_diag = A.lp->d.vc_rhs = nullptr;
