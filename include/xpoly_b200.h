@@ -74,6 +74,11 @@ uint64_t xp_ctx_launch_count(const xp_ctx *ctx);
  * events on the ctx stream (excludes H2D/D2H). */
 float xp_ctx_last_kernel_ms(const xp_ctx *ctx);
 void *xp_ctx_stream(const xp_ctx *ctx); /* cudaStream_t */
+/* Measured non-fused FP64 throughput of this device in 1e12 operations/s (one DMUL or one
+ * DADD of one lane = one operation; ~50 ms).  The update kernels may not fuse the multiply
+ * and the add (lpsol.h:1487-1488 rounds twice), so this -- not the DFMA peak -- is the
+ * roofline bench.py reports against. */
+int xp_probe_fp64_nonfused(xp_ctx *ctx, double *tops, double *ms);
 /* Page-locked host memory (cudaMallocHost) so uploads/downloads of a large
  * tableau run at full PCIe rate; plain malloc'ed buffers work too, slower. */
 int xp_host_alloc(xp_ctx *ctx, size_t bytes, void **out);

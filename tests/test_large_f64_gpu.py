@@ -322,3 +322,40 @@ def test_two_stage_large_phase1_succeeds(ctx, m, n, nneg):
             g = _check_two_stage(ctx, leq, tg, K, ("lb", m, n, s, K))
             seen.add(g["status"])
     assert H.SIX_NO_PRI not in seen and len(seen) >= 1
+
+
+@pytest.mark.parametrize("env", [{"XP_FLUSH_NBUF": "2"}, {"XP_FLUSH_WIDE": "1"}, {"XP_FLUSH_WIDE": "1", "XP_FLUSH_NBUF": "2"}])
+def test_flush_variants_bitwise(ctx, env, monkeypatch):
+    """The alternative schedules of the tableau-update kernel -- two multiplier buffers with a block
+    barrier per unit (the fallback where three buffers would cost the second CTA per SM) and the
+    8 x 4 register tile (k_flush_w) -- against the oracle: whole tableau as uint64, k in {12, 16, 32}.
+    The choice is cached per handle, so every case gets a fresh one."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    for (m, n), seed in (((70, 130), 1), ((129, 64), 2), ((300, 215), 3)):
+        leq, tg = H.gen_dense_lp(8300 + seed, m, n)
+        sf = xp.slack_form(leq, tg)
+        for k in (12, 16, 32):
+            for K in (k, 3 * k + 5):
+                lp = ctx.large_lp(*sf[0].shape)
+                lp.set_block(k)
+                lp.upload(*sf)
+                st = lp.solve(K)
+                g = lp.download(log_cap=1 << 16)
+                g["status"] = st
+                lp.close()
+                assert_same_state(g, H.slack_solve_oracle("f64", *sf, max_iter=K), (env, m, n, k, K))
+    # full-size cross-check of the variant against the default kernel (checksum of all 134 M doubles)
+    m, n = 8192, 8191
+    lp = ctx.large_lp(m, n + m + 1)
+    lp.fill_synthetic(99)
+    lp.solve(64)
+    var = lp.checksum()
+    lp.close()
+    for k in env:
+        monkeypatch.delenv(k)
+    lp = ctx.large_lp(m, n + m + 1)
+    lp.fill_synthetic(99)
+    lp.solve(64)
+    assert lp.checksum() == var
+    lp.close()

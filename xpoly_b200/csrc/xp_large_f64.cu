@@ -1620,6 +1620,212 @@ __global__ void __launch_bounds__(LANES *HALVES) k_flush_t(LpDev d, int groups, 
     }
 }
 
+// ---------------------------------------------------------------------------
+// k_flush_w: k_flush_t with a wider register tile -- 8 rows x 4 columns per thread (two
+// column pairs 2*LANES apart, so every 128-bit shared load of P stays conflict free) instead
+// of 8 x 2.  Per step a thread then issues 6 shared loads (2 of P, 4 broadcast loads of F) for
+// 64 non-fused FP64 operations instead of 5 for 32: the load/store unit, which k_flush_t keeps
+// 66 % busy beside a 72 % busy FP64 pipe, gets 20 % fewer wavefronts per operation and the
+// loop overhead is spread over twice the arithmetic.  The 64 accumulators leave no registers
+// for the next tile at two CTAs per SM, so the next tile is prefetched into L2 instead.
+// Same work units, multiplier staging and closing protocol as k_flush_t; same arithmetic per
+// entry in the same order.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void prefetch_l2(const void *p)
+{
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
+template <int TR, int LANES, int GROUPS>
+__global__ void __launch_bounds__(LANES *GROUPS, 2) k_flush_w(LpDev d, int groups, int nbuf)
+{
+    extern __shared__ double sm[]; // sP[t][4*LANES] | sF[nbuf][t][FT_ROWS] | s_lp[nbuf][FT_ROWS]
+    __shared__ int s_flag;
+    __shared__ unsigned long long s_mbar[3];
+    constexpr int THREADS = LANES * GROUPS, TC = 4 * LANES;
+    constexpr int TPB = FT_ROWS / (GROUPS * TR); // tiles per unit and row group
+    LpState *st = d.st;
+    const int t = st->t;
+    if (t == 0) return;
+    if (t < st->kblk && st->status == XPI_RUNNING) return; // block still open
+    const int par = st->blk & 1, Cl = d.Cl, m = d.m, tid = threadIdx.x;
+    const int lane = tid % LANES, grp = tid / LANES;
+    double *sP = sm, *sF = sm + (size_t)t * TC;
+    int *s_lp = (int *)(sF + (size_t)nbuf * t * FT_ROWS);
+    const double *sPl0 = sP + 2 * lane, *sPl1 = sP + 2 * LANES + 2 * lane;
+    const int nrb = (m + FT_ROWS - 1) / FT_ROWS;
+    const int ctiles = (Cl + TC - 1) / TC;
+    const long long units = (long long)ctiles * nrb;
+    int u0, u1;
+    if (groups > 0) {
+        const int ct = blockIdx.x % ctiles, g = blockIdx.x / ctiles;
+        const int bpg = (nrb + groups - 1) / groups;
+        u0 = ct * nrb + min(nrb, g * bpg);
+        u1 = ct * nrb + min(nrb, (g + 1) * bpg);
+    } else {
+        u0 = (int)(units * blockIdx.x / gridDim.x);
+        u1 = (int)(units * (blockIdx.x + 1) / gridDim.x);
+    }
+    auto load_P = [&](int ct) {
+        for (int e = tid; e < t * (TC / 2); e += THREADS) {
+            const int s = e / (TC / 2), l = e - s * (TC / 2);
+            const int j = ct * TC + 2 * l;
+            double2 v = make_double2(0.0, 0.0);
+            if (j < Cl) v = *reinterpret_cast<const double2 *>(d.P + (size_t)s * Cl + j);
+            *reinterpret_cast<double2 *>(sP + (size_t)s * TC + 2 * l) = v;
+        }
+    };
+    auto copy_F = [&](int rb, int b) {
+        double *dst = sF + (size_t)b * t * FT_ROWS;
+        for (int e = tid; e < t * (FT_ROWS / 2); e += THREADS) {
+            const int s = e / (FT_ROWS / 2), r = 2 * (e - s * (FT_ROWS / 2));
+            const double *row = Fptr(d, d.rank, par, s);
+            const int left = m - (rb + r);
+            cp_async_cg16(dst + (size_t)s * FT_ROWS + r, row + (left > 0 ? rb + r : 0), left >= 2 ? 16 : (left == 1 ? 8 : 0));
+        }
+        if (tid < FT_ROWS) cp_async_ca4(s_lp + b * FT_ROWS + tid, d.last_piv + min(rb + tid, m - 1));
+        cp_async_arrive(&s_mbar[b]);
+    };
+    auto prefetch_tile = [&](int ct, int rb, int k) { // this thread's lines of a tile to come
+        const int r = rb + (k * GROUPS + grp) * TR;
+        const int j = ct * TC + 2 * lane;
+        if ((lane & 7) == 0) { // one request per 128-byte line
+#pragma unroll
+            for (int w = 0; w < TR; w++) {
+                if (r + w >= m) break;
+                if (j < Cl) prefetch_l2(d.tab + (size_t)(r + w) * Cl + j);
+                if (j + 2 * LANES < Cl) prefetch_l2(d.tab + (size_t)(r + w) * Cl + j + 2 * LANES);
+            }
+        }
+    };
+    if (tid == 0) {
+        mbar_init(&s_mbar[0], THREADS);
+        mbar_init(&s_mbar[1], THREADS);
+        mbar_init(&s_mbar[2], THREADS);
+    }
+    __syncthreads();
+    const bool mb = t >= 12 && nbuf == 3;
+    int ct = u0 < u1 ? u0 / nrb : 0, rb = u0 < u1 ? (u0 % nrb) * FT_ROWS : 0;
+    if (u0 < u1) {
+        load_P(ct);
+        copy_F(rb, 0);
+        prefetch_tile(ct, rb, 0);
+    }
+    if (!mb) cp_async_wait_all();
+    __syncthreads();
+    for (int u = u0; u < u1; u++) {
+        int ct1 = ct, rb1 = rb + FT_ROWS;
+        if (rb1 >= nrb * FT_ROWS) {
+            ct1 = ct + 1;
+            rb1 = 0;
+        }
+        const int j0 = ct * TC + 2 * lane, j1 = j0 + 2 * LANES;
+        const bool act0 = j0 < Cl, act1 = j1 < Cl; // Cl is even on this path
+        const int lu = u - u0, buf = lu % nbuf;
+        const double *sFu = sF + (size_t)buf * t * FT_ROWS;
+        const int *lpu = s_lp + buf * FT_ROWS;
+        const bool more = u + 1 < u1;
+        if (mb) mbar_wait(&s_mbar[buf], (unsigned)(lu / 3) & 1u);
+        if (more) copy_F(rb1, (lu + 1) % nbuf);
+#pragma unroll 1
+        for (int k = 0; k < TPB; k++) {
+            const int rc = (k * GROUPS + grp) * TR, row = rb + rc;
+            double2 a[TR], b[TR];
+#pragma unroll
+            for (int w = 0; w < TR; w++) {
+                a[w] = (act0 && row + w < m) ? *reinterpret_cast<const double2 *>(d.tab + (size_t)(row + w) * Cl + j0)
+                                             : make_double2(0.0, 0.0);
+                b[w] = (act1 && row + w < m) ? *reinterpret_cast<const double2 *>(d.tab + (size_t)(row + w) * Cl + j1)
+                                             : make_double2(0.0, 0.0);
+            }
+            if (k + 1 < TPB) prefetch_tile(ct, rb, k + 1);
+            else if (more) prefetch_tile(ct1, rb1, 0);
+            if (!act0 || row >= m) continue;
+            bool special = false;
+            if (TR == 8) {
+                const int4 l0 = *reinterpret_cast<const int4 *>(lpu + rc), l1 = *reinterpret_cast<const int4 *>(lpu + rc + 4);
+                special = (l0.x & l0.y & l0.z & l0.w & l1.x & l1.y & l1.z & l1.w) >= 0;
+            } else {
+#pragma unroll
+                for (int w = 0; w < TR; w++) special |= (row + w < m) && lpu[rc + w] >= 0;
+            }
+            if (!special) {
+#pragma unroll 4
+                for (int s = 0; s < t; s++) {
+                    const double2 p2 = *reinterpret_cast<const double2 *>(sPl0 + (size_t)s * TC);
+                    const double2 q2 = *reinterpret_cast<const double2 *>(sPl1 + (size_t)s * TC);
+                    const double *f = sFu + (size_t)s * FT_ROWS + rc;
+#pragma unroll
+                    for (int w = 0; w < TR; w += 2) {
+                        const double2 f2 = *reinterpret_cast<const double2 *>(f + w);
+                        a[w].x = xp_add(a[w].x, xp_mul(f2.x, p2.x));
+                        a[w].y = xp_add(a[w].y, xp_mul(f2.x, p2.y));
+                        b[w].x = xp_add(b[w].x, xp_mul(f2.x, q2.x));
+                        b[w].y = xp_add(b[w].y, xp_mul(f2.x, q2.y));
+                        a[w + 1].x = xp_add(a[w + 1].x, xp_mul(f2.y, p2.x));
+                        a[w + 1].y = xp_add(a[w + 1].y, xp_mul(f2.y, p2.y));
+                        b[w + 1].x = xp_add(b[w + 1].x, xp_mul(f2.y, q2.x));
+                        b[w + 1].y = xp_add(b[w + 1].y, xp_mul(f2.y, q2.y));
+                    }
+                }
+            } else { // a row of this tile was a pivot row at step s0: restart it from P[s0]
+#pragma unroll
+                for (int w = 0; w < TR; w++) {
+                    if (row + w >= m) continue;
+                    const int s0 = lpu[rc + w];
+                    double2 v = a[w], x = b[w];
+                    if (s0 >= 0) {
+                        v = *reinterpret_cast<const double2 *>(sPl0 + (size_t)s0 * TC);
+                        x = *reinterpret_cast<const double2 *>(sPl1 + (size_t)s0 * TC);
+                    }
+                    for (int s = s0 + 1; s < t; s++) {
+                        const double2 p2 = *reinterpret_cast<const double2 *>(sPl0 + (size_t)s * TC);
+                        const double2 q2 = *reinterpret_cast<const double2 *>(sPl1 + (size_t)s * TC);
+                        const double fs = sFu[(size_t)s * FT_ROWS + rc + w];
+                        v.x = xp_add(v.x, xp_mul(fs, p2.x));
+                        v.y = xp_add(v.y, xp_mul(fs, p2.y));
+                        x.x = xp_add(x.x, xp_mul(fs, q2.x));
+                        x.y = xp_add(x.y, xp_mul(fs, q2.y));
+                    }
+                    a[w] = v;
+                    b[w] = x;
+                }
+            }
+#pragma unroll
+            for (int w = 0; w < TR; w++)
+                if (row + w < m) {
+                    *reinterpret_cast<double2 *>(d.tab + (size_t)(row + w) * Cl + j0) = a[w];
+                    if (act1) *reinterpret_cast<double2 *>(d.tab + (size_t)(row + w) * Cl + j1) = b[w];
+                }
+        }
+        if (more && ct1 != ct) {
+            __syncthreads();
+            load_P(ct1);
+            __syncthreads();
+        }
+        if (!mb) {
+            cp_async_wait_all();
+            __syncthreads();
+        }
+        ct = ct1;
+        rb = rb1;
+    }
+    if (tid == 0) {
+        __threadfence();
+        s_flag = atomicAdd(&d.ctr[2], 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!s_flag) return;
+    if (tid == 0) {
+        d.ctr[2] = 0;
+        for (int k = 0; k < st->n_touched; k++) d.last_piv[st->touched[k]] = -1;
+        st->n_touched = 0;
+        st->t = 0;
+        st->blk += 1;
+        next_block(st);
+    }
+}
+
 // ---- optimal exit: sol + is_feasible (lpsol.h:1089-1127, :783-822) ----
 __global__ void k_feas_sol(LpDev d)
 {
@@ -1773,12 +1979,15 @@ __global__ void k_init(LpDev d, unsigned max_iter, int kblk, int fresh)
 
 // SIX::slack (lpsol.h:1405-1433) + identity basis (:1821-1841): [A | I | b],
 // local slice [col0, col0+Cl) plus the replicated constant column.
+// Rows [r0, r1) of the tableau; the launch that holds row 0 also writes the objective row and
+// the basis maps (a row-chunked upload builds the slack form chunk by chunk as the rows arrive).
 template <class Gen>
-__device__ __forceinline__ void fill_slack_form(const LpDev &d, int nvars, Gen gen)
+__device__ __forceinline__ void fill_slack_form(const LpDev &d, int nvars, Gen gen, int r0 = 0, int r1 = 0x7fffffff)
 {
     const int m = d.m, n = nvars, C = d.C;
-    const size_t total = (size_t)m * d.Cl;
-    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+    if (r1 > m) r1 = m;
+    const size_t total = (size_t)r1 * d.Cl;
+    for (size_t e = (size_t)r0 * d.Cl + (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
          e += (size_t)gridDim.x * blockDim.x) {
         const int i = (int)(e / d.Cl), j = d.col0 + (int)(e % d.Cl);
         double v;
@@ -1787,16 +1996,17 @@ __device__ __forceinline__ void fill_slack_form(const LpDev &d, int nvars, Gen g
         else v = gen(i, n);
         d.tab[e] = v;
     }
+    for (int j = r0 + blockIdx.x * blockDim.x + threadIdx.x; j < r1; j += gridDim.x * blockDim.x) {
+        d.eq2bv[j] = n + j;
+        d.rhsbuf[j] = gen(j, n);
+    }
+    if (r0 > 0) return;
     for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < C; j += gridDim.x * blockDim.x) {
         if (j >= d.col0 && j < d.col0 + d.Cl)
             d.tgtf[j - d.col0] = j < n ? gen(m, j) : (j < n + m ? 0.0 : gen(m, n));
         if (j < n + m) {
             d.nvset[j] = j < n;
             d.bv2eq[j] = j < n ? -1 : j - n;
-        }
-        if (j < m) {
-            d.eq2bv[j] = n + j;
-            d.rhsbuf[j] = gen(j, n);
         }
         if (j == 0) d.st->tg_rhs = gen(m, n);
     }
@@ -1811,14 +2021,14 @@ struct GenLeq { // entries of the caller's leq (rows 0..m-1) and objective (row 
     }
 };
 
-__global__ void k_slack_form(LpDev d, const double *leq, const double *tg, int n)
+__global__ void k_slack_form(LpDev d, const double *leq, const double *tg, int n, int r0, int r1)
 {
     GenLeq g;
     g.leq = leq;
     g.tg = tg;
     g.m = d.m;
     g.n = n;
-    fill_slack_form(d, n, g);
+    fill_slack_form(d, n, g, r0, r1);
 }
 
 __device__ __forceinline__ uint64_t mix64(uint64_t z)
@@ -1894,6 +2104,7 @@ struct xp_lp_f64 {
     int panel_nb = 0, panel_rpc = 0, panel_cpc = 0;
     bool use_panel = true;
     int ft_min = 2, ft_balanced_min = 10, ft_smem_set = 0, ft_occ = 1, ft_occ_k = -1, ft_nbuf = 3; // k_flush_t: smallest k that uses it, launch cache
+    int ft_wide = 1, fw_smem_set = 0, fw_occ = 1, fw_occ_k = -1, fw_nbuf = 3; // k_flush_w (8 x 4 register tile) for the FP64-bound passes
     unsigned long long *panel_dbg = nullptr; // XP_PANEL_DBG=1: per-phase ns accumulators (16 words)
     unsigned long long *wpanel_dbg = nullptr; // the same for the windowed panel
     int window = 0;  // requested window: 0 automatic, < 0 off, > 0 forced width (xp_lp_f64_set_window)
@@ -1944,10 +2155,44 @@ static size_t flush_t_smem(int kblk, int nbuf = 3)
     return ((size_t)kblk * 2 * FT_LANES + (size_t)nbuf * kblk * FT_ROWS) * sizeof(double) + nbuf * FT_ROWS * sizeof(int);
 }
 
+constexpr int FW_LANES = 64, FW_GROUPS = 4; // k_flush_w: same 256-column tile, 8 x 4 entries per thread
+
+static int flush_w_launch(xp_lp_f64 *lp, int kblk)
+{
+    xp_ctx *ctx = lp->ctx;
+    const LpDev &d = lp->d;
+    auto kern = k_flush_w<FT_TR, FW_LANES, FW_GROUPS>;
+    if (lp->fw_smem_set == 0) {
+        XP_CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)flush_t_smem(KMAX)));
+        lp->fw_smem_set = 1;
+    }
+    if (lp->fw_occ_k != kblk) {
+        int occ = 1;
+        XP_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, FT_THREADS, flush_t_smem(kblk)));
+        lp->fw_nbuf = 3;
+        if (occ < 2) {
+            int occ2 = 1;
+            XP_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, kern, FT_THREADS, flush_t_smem(kblk, 2)));
+            if (occ2 > occ) occ = occ2, lp->fw_nbuf = 2;
+        }
+        lp->fw_occ = occ < 1 ? 1 : occ;
+        lp->fw_occ_k = kblk;
+    }
+    const size_t smem = flush_t_smem(kblk, lp->fw_nbuf);
+    const int ctiles = (d.Cl + 4 * FW_LANES - 1) / (4 * FW_LANES);
+    const long long units = (long long)ctiles * ((d.m + FT_ROWS - 1) / FT_ROWS);
+    long long grid = (long long)lp->fw_occ * ctx->sm_count;
+    if (grid > units) grid = units;
+    kern<<<(unsigned)grid, FT_THREADS, smem, ctx->stream>>>(d, 0, lp->fw_nbuf);
+    ctx->launches++;
+    return 0;
+}
+
 static int flush_t_launch(xp_lp_f64 *lp, int kblk)
 {
     xp_ctx *ctx = lp->ctx;
     const LpDev &d = lp->d;
+    if (lp->ft_wide && kblk >= lp->ft_balanced_min) return flush_w_launch(lp, kblk); // FP64-bound passes
     size_t smem = flush_t_smem(kblk);
     if (lp->ft_smem_set < (int)smem) {
         XP_CUDA_OK(ctx, cudaFuncSetAttribute(k_flush_t<FT_TR, FT_LANES, FT_HALVES>,
@@ -2094,6 +2339,8 @@ static int lp_create_fill(xp_ctx *ctx, int m, int C, int rank, int G, xp_lp_f64 
         if (fm) lp->ft_min = atoi(fm);
         const char *fb = getenv("XP_FLUSH_BALANCED_MIN");
         if (fb) lp->ft_balanced_min = atoi(fb);
+        const char *fw = getenv("XP_FLUSH_WIDE");
+        if (fw) lp->ft_wide = atoi(fw);
         const char *u = getenv("XP_NO_PANEL");
         lp->use_panel = !(u && atoi(u));
         // the panel kernel keeps the open block's factors of its rows / columns in shared
@@ -2139,6 +2386,7 @@ static int lp_create_fill(xp_ctx *ctx, int m, int C, int rank, int G, xp_lp_f64 
     XP_CUDA_OK(ctx, cudaFuncGetAttributes(&fa, k_wpanel_peer));
     XP_CUDA_OK(ctx, cudaFuncGetAttributes(&fa, k_prow_bulk));
     XP_CUDA_OK(ctx, cudaFuncGetAttributes(&fa, k_flush_t<FT_TR, FT_LANES, FT_HALVES>));
+    XP_CUDA_OK(ctx, cudaFuncGetAttributes(&fa, k_flush_w<FT_TR, 64, 4>));
     XP_CUDA_OK(ctx, cudaFuncGetAttributes(&fa, k_init));
     XP_CUDA_OK(ctx, cudaFuncGetAttributes(&fa, k_feas_sol));
     XP_CUDA_OK(ctx, cudaFuncGetAttributes(&fa, k_feas_rows));
@@ -2355,7 +2603,7 @@ extern "C" int xp_lp_f64_upload_leq(xp_lp_f64 *lp, const double *leq, const doub
     XP_CUDA_OK(ctx, cudaMemcpyAsync(d_leq, leq, (size_t)m * (n + 1) * sizeof(double),
                                     cudaMemcpyHostToDevice, s));
     XP_CUDA_OK(ctx, cudaMemcpyAsync(d_tg, tgtf, (n + 1) * sizeof(double), cudaMemcpyHostToDevice, s));
-    k_slack_form<<<ctx->sm_count * 4, 256, 0, s>>>(d, d_leq, d_tg, n);
+    k_slack_form<<<ctx->sm_count * 4, 256, 0, s>>>(d, d_leq, d_tg, n, 0, d.m);
     ctx->launches++;
     d.vc_diag = d.vc_rhs = nullptr;
     XP_CUDA_OK(ctx, cudaGetLastError());
@@ -2740,6 +2988,25 @@ void xp_large_release_cached(xp_ctx *ctx)
 {
     if (ctx->cached_lp) xp_lp_f64_destroy((xp_lp_f64 *)ctx->cached_lp);
     ctx->cached_lp = nullptr;
+    if (ctx->cached_aux) xp_lp_f64_destroy((xp_lp_f64 *)ctx->cached_aux);
+    ctx->cached_aux = nullptr;
+}
+
+// Device buffers of the host-pointer entry points are kept on the ctx between calls of the
+// same shape (a 1 GiB cudaMalloc / cudaFree per call would cost more than the upload).
+static int cached_handle(xp_ctx *ctx, void **slot, int m, int C, xp_lp_f64 **out)
+{
+    xp_lp_f64 *lp = (xp_lp_f64 *)*slot;
+    if (!lp || lp->d.m != m || lp->d.C != C || lp->d.G != 1) {
+        if (lp) xp_lp_f64_destroy(lp);
+        *slot = nullptr;
+        lp = nullptr;
+        int rc = xp_lp_f64_create(ctx, m, C, &lp);
+        if (rc) return rc;
+        *slot = lp;
+    }
+    *out = lp;
+    return 0;
 }
 
 // ---------------------------------------------------------------------------
@@ -2936,12 +3203,8 @@ int xpiv_at(xp_lp_f64 *lp, int p, int q)
     return 0;
 }
 
-struct LpGuard { // destroys the handle on every exit path
+struct LpRef { // handles live on the ctx (cached_handle): nothing to release on the exit paths
     xp_lp_f64 *lp = nullptr;
-    ~LpGuard()
-    {
-        if (lp) xp_lp_f64_destroy(lp);
-    }
 };
 
 } // namespace
@@ -2976,28 +3239,51 @@ extern "C" int xp_six_two_stage_f64_large(xp_ctx *ctx, int m, int n, const doubl
     int rc = xp_ctx_scratch(ctx, in_elems * sizeof(double), &scr);
     if (rc) return rc;
     double *d_leq = (double *)scr, *d_tg = d_leq + (size_t)m * (n + 1);
-    XP_CUDA_OK(ctx, cudaMemcpyAsync(d_leq, leq, (size_t)m * (n + 1) * sizeof(double), cudaMemcpyHostToDevice, s));
     XP_CUDA_OK(ctx, cudaMemcpyAsync(d_tg, tgtf, (n + 1) * sizeof(double), cudaMemcpyHostToDevice, s));
+    // No phase 1: the rows go up in chunks on the copy stream and k_slack_form builds [A | I | b]
+    // chunk by chunk behind them, so the slack form is complete one chunk's kernel after the last
+    // byte has arrived.  Phase 1 (rare) needs the whole LP first: one copy.
+    const size_t row_bytes = (size_t)(n + 1) * sizeof(double);
+    int n_chunks = 1;
+    if (!aux && (size_t)m * row_bytes >= ((size_t)64 << 20)) n_chunks = XP_PIPE_MAX < m ? XP_PIPE_MAX : m;
+    if (n_chunks > 1) {
+        rc = xp_ctx_pipe(ctx);
+        if (rc) return rc;
+        XP_CUDA_OK(ctx, cudaEventRecord(ctx->pipe_begin, s)); // d_tg and the previous call's kernels
+        XP_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->pipe_copy, ctx->pipe_begin, 0));
+        for (int c = 0; c < n_chunks; c++) {
+            const int r0 = (int)((long long)m * c / n_chunks), r1 = (int)((long long)m * (c + 1) / n_chunks);
+            XP_CUDA_OK(ctx, cudaMemcpyAsync(d_leq + (size_t)r0 * (n + 1), leq + (size_t)r0 * (n + 1),
+                                            (size_t)(r1 - r0) * row_bytes, cudaMemcpyHostToDevice, ctx->pipe_copy));
+            XP_CUDA_OK(ctx, cudaEventRecord(ctx->pipe_up[c], ctx->pipe_copy));
+        }
+    } else {
+        XP_CUDA_OK(ctx, cudaMemcpyAsync(d_leq, leq, (size_t)m * row_bytes, cudaMemcpyHostToDevice, s));
+    }
     unsigned n_piv = 0;
-    LpGuard A, M;
-    rc = xp_lp_f64_create(ctx, m, Cm, &M.lp);
+    LpRef A, M;
+    rc = cached_handle(ctx, &ctx->cached_lp, m, Cm, &M.lp);
     if (rc) return rc;
     M.lp->kblk = ctx->slack_block;
-    if (ctx->slack_window != 0) {
+    if (M.lp->window != ctx->slack_window) {
         rc = xp_lp_f64_set_window(M.lp, ctx->slack_window);
         if (rc) return rc;
     }
     if (!aux) {
-        k_slack_form<<<ctx->sm_count * 4, 256, 0, s>>>(M.lp->d, d_leq, d_tg, n);
-        ctx->launches++;
+        for (int c = 0; c < n_chunks; c++) {
+            const int r0 = (int)((long long)m * c / n_chunks), r1 = (int)((long long)m * (c + 1) / n_chunks);
+            if (n_chunks > 1) XP_CUDA_OK(ctx, cudaStreamWaitEvent(s, ctx->pipe_up[c], 0));
+            k_slack_form<<<ctx->sm_count * 4, 256, 0, s>>>(M.lp->d, d_leq, d_tg, n, r0, r1);
+            ctx->launches++;
+        }
         M.lp->d.vc_diag = M.lp->d.vc_rhs = nullptr;
         XP_CUDA_OK(ctx, cudaGetLastError());
     } else {
         const int xa = n, Ca = Cm + 1;
-        rc = xp_lp_f64_create(ctx, m, Ca, &A.lp);
+        rc = cached_handle(ctx, &ctx->cached_aux, m, Ca, &A.lp);
         if (rc) return rc;
         A.lp->kblk = ctx->slack_block;
-        if (ctx->slack_window != 0) {
+        if (A.lp->window != ctx->slack_window) {
             rc = xp_lp_f64_set_window(A.lp, ctx->slack_window);
             if (rc) return rc;
         }

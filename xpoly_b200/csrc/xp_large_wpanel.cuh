@@ -524,6 +524,7 @@ __global__ void __launch_bounds__(WB_TH) k_prow_bulk(LpDev d)
                 const WRec rc = s_rec[s];
                 double v = sA[s * WB_TH + tid];
                 if (rc.s0p >= 0) v = sPr[rc.s0p * WB_TH + tid];
+#pragma unroll 8
                 for (int u = rc.s0p + 1; u < s; u++) v = xp_add(v, xp_mul(s_L[s][u], sPr[u * WB_TH + tid]));
                 const double xv = xp_scale(v, rc.r, xp_feq(rc.r, 1.0), xp_feq(rc.r, 0.0));
                 sPr[s * WB_TH + tid] = xv;
