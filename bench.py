@@ -8,8 +8,11 @@
 A "step" is one pass of the hot path over one batch of work: P simplex
 iterations (pricing -> ratio test -> rank-1 pivot) of the HBM-resident tableau.
 `value` is device-resident (inputs in HBM when the timed region starts); `e2e`
-goes through the C-ABI call a maintainer binds (xp_six_slack_f64) with pinned
-HOST buffers, host<->device copies inside the timed region.  Inputs (1 GiB) are
+goes through the C-ABI call that stands where the reference arm's TwoStageMethod(leq, tgtf)
+stands (xp_six_two_stage_f64_large) with pinned HOST buffers, host<->device copies inside the
+timed region (`e2e_slack`: the kernel-level xp_six_slack_f64, whole tableau up and down).
+Two JSON lines are printed: the secondary legs first (c2 / c4 / c5 / has_solution), the
+main line LAST.  Inputs (1 GiB) are
 larger than L2 (126 MB), so no flush is needed between iterations.
 """
 import argparse
@@ -339,11 +342,48 @@ def run_batched(ctx, xp, torch, dev, with_cpu=True, rank=0, world=1, dist=None):
     }
 
 
-def run_exact_and_bnb(ctx, xp):
-    """Config 4 (10k exact 24x48 LPs, fraction-free int64) and config 5 (knapsack-style B&B,
-    node relaxations batched on the GPU; the reference only solves this family up to ~50
-    variables) through the host-pointer C ABI."""
+def _threads(fn, N, T):
+    """fn(lo, hi) on T host threads over [0, N) (the oracle's C loops release the GIL); wall seconds."""
+    t0 = time.perf_counter()
+    th = [threading.Thread(target=fn, args=(N * i // T, N * (i + 1) // T)) for i in range(T)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    return time.perf_counter() - t0
+
+
+def run_exact_and_bnb(ctx, xp, torch, dev, rank=0, world=1, dist=None, with_cpu=True):
+    """Config 4 (10k exact 24x48 LPs, fraction-free int64), config 5 (knapsack-style B&B, node
+    relaxations batched on the GPU; the reference only solves this family up to ~50 variables,
+    SURVEY 8d) and Lineq::has_solution batches, through the host-pointer C ABI.  With N ranks the
+    independent LPs / trees / systems are split N ways (no collective); times are the max
+    over ranks.  CPU baselines (oracle port, 1 core and all cores) and an in-run comparison of a
+    sample with the oracle ride along at N = 1."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import harness as H
     out = {}
+    T = max(1, min(64, len(os.sched_getaffinity(0))))
+
+    def mx(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sm(x):
+        if world == 1:
+            return x
+        t = torch.tensor([float(x)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t)
+        return float(t.item())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def part(n):
+        return n * rank // world, n * (rank + 1) // world
     r = np.random.RandomState(777)
     B, m, n = 10_000, 24, 23
     A = r.randint(0, 4, size=(B, m, n)) * (r.uniform(size=(B, m, n)) < 0.3)
@@ -352,42 +392,95 @@ def run_exact_and_bnb(ctx, xp):
     leq[:, :, n] = r.randint(0, 21, size=(B, m))
     tg = np.zeros((B, n + 1), dtype=np.int64)
     tg[:, :n] = r.randint(1, 6, size=(B, n))
+    lo, hi = part(B)
     ctx.two_stage_i64_batch(leq[:64], tg[:64])
-    ts = []
+    ts, dms = [], []
     for _ in range(3):
+        barrier()
         t0 = time.perf_counter()
-        res = ctx.two_stage_i64_batch(leq, tg)
-        ts.append(time.perf_counter() - t0)
+        res = ctx.two_stage_i64_batch(leq[lo:hi], tg[lo:hi])
+        ts.append(mx(time.perf_counter() - t0))
+        dms.append(mx(ctx.last_kernel_ms))
     st = res["status"]
-    out["exact"] = {"metric": "exact LPs/s", "workload": f"c4: {B} LPs, tableau {m}x{n + m + 1}, "
-                    "fraction-free int64 entries / 128-bit products, e2e through host pointers",
-                    "value": B / float(np.median(ts)), "unit": "LPs/s",
-                    "device_ms": ctx.last_kernel_ms, "device_LPs_per_s": B / (ctx.last_kernel_ms * 1e-3),
-                    "pivots_total": int(res["pivots"].astype(np.int64).sum()),
-                    "status_mix": {str(k): int((st == k).sum()) for k in np.unique(st)}}
+    piv = int(sm(res["pivots"].astype(np.int64).sum()))
+    dev_ms = float(np.median(dms))
+    smem_peak = world * ctx_sm_count(torch, dev) * 128 * sm_clock_hz(torch, dev)  # 128 B/clk/SM
+    smem_bytes = piv * 2.0 * (m + 1) * (n + m + 1) * 8
+    out["exact"] = {"metric": "exact LPs/s", "workload": f"c4: {B} LPs, tableau {m}x{n + m + 1}, fraction-free "
+                    "int64 entries / 128-bit products, e2e through host pointers"
+                    + (f", split over {world} GPUs" if world > 1 else ""),
+                    "value": B / float(np.median(ts)), "unit": "LPs/s", "device_ms": dev_ms,
+                    "device_LPs_per_s": B / (dev_ms * 1e-3), "pivots_total": piv,
+                    "roofline": {"bound": "shared-memory bandwidth (tableau resident in one CTA's shared memory: "
+                                          "2 (m+1) C 8 B per pivot)", "achieved": smem_bytes / (dev_ms * 1e-3) / 1e9,
+                                 "peak": smem_peak / 1e9, "unit": "GB/s",
+                                 "frac": smem_bytes / (dev_ms * 1e-3) / smem_peak,
+                                 "note": "latency-bound: the batch ends with its longest LP on one CTA"},
+                    "status_mix_rank0": {str(k): int((st == k).sum()) for k in np.unique(st)}}
+    if with_cpu and world == 1:
+        o = H.oracle()
+        o.xo_two_stage_rat_many.restype = C.c_double
+        vp = lambda a: a.ctypes.data_as(C.c_void_p)
+        S1, ST = 400, min(B, 400 * T)
+        rl, rt = H.to_rat(leq[:ST]), H.to_rat(tg[:ST])
+        cst, cmv, cap = np.zeros(ST, dtype=np.int32), np.zeros((ST, 2), dtype=np.int32), np.zeros(ST, dtype=np.uint8)
+        t1 = o.xo_two_stage_rat_many(S1, m, n, vp(rl), vp(rt), vp(cst), vp(cmv), vp(cap))
+        # single-threaded pass: per LP, did the reference's lossy appro() fire?  (those are not comparable)
+        ok = cap[:S1] == 0
+        same = bool(np.array_equal(cst[:S1][ok], st[:S1][ok]))
+        for k in np.nonzero(ok & (cst[:S1] == 0))[0]:
+            same &= int(res["maxv"][k][0]) * int(cmv[k][1]) == int(cmv[k][0]) * int(res["maxv"][k][1])
+        tT = _threads(lambda a, b: o.xo_two_stage_rat_many(b - a, m, n, vp(rl[a:b]), vp(rt[a:b]), vp(cst[a:b]),
+                                                           vp(cmv[a:b]), None), ST, T)
+        out["exact"]["cpu_baseline"] = {"value": ST / tT, "unit": "LPs/s", "cores": T, "kind": "port",
+                                        "sample": f"the first {ST} LPs, {T} host threads each looping over its slice",
+                                        "one_core": {"value": S1 / t1, "sample": f"the first {S1} LPs"}}
+        out["exact"]["matches_oracle_sample"] = same
+        out["exact"]["sample_compared"] = int(ok.sum())
+        out["exact"]["sample_skipped_reference_inexact"] = int((~ok).sum())
     # c5: 256 independent 40-item knapsacks (1 + n rows), general-integer B&B
-    T, nk = 256, 40
-    w = r.randint(5, 41, size=(T, nk))
-    pr = r.randint(5, 61, size=(T, nk))
-    L = np.zeros((T, nk + 1, nk + 1), dtype=np.int64)
+    Tn, nk = 256, 40
+    w = r.randint(5, 41, size=(Tn, nk))
+    pr = r.randint(5, 61, size=(Tn, nk))
+    L = np.zeros((Tn, nk + 1, nk + 1), dtype=np.int64)
     L[:, 0, :nk] = w
     L[:, 0, nk] = w.sum(axis=1) // 3
     for j in range(nk):
         L[:, 1 + j, j] = 1
         L[:, 1 + j, nk] = 1
-    G = np.zeros((T, nk + 1), dtype=np.int64)
-    G[:, :nk] = pr
-    ctx.mip_solve_rat_batch(0, 0, L[:4], G[:4])
+    Gm = np.zeros((Tn, nk + 1), dtype=np.int64)
+    Gm[:, :nk] = pr
+    lo, hi = part(Tn)
+    ctx.mip_solve_rat_batch(0, 0, L[:4], Gm[:4])
+    barrier()
     t0 = time.perf_counter()
-    mres = ctx.mip_solve_rat_batch(0, 0, L, G)
-    dt = time.perf_counter() - t0
-    nodes = int(mres["nodes"].astype(np.int64).sum())
-    ms = mres["status"]
-    out["bnb"] = {"metric": "B&B node LPs/s", "workload": f"c5: {T} knapsack MIPs of {nk} items "
+    mres = ctx.mip_solve_rat_batch(0, 0, L[lo:hi], Gm[lo:hi])
+    dt = mx(time.perf_counter() - t0)
+    nodes = int(sm(mres["nodes"].astype(np.int64).sum()))
+    ms_ = mres["status"]
+    out["bnb"] = {"metric": "B&B node LPs/s", "workload": f"c5: {Tn} knapsack MIPs of {nk} items "
                   f"(tableau {nk + 1}x{2 * nk + 2} at the root), trees advanced in lockstep, node "
-                  "relaxations batched on the GPU, decisions replayed in the reference's DFS order",
-                  "value": nodes / dt, "unit": "node LPs/s", "trees_per_s": T / dt, "nodes_total": nodes,
-                  "status_mix": {str(k): int((ms == k).sum()) for k in np.unique(ms)}}
+                  "relaxations batched on the GPU, decisions replayed in the reference's DFS order"
+                  + (f", trees split over {world} GPUs" if world > 1 else ""),
+                  "value": nodes / dt, "unit": "node LPs/s", "trees_per_s": Tn / dt, "nodes_total": nodes,
+                  "status_mix_rank0": {str(k): int((ms_ == k).sum()) for k in np.unique(ms_)}}
+    if with_cpu and world == 1:
+        o.xo_mip_solve_rat_many.restype = C.c_double
+        S1, ST = 8, min(Tn, 4 * T)
+        rl, rt = H.to_rat(L[:ST]), H.to_rat(Gm[:ST])
+        cst, cv, cn = np.zeros(ST, dtype=np.int32), np.zeros((ST, 2), dtype=np.int32), np.zeros(ST, dtype=np.int32)
+        t1 = o.xo_mip_solve_rat_many(S1, 0, 0, nk + 1, nk, vp(rl), vp(rt), vp(cst), vp(cv), vp(cn))
+        same = bool(np.array_equal(cst[:S1], ms_[:S1]) and np.array_equal(cn[:S1], mres["nodes"][:S1]))
+        for k in range(S1):
+            if cst[k] == 0:
+                same &= int(cv[k][0]) * int(mres["v"][k][1]) == int(mres["v"][k][0]) * int(cv[k][1])
+        n1 = int(cn[:S1].sum())
+        tT = _threads(lambda a, b: o.xo_mip_solve_rat_many(b - a, 0, 0, nk + 1, nk, vp(rl[a:b]), vp(rt[a:b]),
+                                                           vp(cst[a:b]), vp(cv[a:b]), vp(cn[a:b])), ST, T)
+        out["bnb"]["cpu_baseline"] = {"value": int(cn.sum()) / tT, "unit": "node LPs/s", "cores": T, "kind": "port",
+                                      "sample": f"the first {ST} trees, {T} host threads each looping over its slice",
+                                      "one_core": {"value": n1 / t1, "sample": f"the first {S1} trees"}}
+        out["bnb"]["matches_oracle_sample"] = same
     # 8(f1/f2): Lineq::has_solution over a dependence-graph build's worth of queries (systems of
     # different sizes, integer solutions wanted), one ragged call; the oracle port beside it
     Q = 20_000
@@ -398,23 +491,34 @@ def run_exact_and_bnb(ctx, xp):
         sysm[:, :nq] = r.randint(-2, 4, size=(mq, nq)) * (r.uniform(size=(mq, nq)) < 0.7)
         sysm[:, nq] = r.randint(0, 25, size=mq)
         systems.append((sysm, None))
+    lo, hi = part(Q)
     ctx.has_solution_ragged(systems[:64])
+    barrier()
     t0 = time.perf_counter()
-    res = ctx.has_solution_ragged(systems)
-    dt = time.perf_counter() - t0
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import harness as H
-    S = 300
-    t0 = time.perf_counter()
-    cpu = [H.has_solution("oracle", H.to_rat(systems[k][0])) for k in range(S)]
-    dtc = time.perf_counter() - t0
+    res = ctx.has_solution_ragged(systems[lo:hi])
+    dt = mx(time.perf_counter() - t0)
     out["has_solution"] = {"metric": "dependence queries/s", "workload": f"{Q} Lineq::has_solution systems, "
                            "2-5 variables x 3-9 inequalities, integer solutions (max then min MIP, B&B trees "
-                           "in lockstep), one xp_has_solution_rat_ragged call from host memory",
-                           "value": Q / dt, "unit": "queries/s", "feasible": int((res == 1).sum()),
-                           "cpu_baseline": {"value": S / dtc, "unit": "queries/s", "cores": 1, "kind": "port",
-                                            "sample": f"the first {S} systems",
-                                            "answers_match_gpu": bool(np.array_equal(np.array(cpu), res[:S]))}}
+                           "in lockstep), one xp_has_solution_rat_ragged call from host memory"
+                           + (f" per rank, split over {world} GPUs" if world > 1 else ""),
+                           "value": Q / dt, "unit": "queries/s", "feasible": int(sm((res == 1).sum()))}
+    if with_cpu and world == 1:
+        o.xo_has_solution_rat_many.restype = C.c_double
+        S1, ST = 1000, min(Q, 1000 * T)
+        msq = np.array([sy[0].shape[0] for sy in systems[:ST]], dtype=np.int32)
+        nsq = np.array([sy[0].shape[1] - 1 for sy in systems[:ST]], dtype=np.int32)
+        off = np.zeros(ST, dtype=np.int64)
+        off[1:] = np.cumsum(msq[:-1].astype(np.int64) * (nsq[:-1] + 1))
+        pool = np.ascontiguousarray(np.concatenate([H.to_rat(sy[0]).reshape(-1, 2) for sy in systems[:ST]]))
+        cres = np.zeros(ST, dtype=np.int32)
+        t1 = o.xo_has_solution_rat_many(S1, vp(msq), vp(nsq), vp(off), vp(pool), 1, 1, vp(cres))
+        same = bool(np.array_equal(cres[:S1], res[:S1]))
+        tT = _threads(lambda a, b: o.xo_has_solution_rat_many(b - a, vp(msq[a:b]), vp(nsq[a:b]), vp(off[a:b]), vp(pool),
+                                                              1, 1, vp(cres[a:b])), ST, T)
+        out["has_solution"]["cpu_baseline"] = {"value": ST / tT, "unit": "queries/s", "cores": T, "kind": "port",
+                                               "sample": f"the first {ST} systems, {T} host threads each looping over its slice",
+                                               "one_core": {"value": S1 / t1, "sample": f"the first {S1} systems"}}
+        out["has_solution"]["matches_oracle_sample"] = same
     return out
 
 
@@ -439,6 +543,23 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def all_sum_u64(x):
+        """Sum of one uint64 per rank, mod 2^64."""
+        if world == 1:
+            return int(x) % (1 << 64)
+        t = torch.tensor([int(x) & 0xFFFFFFFF, int(x) >> 32], dtype=torch.int64, device=dev)
+        g = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(g, t)
+        return sum(int(v[0].item()) + (int(v[1].item()) << 32) for v in g) % (1 << 64)
+
+    def bcast_flag(ok):
+        """rank 0's verdict to everyone (so that every rank exits the same way)."""
+        if world == 1:
+            return ok
+        t = torch.tensor([1 if ok else 0], dtype=torch.int64, device=dev)
+        dist.broadcast(t, src=0)
+        return bool(t.item())
+
     sampler = ClockSampler(local_rank)
     sampler.start()
     ctx = xp.Context(local_rank)
@@ -446,11 +567,19 @@ def run_ours(args):
     m, n = args.m, args.n
     Ccols = n + m + 1
     P = args.pivots
+    # the binding roof of the tableau pass at k >= ~23: separate DMUL + DADD (no DFMA: the reference
+    # rounds twice), measured on this device now
+    tops, pms = C.c_double(0), C.c_double(0)
+    ctx.check(lib.xp_probe_fp64_nonfused(ctx._h, C.byref(tops), C.byref(pms)))
+    fp64_peak = tops.value * 1e12
+    fp64_nominal = ctx_sm_count(torch, dev) * 64 * sm_clock_hz(torch, dev)
     if world > 1:
         from xpoly_b200 import sharded
         lp = sharded.ShardedLP(ctx, m, Ccols, rank, world, dist)
     else:
         lp = ctx.large_lp(m, Ccols)
+    if args.window is not None:
+        lp.set_window(args.window)
     local_cols = lp.local_cols
     peak, peak_src = measured_peak_gbs()
     B_pivot = 2.0 * (m + 1) * local_cols * 8  # read+write of every entry, per pivot
@@ -508,55 +637,90 @@ def run_ours(args):
     sampler.stop()
     clocks = sampler.window(main["t0"], main["t2"])
     clocks["window"] = ("timed region" if main["extra_steps"] == 0 else
-                        f"timed region + {main['extra_steps']} untimed steps of the identical load "
-                        "(the timed region alone is shorter than the sampling period)")
+                        f"timed region + {main['extra_steps']} untimed steps of the identical load")
     value = main["pivots"] / (main["dev_ms"] * 1e-3)
     k_eff = main["pivots"] / max(main["flushes"], 1)  # pivots applied per k_flush launch
     flush_avg_ms = main["flush_ms"] / max(main["flushes"], 1)
     moved = 2.0 * m * local_cols * 8  # one read + one write of the slice per launch
-    achieved = k_eff * B_pivot / (flush_avg_ms * 1e-3) / 1e9 if flush_avg_ms > 0 else 0.0
     traffic = None
-    prof = os.path.join(ROOT, "profiles", "r01_flush_ncu_full.json")
-    if os.path.exists(prof) and world == 1:
-        try:
-            traffic = json.load(open(prof)).get("dram_bytes_per_launch")
-        except Exception:
-            traffic = None
-    roofline = {
-        "bound": "hbm", "kernel": "k_flush (rank-k tableau update, k pivots per pass)",
-        "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-        "peak_source": peak_src, "traffic": traffic,
-        "algorithmic_bytes_per_launch": k_eff * B_pivot, "pivots_per_launch": k_eff,
-        "avg_launch_ms": flush_avg_ms, "launches_timed": main["flushes"],
-        "hbm_bytes_moved_per_launch": moved,
-        "hbm_moved_GBps": moved / (flush_avg_ms * 1e-3) / 1e9 if flush_avg_ms > 0 else None,
-        "hbm_moved_frac_of_peak": (moved / (flush_avg_ms * 1e-3) / 1e9 / peak) if flush_avg_ms > 0 else None,
-        "flush_share_of_step": main["flush_ms"] / main["dev_ms"] if main["dev_ms"] > 0 else None,
-        "note": "frac > 1 is expected: one launch applies k pivots to every entry in the "
-                "reference's rounding order, so the bytes the reference's schedule would move "
-                "(k x 2(m+1)C x 8) exceed the bytes this kernel moves (2 m C x 8); see DESIGN.md",
-        "whole_pivot_frac_of_peak": value * B_pivot / 1e9 / peak,
-        "whole_pivot_frac_of_8TBps": value * B_pivot / 8e12}
-    # what actually limits this launch at k >= ~23: the FP64 pipe (mul and add not fused, as the
-    # reference's rounding order demands): 2 m C operations per pivot, 64 lanes/clk/SM
-    # (tools/fp64_peak.cu measures 18.5 T lanes/s on B200)
-    fp64_peak = ctx_sm_count(torch, dev) * 64 * sm_clock_hz(torch, dev)
-    fp64_ops = k_eff * 2.0 * m * local_cols
-    roofline["limiter_at_this_k"] = {
-        "bound": "fp64 pipe (non-fused mul + add)", "unit": "Tops/s", "peak": fp64_peak / 1e12,
-        "achieved": fp64_ops / (flush_avg_ms * 1e-3) / 1e12 if flush_avg_ms > 0 else None,
-        "frac": fp64_ops / (flush_avg_ms * 1e-3) / fp64_peak if flush_avg_ms > 0 else None}
-
+    for prof in ("r02_flush_ncu_full.json", "r01_flush_ncu_full.json"):
+        pth = os.path.join(ROOT, "profiles", prof)
+        if os.path.exists(pth) and world == 1:
+            try:
+                traffic = json.load(open(pth)).get("dram_bytes_per_launch")
+                break
+            except Exception:
+                traffic = None
     # the reference's own schedule (one tableau pass per pivot), same kernels with k = 1
     r1 = timed_run(1, args.rank1_pivots, 3, 1)
     r1_value = r1["pivots"] / (r1["dev_ms"] * 1e-3)
     r1_sweep_ms = r1["flush_ms"] / max(r1["flushes"], 1)
-    rank1 = {"value": r1_value, "unit": "pivots/s", "pivots_per_launch": 1,
-             "avg_launch_ms": r1_sweep_ms,
-             "achieved": B_pivot / (r1_sweep_ms * 1e-3) / 1e9 if r1_sweep_ms > 0 else None,
-             "frac": (B_pivot / (r1_sweep_ms * 1e-3) / 1e9 / peak) if r1_sweep_ms > 0 else None,
-             "whole_pivot_frac_of_peak": r1_value * B_pivot / 1e9 / peak,
-             "whole_pivot_frac_of_8TBps": r1_value * B_pivot / 8e12}
+    fp64_ops = k_eff * 2.0 * m * local_cols  # non-fused operations of one launch (DMUL + DADD per entry and pivot)
+    ach = fp64_ops / (flush_avg_ms * 1e-3) if flush_avg_ms > 0 else 0.0
+    roofline = {
+        "bound": "fp64_pipe_nonfused", "kernel": "k_flush_w (rank-k tableau pass, k pivots per launch, DMUL + DADD per entry and pivot)",
+        "achieved": ach / 1e12, "peak": fp64_peak / 1e12, "unit": "Tops/s",
+        "frac": ach / fp64_peak if fp64_peak > 0 else None,
+        "peak_source": f"measured in this run (xp_probe_fp64_nonfused, {pms.value:.1f} ms; nominal 64 lanes/clk/SM = "
+                       f"{fp64_nominal / 1e12:.2f})",
+        "traffic": traffic, "ops_per_launch": fp64_ops, "pivots_per_launch": k_eff,
+        "avg_launch_ms": flush_avg_ms, "launches_timed": main["flushes"],
+        "flush_share_of_step": main["flush_ms"] / main["dev_ms"] if main["dev_ms"] > 0 else None,
+        "step_frac": value * 2.0 * m * local_cols / fp64_peak if fp64_peak > 0 else None,
+        "hbm_peak_GBps": peak, "hbm_peak_source": peak_src,
+        "hbm_moved_frac": (moved / (flush_avg_ms * 1e-3) / 1e9 / peak) if flush_avg_ms > 0 else None,
+        "algorithmic_hbm_equiv_frac": (k_eff * B_pivot / (flush_avg_ms * 1e-3) / 1e9 / peak) if flush_avg_ms > 0 else None,
+        "rank1_pivots_per_s": r1_value,
+        "rank1_kernel_hbm_frac": (B_pivot / (r1_sweep_ms * 1e-3) / 1e9 / peak) if r1_sweep_ms > 0 else None,
+        "rank1_whole_pivot_frac_of_8TBps": r1_value * B_pivot / 8e12}
+
+    # ---- parity, in the run: the state after 200 pivots against the CPU side ----
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    parity = {}
+    Kp = 200
+    lp.set_block(args.block)
+    lp.fill_synthetic(SEED)
+    lp.solve(Kp)
+    ct, cg = lp.checksum()
+    ct, cg = all_sum_u64(ct), all_sum_u64(cg)
+    e2b_K = lp.download(want_tab=False)["eq2bv"]
+    gold_path = os.path.join(ROOT, "tests", "golden", "c3_checkpoints.json")
+    if os.path.exists(gold_path):
+        gold = json.load(open(gold_path))
+        if (gold["m"], gold["n"], gold["seed"]) == (m, n, SEED):
+            ref = gold["reference"][str(Kp)]
+            wts = np.arange(1, m + 1, dtype=np.int64)
+            parity["checksum_matches_reference"] = bool(
+                ct == ref["tab"] and cg == ref["tgtf"] and int(e2b_K.astype(np.int64).dot(wts)) == ref["eq2bv_sum"])
+            parity["reference_checkpoint"] = (f"tableau + objective-row checksums and basis after {Kp} pivots, computed "
+                                              "by the unmodified reference (tests/golden/c3_checkpoints.json)")
+    if world > 1:  # the shards against ONE GPU running the same LP
+        ok1 = True
+        if rank == 0:
+            one = ctx.large_lp(m, Ccols)
+            one.set_block(args.block)
+            one.fill_synthetic(SEED)
+            one.solve(Kp)
+            o1 = one.checksum()
+            ok1 = (o1[0] == ct and o1[1] == cg and np.array_equal(one.download(want_tab=False)["eq2bv"], e2b_K))
+            one.close()
+        parity["checksum_matches_1gpu"] = bcast_flag(ok1)
+    if not args.no_cpu:
+        okb = True
+        Kc = args.cpu_pivots
+        lp.fill_synthetic(SEED)
+        lp.solve(Kc)
+        g = lp.download(want_tab=False, log_cap=Kc)
+        if rank == 0:
+            from xpoly_b200.synth import dense_lp
+            leq_h, tg_h = dense_lp(SEED, m, n)
+            rate, kind, info = cpu_pivot_rate(leq_h, tg_h, Kc, prefer_ref=False)
+            okb = bool(np.array_equal(g["eq2bv"], info["eq2bv"]))
+            cpu_line = {"value": rate, "unit": "pivots/s", "cores": 1, "kind": kind,
+                        "sample": f"{Kc} pivots of the same {m}x{Ccols} LP (single thread; the reference has no "
+                                  "intra-LP parallelism); solve loop timed inside the checker"}
+        parity["basis_matches_oracle"] = bcast_flag(okb)
+    parity_ok = all(v for k, v in parity.items() if isinstance(v, bool))
 
     line = {
         "metric": "pivots/s", "value": value, "unit": "pivots/s", "n_gpus": world,
@@ -565,72 +729,81 @@ def run_ours(args):
         "data": "synthetic",
         "config": {"workload": f"c3: dense FP64 LP, tableau {m}x{Ccols}, simplex iterations "
                                "under the reference pivot rule from the slack basis",
-                   "placement": "HBM-resident, bit-identical state"
-                                + (f", column-sharded over {world} GPUs" if world > 1 else ""),
+                   "placement": "HBM-resident" + (f", column-sharded over {world} GPUs" if world > 1 else ""),
                    "l2": "inputs (1 GiB) larger than L2 (126 MB): no flush between iterations",
-                   "pivots_per_step": P, "pivots_per_tableau_pass": k_eff},
-        "gpu_launches": int(main["launches"]), "wall_s": main["wall"], "clocks": clocks,
-        "roofline": roofline, "rank1_schedule": rank1,
+                   "pivots_per_step": P, "pivots_per_tableau_pass": k_eff, "pricing_window": lp.window},
+        "gpu_launches": int(main["launches"]), "clocks": clocks, "roofline": roofline, "parity": parity,
     }
+    details = {"details_of": "bench.py secondary legs (the main line follows)", "n_gpus": world}
 
     if world == 1:
-        # ---- e2e: the C-ABI call with pinned host buffers (H2D + P pivots + D2H per step)
-        tab_bytes = m * Ccols * 8
+        # ---- e2e: the C-ABI call the reference arm's TwoStageMethod(leq, tgtf) corresponds to --
+        # xp_six_two_stage_f64_large with PINNED host buffers: leq goes up (half the slack form),
+        # slack form + P pivots on the device, O(C) comes down
+        from xpoly_b200.synth import dense_lp
+        leq_h, tg_h = dense_lp(SEED, m, n)
         hp = C.c_void_p()
-        ctx.check(lib.xp_host_alloc(ctx._h, C.c_size_t(tab_bytes), C.byref(hp)))
-        lp.set_block(args.block)
-        lp.fill_synthetic(SEED)
-        st0 = lp.download(want_tab=False)
-        ctx.check(lib.xp_lp_f64_download(lp._h, hp, None, None, None, None, None, None, None, None,
-                                         None, 0))
-        lp.close()
+        ctx.check(lib.xp_host_alloc(ctx._h, C.c_size_t(leq_h.nbytes), C.byref(hp)))
+        h_leq = np.ctypeslib.as_array(C.cast(hp, C.POINTER(C.c_double)), shape=leq_h.shape)
+        h_leq[...] = leq_h
         ctx.set_block(args.block)
-        tg, nv, bvs = st0["tgtf"].copy(), st0["nvset"].copy(), st0["bvset"].copy()
-        b2e, e2b = st0["bv2eq"].copy(), st0["eq2bv"].copy()
-        maxv, sol = np.zeros(1), np.zeros(Ccols)
-        iters = np.zeros(1, dtype=np.uint32)
+        if args.window is not None:
+            ctx.set_window(args.window)
+        stv = C.c_int32(0)
+        mv, ssol, otg = np.zeros(1), np.zeros(Ccols), np.zeros(Ccols)
+        e2b, its, pvs = np.zeros(m, dtype=np.int32), np.zeros(1, dtype=np.uint32), np.zeros(1, dtype=np.uint32)
         p = lambda a: a.ctypes.data_as(C.c_void_p)
 
         def e2e_step():
             t0 = time.perf_counter()
-            st = lib.xp_six_slack_f64(ctx._h, hp, p(tg), m, Ccols, p(nv), p(bvs), p(b2e), p(e2b),
-                                      None, None, C.c_uint32(P), 0, p(maxv), p(sol), p(iters),
-                                      None, 0)
-            ctx.check(st)
-            return time.perf_counter() - t0, int(iters[0])
+            ctx.check(lib.xp_six_two_stage_f64_large(ctx._h, m, n, hp, p(tg_h), C.c_uint32(P), 0, C.byref(stv),
+                                                     p(mv), p(ssol), p(otg), p(e2b), p(its), p(pvs)))
+            return time.perf_counter() - t0, int(its[0])
         e2e_step()
-        ts, its = [], 0
-        for _ in range(max(2, min(args.steps, 4))):
+        ts, itn = [], 0
+        for _ in range(max(3, min(args.steps, 8))):
             dt, it = e2e_step()
             ts.append(dt)
-            its += it
-        e2e_value = its / sum(ts)
-        small = Ccols * 8 + (Ccols - 1) * (1 + 1 + 4) + m * 4
-        line["e2e"] = {"value": e2e_value, "unit": "pivots/s",
-                       "h2d_bytes_per_step": int(tab_bytes + small),
-                       "d2h_bytes_per_step": int(tab_bytes + small + Ccols * 8),
+            itn += it
+        line["e2e"] = {"value": itn / sum(ts), "unit": "pivots/s",
+                       "h2d_bytes_per_step": int(leq_h.nbytes + tg_h.nbytes),
+                       "d2h_bytes_per_step": int(2 * Ccols * 8 + m * 4 + 64),
                        "ms_per_step": 1000.0 * sum(ts) / len(ts), "pivots_per_step": P,
-                       "api": "xp_six_slack_f64 (pinned host buffers)"}
-        # ---- CPU baseline on a bounded sample of the same workload (rank 0, N=1)
-        if not args.no_cpu:
-            from xpoly_b200.synth import dense_lp
-            leq, tgtf = dense_lp(SEED, m, n)
-            Kc = args.cpu_pivots
-            rate, kind, info = cpu_pivot_rate(leq, tgtf, Kc, prefer_ref=False)
-            chk = ctx.large_lp(m, Ccols)
-            chk.fill_synthetic(SEED)
-            chk.solve(Kc)
-            same = bool(np.array_equal(chk.download(want_tab=False)["eq2bv"], info["eq2bv"]))
-            chk.close()
-            line["cpu_baseline"] = {
-                "value": rate, "unit": "pivots/s", "cores": 1, "kind": kind,
-                "sample": f"{Kc} pivots of the same {m}x{Ccols} LP (single thread; the reference "
-                          "has no intra-LP parallelism); solve loop timed inside the checker",
-                "basis_after_sample_matches_gpu": same}
+                       "api": "xp_six_two_stage_f64_large (pinned host leq; slack form on the device)",
+                       "basis_matches_device_run": bool(np.array_equal(e2b, e2b_K)) if P == Kp else None}
         ctx.check(lib.xp_host_free(ctx._h, hp))
+        del h_leq
+        # the kernel-level entry (replaces the private solveSlackForm: whole tableau up and down)
+        tab_bytes = m * Ccols * 8
+        ctx.check(lib.xp_host_alloc(ctx._h, C.c_size_t(tab_bytes), C.byref(hp)))
+        lp.set_block(args.block)
+        lp.fill_synthetic(SEED)
+        st0 = lp.download(want_tab=False)
+        ctx.check(lib.xp_lp_f64_download(lp._h, hp, None, None, None, None, None, None, None, None, None, 0))
+        lp.close()
+        tg, nv, bvs = st0["tgtf"].copy(), st0["nvset"].copy(), st0["bvset"].copy()
+        b2e, e2b2 = st0["bv2eq"].copy(), st0["eq2bv"].copy()
+        sol = np.zeros(Ccols)
+
+        def slack_step():
+            t0 = time.perf_counter()
+            ctx.check(lib.xp_six_slack_f64(ctx._h, hp, p(tg), m, Ccols, p(nv), p(bvs), p(b2e), p(e2b2), None, None,
+                                           C.c_uint32(P), 0, p(mv), p(sol), p(its), None, 0))
+            return time.perf_counter() - t0, int(its[0])
+        slack_step()
+        ts, itn = [], 0
+        for _ in range(2):
+            dt, it = slack_step()
+            ts.append(dt)
+            itn += it
+        line["e2e_slack"] = {"value": itn / sum(ts), "unit": "pivots/s", "bytes_each_way": int(tab_bytes),
+                             "api": "xp_six_slack_f64 (whole tableau up and down per step)"}
+        ctx.check(lib.xp_host_free(ctx._h, hp))
+        if not args.no_cpu:
+            line["cpu_baseline"] = cpu_line
         if not args.no_batched:
-            line["batched"] = run_batched(ctx, xp, torch, dev, with_cpu=not args.no_cpu)
-            line.update(run_exact_and_bnb(ctx, xp))
+            details["batched"] = run_batched(ctx, xp, torch, dev, with_cpu=not args.no_cpu)
+            details.update(run_exact_and_bnb(ctx, xp, torch, dev, with_cpu=not args.no_cpu))
     else:
         # ---- e2e at N GPUs: every rank moves ITS column slice of the host tableau through the
         # C-ABI handle calls (upload of the full host arrays keeps the rank's slice, download
@@ -686,20 +859,30 @@ def run_ours(args):
                        "ms_per_step": 1000.0 * float(tt.item()) / len(ts), "pivots_per_step": P,
                        "api": "xp_lp_f64_upload + xp_lp_f64_solve + xp_lp_f64_download on the "
                               "column-sharded handle (pinned host buffers, each rank moves its "
-                              "own column slice over its own PCIe link)"}
+                              "own column slice over its own PCIe link)",
+                       "basis_matches_device_run": bool(np.array_equal(e2b1, e2b_K)) if P == Kp else None}
         ctx.check(lib.xp_host_free(ctx._h, hp_in))
         ctx.check(lib.xp_host_free(ctx._h, hp_out))
         barrier()
         lp.close()
         barrier()
         if not args.no_batched:
-            line["batched"] = run_batched(ctx, xp, torch, dev, with_cpu=False, rank=rank,
-                                          world=world, dist=dist)
+            details["batched"] = run_batched(ctx, xp, torch, dev, with_cpu=False, rank=rank,
+                                             world=world, dist=dist)
+            details.update(run_exact_and_bnb(ctx, xp, torch, dev, rank=rank, world=world, dist=dist,
+                                             with_cpu=False))
+    # flat copies of the secondary figures in the main line (the driver keeps one line)
+    for k, key in (("batched", "c2_LPs_per_s"), ("exact", "c4_exact_LPs_per_s"), ("bnb", "c5_node_LPs_per_s"),
+                   ("has_solution", "has_solution_queries_per_s")):
+        if k in details:
+            line[key] = details[k]["value"]
     if rank == 0:
+        if len(details) > 2:
+            print(json.dumps(details), flush=True)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
-    return 0
+    return 0 if parity_ok else 3
 
 
 def main():
@@ -718,6 +901,7 @@ def main():
     ap.add_argument("--port", action="store_true", help="reference arm: force the oracle port")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-batched", action="store_true")
+    ap.add_argument("--window", type=int, default=None, help="pricing window of the panel kernel (default: automatic; -1 off)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

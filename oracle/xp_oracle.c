@@ -533,3 +533,61 @@ double xo_two_stage_f64_many(int batch, int m, int n, const double *leq, const d
     free(tab); free(otg); free(ssol); free(eq2bv); free(bv2eq); free(nv); free(bv);
     return dt;
 }
+
+/* The same for the exact side (bench.py's all-core baselines of c4 / c5 / has_solution): plain
+ * loops over independent problems, re-entrant (one call per host thread on disjoint slices; the
+ * appro counter is a diagnostic and may race).  appro_flag[k] (optional) = 1 when the
+ * reference's lossy appro() fired while LP k was being solved -- only meaningful single-threaded. */
+double xo_two_stage_rat_many(int batch, int m, int n, const xo_rat *leq, const xo_rat *tgtf,
+                             int32_t *status, xo_rat *maxv_out, uint8_t *appro_flag)
+{
+    int cap = n + m + 2;
+    xo_rat *tab = (xo_rat *)malloc((size_t)m * cap * sizeof(xo_rat));
+    xo_rat *otg = (xo_rat *)malloc((size_t)cap * sizeof(xo_rat));
+    xo_rat *ssol = (xo_rat *)malloc((size_t)cap * sizeof(xo_rat));
+    int32_t *eq2bv = (int32_t *)malloc((size_t)m * sizeof(int32_t));
+    int32_t *bv2eq = (int32_t *)malloc((size_t)cap * sizeof(int32_t));
+    uint8_t *nv = (uint8_t *)malloc((size_t)cap), *bv = (uint8_t *)malloc((size_t)cap);
+    double t0 = xo_now();
+    for (int k = 0; k < batch; k++) {
+        int dims[4];
+        xo_rat maxv = {0, 1};
+        long long a0 = g_xo_appro;
+        status[k] = xo_two_stage_rat(m, n, leq + (size_t)k * m * (n + 1), tgtf + (size_t)k * (n + 1),
+                                     0xFFFFFFFFu, dims, tab, otg, eq2bv, bv2eq, nv, bv, &maxv, ssol,
+                                     NULL, 0, NULL);
+        if (maxv_out) maxv_out[k] = maxv;
+        if (appro_flag) appro_flag[k] = g_xo_appro != a0;
+    }
+    double dt = xo_now() - t0;
+    free(tab); free(otg); free(ssol); free(eq2bv); free(bv2eq); free(nv); free(bv);
+    return dt;
+}
+
+double xo_mip_solve_rat_many(int batch, int is_min, int is_bin, int m, int n, const xo_rat *leq,
+                             const xo_rat *tgtf, int32_t *status, xo_rat *v_out, int32_t *nodes)
+{
+    xo_rat *sol = (xo_rat *)malloc((size_t)(n + 1) * sizeof(xo_rat));
+    double t0 = xo_now();
+    for (int k = 0; k < batch; k++) {
+        xo_rat v = {0, 1};
+        int nn = 0;
+        status[k] = xo_mip_solve_rat(is_min, is_bin, m, n, leq + (size_t)k * m * (n + 1),
+                                     tgtf + (size_t)k * (n + 1), 0, NULL, &v, sol, &nn);
+        if (v_out) v_out[k] = v;
+        if (nodes) nodes[k] = nn;
+    }
+    double dt = xo_now() - t0;
+    free(sol);
+    return dt;
+}
+
+/* systems of different sizes: system k has ms[k] rows of ns[k]+1 entries at pool + off[k] */
+double xo_has_solution_rat_many(int batch, const int32_t *ms, const int32_t *ns, const int64_t *off,
+                                const xo_rat *pool, int is_int_sol, int is_unique_sol, int32_t *res)
+{
+    double t0 = xo_now();
+    for (int k = 0; k < batch; k++)
+        res[k] = xo_has_solution_rat(ms[k], ns[k], pool + off[k], 0, NULL, is_int_sol, is_unique_sol);
+    return xo_now() - t0;
+}

@@ -104,6 +104,14 @@ double xo_last_solve_seconds(void);
 double xo_two_stage_f64_many(int batch, int m, int n, const double *leq, const double *tgtf,
                              int32_t *status, double *maxv_out /* optional: maxv on SUCC, else 0 */);
 
+/* Exact-side loops for bench.py's CPU baselines (one call per host thread on disjoint slices). */
+double xo_two_stage_rat_many(int batch, int m, int n, const xo_rat *leq, const xo_rat *tgtf,
+                             int32_t *status, xo_rat *maxv_out, uint8_t *appro_flag);
+double xo_mip_solve_rat_many(int batch, int is_min, int is_bin, int m, int n, const xo_rat *leq,
+                             const xo_rat *tgtf, int32_t *status, xo_rat *v_out, int32_t *nodes);
+double xo_has_solution_rat_many(int batch, const int32_t *ms, const int32_t *ns, const int64_t *off,
+                                const xo_rat *pool, int is_int_sol, int is_unique_sol, int32_t *res);
+
 /* Position-keyed checksum of an FP64 matrix (same key function as xp_lp_f64_checksum). */
 uint64_t xo_checksum_f64(const double *a, int rows, int cols);
 
