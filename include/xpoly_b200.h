@@ -214,11 +214,21 @@ int xp_six_two_stage_f64_ragged(xp_ctx *ctx, int batch, const int32_t *ms, const
  * (constructBasicFeasibleSolution, lpsol.h:838-988: auxiliary column, forced first
  * pivot, auxiliary solve, pivoting xa out, objective restoration, column deletion)
  * runs on the device: the only bulk transfer is the upload of leq.  *status
- * receives the SIX status; the return value is 0 or a negative error. */
+ * receives the SIX status; the return value is 0 or a negative error.
+ * A large bounded run without phase 1 uploads BEHIND the solve: the columns of the
+ * pricing window go up first and the device starts deciding pivots on them (plus the
+ * slack identity it generates itself) while the remaining columns of leq are still
+ * crossing PCIe; those replay the decided blocks when they land.  Same operations per
+ * entry in the same order (tests compare every bit), the upload is hidden behind the
+ * first half of the work. */
 int xp_six_two_stage_f64_large(xp_ctx *ctx, int m, int n, const double *leq, const double *tgtf,
                                uint32_t max_iter, int rule, int32_t *status, double *maxv,
                                double *slack_sol, double *tgtf_out, int32_t *eq2bv,
                                uint32_t *iters, uint32_t *pivots);
+
+/* Checksums (as xp_lp_f64_checksum) of the tableau / objective row that the last
+ * xp_six_two_stage_f64_large or xp_six_slack_f64 call on this ctx left on the device. */
+int xp_ctx_last_lp_checksum(xp_ctx *ctx, uint64_t *sum_tableau, uint64_t *sum_tgtf);
 
 /* ------------------------- TwoStageMethod level: batched exact (fraction-free)
  * The exact twin of SIX<RMat,Rational>::TwoStageMethod: integer tableau N with

@@ -272,6 +272,12 @@ def _check_two_stage(ctx, leq, tg, K, tag):
     assert np.array_equal(H.bits(g["tgtf"]), H.bits(o["tgtf"])), (tag, "tgtf")
     assert np.array_equal(H.bits(g["maxv"]), H.bits(o["maxv"])), (tag, "maxv")
     assert np.array_equal(H.bits(g["slack_sol"]), H.bits(o["slack_sol"])), (tag, "sol")
+    # the final tableau stays on the device: compare all of it through the position-keyed checksum
+    import ctypes as C
+    f = H.oracle().xo_checksum_f64
+    f.restype = C.c_uint64
+    tab = np.ascontiguousarray(o["tab"], dtype=np.float64)
+    assert ctx.last_lp_checksum()[0] == int(f(H.P(tab), tab.shape[0], tab.shape[1])), (tag, "tableau checksum")
     return g
 
 
@@ -359,3 +365,24 @@ def test_flush_variants_bitwise(ctx, env, monkeypatch):
     lp.solve(64)
     assert lp.checksum() == var
     lp.close()
+
+
+@pytest.mark.parametrize("m,n,window,K", [(300, 1500, 512, 128), (300, 1500, 256, 100), (300, 1500, 1024, 64),
+                                          (520, 2100, 512, 120), (520, 2101, 512, 120), (257, 1300, 768, 97)])
+def test_two_stage_large_streamed_upload(ctx, m, n, window, K, monkeypatch):
+    """xp_six_two_stage_f64_large uploading behind the solve: window columns first, the bounded
+    solve runs on the early tiles while the rest of A is still on its way, the late tiles replay
+    the closed blocks out of the ring.  Bit for bit against the oracle, for runs the window decides
+    alone and for runs a pricing scan leaves it (the full-width solve then continues)."""
+    monkeypatch.setenv("XP_STREAM_MIN_MB", "0")
+    ctx.set_window(window)
+    try:
+        for seed in range(3):
+            leq, tg = H.gen_dense_lp(8400 + seed, m, n)
+            _check_two_stage(ctx, leq, tg, K, ("streamed", m, n, window, K, seed))
+        leq, tg = H.gen_mixed_lp(8500, m, n)  # mixed signs: ratio-test failures inside the window run
+        leq[:, n] = np.abs(leq[:, n])
+        tg[:n] = np.abs(tg[:n])
+        _check_two_stage(ctx, leq, tg, K, ("streamed-mixed", m, n, window, K))
+    finally:
+        ctx.set_window(0)

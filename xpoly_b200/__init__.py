@@ -136,6 +136,12 @@ class Context:
         """Pricing window for six_slack_f64 / two_stage_f64_large: 0 automatic, < 0 off, > 0 forced."""
         self.check(lib().xp_ctx_set_window(self._h, int(w)))
 
+    def last_lp_checksum(self):
+        """(tableau, objective row) checksums of what the last large two-stage / slack call left on the device."""
+        a, b = C.c_uint64(0), C.c_uint64(0)
+        self.check(lib().xp_ctx_last_lp_checksum(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     def large_lp(self, m, Cc, rank=0, nranks=1):
         return LargeLP(self, m, Cc, rank, nranks)
 

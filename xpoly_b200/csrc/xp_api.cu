@@ -37,6 +37,7 @@ extern "C" void xp_ctx_destroy(xp_ctx *ctx)
         cudaStreamSynchronize(ctx->stream);
         xp_large_release_cached(ctx);
         if (ctx->scratch) cudaFree(ctx->scratch);
+        if (ctx->stage) cudaFreeHost(ctx->stage);
         if (ctx->gws) cudaFree(ctx->gws);
         if (ctx->pipe_copy) {
             cudaStreamDestroy(ctx->pipe_copy);

@@ -30,6 +30,8 @@ struct xp_ctx {
     void *scratch = nullptr;
     size_t scratch_bytes = 0;
     void *cached_lp = nullptr; // xp_lp_f64 reused by xp_six_slack_f64 / xp_six_two_stage_f64_large
+    void *stage = nullptr;      // small pinned staging buffer (gathered constant column of an uploaded LP)
+    size_t stage_bytes = 0;
     void *cached_aux = nullptr; // the auxiliary (phase 1) handle of xp_six_two_stage_f64_large
     int slack_block = 0;       // pivots per flush for xp_six_slack_f64 (0 = automatic)
     int slack_window = 0;      // pricing window for xp_six_slack_f64 / xp_six_two_stage_f64_large (0 = automatic)

@@ -61,6 +61,7 @@ namespace {
 
 constexpr int MAXR = XP_MAX_RANKS;
 constexpr int KMAX = XP_MAX_BLOCK; // pivots per flush, upper bound
+constexpr int NH = 8;              // blocks whose factors (F, records, pivot-row marks) are kept: ring slot = blk % NH
 constexpr int TH = 256;            // threads per CTA of the panel kernels / the slow path
 constexpr int INT_BIG = 0x7fffffff;
 constexpr unsigned long long SPIN_LIMIT = 6000000000ULL; // ~3 s of SM clocks
@@ -90,6 +91,7 @@ struct LpState {
     int wb_pending; // k_wpanel made pivots [wb_t0, t): their P rows / objective entries beyond the window are due
     int n_touched;
     int touched[KMAX]; // rows with last_piv >= 0
+    int hist_t[NH];    // pivots of the closed blocks still in the ring (k_block_snapshot)
     double r, cq, prow_rhs;
     double maxv;
     double tg_rhs; // replica of the objective row's constant term
@@ -133,6 +135,7 @@ struct LpDev {
     const double *vc_diag, *vc_rhs; // may be null
     uint8_t *nvset;
     int32_t *bv2eq, *eq2bv, *last_piv;
+    int32_t *hist_lp; // [NH][m] pivot-row marks of closed blocks (null unless the handle keeps a history)
     uint32_t *tabu;
     int32_t *row_cnt, *col_cnt;
     int32_t *log;
@@ -147,29 +150,29 @@ struct LpDev {
 // ---- exchange-block addressing ----
 __host__ __device__ __forceinline__ size_t xoff_F(const LpDev &d, int par, int s)
 {
-    return XHDR_BYTES + ((size_t)(par * KMAX + s) * d.mpad) * sizeof(double);
+    return XHDR_BYTES + ((size_t)(par * KMAX + s) * d.mpad) * sizeof(double); // par: ring slot of the block
 }
 __host__ __device__ __forceinline__ size_t xoff_feas(const LpDev &d)
 {
-    return XHDR_BYTES + ((size_t)(2 * KMAX) * d.mpad) * sizeof(double);
+    return XHDR_BYTES + ((size_t)(NH * KMAX) * d.mpad) * sizeof(double);
 }
 // k_panel, sharded: landing zone of the entering column, two tagged 8-byte words per row
 __host__ __device__ __forceinline__ size_t xoff_land(const LpDev &d, int par)
 {
-    return XHDR_BYTES + ((size_t)(2 * KMAX + 1 + 2 * par) * d.mpad) * sizeof(double);
+    return XHDR_BYTES + ((size_t)(NH * KMAX + 1 + 2 * par) * d.mpad) * sizeof(double); // par: parity of the column event
 }
-// k_wpanel: one record per pivot of the open block, by block parity
+// k_wpanel: one record per pivot of a block, by ring slot of the block
 struct WRec {
     double r, cq, prow_rhs; // 1 / pivot element, c_q, scaled constant term of the pivot row
     int p, q, bv, s0p;      // pivot row, entering / leaving variable, last_piv[p] before this pivot
 };
 __host__ __device__ __forceinline__ size_t xoff_rec(const LpDev &d, int par)
 {
-    return XHDR_BYTES + ((size_t)(2 * KMAX + 5) * d.mpad) * sizeof(double) + (size_t)par * KMAX * sizeof(WRec);
+    return XHDR_BYTES + ((size_t)(NH * KMAX + 5) * d.mpad) * sizeof(double) + (size_t)par * KMAX * sizeof(WRec);
 }
 __host__ __device__ __forceinline__ size_t xblock_bytes(const LpDev &d)
 {
-    return XHDR_BYTES + ((size_t)(2 * KMAX + 5) * d.mpad) * sizeof(double) + (size_t)2 * KMAX * sizeof(WRec);
+    return XHDR_BYTES + ((size_t)(NH * KMAX + 5) * d.mpad) * sizeof(double) + (size_t)NH * KMAX * sizeof(WRec);
 }
 __device__ __forceinline__ double *Fptr(const LpDev &d, int r, int par, int s)
 {
@@ -571,7 +574,7 @@ __global__ void __launch_bounds__(TH) k_pcol(LpDev d)
         if (blockIdx.x == 0 && tid == 0) st->status = XP_SIX_TIME_OUT;
         return;
     }
-    const int t = st->t, par = st->blk & 1;
+    const int t = st->t, par = st->blk & (NH - 1);
     if (t >= st->kblk) return; // block full: k_flush comes first
     Seq x;
     x.xseq = st->xseq;
@@ -665,7 +668,7 @@ __global__ void __launch_bounds__(TH) k_prow(LpDev d)
     LpState *st = d.st;
     const int tid = threadIdx.x;
     if (!st->pivot_pending || st->status != XPI_RUNNING) return;
-    const int t = st->t, par = st->blk & 1, n = d.n, Cl = d.Cl;
+    const int t = st->t, par = st->blk & (NH - 1), n = d.n, Cl = d.Cl;
     const int p = st->p, q = st->q, bv = st->bv, s0p = st->s0p, zero_upto = st->zero_upto;
     const double r = st->r, cq = st->cq, prow_rhs = st->prow_rhs;
     const bool r_one = xp_feq(r, 1.0), r_zero = xp_feq(r, 0.0);
@@ -917,7 +920,7 @@ k_panel(LpDev d, PanA *partA, PanB *partB, unsigned long long *bar, unsigned lon
     const int c_lo = min(Cl, c * cpc), c_hi = min(Cl, c_lo + cpc);
 
     int t = st->t;
-    const int kblk = st->kblk, par = st->blk & 1;
+    const int kblk = st->kblk, par = st->blk & (NH - 1);
     unsigned cnt = st->cnt;
     const unsigned max_iter = st->max_iter;
     int q = st->q, zero_upto = st->zero_upto, anypos = st->anypos;
@@ -1277,7 +1280,54 @@ k_panel(LpDev d, PanA *partA, PanB *partB, unsigned long long *bar, unsigned lon
     }
 }
 
+// Which column tiles (of FT_TC = 256 columns) and which block a tableau pass works on.  The
+// default is "every tile, the open block, close it".  A handle whose columns arrive in pieces
+// (xp_six_two_stage_f64_large uploading behind the solve) runs the live pass on the tiles it
+// has, and later replays closed blocks out of the ring (slot >= 0: F, records and pivot-row
+// marks of that block, no closing) on the tiles that arrived late.
+struct ColSet {
+    int ct0a, ct1a, ct0b, ct1b; // tile ranges [ct0a, ct1a) u [ct0b, ct1b)
+    int slot;                   // -1: the open block (live); >= 0: ring slot of a closed block
+    int close;                  // the last CTA closes the block
+};
+
 #include "xp_large_wpanel.cuh"
+
+// First pricing of a fresh solve restricted to the window (lpsol.h:1054-1069): the lowest
+// eligible non-basic column with c_j > 0, handed to k_wpanel exactly as k_prow hands over its
+// pricing result (the zeroing of basic columns passed by the scan is owed, zero_upto).  The
+// ordinary start -- sp_select on the slow path -- needs every column; a handle whose columns are
+// still arriving starts here.  Finds nothing inside the window: the state stays "slow".
+__global__ void __launch_bounds__(1024) k_first_price_window(LpDev d)
+{
+    __shared__ int shi[33];
+    LpState *st = d.st;
+    if (st->status != XPI_RUNNING || !st->slow || st->pivot_pending || st->cnt != 0 || st->t != 0) return;
+    const int lim = min(d.w, d.n);
+    int best = INT_BIG;
+    for (int j = threadIdx.x; j < lim; j += blockDim.x)
+        if (best == INT_BIG && d.nvset[j] && d.tgtf[j] > 0.0 && d.row_cnt[j] < d.n - 1) best = j;
+    best = xp_block_min_int(best, shi);
+    if (threadIdx.x == 0 && best != INT_BIG) {
+        st->q = best;
+        st->anypos = 1;
+        st->zero_upto = best;
+        st->slow = 0;
+    }
+}
+
+// Before a live pass on a handle that keeps a history: pivot count and pivot-row marks of the
+// block about to close go into its ring slot.
+__global__ void k_block_snapshot(LpDev d)
+{
+    LpState *st = d.st;
+    const int t = st->t;
+    if (t == 0 || (t < st->kblk && st->status == XPI_RUNNING)) return; // nothing to close
+    const int slot = st->blk & (NH - 1);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < d.m; i += gridDim.x * blockDim.x)
+        d.hist_lp[(size_t)slot * d.m + i] = d.last_piv[i];
+    if (blockIdx.x == 0 && threadIdx.x == 0) st->hist_t[slot] = t;
+}
 
 // ---------------------------------------------------------------------------
 // k_flush: apply the t pending pivots to the tableau slice.
@@ -1293,7 +1343,7 @@ __global__ void __launch_bounds__(THREADS) k_flush(LpDev d, int rows_per_cta)
     const int t = st->t;
     if (t == 0) return;
     if (t < st->kblk && st->status == XPI_RUNNING) return; // block still open
-    const int par = st->blk & 1, Cl = d.Cl, m = d.m;
+    const int par = st->blk & (NH - 1), Cl = d.Cl, m = d.m;
     int *s_lp = (int *)(s_f + (size_t)rows_per_cta * KB);
     const int r0 = blockIdx.y * rows_per_cta;
     const int r1 = min(m, r0 + rows_per_cta);
@@ -1453,7 +1503,7 @@ __global__ void __launch_bounds__(LANES *HALVES) k_flush_t(LpDev d, int groups, 
     const int t = st->t;
     if (t == 0) return;
     if (t < st->kblk && st->status == XPI_RUNNING) return; // block still open
-    const int par = st->blk & 1, Cl = d.Cl, m = d.m, tid = threadIdx.x;
+    const int par = st->blk & (NH - 1), Cl = d.Cl, m = d.m, tid = threadIdx.x;
     const int lane = tid % LANES, half = tid / LANES;
     double *sP = sm, *sF = sm + (size_t)t * TC;
     int *s_lp = (int *)(sF + (size_t)nbuf * t * FT_ROWS);
@@ -1637,7 +1687,7 @@ __device__ __forceinline__ void prefetch_l2(const void *p)
 }
 
 template <int TR, int LANES, int GROUPS>
-__global__ void __launch_bounds__(LANES *GROUPS, 2) k_flush_w(LpDev d, int groups, int nbuf)
+__global__ void __launch_bounds__(LANES *GROUPS, 2) k_flush_w(LpDev d, ColSet cs, int nbuf)
 {
     extern __shared__ double sm[]; // sP[t][4*LANES] | sF[nbuf][t][FT_ROWS] | s_lp[nbuf][FT_ROWS]
     __shared__ int s_flag;
@@ -1645,27 +1695,21 @@ __global__ void __launch_bounds__(LANES *GROUPS, 2) k_flush_w(LpDev d, int group
     constexpr int THREADS = LANES * GROUPS, TC = 4 * LANES;
     constexpr int TPB = FT_ROWS / (GROUPS * TR); // tiles per unit and row group
     LpState *st = d.st;
-    const int t = st->t;
+    const bool live = cs.slot < 0;
+    const int t = live ? st->t : st->hist_t[cs.slot];
     if (t == 0) return;
-    if (t < st->kblk && st->status == XPI_RUNNING) return; // block still open
-    const int par = st->blk & 1, Cl = d.Cl, m = d.m, tid = threadIdx.x;
+    if (live && t < st->kblk && st->status == XPI_RUNNING) return; // block still open
+    const int par = live ? (st->blk & (NH - 1)) : cs.slot, Cl = d.Cl, m = d.m, tid = threadIdx.x;
+    const int32_t *marks = live ? d.last_piv : d.hist_lp + (size_t)cs.slot * m;
     const int lane = tid % LANES, grp = tid / LANES;
     double *sP = sm, *sF = sm + (size_t)t * TC;
     int *s_lp = (int *)(sF + (size_t)nbuf * t * FT_ROWS);
     const double *sPl0 = sP + 2 * lane, *sPl1 = sP + 2 * LANES + 2 * lane;
     const int nrb = (m + FT_ROWS - 1) / FT_ROWS;
-    const int ctiles = (Cl + TC - 1) / TC;
+    const int nta = cs.ct1a - cs.ct0a, ctiles = nta + (cs.ct1b - cs.ct0b); // tiles of the set, in order
     const long long units = (long long)ctiles * nrb;
-    int u0, u1;
-    if (groups > 0) {
-        const int ct = blockIdx.x % ctiles, g = blockIdx.x / ctiles;
-        const int bpg = (nrb + groups - 1) / groups;
-        u0 = ct * nrb + min(nrb, g * bpg);
-        u1 = ct * nrb + min(nrb, (g + 1) * bpg);
-    } else {
-        u0 = (int)(units * blockIdx.x / gridDim.x);
-        u1 = (int)(units * (blockIdx.x + 1) / gridDim.x);
-    }
+    const int u0 = (int)(units * blockIdx.x / gridDim.x), u1 = (int)(units * (blockIdx.x + 1) / gridDim.x);
+    auto tile_of = [&](int k) { return k < nta ? cs.ct0a + k : cs.ct0b + (k - nta); };
     auto load_P = [&](int ct) {
         for (int e = tid; e < t * (TC / 2); e += THREADS) {
             const int s = e / (TC / 2), l = e - s * (TC / 2);
@@ -1683,7 +1727,7 @@ __global__ void __launch_bounds__(LANES *GROUPS, 2) k_flush_w(LpDev d, int group
             const int left = m - (rb + r);
             cp_async_cg16(dst + (size_t)s * FT_ROWS + r, row + (left > 0 ? rb + r : 0), left >= 2 ? 16 : (left == 1 ? 8 : 0));
         }
-        if (tid < FT_ROWS) cp_async_ca4(s_lp + b * FT_ROWS + tid, d.last_piv + min(rb + tid, m - 1));
+        if (tid < FT_ROWS) cp_async_ca4(s_lp + b * FT_ROWS + tid, marks + min(rb + tid, m - 1));
         cp_async_arrive(&s_mbar[b]);
     };
     auto prefetch_tile = [&](int ct, int rb, int k) { // this thread's lines of a tile to come
@@ -1705,7 +1749,8 @@ __global__ void __launch_bounds__(LANES *GROUPS, 2) k_flush_w(LpDev d, int group
     }
     __syncthreads();
     const bool mb = t >= 12 && nbuf == 3;
-    int ct = u0 < u1 ? u0 / nrb : 0, rb = u0 < u1 ? (u0 % nrb) * FT_ROWS : 0;
+    int cti = u0 < u1 ? u0 / nrb : 0, rb = u0 < u1 ? (u0 % nrb) * FT_ROWS : 0; // tile index in the set
+    int ct = tile_of(cti);
     if (u0 < u1) {
         load_P(ct);
         copy_F(rb, 0);
@@ -1714,9 +1759,10 @@ __global__ void __launch_bounds__(LANES *GROUPS, 2) k_flush_w(LpDev d, int group
     if (!mb) cp_async_wait_all();
     __syncthreads();
     for (int u = u0; u < u1; u++) {
-        int ct1 = ct, rb1 = rb + FT_ROWS;
+        int ct1 = ct, cti1 = cti, rb1 = rb + FT_ROWS;
         if (rb1 >= nrb * FT_ROWS) {
-            ct1 = ct + 1;
+            cti1 = cti + 1;
+            ct1 = tile_of(cti1);
             rb1 = 0;
         }
         const int j0 = ct * TC + 2 * lane, j1 = j0 + 2 * LANES;
@@ -1808,8 +1854,10 @@ __global__ void __launch_bounds__(LANES *GROUPS, 2) k_flush_w(LpDev d, int group
             __syncthreads();
         }
         ct = ct1;
+        cti = cti1;
         rb = rb1;
     }
+    if (!cs.close) return;
     if (tid == 0) {
         __threadfence();
         s_flag = atomicAdd(&d.ctr[2], 1u) == gridDim.x - 1;
@@ -1965,6 +2013,9 @@ __global__ void k_init(LpDev d, unsigned max_iter, int kblk, int fresh)
             st->status = XPI_RUNNING;
             st->kblk = kblk > 0 ? kblk : 1;
             st->kadapt = 0;
+            st->blk = 0; // ring slots restart (the previous solve is over on every rank)
+            st->wb_pending = 0;
+            for (int k = 0; k < NH; k++) st->hist_t[k] = 0;
         } else {
             if (st->status == XP_SIX_TIME_OUT && st->cnt < max_iter) st->status = XPI_RUNNING; // resume
             if (kblk != 0 && st->t == 0) { // kblk < 0: adaptive with upper bound -kblk
@@ -2063,6 +2114,37 @@ __global__ void k_fill_synth(LpDev d, int n, uint64_t seed)
     fill_slack_form(d, n, g);
 }
 
+// The same for global columns [g0, g1) only (single GPU), the constant column coming from a
+// separate vector b: a column-chunked upload builds the slack form as the chunks arrive.
+__global__ void k_slack_form_cols(LpDev d, const double *leq, const double *b, const double *tg, int n, int g0,
+                                  int g1, int first)
+{
+    const int m = d.m, C = d.C, wd = g1 - g0;
+    const size_t total = (size_t)m * wd;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        const int i = (int)(e / wd), j = g0 + (int)(e % wd);
+        double v;
+        if (j < n) v = leq[(size_t)i * (n + 1) + j];
+        else if (j < n + m) v = (j - n == i) ? 1.0 : 0.0;
+        else v = b[i];
+        d.tab[(size_t)i * C + j] = v;
+    }
+    for (int j = g0 + blockIdx.x * blockDim.x + threadIdx.x; j < g1; j += gridDim.x * blockDim.x)
+        d.tgtf[j] = j < n ? tg[j] : (j < n + m ? 0.0 : tg[n]);
+    if (!first) return;
+    // the basis maps belong to the solve, not to a piece of columns: all of them with the first
+    // piece (a later piece must not undo the swaps made while it was on its way)
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n + m; j += gridDim.x * blockDim.x) {
+        d.nvset[j] = j < n;
+        d.bv2eq[j] = j < n ? -1 : j - n;
+    }
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
+        d.eq2bv[i] = n + i;
+        d.rhsbuf[i] = b[i];
+        if (i == 0) d.st->tg_rhs = tg[n];
+    }
+}
+
 // replicas after a raw upload (the caller's full arrays)
 __global__ void k_set_tg_rhs(LpDev d, double v) { d.st->tg_rhs = v; }
 __global__ void k_rhs_from_tab(LpDev d)
@@ -2149,18 +2231,29 @@ static void flush_launch_kb(xp_ctx *ctx, const LpDev &d)
 }
 
 constexpr int FT_TR = 8, FT_LANES = 128, FT_HALVES = 2, FT_THREADS = FT_LANES * FT_HALVES;
+constexpr int FW_LANES = 64, FW_GROUPS = 4; // k_flush_w: same 256-column tile, 8 x 4 entries per thread
 
 static size_t flush_t_smem(int kblk, int nbuf = 3)
 {
     return ((size_t)kblk * 2 * FT_LANES + (size_t)nbuf * kblk * FT_ROWS) * sizeof(double) + nbuf * FT_ROWS * sizeof(int);
 }
 
-constexpr int FW_LANES = 64, FW_GROUPS = 4; // k_flush_w: same 256-column tile, 8 x 4 entries per thread
+static ColSet all_tiles(const LpDev &d)
+{
+    ColSet cs;
+    cs.ct0a = 0;
+    cs.ct1a = (d.Cl + 4 * FW_LANES - 1) / (4 * FW_LANES);
+    cs.ct0b = cs.ct1b = 0;
+    cs.slot = -1;
+    cs.close = 1;
+    return cs;
+}
 
-static int flush_w_launch(xp_lp_f64 *lp, int kblk)
+static int flush_w_launch(xp_lp_f64 *lp, int kblk, const ColSet *set = nullptr)
 {
     xp_ctx *ctx = lp->ctx;
     const LpDev &d = lp->d;
+    const ColSet cs = set ? *set : all_tiles(d);
     auto kern = k_flush_w<FT_TR, FW_LANES, FW_GROUPS>;
     if (lp->fw_smem_set == 0) {
         XP_CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)flush_t_smem(KMAX)));
@@ -2179,11 +2272,12 @@ static int flush_w_launch(xp_lp_f64 *lp, int kblk)
         lp->fw_occ_k = kblk;
     }
     const size_t smem = flush_t_smem(kblk, lp->fw_nbuf);
-    const int ctiles = (d.Cl + 4 * FW_LANES - 1) / (4 * FW_LANES);
+    const int ctiles = (cs.ct1a - cs.ct0a) + (cs.ct1b - cs.ct0b);
     const long long units = (long long)ctiles * ((d.m + FT_ROWS - 1) / FT_ROWS);
     long long grid = (long long)lp->fw_occ * ctx->sm_count;
     if (grid > units) grid = units;
-    kern<<<(unsigned)grid, FT_THREADS, smem, ctx->stream>>>(d, 0, lp->fw_nbuf);
+    if (grid < 1) return 0;
+    kern<<<(unsigned)grid, FT_THREADS, smem, ctx->stream>>>(d, cs, lp->fw_nbuf);
     ctx->launches++;
     return 0;
 }
@@ -2324,6 +2418,7 @@ static int lp_create_fill(xp_ctx *ctx, int m, int C, int rank, int G, xp_lp_f64 
     ALLOC(d.ctr, 64);
     ALLOC(d.st, sizeof(LpState));
     ALLOC(lp->xblock, xblock_bytes(d));
+    ALLOC(d.hist_lp, (size_t)NH * m * sizeof(int32_t));
 #undef ALLOC
     {
         int span2 = d.Cl > m ? d.Cl : m;
@@ -2505,7 +2600,7 @@ extern "C" void xp_lp_f64_destroy(xp_lp_f64 *lp)
         if (lp->peer_map[r]) cudaIpcCloseMemHandle(lp->peer_map[r]);
     void *ptrs[] = {d.tab,   d.tgtf,     d.P,     d.rhsbuf, d.sol,     lp->vc_diag, lp->vc_rhs,
                     d.nvset, d.bv2eq,    d.eq2bv, d.tabu,   d.row_cnt, d.col_cnt,   d.log,
-                    d.st,    d.last_piv, d.partA, d.partB,  d.ctr,     lp->xblock};
+                    d.st,    d.last_piv, d.partA, d.partB,  d.ctr,     lp->xblock, d.hist_lp};
     for (void *p : ptrs) cudaFree(p);
     cudaFree(lp->panA);
     cudaFree(lp->panB);
@@ -2686,7 +2781,7 @@ static int window_config(xp_lp_f64 *lp)
     return 0;
 }
 
-static cudaError_t wpanel_launch(xp_lp_f64 *lp)
+static cudaError_t wpanel_launch(xp_lp_f64 *lp, int bulk_lo = -1, int bulk_hi = -1)
 {
     const LpDev &d = lp->d;
     cudaStream_t s = lp->ctx->stream;
@@ -2711,11 +2806,12 @@ static cudaError_t wpanel_launch(xp_lp_f64 *lp)
     }
     if (e != cudaSuccess) return e;
     // the columns the window left out (and, on peers, the replicated bookkeeping)
-    const int jl0 = d.w - d.col0 > 0 ? d.w - d.col0 : 0;
-    int grid = (d.Cl - jl0 + WB_TH - 1) / WB_TH;
+    const int jl0 = bulk_lo >= 0 ? bulk_lo : (d.w - d.col0 > 0 ? d.w - d.col0 : 0);
+    const int jl1 = bulk_hi >= 0 ? bulk_hi : d.Cl;
+    int grid = (jl1 - jl0 + WB_TH - 1) / WB_TH;
     if (grid < 1) grid = 1;
     if (grid > 2 * lp->ctx->sm_count) grid = 2 * lp->ctx->sm_count;
-    k_prow_bulk<<<grid, WB_TH, 2 * KMAX * WB_TH * sizeof(double), s>>>(d);
+    k_prow_bulk<<<grid, WB_TH, 2 * KMAX * WB_TH * sizeof(double), s>>>(d, 0, 0, jl0, jl1);
     return cudaGetLastError();
 }
 
@@ -3209,6 +3305,115 @@ struct LpRef { // handles live on the ctx (cached_handle): nothing to release on
 
 } // namespace
 
+// Upload behind the solve (no phase 1, bounded run of at most NH blocks).  The pricing window
+// holds the columns that can enter, so the caller's LP goes up in two column pieces: the window
+// [0, w) first, the rest of A -- [w, n) -- while the device is already deciding.  The "early"
+// tiles (window + slack identity + constant column, the latter two generated on the device)
+// run the whole bounded solve: k_wpanel decides, k_prow_bulk / k_flush_w keep the early tiles up
+// to date and every closed block stays in the ring (F, records, pivot-row marks).  When the
+// late piece has landed its tiles replay the closed blocks in order -- the same operations per
+// entry in the same order, only later.  Anything the window cannot decide (a pricing scan that
+// leaves it, a failing ratio test) simply leaves the block open: by the time the host looks,
+// the late tiles have caught up and the ordinary full-width solve continues from that state.
+// Returns 1 if it took the job (state ready for xp_lp_f64_solve), 0 if the shape does not
+// qualify (caller uploads the plain way), < 0 on error.
+static int two_stage_streamed(xp_ctx *ctx, xp_lp_f64 *lp, int m, int n, const double *leq, double *d_leq,
+                              const double *d_tg, const double *d_b, uint32_t max_iter)
+{
+    LpDev &d = lp->d;
+    const int TCW = 4 * FW_LANES, C = d.C, w = d.w;
+    const int kblk = lp->kblk > 0 ? lp->kblk : auto_block(d);
+    if (getenv("XP_NO_STREAM_UPLOAD")) return 0;
+    if (!lp->use_panel || w <= 0 || w % TCW || n <= w + TCW || !lp->ft_wide || (d.Cl & 1)) return 0;
+    if (max_iter == XP_NO_ITER_LIMIT || max_iter < 64 || kblk < 16) return 0;
+    const unsigned nb = (max_iter + kblk - 1) / kblk;
+    if (nb > (unsigned)NH) return 0;
+    size_t min_mb = 64; // small uploads: nothing to hide
+    if (const char *e = getenv("XP_STREAM_MIN_MB")) min_mb = (size_t)atoi(e); // (tests)
+    if ((size_t)m * (n + 1) * sizeof(double) < (min_mb << 20)) return 0;
+    cudaStream_t s = ctx->stream;
+    int rc = xp_ctx_pipe(ctx);
+    if (rc) return rc;
+    const int late_end = ((n + TCW - 1) / TCW) * TCW < C ? ((n + TCW - 1) / TCW) * TCW : C;
+    const int tiles = (C + TCW - 1) / TCW;
+    const size_t pitch = (size_t)(n + 1) * sizeof(double);
+    const bool dbg = getenv("XP_STREAM_DBG") != nullptr;
+    cudaEvent_t te[6] = {};
+    if (dbg)
+        for (auto &e : te) cudaEventCreate(&e);
+    XP_CUDA_OK(ctx, cudaEventRecord(ctx->pipe_begin, s)); // d_tg, d_b and the previous call's kernels
+    XP_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->pipe_copy, ctx->pipe_begin, 0));
+    if (dbg) cudaEventRecord(te[0], ctx->pipe_copy);
+    XP_CUDA_OK(ctx, cudaMemcpy2DAsync(d_leq, pitch, leq, pitch, (size_t)w * sizeof(double), m, cudaMemcpyHostToDevice,
+                                      ctx->pipe_copy));
+    XP_CUDA_OK(ctx, cudaEventRecord(ctx->pipe_up[0], ctx->pipe_copy));
+    if (dbg) cudaEventRecord(te[1], ctx->pipe_copy);
+    XP_CUDA_OK(ctx, cudaMemcpy2DAsync(d_leq + w, pitch, leq + w, pitch, (size_t)(n - w) * sizeof(double), m,
+                                      cudaMemcpyHostToDevice, ctx->pipe_copy));
+    XP_CUDA_OK(ctx, cudaEventRecord(ctx->pipe_up[1], ctx->pipe_copy));
+    if (dbg) cudaEventRecord(te[2], ctx->pipe_copy);
+    rc = lp_reset(lp);
+    if (rc) return rc;
+    // ---- early tiles: slack form, then the whole bounded solve ----
+    XP_CUDA_OK(ctx, cudaStreamWaitEvent(s, ctx->pipe_up[0], 0));
+    const int g = ctx->sm_count * 4;
+    k_slack_form_cols<<<g, 256, 0, s>>>(d, d_leq, d_b, d_tg, n, 0, w, 1);
+    if (late_end < C) k_slack_form_cols<<<g, 256, 0, s>>>(d, d_leq, d_b, d_tg, n, late_end, C, 0);
+    k_init<<<1, 32, 0, s>>>(d, max_iter, lp->kblk == 0 ? -kblk : kblk, 0);
+    k_first_price_window<<<1, 1024, 0, s>>>(d);
+    ctx->launches += 4;
+    ColSet early;
+    early.ct0a = 0, early.ct1a = w / TCW, early.ct0b = late_end / TCW, early.ct1b = late_end < C ? tiles : late_end / TCW;
+    early.slot = -1, early.close = 1;
+    for (unsigned b = 0; b < nb; b++) {
+        XP_CUDA_OK(ctx, wpanel_launch(lp, late_end, C));
+        k_block_snapshot<<<32, 256, 0, s>>>(d);
+        ctx->launches++;
+        rc = flush_w_launch(lp, kblk, &early);
+        if (rc) return rc;
+    }
+    // ---- late tiles: slack form when they have landed, then the closed blocks in order ----
+    if (dbg) cudaEventRecord(te[3], s);
+    XP_CUDA_OK(ctx, cudaStreamWaitEvent(s, ctx->pipe_up[1], 0));
+    if (dbg) cudaEventRecord(te[4], s);
+    k_slack_form_cols<<<g, 256, 0, s>>>(d, d_leq, d_b, d_tg, n, w, late_end, 0);
+    ctx->launches++;
+    ColSet late;
+    late.ct0a = w / TCW, late.ct1a = late_end / TCW, late.ct0b = late.ct1b = 0;
+    late.close = 0;
+    int bg = (late_end - w + WB_TH - 1) / WB_TH;
+    if (bg > 2 * ctx->sm_count) bg = 2 * ctx->sm_count;
+    for (unsigned b = 0; b < nb; b++) {
+        k_prow_bulk<<<bg, WB_TH, 2 * KMAX * WB_TH * sizeof(double), s>>>(d, 1, (int)b, w, late_end);
+        ctx->launches++;
+        late.slot = (int)b;
+        rc = flush_w_launch(lp, kblk, &late);
+        if (rc) return rc;
+    }
+    XP_CUDA_OK(ctx, cudaGetLastError());
+    if (dbg) cudaEventRecord(te[5], s);
+    XP_CUDA_OK(ctx, cudaMemcpyAsync(lp->h_st, d.st, sizeof(LpState), cudaMemcpyDeviceToHost, s));
+    XP_CUDA_OK(ctx, cudaStreamSynchronize(s));
+    if (dbg) {
+        float a = 0, b = 0, c = 0, e = 0, f = 0;
+        cudaEventElapsedTime(&a, te[0], te[1]);
+        cudaEventElapsedTime(&b, te[0], te[2]);
+        cudaEventElapsedTime(&c, te[0], te[3]);
+        cudaEventElapsedTime(&e, te[0], te[4]);
+        cudaEventElapsedTime(&f, te[0], te[5]);
+        fprintf(stderr, "[xp stream] window piece up at %.2f ms, late piece at %.2f; early solve done at %.2f, late replay "
+                        "%.2f -> %.2f ms (cnt %u, t %d, status %d)\n", a, b, c, e, f, lp->h_st->cnt, lp->h_st->t, lp->h_st->status);
+        for (auto &ev : te) cudaEventDestroy(ev);
+    }
+    if (lp->h_st->t > 0) { // a block was left open (exception inside the window run): its pivot rows for the late tiles
+        k_prow_bulk<<<bg, WB_TH, 2 * KMAX * WB_TH * sizeof(double), s>>>(d, 2, 0, w, late_end);
+        ctx->launches++;
+        XP_CUDA_OK(ctx, cudaGetLastError());
+    }
+    lp->cnt_host = lp->h_st->cnt;
+    return 1;
+}
+
 extern "C" int xp_six_two_stage_f64_large(xp_ctx *ctx, int m, int n, const double *leq,
                                           const double *tgtf, uint32_t max_iter, int rule,
                                           int32_t *status, double *maxv, double *slack_sol,
@@ -3220,14 +3425,24 @@ extern "C" int xp_six_two_stage_f64_large(xp_ctx *ctx, int m, int n, const doubl
     XP_CUDA_OK(ctx, cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream;
     const int Cm = n + m + 1;
-    // stage1 decision on the caller's arrays, :1794-1803
+    // stage1 decision on the caller's arrays, :1794-1803 (the constant column is gathered into a
+    // small pinned buffer on the way: the piecewise upload below sends it ahead of the matrix)
+    if (ctx->stage_bytes < (size_t)m * sizeof(double)) {
+        if (ctx->stage) cudaFreeHost(ctx->stage);
+        ctx->stage = nullptr;
+        ctx->stage_bytes = 0;
+        XP_CUDA_OK(ctx, cudaMallocHost(&ctx->stage, (size_t)m * sizeof(double)));
+        ctx->stage_bytes = (size_t)m * sizeof(double);
+    }
+    double *h_b = (double *)ctx->stage;
     bool pos = false, bneg = false;
     for (int j = 0; j < n; j++) pos |= tgtf[j] > 0.0;
     int prow = 0; // row of the first minimum constant term, :894-904
     for (int i = 0; i < m; i++) {
         const double b = leq[(size_t)i * (n + 1) + n];
+        h_b[i] = b;
         bneg |= b < 0.0;
-        if (leq[(size_t)prow * (n + 1) + n] > b) prow = i;
+        if (h_b[prow] > b) prow = i;
     }
     const bool aux = !pos || bneg;
     if (maxv) *maxv = 0.0;
@@ -3235,11 +3450,28 @@ extern "C" int xp_six_two_stage_f64_large(xp_ctx *ctx, int m, int n, const doubl
     if (pivots) *pivots = 0;
     // the caller's LP in device scratch (the only bulk upload of the call)
     void *scr = nullptr;
-    const size_t in_elems = (size_t)m * (n + 1) + (n + 1);
+    const size_t in_elems = (size_t)m * (n + 1) + (n + 1) + m;
     int rc = xp_ctx_scratch(ctx, in_elems * sizeof(double), &scr);
     if (rc) return rc;
-    double *d_leq = (double *)scr, *d_tg = d_leq + (size_t)m * (n + 1);
+    double *d_leq = (double *)scr, *d_tg = d_leq + (size_t)m * (n + 1), *d_b = d_tg + (n + 1);
     XP_CUDA_OK(ctx, cudaMemcpyAsync(d_tg, tgtf, (n + 1) * sizeof(double), cudaMemcpyHostToDevice, s));
+    XP_CUDA_OK(ctx, cudaMemcpyAsync(d_b, h_b, (size_t)m * sizeof(double), cudaMemcpyHostToDevice, s));
+    unsigned n_piv = 0;
+    LpRef A, M;
+    rc = cached_handle(ctx, &ctx->cached_lp, m, Cm, &M.lp);
+    if (rc) return rc;
+    M.lp->kblk = ctx->slack_block;
+    if (M.lp->window != ctx->slack_window) {
+        rc = xp_lp_f64_set_window(M.lp, ctx->slack_window);
+        if (rc) return rc;
+    }
+    int streamed = 0;
+    if (!aux) {
+        streamed = two_stage_streamed(ctx, M.lp, m, n, leq, d_leq, d_tg, d_b, max_iter);
+        if (streamed < 0) return streamed;
+        if (streamed) M.lp->d.vc_diag = M.lp->d.vc_rhs = nullptr;
+    }
+    if (!streamed) {
     // No phase 1: the rows go up in chunks on the copy stream and k_slack_form builds [A | I | b]
     // chunk by chunk behind them, so the slack form is complete one chunk's kernel after the last
     // byte has arrived.  Phase 1 (rare) needs the whole LP first: one copy.
@@ -3259,15 +3491,6 @@ extern "C" int xp_six_two_stage_f64_large(xp_ctx *ctx, int m, int n, const doubl
         }
     } else {
         XP_CUDA_OK(ctx, cudaMemcpyAsync(d_leq, leq, (size_t)m * row_bytes, cudaMemcpyHostToDevice, s));
-    }
-    unsigned n_piv = 0;
-    LpRef A, M;
-    rc = cached_handle(ctx, &ctx->cached_lp, m, Cm, &M.lp);
-    if (rc) return rc;
-    M.lp->kblk = ctx->slack_block;
-    if (M.lp->window != ctx->slack_window) {
-        rc = xp_lp_f64_set_window(M.lp, ctx->slack_window);
-        if (rc) return rc;
     }
     if (!aux) {
         for (int c = 0; c < n_chunks; c++) {
@@ -3339,6 +3562,7 @@ extern "C" int xp_six_two_stage_f64_large(xp_ctx *ctx, int m, int n, const doubl
     }
     rc = lp_reset(M.lp);
     if (rc) return rc;
+    } // !streamed
     int st = xp_lp_f64_solve(M.lp, max_iter, rule);
     if (st < 0) return st;
     uint32_t it = 0;
@@ -3349,4 +3573,13 @@ extern "C" int xp_six_two_stage_f64_large(xp_ctx *ctx, int m, int n, const doubl
     if (pivots) *pivots = n_piv + it;
     *status = st;
     return 0;
+}
+
+// Position-keyed checksums (xp_lp_f64_checksum) of the tableau and objective row the last
+// xp_six_two_stage_f64_large / xp_six_slack_f64 call on this ctx left on the device: the final
+// tableau never travels to the host on that path, this is how a test still sees all of it.
+extern "C" int xp_ctx_last_lp_checksum(xp_ctx *ctx, uint64_t *sum_tableau, uint64_t *sum_tgtf)
+{
+    if (!ctx || !ctx->cached_lp) return XP_ERR_BAD_ARG;
+    return xp_lp_f64_checksum((xp_lp_f64 *)ctx->cached_lp, sum_tableau, sum_tgtf);
 }

@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(WTHB, 1) k_wpanel(LpDev d, unsigned long long 
     const int n = d.n, m = d.m, Cl = d.Cl, G = d.G, rpc = d.wrpc, wpc = d.wwpc;
 
     int t = st->t;
-    const int kblk = st->kblk, par = st->blk & 1;
+    const int kblk = st->kblk, par = st->blk & (NH - 1);
     unsigned cnt = st->cnt;
     const unsigned max_iter = st->max_iter;
     int q = st->q, zero_upto = st->zero_upto, anypos = st->anypos;
@@ -494,15 +494,22 @@ __global__ void k_wpanel_peer(LpDev d)
 // ---------------------------------------------------------------------------
 constexpr int WB_TH = 128;
 
-__global__ void __launch_bounds__(WB_TH) k_prow_bulk(LpDev d)
+// mode 0 (live): pivots [wb_t0, t) of the open block, local columns [jlo, jhi) -- what the run
+//   of k_wpanel just before left out;
+// mode 1 (replay): every pivot of the closed block in ring slot `slot`, for columns that were
+//   not there when the block was decided (a piecewise upload);
+// mode 2: every pivot so far of the OPEN block (all made by k_wpanel), for such columns.
+__global__ void __launch_bounds__(WB_TH) k_prow_bulk(LpDev d, int mode, int slot, int jlo, int jhi)
 {
     extern __shared__ double s_bulk[]; // sA[KMAX][WB_TH] | sPr[KMAX][WB_TH]
     __shared__ double s_L[KMAX][KMAX]; // s_L[s][u] = F[u][p_s], u < s
     __shared__ WRec s_rec[KMAX];
     LpState *st = d.st;
-    if (!st->wb_pending) return;
-    const int t0 = st->wb_t0, t1 = st->t, par = st->blk & 1, tid = threadIdx.x;
-    const int n = d.n, Cl = d.Cl;
+    if (mode == 0 && !st->wb_pending) return;
+    const int t0 = mode == 0 ? st->wb_t0 : 0, t1 = mode == 1 ? st->hist_t[slot] : st->t;
+    const int par = mode == 1 ? slot : (st->blk & (NH - 1)), tid = threadIdx.x;
+    const int n = d.n, Cl = jhi;
+    if (t1 <= t0) return;
     const WRec *recs = (const WRec *)(d.xb[d.rank] + xoff_rec(d, par));
     for (int s = t0 + tid; s < t1; s += WB_TH) s_rec[s] = recs[s];
     __syncthreads();
@@ -512,13 +519,13 @@ __global__ void __launch_bounds__(WB_TH) k_prow_bulk(LpDev d)
     }
     __syncthreads();
     double *sA = s_bulk, *sPr = s_bulk + (size_t)KMAX * WB_TH;
-    const int jl0 = max(0, d.w - d.col0); // first local column outside the window
-    for (int jb = jl0 + blockIdx.x * WB_TH; jb < Cl; jb += gridDim.x * WB_TH) {
+    const int ld = d.Cl;
+    for (int jb = jlo + blockIdx.x * WB_TH; jb < Cl; jb += gridDim.x * WB_TH) {
         const int jl = jb + tid;
         if (jl < Cl) {
             const int g = d.col0 + jl;
-            for (int s = t0; s < t1; s++) sA[s * WB_TH + tid] = d.tab[(size_t)s_rec[s].p * Cl + jl];
-            for (int u = 0; u < t0; u++) sPr[u * WB_TH + tid] = ld_cg(d.P + (size_t)u * Cl + jl);
+            for (int s = t0; s < t1; s++) sA[s * WB_TH + tid] = d.tab[(size_t)s_rec[s].p * ld + jl];
+            for (int u = 0; u < t0; u++) sPr[u * WB_TH + tid] = ld_cg(d.P + (size_t)u * ld + jl);
             double tg = d.tgtf[jl];
             for (int s = t0; s < t1; s++) {
                 const WRec rc = s_rec[s];
@@ -528,7 +535,7 @@ __global__ void __launch_bounds__(WB_TH) k_prow_bulk(LpDev d)
                 for (int u = rc.s0p + 1; u < s; u++) v = xp_add(v, xp_mul(s_L[s][u], sPr[u * WB_TH + tid]));
                 const double xv = xp_scale(v, rc.r, xp_feq(rc.r, 1.0), xp_feq(rc.r, 0.0));
                 sPr[s * WB_TH + tid] = xv;
-                d.P[(size_t)s * Cl + jl] = xv;
+                d.P[(size_t)s * ld + jl] = xv;
                 double tt = xp_mul(xv, -1.0);
                 if (g >= n) tt = -tt;
                 tt = xp_feq(rc.cq, 0.0) ? 0.0 : (xp_feq(rc.cq, 1.0) ? tt : xp_mul(tt, rc.cq));
@@ -537,7 +544,7 @@ __global__ void __launch_bounds__(WB_TH) k_prow_bulk(LpDev d)
             d.tgtf[jl] = tg;
         }
     }
-    if (d.rank > 0) { // replicated state the leader kept while deciding
+    if (d.rank > 0 && mode == 0) { // replicated state the leader kept while deciding
         for (int i = blockIdx.x * WB_TH + tid; i < d.m; i += gridDim.x * WB_TH) {
             double rh = d.rhsbuf[i];
             for (int s = t0; s < t1; s++) {
