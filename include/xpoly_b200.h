@@ -226,6 +226,19 @@ int xp_six_two_stage_f64_large(xp_ctx *ctx, int m, int n, const double *leq, con
                                double *slack_sol, double *tgtf_out, int32_t *eq2bv,
                                uint32_t *iters, uint32_t *pivots);
 
+/* The same with the caller's variable constraints: vc_diag[j] = vc(j,j), vc_rhs[j] = vc(j,rhs)
+ * for the n structural variables -- the only entries of `vc` the solver reads, in the
+ * feasibility check of the optimal exit (lpsol.h:798-802); NULL = -1 / 0. */
+int xp_six_two_stage_f64_large_vc(xp_ctx *ctx, int m, int n, const double *leq, const double *tgtf,
+                                  const double *vc_diag, const double *vc_rhs, uint32_t max_iter,
+                                  int rule, int32_t *status, double *maxv, double *slack_sol,
+                                  double *tgtf_out, int32_t *eq2bv, uint32_t *iters, uint32_t *pivots);
+/* What SIX::TwoStageMethod hands back through its IN OUT arguments (lpsol.h:291-301) after
+ * the last xp_six_two_stage_f64_large[_vc] / xp_six_slack_f64 call on this ctx: the final
+ * tableau m x C (C = n+m+1), objective row (C), nvset / bvset / bv2eq (C-1), eq2bv (m).
+ * Any pointer may be NULL; the tableau is the only large transfer and is optional. */
+int xp_ctx_last_lp_download(xp_ctx *ctx, double *tableau, double *tgtf, uint8_t *nvset,
+                            uint8_t *bvset, int32_t *bv2eq, int32_t *eq2bv);
 /* Checksums (as xp_lp_f64_checksum) of the tableau / objective row that the last
  * xp_six_two_stage_f64_large or xp_six_slack_f64 call on this ctx left on the device. */
 int xp_ctx_last_lp_checksum(xp_ctx *ctx, uint64_t *sum_tableau, uint64_t *sum_tgtf);
@@ -298,6 +311,12 @@ int xp_six_solve_rat_batch(xp_ctx *ctx, int is_min, int batch, int m, int n, con
 int xp_mip_solve_rat(xp_ctx *ctx, int is_min, int is_bin, int m, int n, const xp_rat *tgtf,
                      int k, const xp_rat *eq, const xp_rat *leq, xp_rat *v, xp_rat *sol,
                      int32_t *n_nodes);
+/* The same with MIP's rational_indicator (lpsol.h:2626-2630, :2369-2391): n+1 flags, a
+ * non-zero flag lets that entry of the solution stay rational (it is never branched on). */
+int xp_mip_solve_rat_ri(xp_ctx *ctx, int is_min, int is_bin, int m, int n, const xp_rat *tgtf,
+                        int k, const xp_rat *eq, const xp_rat *leq,
+                        const uint8_t *rational_indicator, xp_rat *v, xp_rat *sol,
+                        int32_t *n_nodes);
 int xp_mip_solve_f64(xp_ctx *ctx, int is_min, int is_bin, int m, int n, const double *tgtf, int k,
                      const double *eq, const double *leq, double *v, double *sol,
                      int32_t *n_nodes);

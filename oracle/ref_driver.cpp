@@ -244,6 +244,26 @@ int ref_mip_solve_rat(int is_min, int is_bin, int m, int n, const int32_t * leq,
     return (int)st;
 }
 
+// ... with rational_indicator (lpsol.h:2626-2657): n+1 flags.
+int ref_mip_solve_rat_ri(int is_min, int is_bin, int m, int n, const int32_t * leq, const int32_t * tgtf, int k,
+                         const int32_t * eq, const uint8_t * indicator, int32_t * v, int32_t * sol)
+{
+    RMat L, T, V, E, S;
+    fill_rat(L, m, n + 1, leq);
+    fill_rat(T, 1, n + 1, tgtf);
+    neg_identity_rat(V, n);
+    if (k > 0) fill_rat(E, k, n + 1, eq);
+    BMat ri(1, n + 1);
+    for (int j = 0; j <= n; j++) ri.set(0, j, indicator[j] != 0);
+    MIP<RMat, Rational> mip;
+    Rational val;
+    UINT st = is_min ? mip.minm(val, S, T, V, E, L, is_bin != 0, &ri) : mip.maxm(val, S, T, V, E, L, is_bin != 0, &ri);
+    v[0] = val.num();
+    v[1] = val.den();
+    if (st == IP_SUCC) dump_rat(S, sol, (size_t)n + 1);
+    return (int)st;
+}
+
 int ref_mip_solve_f64(int is_min, int is_bin, int m, int n, const double * leq,
                       const double * tgtf, int k, const double * eq, double * v, double * sol)
 {

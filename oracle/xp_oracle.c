@@ -453,7 +453,7 @@ static double xo_now(void)
         mat_##SFX L = mat_from_##SFX(m, n + 1, leq), Tg = mat_from_##SFX(1, n + 1, tgtf);         \
         mat_##SFX V = default_vc_##SFX(n);                                                        \
         mat_##SFX E = k > 0 ? mat_from_##SFX(k, n + 1, eq) : mat_new_##SFX(0, 0);                 \
-        int st = mip_solve_##SFX(is_min, is_bin, &Tg, &V, &E, &L, v, sol, n_nodes);               \
+        int st = mip_solve_##SFX(is_min, is_bin, &Tg, &V, &E, &L, v, sol, n_nodes, NULL);               \
         mat_free_##SFX(&L);                                                                       \
         mat_free_##SFX(&Tg);                                                                      \
         mat_free_##SFX(&V);                                                                       \
@@ -485,10 +485,10 @@ int xo_has_solution_rat(int m, int n, const xo_rat *leq, int k, const xo_rat *eq
     xo_rat *sol = (xo_rat *)calloc((size_t)n + 2, sizeof(xo_rat));
     int res = 0, st;
     if (is_int_sol) {
-        st = mip_solve_rat(0, 0, &Tg, &V, &E, &L, &v, sol, NULL);
+        st = mip_solve_rat(0, 0, &Tg, &V, &E, &L, &v, sol, NULL, NULL);
         if (st == XO_IP_SUCC || (!is_unique_sol && st == XO_IP_UNBOUND)) res = 1;
         if (!res) {
-            st = mip_solve_rat(1, 0, &Tg, &V, &E, &L, &v, sol, NULL);
+            st = mip_solve_rat(1, 0, &Tg, &V, &E, &L, &v, sol, NULL, NULL);
             if (st == XO_IP_SUCC || (!is_unique_sol && st == XO_IP_UNBOUND)) res = 1;
         }
     } else {
@@ -590,4 +590,19 @@ double xo_has_solution_rat_many(int batch, const int32_t *ms, const int32_t *ns,
     for (int k = 0; k < batch; k++)
         res[k] = xo_has_solution_rat(ms[k], ns[k], pool + off[k], 0, NULL, is_int_sol, is_unique_sol);
     return xo_now() - t0;
+}
+
+/* MIP::maxm / minm with rational_indicator (lpsol.h:2626-2657): n+1 flags, non-zero = that
+ * entry of the solution may stay rational. */
+int xo_mip_solve_rat_ri(int is_min, int is_bin, int m, int n, const xo_rat *leq, const xo_rat *tgtf, int k,
+                        const xo_rat *eq, const uint8_t *rational_indicator, xo_rat *v, xo_rat *sol, int *n_nodes)
+{
+    mat_rat L = mat_from_rat(m, n + 1, leq), Tg = mat_from_rat(1, n + 1, tgtf), V = default_vc_rat(n);
+    mat_rat E = k > 0 ? mat_from_rat(k, n + 1, eq) : mat_new_rat(0, 0);
+    int st = mip_solve_rat(is_min, is_bin, &Tg, &V, &E, &L, v, sol, n_nodes, rational_indicator);
+    mat_free_rat(&L);
+    mat_free_rat(&Tg);
+    mat_free_rat(&V);
+    mat_free_rat(&E);
+    return st;
 }

@@ -94,6 +94,10 @@ int xo_mip_solve_f64(int is_min, int is_bin, int m, int n, const double *leq, co
 int xo_mip_solve_rat(int is_min, int is_bin, int m, int n, const xo_rat *leq, const xo_rat *tgtf,
                      int k, const xo_rat *eq, xo_rat *v, xo_rat *sol, int *n_nodes);
 
+/* ... with MIP's rational_indicator (lpsol.h:2626-2657): n+1 flags, non-zero = may stay rational. */
+int xo_mip_solve_rat_ri(int is_min, int is_bin, int m, int n, const xo_rat *leq, const xo_rat *tgtf, int k,
+                        const xo_rat *eq, const uint8_t *rational_indicator, xo_rat *v, xo_rat *sol, int *n_nodes);
+
 /* Lineq::has_solution (linsys.cpp:830-906), vc = -I. */
 int xo_has_solution_rat(int m, int n, const xo_rat *leq, int k, const xo_rat *eq, int is_int_sol,
                         int is_unique_sol);

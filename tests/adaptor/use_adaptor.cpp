@@ -36,6 +36,30 @@ int main()
     UINT st = six.maxm(maxv, sol, tgtf, vc, eq, leq);
     printf("status %u max %.17g x = (%.17g, %.17g)\n", st, maxv.f(), sol.get(0, 0).f(), sol.get(0, 1).f());
 
+    {   // the only reference entry that exposes the solver state: TwoStageMethod (lpsol.h:291-301),
+        // here with phase 1 (b has a negative entry); every IN OUT argument is printed
+        FloatMat l2(leq), t2(tgtf), v2(vc), ssol;
+        Vector<bool> nvs, bvs;
+        Vector<INT> b2e, e2b;
+        Float mv(0.0);
+        INT rhs = 2;
+        SIX<FloatMat, Float> s2;
+        UINT stt = s2.TwoStageMethod(l2, v2, t2, ssol, mv, nvs, bvs, b2e, e2b, rhs);
+        printf("two_stage status %u maxv %.17g rhs_idx %d eq2bv %d %d bv2eq %d %d %d %d nv %d%d%d%d\n", stt, mv.f(), (int)rhs,
+               (int)e2b.get(0), (int)e2b.get(1), (int)b2e.get(0), (int)b2e.get(1), (int)b2e.get(2), (int)b2e.get(3),
+               (int)nvs.get(0), (int)nvs.get(1), (int)nvs.get(2), (int)nvs.get(3));
+        printf("two_stage tableau %u x %u:", l2.get_row_size(), l2.get_col_size());
+        for (UINT i = 0; i < l2.get_row_size(); i++)
+            for (UINT j = 0; j < l2.get_col_size(); j++) printf(" %.17g", l2.get(i, j).f());
+        printf("\ntwo_stage tgtf:");
+        for (UINT j = 0; j < t2.get_col_size(); j++) printf(" %.17g", t2.get(0, j).f());
+        printf("\ntwo_stage slack_sol:");
+        for (UINT j = 0; j < ssol.get_col_size(); j++) printf(" %.17g", ssol.get(0, j).f());
+        printf("\ntwo_stage vc %u x %u diag:", v2.get_row_size(), v2.get_col_size());
+        for (UINT j = 0; j < v2.get_row_size(); j++) printf(" %.17g", v2.get(j, j).f());
+        printf("\n");
+    }
+
     RMat rleq(2, 3), rtg(1, 3), rvc(2, 3), req, rsol;
     for (int i = 0; i < 2; i++)
         for (int j = 0; j < 3; j++) rleq.set(i, j, Rational((int)L[i][j], 1));

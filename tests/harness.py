@@ -180,6 +180,23 @@ def two_stage(which, kind, leq, tgtf, max_iter=NO_LIMIT, want_log=False):
                 slack_sol=ssol[: int(dims[3])].copy(), log=log)
 
 
+def mip_solve_ri(which, is_min, is_bin, leq, tgtf, indicator, eq=None):
+    """MIP<RMat,Rational>::maxm / minm with rational_indicator (n+1 flags)."""
+    lib, pre = _lib_and_prefix(which)
+    m, n1 = leq.shape[0], leq.shape[1]
+    k = 0 if eq is None else eq.shape[0]
+    v = np.zeros(2, dtype=np.int32)
+    sol = np.zeros((n1, 2), dtype=np.int32)
+    ind = np.ascontiguousarray(indicator, dtype=np.uint8)
+    args = [int(is_min), int(is_bin), m, n1 - 1, P(np.ascontiguousarray(leq)), P(np.ascontiguousarray(tgtf)), k,
+            P(None if eq is None else np.ascontiguousarray(eq)), P(ind), P(v), P(sol)]
+    nodes = C.c_int(0)
+    if which == "oracle":
+        args.append(C.byref(nodes))
+    st = getattr(lib, f"{pre}mip_solve_rat_ri")(*args)
+    return dict(status=st, v=v, sol=sol, nodes=nodes.value)
+
+
 def mip_solve(which, kind, is_min, is_bin, leq, tgtf, eq=None):
     lib, pre = _lib_and_prefix(which)
     m = 0 if leq is None else leq.shape[0]

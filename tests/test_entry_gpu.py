@@ -342,3 +342,64 @@ def test_golden_reference_answers_for_the_8f_callers(ctx):
     systems = [(np.array(d["leq"], dtype=np.int64), np.array(d["eq"], dtype=np.int64)) for d in gold["has_solution_eq"]]
     res = ctx.has_solution_ragged(systems)
     assert res.tolist() == [d["result"] for d in gold["has_solution_eq"]]
+
+
+def test_mip_rational_indicator(ctx):
+    """MIP with rational_indicator (lpsol.h:2369-2391) through xp_mip_solve_rat_ri: the cases the
+    unmodified reference answered (tests/golden/mip_indicator_vectors.json) and live oracle cases."""
+    import json
+    import os
+    cases = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "mip_indicator_vectors.json")))["cases"]
+    n_ok = 0
+    for k, c in enumerate(cases):
+        if c["is_bin"]:
+            continue
+        leq, tg = np.array(c["leq"], dtype=np.int64), np.array(c["tgtf"], dtype=np.int64)
+        g = ctx.mip_solve_rat_ri(c["is_min"], 0, leq, tg, c["indicator"])
+        assert g["status"] == c["status"], (k, g["status"], c["status"])
+        assert g["v"].tolist() == c["v"], k
+        if c["status"] == 0:
+            assert g["sol"].tolist() == c["sol"], k
+            n_ok += 1
+    assert n_ok > 10
+    rs = np.random.RandomState(3)
+    for seed in range(30):
+        leq, tg = H.gen_int_lp(2900 + seed, 6, 5, alo=-1, ahi=4, density=0.7, blo=1, bhi=17)
+        ind = (rs.uniform(size=6) < 0.4).astype(np.uint8)
+        a0 = H.appro_count("oracle")
+        o = H.mip_solve_ri("oracle", 0, 0, H.to_rat(leq), H.to_rat(tg), ind)
+        if H.appro_count("oracle") != a0:
+            continue
+        g = ctx.mip_solve_rat_ri(0, 0, leq.astype(np.int64), tg.astype(np.int64), ind)
+        assert g["status"] == o["status"] and g["nodes"] == o["nodes"], seed
+        assert np.array_equal(g["v"], o["v"]), seed
+
+
+def test_general_variable_constraints(ctx):
+    """vc beyond -x <= 0 (other diagonals, constant terms, free variables): only the feasibility
+    check of the optimal exit reads it (lpsol.h:798-802).  FP64 goes through the HBM-resident path
+    with the two vectors on the device, the exact path re-decides the verdict on the solution row."""
+    r = np.random.RandomState(77)
+    seen = set()
+    for seed in range(120):
+        m, n = r.randint(3, 8), r.randint(2, 6)
+        leq, tg = H.gen_int_lp(3000 + seed, m, n, alo=-1, ahi=3, density=0.7, blo=0, bhi=15)
+        vc = np.zeros((n, n + 1))
+        for i in range(n):
+            u = r.uniform()
+            if u < 0.2:
+                continue
+            vc[i, i] = -r.randint(1, 4)
+            if u > 0.5:
+                vc[i, n] = r.randint(-6, 4)
+        for is_min in (0, 1):
+            same_f64(ctx.six_solve("f64", is_min, leq, tg, vc=vc),
+                     H.six_solve("oracle", "f64", is_min, leq, tg, vc), ("vc-f64", seed, is_min))
+            a0 = H.appro_count("oracle")
+            o = H.six_solve("oracle", "rat", is_min, H.to_rat(leq), H.to_rat(tg), H.to_rat(vc))
+            if H.appro_count("oracle") != a0:
+                continue
+            g = ctx.six_solve("rat", is_min, leq.astype(np.int64), tg.astype(np.int64), vc=vc.astype(np.int64))
+            same_rat(g, o, ("vc-rat", seed, is_min))
+            seen.add((is_min, o["status"]))
+    assert (0, 0) in seen and (0, 3) in seen

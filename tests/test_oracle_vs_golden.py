@@ -146,3 +146,20 @@ def test_fea_schedule_and_has_solution_with_equalities():
     for k, d in enumerate(GOLD["has_solution_eq"]):
         leq, eq = np.array(d["leq"], dtype=np.int64), np.array(d["eq"], dtype=np.int64)
         assert H.has_solution("oracle", H.to_rat(leq), H.to_rat(eq)) == d["result"], k
+
+
+def test_mip_rational_indicator_golden():
+    """rational_indicator cases recorded from the unmodified reference (make_golden_ri.py)."""
+    import json
+    import os
+    cases = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "mip_indicator_vectors.json")))["cases"]
+    assert len(cases) > 50
+    for k, c in enumerate(cases):
+        if c["is_bin"]:
+            continue  # is_bin appends equalities and walks into convertEq2Ineq's column bug: reference-UB territory
+        leq, tg = np.array(c["leq"], dtype=np.int64), np.array(c["tgtf"], dtype=np.int64)
+        o = H.mip_solve_ri("oracle", c["is_min"], c["is_bin"], H.to_rat(leq), H.to_rat(tg), c["indicator"])
+        assert o["status"] == c["status"], (k, o["status"], c["status"])
+        assert o["v"].tolist() == c["v"], k
+        if c["status"] == 0:
+            assert o["sol"].tolist() == c["sol"], k

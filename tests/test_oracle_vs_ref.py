@@ -143,3 +143,63 @@ def test_fea_schedule_shape_mip_and_has_solution_with_equalities():
         assert H.has_solution("oracle", H.to_rat(leq), H.to_rat(eq)) == \
             H.has_solution("ref", H.to_rat(leq), H.to_rat(eq)), k
     assert checked >= 15
+
+
+def test_mip_rational_indicator():
+    """MIP::is_satisfying with rational_indicator (lpsol.h:2369-2391): marked entries may stay
+    rational and are never branched on -- status, value and solution against the unmodified
+    reference, general-integer and 0-1, max and min."""
+    rs = np.random.RandomState(5)
+    seen = set()
+    for seed in range(40):
+        m, n = [(4, 3), (6, 4), (7, 5)][seed % 3]
+        leq, tg = H.gen_int_lp(900 + seed, m, n, alo=-1, ahi=4, density=0.7, blo=1, bhi=17)
+        ind = (rs.uniform(size=n + 1) < 0.5).astype(np.uint8)
+        for is_min in (0, 1):
+            a0 = H.appro_count("ref")
+            b = H.mip_solve_ri("ref", is_min, 0, H.to_rat(leq), H.to_rat(tg), ind)
+            if H.appro_count("ref") != a0:
+                continue
+            a = H.mip_solve_ri("oracle", is_min, 0, H.to_rat(leq), H.to_rat(tg), ind)
+            assert a["status"] == b["status"], (seed, is_min, a["status"], b["status"])
+            assert np.array_equal(a["v"], b["v"]), (seed, is_min)
+            if a["status"] == 0:
+                assert np.array_equal(a["sol"], b["sol"]), (seed, is_min)
+                seen.add(bool((a["sol"][:, 1] != 1).any()))  # some accepted solutions really are fractional
+    assert seen == {False, True}
+
+
+def general_vc(r, n):
+    """Variable constraints beyond -x <= 0: other negative diagonals and non-zero constant terms
+    (lower bounds x >= c/d).  No free variables here: the reference records the split of a free
+    variable with the variadic INTMat::sete (lpsol.h:1377), which is broken on x86-64 (SURVEY 8c
+    caveat 2) -- the compiled reference crashes on them; the oracle-only tests cover that path."""
+    vc = np.zeros((n, n + 1))
+    for i in range(n):
+        u = r.uniform()
+        vc[i, i] = -r.randint(1, 4)
+        if u > 0.5:
+            vc[i, n] = r.randint(-6, 4)
+    return vc
+
+
+def test_general_variable_constraints():
+    """is_feasible reads vc(i,i) and vc(i,rhs) (lpsol.h:798-802): the final verdict for general
+    variable constraints, FP64 and exact, max and min."""
+    r = np.random.RandomState(77)
+    seen = set()
+    for seed in range(150):
+        m, n = r.randint(3, 8), r.randint(2, 6)
+        leq, tg = H.gen_int_lp(3000 + seed, m, n, alo=-1, ahi=3, density=0.7, blo=0, bhi=15)
+        vc = general_vc(r, n)
+        for is_min in (0, 1):
+            a = H.six_solve("oracle", "f64", is_min, leq, tg, vc)
+            b = H.six_solve("ref", "f64", is_min, leq, tg, vc)
+            assert a["status"] == b["status"] and eqv("f64", a["v"], b["v"]), (seed, is_min, "f64")
+            a0 = H.appro_count("ref")
+            b = H.six_solve("ref", "rat", is_min, H.to_rat(leq), H.to_rat(tg), H.to_rat(vc))
+            if H.appro_count("ref") == a0:
+                a = H.six_solve("oracle", "rat", is_min, H.to_rat(leq), H.to_rat(tg), H.to_rat(vc))
+                assert a["status"] == b["status"] and np.array_equal(a["v"], b["v"]), (seed, is_min, "rat")
+                seen.add((is_min, a["status"]))
+    assert (0, 0) in seen and (0, 3) in seen

@@ -463,6 +463,23 @@ def _mip_solve(self, kind, is_min, is_bin, leq, tgtf, eq=None):
     return dict(status=st, v=v, sol=sol, nodes=nodes.value)
 
 
+def _mip_solve_rat_ri(self, is_min, is_bin, leq, tgtf, indicator, eq=None):
+    """MIP<RMat,Rational> with rational_indicator: n+1 flags, non-zero = may stay rational."""
+    leq = None if leq is None else _rat(leq)
+    eq = None if eq is None else _rat(eq)
+    tgtf = _rat(tgtf)
+    n = tgtf.shape[0] - 1
+    m = 0 if leq is None else leq.shape[0]
+    k = 0 if eq is None else eq.shape[0]
+    v = np.zeros(2, dtype=np.int32)
+    sol = np.zeros((n + 1, 2), dtype=np.int32)
+    nodes = C.c_int32(0)
+    ind = np.ascontiguousarray(indicator, dtype=np.uint8)
+    st = self.check(lib().xp_mip_solve_rat_ri(self._h, int(is_min), int(is_bin), m, n, _p(tgtf), k, _p(eq),
+                                              _p(leq), _p(ind), _p(v), _p(sol), C.byref(nodes)))
+    return dict(status=st, v=v, sol=sol, nodes=nodes.value)
+
+
 def _mip_solve_rat_batch(self, is_min, is_bin, leq, tgtf):
     leq, tgtf = _rat(leq), _rat(tgtf)
     B, m, n1 = leq.shape[:3]
@@ -522,5 +539,6 @@ Context.has_solution_ragged = _has_solution_ragged
 Context.six_solve = _six_solve
 Context.six_solve_batch = _six_solve_batch
 Context.mip_solve = _mip_solve
+Context.mip_solve_rat_ri = _mip_solve_rat_ri
 Context.mip_solve_rat_batch = _mip_solve_rat_batch
 Context.has_solution_batch = _has_solution_batch

@@ -141,7 +141,8 @@ void for_items(size_t n, std::vector<char> &ovf, F f)
 // TwoStageMethod (lpsol.h:1906-1930) for one FP64 LP on the HBM-resident path; phase 1
 // (constructBasicFeasibleSolution, :838-988) runs on the device as well.
 int two_stage_large_f64(xp_ctx *ctx, const Mat<F64> &leq, const Mat<F64> &tg, uint32_t max_iter,
-                        ResF &R)
+                        ResF &R, const std::vector<double> *vc_diag = nullptr,
+                        const std::vector<double> *vc_rhs = nullptr)
 {
     const int m = leq.r, n = leq.c - 1, Cm = n + m + 1;
     R.slack_sol.assign(Cm, 0.0);
@@ -149,9 +150,10 @@ int two_stage_large_f64(xp_ctx *ctx, const Mat<F64> &leq, const Mat<F64> &tg, ui
     R.eq2bv.assign(m, 0);
     R.maxv = 0.0;
     int32_t st = 0;
-    int rc = xp_six_two_stage_f64_large(ctx, m, n, leq.a.data(), tg.a.data(), max_iter, XP_RULE_REFERENCE,
-                                        &st, &R.maxv, R.slack_sol.data(), R.tgtf.data(), R.eq2bv.data(),
-                                        nullptr, nullptr);
+    int rc = xp_six_two_stage_f64_large_vc(ctx, m, n, leq.a.data(), tg.a.data(), vc_diag ? vc_diag->data() : nullptr,
+                                           vc_rhs ? vc_rhs->data() : nullptr, max_iter, XP_RULE_REFERENCE, &st,
+                                           &R.maxv, R.slack_sol.data(), R.tgtf.data(), R.eq2bv.data(), nullptr,
+                                           nullptr);
     if (rc) return rc;
     R.status = st;
     return 0;
@@ -392,6 +394,29 @@ struct Many<Q> {
     }
 };
 
+// General variable constraints (lpsol.h:798-802 reads vc(i,i) and vc(i,rhs) in the feasibility
+// check of the optimal exit, nothing else).  FP64: the HBM-resident path takes the two vectors
+// and checks them on the device.  Exact: the row-sum half of is_feasible is an identity, so the
+// verdict of the batched kernel (which assumes -x <= 0) is re-decided on the solution row.
+int two_stage_vc(xp_ctx *ctx, const SixJob<F64> &job, uint32_t max_iter, std::vector<ResF> &R)
+{
+    R.assign(1, ResF());
+    return two_stage_large_f64(ctx, job.lp_leq, job.lp_tgtf, max_iter, R[0], &job.N.vc_diag, &job.N.vc_rhs);
+}
+int two_stage_vc(xp_ctx *ctx, const SixJob<Q> &job, uint32_t max_iter, std::vector<ResQ> &R)
+{
+    std::vector<const Mat<Q> *> l{&job.lp_leq}, t{&job.lp_tgtf};
+    int rc = two_stage_many_q(ctx, l, t, max_iter, R);
+    if (rc) return rc;
+    if (R[0].status == XP_SIX_SUCC || R[0].status == XP_SIX_OPTIMAL_IS_INFEASIBLE) {
+        const int rhs = job.lp_leq.r + job.lp_leq.c - 1;
+        const bool bad = violates_vc<Q>(R[0].slack_sol, rhs, job.N.vc_diag, job.N.vc_rhs);
+        R[0].status = bad ? XP_SIX_OPTIMAL_IS_INFEASIBLE : XP_SIX_SUCC;
+        R[0].maxv = bad ? Q::zero() : R[0].tgtf[rhs]; // maxv = tgtf[rhs] on success (:1119), 0 otherwise
+    }
+    return 0;
+}
+
 // One SIX::maxm / minm.
 template <class P>
 int solve_one(xp_ctx *ctx, bool is_min, const Mat<P> &tg, const Mat<P> &vc, const Mat<P> &eq,
@@ -404,7 +429,8 @@ int solve_one(xp_ctx *ctx, bool is_min, const Mat<P> &tg, const Mat<P> &vc, cons
     if (st) return st;
     std::vector<TwoStageResult<P>> R;
     std::vector<const Mat<P> *> l{&job.lp_leq}, t{&job.lp_tgtf};
-    int rc = Many<P>::run(ctx, l, t, max_iter, R);
+    // (minm solves the explicit dual, whose variable constraints are its own -I, :1630-1636)
+    int rc = (!job.N.std_vc && !is_min) ? two_stage_vc(ctx, job, max_iter, R) : Many<P>::run(ctx, l, t, max_iter, R);
     if (rc) return rc;
     if (eq2bv) *eq2bv = R[0].eq2bv;
     return job.finish(R[0], v, sol);
@@ -627,9 +653,18 @@ extern "C" int xp_mip_solve_rat(xp_ctx *ctx, int is_min, int is_bin, int m, int 
                                 const xp_rat *tgtf, int k, const xp_rat *eq, const xp_rat *leq,
                                 xp_rat *v, xp_rat *sol, int32_t *n_nodes)
 {
+    return xp_mip_solve_rat_ri(ctx, is_min, is_bin, m, n, tgtf, k, eq, leq, nullptr, v, sol, n_nodes);
+}
+
+extern "C" int xp_mip_solve_rat_ri(xp_ctx *ctx, int is_min, int is_bin, int m, int n,
+                                   const xp_rat *tgtf, int k, const xp_rat *eq, const xp_rat *leq,
+                                   const uint8_t *rational_indicator, xp_rat *v, xp_rat *sol,
+                                   int32_t *n_nodes)
+{
     XP_ENTRY_GUARD(ctx);
     if (n < 1 || (m < 1 && k < 1) || !tgtf || !v) return XP_ERR_BAD_ARG;
     std::vector<MipTree<Q>> trees(1);
+    if (rational_indicator) trees[0].allow_rational.assign(rational_indicator, rational_indicator + n + 1);
     trees[0].start(mat_q(1, n + 1, tgtf), default_vc<Q>(n), k > 0 ? mat_q(k, n + 1, eq) : Mat<Q>(),
                    m > 0 ? mat_q(m, n + 1, leq) : Mat<Q>(), !is_min, is_bin != 0);
     int rc = run_trees<Q>(ctx, trees);

@@ -3414,11 +3414,59 @@ static int two_stage_streamed(xp_ctx *ctx, xp_lp_f64 *lp, int m, int n, const do
     return 1;
 }
 
+// Variable constraints of a handle: `vd` / `vr` (n_struct entries: diagonal and constant column of
+// the caller's `vc`, lpsol.h:798-802) for the structural variables, -1 / 0 for everything the
+// solver adds itself (slacks; the auxiliary variable at column `xa` if xa >= 0).
+static int set_vc(xp_lp_f64 *lp, const double *vd, const double *vr, int n_struct, int xa)
+{
+    xp_ctx *ctx = lp->ctx;
+    LpDev &d = lp->d;
+    d.vc_diag = d.vc_rhs = nullptr;
+    if (!vd && !vr) return 0;
+    std::vector<double> hd(d.n, -1.0), hr(d.n, 0.0);
+    for (int j = 0; j < n_struct; j++) {
+        const int k = (xa >= 0 && j >= xa) ? j + 1 : j;
+        if (vd) hd[k] = vd[j];
+        if (vr) hr[k] = vr[j];
+    }
+    XP_CUDA_OK(ctx, cudaMemcpyAsync(lp->vc_diag, hd.data(), d.n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    XP_CUDA_OK(ctx, cudaMemcpyAsync(lp->vc_rhs, hr.data(), d.n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    XP_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream)); // hd / hr go out of scope
+    d.vc_diag = lp->vc_diag;
+    d.vc_rhs = lp->vc_rhs;
+    return 0;
+}
+
+extern "C" int xp_six_two_stage_f64_large_vc(xp_ctx *ctx, int m, int n, const double *leq, const double *tgtf,
+                                             const double *vc_diag, const double *vc_rhs, uint32_t max_iter,
+                                             int rule, int32_t *status, double *maxv, double *slack_sol,
+                                             double *tgtf_out, int32_t *eq2bv, uint32_t *iters, uint32_t *pivots);
+
 extern "C" int xp_six_two_stage_f64_large(xp_ctx *ctx, int m, int n, const double *leq,
                                           const double *tgtf, uint32_t max_iter, int rule,
                                           int32_t *status, double *maxv, double *slack_sol,
                                           double *tgtf_out, int32_t *eq2bv, uint32_t *iters,
                                           uint32_t *pivots)
+{
+    return xp_six_two_stage_f64_large_vc(ctx, m, n, leq, tgtf, nullptr, nullptr, max_iter, rule, status, maxv,
+                                         slack_sol, tgtf_out, eq2bv, iters, pivots);
+}
+
+// State the last xp_six_two_stage_f64_large[_vc] / xp_six_slack_f64 call left on the device, as
+// SIX::TwoStageMethod hands it back through its IN OUT arguments (lpsol.h:291-301): the final
+// tableau m x C, objective row, basis maps.  Any pointer may be NULL.
+extern "C" int xp_ctx_last_lp_download(xp_ctx *ctx, double *tableau, double *tgtf, uint8_t *nvset, uint8_t *bvset,
+                                       int32_t *bv2eq, int32_t *eq2bv)
+{
+    if (!ctx || !ctx->cached_lp) return XP_ERR_BAD_ARG;
+    return xp_lp_f64_download((xp_lp_f64 *)ctx->cached_lp, tableau, tgtf, nvset, bvset, bv2eq, eq2bv, nullptr, nullptr,
+                              nullptr, nullptr, 0);
+}
+
+extern "C" int xp_six_two_stage_f64_large_vc(xp_ctx *ctx, int m, int n, const double *leq, const double *tgtf,
+                                             const double *vc_diag, const double *vc_rhs, uint32_t max_iter,
+                                             int rule, int32_t *status, double *maxv, double *slack_sol,
+                                             double *tgtf_out, int32_t *eq2bv, uint32_t *iters, uint32_t *pivots)
 {
     if (!ctx || m < 1 || n < 1 || !leq || !tgtf || !status) return XP_ERR_BAD_ARG;
     if (rule != XP_RULE_REFERENCE) return XP_ERR_BAD_ARG;
@@ -3467,9 +3515,10 @@ extern "C" int xp_six_two_stage_f64_large(xp_ctx *ctx, int m, int n, const doubl
     }
     int streamed = 0;
     if (!aux) {
+        rc = set_vc(M.lp, vc_diag, vc_rhs, n, -1); // (only the optimal exit reads it)
+        if (rc) return rc;
         streamed = two_stage_streamed(ctx, M.lp, m, n, leq, d_leq, d_tg, d_b, max_iter);
         if (streamed < 0) return streamed;
-        if (streamed) M.lp->d.vc_diag = M.lp->d.vc_rhs = nullptr;
     }
     if (!streamed) {
     // No phase 1: the rows go up in chunks on the copy stream and k_slack_form builds [A | I | b]
@@ -3499,7 +3548,6 @@ extern "C" int xp_six_two_stage_f64_large(xp_ctx *ctx, int m, int n, const doubl
             k_slack_form<<<ctx->sm_count * 4, 256, 0, s>>>(M.lp->d, d_leq, d_tg, n, r0, r1);
             ctx->launches++;
         }
-        M.lp->d.vc_diag = M.lp->d.vc_rhs = nullptr;
         XP_CUDA_OK(ctx, cudaGetLastError());
     } else {
         const int xa = n, Ca = Cm + 1;
@@ -3512,7 +3560,8 @@ extern "C" int xp_six_two_stage_f64_large(xp_ctx *ctx, int m, int n, const doubl
         }
         k_aux_form<<<ctx->sm_count * 4, 256, 0, s>>>(A.lp->d, d_leq, n);
         ctx->launches++;
-        A.lp->d.vc_diag = A.lp->d.vc_rhs = nullptr;
+        rc = set_vc(A.lp, vc_diag, vc_rhs, n, xa); // the auxiliary solve's own optimal exit checks them too
+        if (rc) return rc;
         rc = xpiv_at(A.lp, prow, xa); // forced first pivot, :892-908
         if (rc) return rc;
         n_piv++;
@@ -3557,8 +3606,9 @@ extern "C" int xp_six_two_stage_f64_large(xp_ctx *ctx, int m, int n, const doubl
         k_restore_objective<<<1, 1024, 0, s>>>(A.lp->d, d_tg, n); // :944-953
         k_drop_column<<<ctx->sm_count * 4, 256, 0, s>>>(A.lp->d, M.lp->d, xa); // :956-986
         ctx->launches += 2;
-        M.lp->d.vc_diag = M.lp->d.vc_rhs = nullptr;
         XP_CUDA_OK(ctx, cudaGetLastError());
+        rc = set_vc(M.lp, vc_diag, vc_rhs, n, -1);
+        if (rc) return rc;
     }
     rc = lp_reset(M.lp);
     if (rc) return rc;

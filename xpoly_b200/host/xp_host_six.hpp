@@ -296,6 +296,9 @@ struct Normalized {
     int rhs_idx = 0;
     std::vector<int32_t> vcmap; // triples {real, dummy1, dummy2}, lpsol.h:1376-1378
     bool std_vc = true;         // every variable constraint is -x <= 0
+    // newvc(i,i) and newvc(i,rhs) for the rhs_idx normalised variables: the only entries of the
+    // variable constraints the solver reads (is_feasible, lpsol.h:798-802)
+    std::vector<typename P::T> vc_diag, vc_rhs;
 };
 
 // normalize, lpsol.h:1289-1394.  vc: n x (n+1).
@@ -334,7 +337,30 @@ int normalize(Normalized<P> &N, const Mat<P> &vc, const Mat<P> &eq, const Mat<P>
         last++;
     }
     N.rhs_idx = last + 1;
+    // newvc as normalize leaves it (:1341-1373): the caller's square part and constant column for
+    // the original variables, -1 / 0 for both halves of a split free variable and for every dummy
+    N.vc_diag.assign(N.rhs_idx, P::from_int(-1));
+    N.vc_rhs.assign(N.rhs_idx, P::zero());
+    for (int i = 0; i < vars; i++) {
+        if (vc.col_all_eq(i, P::zero())) continue;
+        N.vc_diag[i] = i < vc.r ? vc.at(i, i) : P::zero();
+        N.vc_rhs[i] = i < vc.r ? vc.at(i, vc.c - 1) : P::zero();
+    }
     return 0;
+}
+
+// The variable-constraint half of is_feasible (lpsol.h:798-802) on a solution row: true if some
+// vc(i,i) * sol(i) > vc(i,rhs).  slack / auxiliary variables beyond `diag` are -x <= 0.
+template <class P>
+bool violates_vc(const std::vector<typename P::T> &sol, int rhs_idx, const std::vector<typename P::T> &diag,
+                 const std::vector<typename P::T> &rhs)
+{
+    for (int i = 0; i < rhs_idx && i < (int)sol.size(); i++) {
+        const typename P::T d = i < (int)diag.size() ? diag[i] : P::from_int(-1);
+        const typename P::T r = i < (int)rhs.size() ? rhs[i] : P::zero();
+        if (P::lt(r, P::mul(d, sol[i]))) return true;
+    }
+    return false;
 }
 
 // calcFinalSolution, lpsol.h:1850-1899.
@@ -384,8 +410,7 @@ struct SixJob {
         m_rhs = maxc - 1;
         int st = normalize(N, vc, eq, leq, tgtf, m_rhs);
         if (st) return st;
-        if (!N.std_vc) return XP_ERR_BAD_ARG;
-        if (!is_min) {
+        if (!is_min) { // (a non-standard vc only changes the final feasibility verdict: the caller routes it)
             lp_leq = N.leq;
             lp_tgtf = N.tgtf;
             return 0;
@@ -491,8 +516,20 @@ struct MipTree {
             best_v = v;
         }
     }
+    std::vector<uint8_t> allow_rational; // rational_indicator (1 x n1, :2626-2630); empty = none
     bool satisfying(int &col)
-    { // MIP::is_satisfying without rational_indicator, :2363-2408
+    { // MIP::is_satisfying, :2363-2408
+        if (!allow_rational.empty()) { // entries marked true may stay rational (:2369-2391)
+            for (int j = 0; j < n1; j++) {
+                if (allow_rational[j]) continue;
+                if (!P::is_int(sol[j]) ||
+                    (is_bin && !P::eq(sol[j], P::zero()) && !P::eq(sol[j], P::from_int(1)))) {
+                    col = j;
+                    return false;
+                }
+            }
+            return true;
+        }
         for (int j = 0; j < n1; j++) {
             if (is_bin) {
                 if (!P::eq(sol[j], P::zero()) && !P::eq(sol[j], P::from_int(1))) {

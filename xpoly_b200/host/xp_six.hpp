@@ -6,8 +6,8 @@
 //     #include "xp_six.hpp"
 // The explicit specialisations below replace the generic template bodies of lpsol.h
 // (maxm :1992, minm :1661, MIP::maxm :2635, MIP::minm :2680) for these instantiations only;
-// every other member (set_param, reviseTargetFunc, TwoStageMethod, ...) stays the
-// reference's.  Link with -lxpoly_b200 -lcudart.  See INTEGRATION.md.
+// SIX<FloatMat,Float>::TwoStageMethod is routed too; every other member (set_param,
+// reviseTargetFunc, ...) stays the reference's.  Link with -lxpoly_b200 -lcudart.  See INTEGRATION.md.
 //
 // This header needs the reference's headers and is therefore NOT compiled into the product
 // library; tests/test_adaptor_cpu.py compiles and links it where /root/reference exists.
@@ -84,6 +84,61 @@ inline UINT SIX<FloatMat, Float>::minm(OUT Float &minv, OUT FloatMat &sol, Float
     return xp_status(st);
 }
 
+// SIX<FloatMat,Float>::TwoStageMethod (lpsol.h:1906-1930) -- the one public entry that exposes
+// the solver state.  IN: the normalised LP (newleq m x (n+1), newtgtf 1 x (n+1), newvc n x (n+1),
+// new_rhs_idx = n).  OUT, exactly as stage1 + slack + solveSlackForm leave them (:1405-1433,
+// :1783-1844, :1007-1191): newleq = final tableau m x (n+m+1), newtgtf = final objective row,
+// newvc grown by the slack variables' -1 diagonal, slack_sol, maxv, the four basis maps and
+// new_rhs_idx = n + m.  Phase 1 (auxiliary LP) runs on the device as well.  On
+// SIX_NO_PRI_FEASIBLE_SOL the reference returns out of stage1 with its arguments half reshaped;
+// here they are left untouched.
+template <>
+inline UINT SIX<FloatMat, Float>::TwoStageMethod(IN OUT FloatMat &newleq, IN OUT FloatMat &newvc,
+                                                 IN OUT FloatMat &newtgtf, IN OUT FloatMat &slack_sol,
+                                                 IN OUT Float &maxv, IN OUT Vector<bool> &nvset,
+                                                 IN OUT Vector<bool> &bvset, IN OUT Vector<INT> &bv2eqmap,
+                                                 IN OUT Vector<INT> &eq2bvmap, IN OUT INT &new_rhs_idx)
+{
+    const int m = (int)newleq.get_row_size(), n = (int)new_rhs_idx, C = n + m + 1;
+    ASSERT((int)newleq.get_col_size() == n + 1 && (int)newtgtf.get_col_size() == n + 1, ("normalised LP expected"));
+    std::vector<double> vd(n, -1.0), vr(n, 0.0), ss(C, 0.0), tg(C, 0.0);
+    for (int j = 0; j < n && j < (int)newvc.get_row_size(); j++) { // the entries is_feasible reads, :798-802
+        vd[j] = newvc.get(j, j).f();
+        vr[j] = newvc.get(j, n).f();
+    }
+    std::vector<int32_t> e2b(m, 0), b2e(C - 1, 0);
+    std::vector<uint8_t> nv(C - 1, 0), bv(C - 1, 0);
+    int32_t st = 0;
+    double mv = 0.0;
+    int rc = xp_six_two_stage_f64_large_vc(xp_thread_ctx(), m, n, (const double *)xp_raw(newleq),
+                                           (const double *)xp_raw(newtgtf), vd.data(), vr.data(), m_max_iter,
+                                           XP_RULE_REFERENCE, &st, &mv, ss.data(), tg.data(), e2b.data(), NULL, NULL);
+    if (rc) return xp_status(rc);
+    if (st == XP_SIX_NO_PRI_FEASIBLE_SOL) return (UINT)st;
+    newvc.insertColumnsBefore(n, m); // SIX::slack, :1414-1432
+    newvc.grow_row(m);
+    for (int i = 0; i < m; i++) newvc.set(n + i, n + i, Float(-1.0));
+    newleq.reinit(m, C);
+    rc = xp_ctx_last_lp_download(xp_thread_ctx(), (double *)newleq.get_matrix(), NULL, nv.data(), bv.data(),
+                                 b2e.data(), NULL);
+    if (rc) return xp_status(rc);
+    newtgtf.reinit(1, C);
+    slack_sol.reinit(1, C);
+    for (int j = 0; j < C; j++) {
+        newtgtf.set(0, j, Float(tg[j]));
+        slack_sol.set(0, j, Float(ss[j]));
+    }
+    for (int j = 0; j < C - 1; j++) {
+        nvset.set(j, nv[j] != 0);
+        bvset.set(j, bv[j] != 0);
+        bv2eqmap.set(j, b2e[j]);
+    }
+    for (int i = 0; i < m; i++) eq2bvmap.set(i, e2b[i]);
+    maxv = Float(mv);
+    new_rhs_idx = n + m;
+    return (UINT)st;
+}
+
 // ---------------------------------------------------------------- SIX<RMat,Rational>
 // XP_ERR_OVERFLOW: the exact result does not fit int32/int32 -- the case in which the reference
 // would have silently replaced it by a 7-digit approximation (rational.cpp:189-226).
@@ -116,6 +171,13 @@ inline UINT SIX<RMat, Rational>::minm(OUT Rational &minv, OUT RMat &sol, RMat co
     return xp_status(st);
 }
 
+// BMat is Matrix<bool> (xmat.h:166): one byte per flag, row-major
+inline const uint8_t *xp_indicator(BMat *ri)
+{
+    static_assert(sizeof(bool) == 1, "bool flags are passed as bytes");
+    return ri ? (const uint8_t *)ri->get_matrix() : NULL;
+}
+
 // ---------------------------------------------------------------- MIP<RMat,Rational>
 // vc must be -I | 0 (MIP::verify, lpsol.h:2349-2358), which is what the C ABI assumes.
 template <>
@@ -123,16 +185,19 @@ inline UINT MIP<RMat, Rational>::maxm(OUT Rational &maxv, OUT RMat &sol, RMat co
                                       RMat const &eq, RMat const &leq, bool is_bin, IN BMat *rational_indicator,
                                       INT rhs_idx)
 {
-    ASSERT(rational_indicator == NULL, ("per-variable rational mask: use the reference path"));
+    ASSERT(rational_indicator == NULL || (rational_indicator->get_row_size() == 1 &&
+                                          rational_indicator->get_col_size() == tgtf.get_col_size()),
+           ("rational_indicator must be 1 x (n+1)")); // MIP::verify, lpsol.h:2341-2346
     const int n = (int)tgtf.get_col_size() - 1;
     ASSERT(rhs_idx == -1 || rhs_idx == n, ("unsupported rhs_idx"));
     (void)vc;
     sol.reinit(1, n + 1);
     xp_rat v = {0, 1};
     int32_t nodes = 0;
-    int st = xp_mip_solve_rat(xp_thread_ctx(), /*is_min=*/0, is_bin ? 1 : 0, (int)leq.get_row_size(), n,
-                              (const xp_rat *)xp_raw(tgtf), (int)eq.get_row_size(), (const xp_rat *)xp_raw(eq),
-                              (const xp_rat *)xp_raw(leq), &v, (xp_rat *)sol.get_matrix(), &nodes);
+    int st = xp_mip_solve_rat_ri(xp_thread_ctx(), /*is_min=*/0, is_bin ? 1 : 0, (int)leq.get_row_size(), n,
+                                 (const xp_rat *)xp_raw(tgtf), (int)eq.get_row_size(), (const xp_rat *)xp_raw(eq),
+                                 (const xp_rat *)xp_raw(leq), xp_indicator(rational_indicator), &v,
+                                 (xp_rat *)sol.get_matrix(), &nodes);
     maxv = Rational(v.num, v.den);
     m_times = (UINT)nodes; // lpsol.h:2443
     return xp_status(st);
@@ -142,16 +207,19 @@ inline UINT MIP<RMat, Rational>::minm(OUT Rational &minv, OUT RMat &sol, RMat co
                                       RMat const &eq, RMat const &leq, bool is_bin, IN BMat *rational_indicator,
                                       INT rhs_idx)
 {
-    ASSERT(rational_indicator == NULL, ("per-variable rational mask: use the reference path"));
+    ASSERT(rational_indicator == NULL || (rational_indicator->get_row_size() == 1 &&
+                                          rational_indicator->get_col_size() == tgtf.get_col_size()),
+           ("rational_indicator must be 1 x (n+1)")); // MIP::verify, lpsol.h:2341-2346
     const int n = (int)tgtf.get_col_size() - 1;
     ASSERT(rhs_idx == -1 || rhs_idx == n, ("unsupported rhs_idx"));
     (void)vc;
     sol.reinit(1, n + 1);
     xp_rat v = {0, 1};
     int32_t nodes = 0;
-    int st = xp_mip_solve_rat(xp_thread_ctx(), /*is_min=*/1, is_bin ? 1 : 0, (int)leq.get_row_size(), n,
-                              (const xp_rat *)xp_raw(tgtf), (int)eq.get_row_size(), (const xp_rat *)xp_raw(eq),
-                              (const xp_rat *)xp_raw(leq), &v, (xp_rat *)sol.get_matrix(), &nodes);
+    int st = xp_mip_solve_rat_ri(xp_thread_ctx(), /*is_min=*/1, is_bin ? 1 : 0, (int)leq.get_row_size(), n,
+                                 (const xp_rat *)xp_raw(tgtf), (int)eq.get_row_size(), (const xp_rat *)xp_raw(eq),
+                                 (const xp_rat *)xp_raw(leq), xp_indicator(rational_indicator), &v,
+                                 (xp_rat *)sol.get_matrix(), &nodes);
     minv = Rational(v.num, v.den);
     m_times = (UINT)nodes;
     return xp_status(st);
