@@ -1777,12 +1777,21 @@ __global__ void __launch_bounds__(LANES *GROUPS, 2) k_flush_w(LpDev d, ColSet cs
         for (int k = 0; k < TPB; k++) {
             const int rc = (k * GROUPS + grp) * TR, row = rb + rc;
             double2 a[TR], b[TR];
+            const bool full = act1 && row + TR <= m; // interior tile: no per-entry predicates or selects
+            double *t0p = d.tab + (size_t)row * Cl + j0;
+            if (full) {
 #pragma unroll
-            for (int w = 0; w < TR; w++) {
-                a[w] = (act0 && row + w < m) ? *reinterpret_cast<const double2 *>(d.tab + (size_t)(row + w) * Cl + j0)
-                                             : make_double2(0.0, 0.0);
-                b[w] = (act1 && row + w < m) ? *reinterpret_cast<const double2 *>(d.tab + (size_t)(row + w) * Cl + j1)
-                                             : make_double2(0.0, 0.0);
+                for (int w = 0; w < TR; w++) {
+                    a[w] = *reinterpret_cast<const double2 *>(t0p + (size_t)w * Cl);
+                    b[w] = *reinterpret_cast<const double2 *>(t0p + (size_t)w * Cl + 2 * LANES);
+                }
+            } else {
+#pragma unroll
+                for (int w = 0; w < TR; w++) {
+                    a[w] = (act0 && row + w < m) ? *reinterpret_cast<const double2 *>(t0p + (size_t)w * Cl) : make_double2(0.0, 0.0);
+                    b[w] = (act1 && row + w < m) ? *reinterpret_cast<const double2 *>(t0p + (size_t)w * Cl + 2 * LANES)
+                                                 : make_double2(0.0, 0.0);
+                }
             }
             if (k + 1 < TPB) prefetch_tile(ct, rb, k + 1);
             else if (more) prefetch_tile(ct1, rb1, 0);
@@ -1837,12 +1846,20 @@ __global__ void __launch_bounds__(LANES *GROUPS, 2) k_flush_w(LpDev d, ColSet cs
                     b[w] = x;
                 }
             }
+            if (full) {
 #pragma unroll
-            for (int w = 0; w < TR; w++)
-                if (row + w < m) {
-                    *reinterpret_cast<double2 *>(d.tab + (size_t)(row + w) * Cl + j0) = a[w];
-                    if (act1) *reinterpret_cast<double2 *>(d.tab + (size_t)(row + w) * Cl + j1) = b[w];
+                for (int w = 0; w < TR; w++) {
+                    *reinterpret_cast<double2 *>(t0p + (size_t)w * Cl) = a[w];
+                    *reinterpret_cast<double2 *>(t0p + (size_t)w * Cl + 2 * LANES) = b[w];
                 }
+            } else {
+#pragma unroll
+                for (int w = 0; w < TR; w++)
+                    if (row + w < m) {
+                        *reinterpret_cast<double2 *>(t0p + (size_t)w * Cl) = a[w];
+                        if (act1) *reinterpret_cast<double2 *>(t0p + (size_t)w * Cl + 2 * LANES) = b[w];
+                    }
+            }
         }
         if (more && ct1 != ct) {
             __syncthreads();
