@@ -233,6 +233,16 @@ int xp_six_two_stage_f64_large_vc(xp_ctx *ctx, int m, int n, const double *leq, 
                                   const double *vc_diag, const double *vc_rhs, uint32_t max_iter,
                                   int rule, int32_t *status, double *maxv, double *slack_sol,
                                   double *tgtf_out, int32_t *eq2bv, uint32_t *iters, uint32_t *pivots);
+/* TwoStageMethod on the explicit DUAL of a normalised primal (what SIX::minm solves,
+ * lpsol.h:1661-1732 + calcDualMaxm :1585-1655), the dual built on the device: pass the
+ * PRIMAL (leq mp x (np+1), tgtf np+1; x >= 0, no equalities); -A^T | c, the dual objective
+ * -b and the slack form never exist on the host.  Outputs are the dual LP's (np rows, mp
+ * variables): slack_sol / tgtf_out mp+np+1 entries, eq2bv np. */
+int xp_six_two_stage_f64_large_dual(xp_ctx *ctx, int mp, int np, const double *leq,
+                                    const double *tgtf, uint32_t max_iter, int rule,
+                                    int32_t *status, double *maxv, double *slack_sol,
+                                    double *tgtf_out, int32_t *eq2bv, uint32_t *iters,
+                                    uint32_t *pivots);
 /* What SIX::TwoStageMethod hands back through its IN OUT arguments (lpsol.h:291-301) after
  * the last xp_six_two_stage_f64_large[_vc] / xp_six_slack_f64 call on this ctx: the final
  * tableau m x C (C = n+m+1), objective row (C), nvset / bvset / bv2eq (C-1), eq2bv (m).
@@ -350,6 +360,34 @@ int xp_has_solution_rat_ragged(xp_ctx *ctx, int batch, const int32_t *ns, const 
                                const int64_t *eq_off, const xp_rat *eq_pool,
                                size_t eq_pool_len /* xp_rat elements */, int is_int_sol,
                                int is_unique_sol, int32_t *result);
+
+/* ------------------------------------------------ batches across several GPUs
+ * small-LP batches, B&B trees and dependence queries are independent
+ * units.  `ctxs` holds nctx contexts (normally one per device of this process; several
+ * on one device also work); the batch is cut into nctx contiguous slices, every slice
+ * is solved by its context on its own device, stream and host thread -- no collective --
+ * and the outputs land in the caller's arrays at the slice's offset.  Arguments as in
+ * the single-context calls. */
+int xp_six_two_stage_f64_batch_multi(xp_ctx *const *ctxs, int nctx, int batch, int m, int n,
+                                     const double *leq, const double *tgtf, uint32_t max_iter,
+                                     int rule, int32_t *status, double *maxv, double *slack_sol,
+                                     double *tgtf_out, int32_t *eq2bv, uint32_t *iters,
+                                     uint32_t *pivots);
+int xp_six_two_stage_i64_batch_multi(xp_ctx *const *ctxs, int nctx, int batch, int m, int n,
+                                     const int64_t *leq, const int64_t *tgtf, uint32_t max_iter,
+                                     int rule, int32_t *status, int64_t *maxv_num_den,
+                                     int64_t *slack_sol_num, int64_t *slack_sol_den,
+                                     int64_t *tgtf_out_num, int64_t *tgtf_out_den, int32_t *eq2bv,
+                                     uint32_t *iters, uint32_t *pivots);
+int xp_mip_solve_rat_batch_multi(xp_ctx *const *ctxs, int nctx, int is_min, int is_bin, int batch,
+                                 int m, int n, const xp_rat *tgtf, const xp_rat *leq,
+                                 int32_t *status, xp_rat *v, xp_rat *sol, int32_t *n_nodes);
+int xp_has_solution_rat_ragged_multi(xp_ctx *const *ctxs, int nctx, int batch, const int32_t *ns,
+                                     const int32_t *ms, const int64_t *leq_off,
+                                     const xp_rat *leq_pool, size_t leq_pool_len, const int32_t *ks,
+                                     const int64_t *eq_off, const xp_rat *eq_pool,
+                                     size_t eq_pool_len, int is_int_sol, int is_unique_sol,
+                                     int32_t *result);
 
 #ifdef __cplusplus
 }

@@ -233,3 +233,61 @@ def test_phase1_succeeds_objective_restored(ctx, m, n, nneg):
         finally:
             os.environ.pop("XP_BATCH_WARP", None)
         assert H.SIX_NO_PRI not in set(g["status"].tolist())
+
+
+def test_batches_split_across_contexts(ctx):
+    """xp_*_batch_multi: the batch is cut into contiguous slices, one context (device, stream, host
+    thread) per slice, no collective.  Contexts on every visible GPU (three on cuda:0 where there is
+    only one): bit-identical to the single-context call."""
+    import ctypes as C
+    import torch
+    ndev = torch.cuda.device_count()
+    devs = list(range(ndev)) if ndev > 1 else [0, 0, 0]
+    ctxs = [xp.Context(d) for d in devs]
+    arr = (C.c_void_p * len(ctxs))(*[c._h for c in ctxs])
+    lib = xp.lib()
+    P = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+    B, m, n = 1001, 12, 9
+    lps = [H.gen_dense_lp(9100 + k, m, n) for k in range(B)]
+    leq = np.ascontiguousarray(np.stack([l for l, _ in lps]))
+    tg = np.ascontiguousarray(np.stack([t for _, t in lps]))
+    one = ctx.two_stage_f64_batch(leq, tg)
+    st, mv = np.zeros(B, dtype=np.int32), np.zeros(B)
+    sol, tgo = np.zeros((B, n + m + 1)), np.zeros((B, n + m + 1))
+    e2b, it, pv = np.zeros((B, m), dtype=np.int32), np.zeros(B, dtype=np.uint32), np.zeros(B, dtype=np.uint32)
+    rc = lib.xp_six_two_stage_f64_batch_multi(arr, len(ctxs), B, m, n, P(leq), P(tg), C.c_uint32(xp.NO_ITER_LIMIT), 0,
+                                              P(st), P(mv), P(sol), P(tgo), P(e2b), P(it), P(pv))
+    assert rc == 0
+    assert np.array_equal(st, one["status"]) and np.array_equal(H.bits(mv), H.bits(one["maxv"]))
+    assert np.array_equal(H.bits(sol), H.bits(one["slack_sol"])) and np.array_equal(e2b, one["eq2bv"])
+    assert np.array_equal(pv, one["pivots"])
+    # exact LPs
+    ilps = [H.gen_int_lp(9200 + k, 7, 4, alo=-1, ahi=3, density=0.7, blo=0, bhi=15) for k in range(B)]
+    il = np.ascontiguousarray(np.stack([l for l, _ in ilps]).astype(np.int64))
+    itg = np.ascontiguousarray(np.stack([t for _, t in ilps]).astype(np.int64))
+    e1 = ctx.two_stage_i64_batch(il, itg)
+    st2, mv2 = np.zeros(B, dtype=np.int32), np.zeros((B, 2), dtype=np.int64)
+    rc = lib.xp_six_two_stage_i64_batch_multi(arr, len(ctxs), B, 7, 4, P(il), P(itg), C.c_uint32(xp.NO_ITER_LIMIT), 0,
+                                              P(st2), P(mv2), None, None, None, None, None, None, None)
+    assert rc == 0 and np.array_equal(st2, e1["status"]) and np.array_equal(mv2, e1["maxv"])
+    # B&B trees and dependence queries
+    T = 37
+    mip1 = ctx.mip_solve_rat_batch(0, 0, il[:T], itg[:T])
+    rl, rt = xp._rat(il[:T]), xp._rat(itg[:T])
+    ms_, mv_ = np.zeros(T, dtype=np.int32), np.zeros((T, 2), dtype=np.int32)
+    msol, mn = np.zeros((T, 5, 2), dtype=np.int32), np.zeros(T, dtype=np.int32)
+    rc = lib.xp_mip_solve_rat_batch_multi(arr, len(ctxs), 0, 0, T, 7, 4, P(rt), P(rl), P(ms_), P(mv_), P(msol), P(mn))
+    assert rc == 0 and np.array_equal(ms_, mip1["status"]) and np.array_equal(mv_, mip1["v"])
+    assert np.array_equal(mn, mip1["nodes"])
+    systems = [(il[k], None) for k in range(200)]
+    h1 = ctx.has_solution_ragged(systems)
+    ns = np.full(200, 4, dtype=np.int32)
+    msq = np.full(200, 7, dtype=np.int32)
+    off = (np.arange(200, dtype=np.int64) * 35)
+    pool = np.ascontiguousarray(xp._rat(il[:200]).reshape(-1, 2))
+    res = np.zeros(200, dtype=np.int32)
+    rc = lib.xp_has_solution_rat_ragged_multi(arr, len(ctxs), 200, P(ns), P(msq), P(off), P(pool), C.c_size_t(len(pool)),
+                                              None, None, None, C.c_size_t(0), 1, 1, P(res))
+    assert rc == 0 and np.array_equal(res, h1)
+    for c in ctxs:
+        c.close()

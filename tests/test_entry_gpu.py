@@ -403,3 +403,41 @@ def test_general_variable_constraints(ctx):
             same_rat(g, o, ("vc-rat", seed, is_min))
             seen.add((is_min, o["status"]))
     assert (0, 0) in seen and (0, 3) in seen
+
+
+def test_minm_large_dual_built_on_device(ctx, monkeypatch):
+    """SIX::minm of LPs beyond shared memory: the explicit dual (calcDualMaxm) is built on the device
+    from the caller's primal (tiled transposition, -A^T | c, objective -b) -- same bits as the oracle
+    and as the host-built dual (XP_HOST_DUAL=1), for bounded covering problems (phase 1 on the dual:
+    its constant column c has no negative entry but the dual objective -b has no positive one) and for
+    dense LPs."""
+    r = np.random.RandomState(12)
+    seen = set()
+    for seed, (m, n) in enumerate([(150, 140), (97, 260), (300, 120), (180, 181)]):
+        A = r.randint(0, 4, size=(m, n)).astype(float) * (r.uniform(size=(m, n)) < 0.4)
+        leq = np.zeros((m, n + 1))
+        leq[:, :n] = -A
+        leq[:, n] = -r.randint(1, 10, size=m)       # A x >= b
+        tg = np.zeros(n + 1)
+        tg[:n] = r.randint(1, 9, size=n)            # min c x
+        o = H.six_solve("oracle", "f64", 1, leq, tg)
+        g = ctx.six_solve("f64", 1, leq, tg)
+        same_f64(g, o, ("cover", m, n))
+        seen.add(o["status"])
+        leq2, tg2 = H.gen_dense_lp(9300 + seed, m, n)
+        same_f64(ctx.six_solve("f64", 1, leq2, tg2, max_iter=60), H.six_solve("oracle", "f64", 1, leq2, tg2, max_iter=60),
+                 ("dense-min", m, n))
+        monkeypatch.setenv("XP_HOST_DUAL", "1")
+        h = ctx.six_solve("f64", 1, leq, tg)
+        monkeypatch.delenv("XP_HOST_DUAL")
+        same_f64(g, h, ("host-vs-device dual", m, n))
+        assert np.array_equal(g["eq2bv"][: n], h["eq2bv"][: n])
+    # (sparse covering LPs of this size end SIX_UNBOUND in the reference -- tabu exhaustion, SURVEY
+    # App. B 5b; min problems that succeed go the same way in test_large_lp_through_entry_goes_to_hbm_path)
+    from test_large_f64_gpu import lower_bound_lp
+    for s_ in range(3):
+        l3, t3 = lower_bound_lp(10 + s_, 140, 120, 3)
+        o = H.six_solve("oracle", "f64", 1, l3, t3, max_iter=300)
+        same_f64(ctx.six_solve("f64", 1, l3, t3, max_iter=300), o, ("lb-min", s_))
+        seen.add(o["status"])
+    assert len(seen) >= 1

@@ -417,12 +417,63 @@ int two_stage_vc(xp_ctx *ctx, const SixJob<Q> &job, uint32_t max_iter, std::vect
     return 0;
 }
 
+// SIX::minm of an LP beyond shared memory whose normalisation is the identity (no equalities,
+// every variable constrained by -x <= 0): the explicit dual (calcDualMaxm, lpsol.h:1585-1655)
+// is built ON THE DEVICE from the caller's primal -- no host copy, no host transposition of the
+// constraint matrix.  Returns false if the LP does not qualify (the general host path runs).
+bool minm_dual_on_device(xp_ctx *, const Mat<Q> &, const Mat<Q> &, const Mat<Q> &, const Mat<Q> &, uint32_t, int &,
+                         Q::T &, std::vector<Q::T> &, std::vector<int32_t> *)
+{
+    return false;
+}
+bool minm_dual_on_device(xp_ctx *ctx, const Mat<F64> &tg, const Mat<F64> &vc, const Mat<F64> &eq,
+                         const Mat<F64> &leq, uint32_t max_iter, int &st_out, double &v, std::vector<double> &sol,
+                         std::vector<int32_t> *eq2bv)
+{
+    if (!eq.empty() || leq.empty() || getenv("XP_HOST_DUAL")) return false;
+    const int m = leq.r, n = leq.c - 1;
+    if (fits_smem(ctx, n, m, 16)) return false; // the dual has n rows and m variables
+    if (vc.r != n || vc.c != n + 1) return false;
+    for (int i = 0; i < n; i++) // -x_i <= 0 and nothing else in row / column i
+        for (int j = 0; j <= n; j++)
+            if (j == i ? !(vc.at(i, i) < 0.0) : vc.at(i, j) != 0.0) return false;
+    SixJob<F64> job; // only what finish() reads for a min problem (:1713-1716)
+    job.is_min = true;
+    job.tgtf_orig = tg;
+    job.m_rhs = n;
+    job.dn = m;
+    job.dm = n;
+    job.N.rhs_idx = n;
+    ResF R;
+    R.slack_sol.assign((size_t)m + n + 1, 0.0);
+    R.tgtf.assign((size_t)m + n + 1, 0.0);
+    R.eq2bv.assign(n, 0);
+    R.maxv = 0.0;
+    int32_t st = 0;
+    int rc = xp_six_two_stage_f64_large_dual(ctx, m, n, leq.a.data(), tg.a.data(), max_iter, XP_RULE_REFERENCE, &st,
+                                             &R.maxv, R.slack_sol.data(), R.tgtf.data(), R.eq2bv.data(), nullptr,
+                                             nullptr);
+    if (rc) {
+        st_out = rc;
+        return true;
+    }
+    R.status = st;
+    if (eq2bv) *eq2bv = R.eq2bv;
+    st_out = job.finish(R, v, sol);
+    return true;
+}
+
 // One SIX::maxm / minm.
 template <class P>
 int solve_one(xp_ctx *ctx, bool is_min, const Mat<P> &tg, const Mat<P> &vc, const Mat<P> &eq,
               const Mat<P> &leq, uint32_t max_iter, typename P::T &v,
               std::vector<typename P::T> &sol, std::vector<int32_t> *eq2bv)
 {
+    if (is_min) {
+        int st_dev = 0;
+        v = P::zero();
+        if (minm_dual_on_device(ctx, tg, vc, eq, leq, max_iter, st_dev, v, sol, eq2bv)) return st_dev;
+    }
     SixJob<P> job;
     int st = job.prepare(is_min, tg, vc, eq, leq);
     v = P::zero();

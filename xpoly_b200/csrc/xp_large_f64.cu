@@ -3480,47 +3480,58 @@ extern "C" int xp_ctx_last_lp_download(xp_ctx *ctx, double *tableau, double *tgt
                               nullptr, nullptr, 0);
 }
 
-extern "C" int xp_six_two_stage_f64_large_vc(xp_ctx *ctx, int m, int n, const double *leq, const double *tgtf,
-                                             const double *vc_diag, const double *vc_rhs, uint32_t max_iter,
-                                             int rule, int32_t *status, double *maxv, double *slack_sol,
-                                             double *tgtf_out, int32_t *eq2bv, uint32_t *iters, uint32_t *pivots)
-{
-    if (!ctx || m < 1 || n < 1 || !leq || !tgtf || !status) return XP_ERR_BAD_ARG;
-    if (rule != XP_RULE_REFERENCE) return XP_ERR_BAD_ARG;
-    XP_CUDA_OK(ctx, cudaSetDevice(ctx->device));
-    cudaStream_t s = ctx->stream;
-    const int Cm = n + m + 1;
-    // stage1 decision on the caller's arrays, :1794-1803 (the constant column is gathered into a
-    // small pinned buffer on the way: the piecewise upload below sends it ahead of the matrix)
-    if (ctx->stage_bytes < (size_t)m * sizeof(double)) {
-        if (ctx->stage) cudaFreeHost(ctx->stage);
-        ctx->stage = nullptr;
-        ctx->stage_bytes = 0;
-        XP_CUDA_OK(ctx, cudaMallocHost(&ctx->stage, (size_t)m * sizeof(double)));
-        ctx->stage_bytes = (size_t)m * sizeof(double);
-    }
-    double *h_b = (double *)ctx->stage;
+namespace {
+
+struct Stage1 { // the stage1 decision (lpsol.h:1794-1803) and the forced first pivot row (:894-904)
     bool pos = false, bneg = false;
-    for (int j = 0; j < n; j++) pos |= tgtf[j] > 0.0;
-    int prow = 0; // row of the first minimum constant term, :894-904
-    for (int i = 0; i < m; i++) {
-        const double b = leq[(size_t)i * (n + 1) + n];
-        h_b[i] = b;
-        bneg |= b < 0.0;
-        if (h_b[prow] > b) prow = i;
+    int prow = 0;
+};
+
+// (-A^T | c) and -b^T of calcDualMaxm (lpsol.h:1602-1623) from the primal on the device:
+// dual[i][j] = (-1) * A[j][i], dual[i][mp] = c_i, dual objective = (-1) * b_j, constant (-1) * 0.
+// 32 x 32 tiles through shared memory: both sides coalesced.
+__global__ void k_build_dual(const double *leq, const double *tg, int mp, int np, double *dleq, double *dtg, double *db)
+{
+    __shared__ double tile[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5; // 32 x 8
+    const int tiles_i = (np + 31) / 32, tiles_j = (mp + 31) / 32;
+    for (int tix = blockIdx.x; tix < tiles_i * tiles_j; tix += gridDim.x) {
+        const int bi = (tix % tiles_i) * 32, bj = (tix / tiles_i) * 32; // dual rows bi.., dual columns bj..
+        for (int r = ty; r < 32; r += 8) { // primal row bj + r, primal columns bi + tx
+            const int pj = bj + r, pi = bi + tx;
+            tile[r][tx] = (pj < mp && pi < np) ? leq[(size_t)pj * (np + 1) + pi] : 0.0;
+        }
+        __syncthreads();
+        for (int r = ty; r < 32; r += 8) {
+            const int di = bi + r, dj = bj + tx;
+            if (di < np && dj < mp) dleq[(size_t)di * (mp + 1) + dj] = xp_mul(tile[tx][r], -1.0);
+        }
+        __syncthreads();
     }
-    const bool aux = !pos || bneg;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < np; i += gridDim.x * blockDim.x) {
+        dleq[(size_t)i * (mp + 1) + mp] = tg[i];
+        db[i] = tg[i];
+    }
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j <= mp; j += gridDim.x * blockDim.x)
+        dtg[j] = xp_mul(j < mp ? leq[(size_t)j * (np + 1) + np] : 0.0, -1.0);
+}
+
+} // namespace
+
+// The normalised LP (m x (n+1), objective, constant column) is either still on the host (`leq`
+// non-null: uploaded here, behind the solve where that pays) or already in d_leq / d_tg / d_b.
+static int two_stage_impl(xp_ctx *ctx, int m, int n, const double *leq, Stage1 s1, double *d_leq, double *d_tg,
+                          double *d_b, const double *vc_diag, const double *vc_rhs, uint32_t max_iter, int rule,
+                          int32_t *status, double *maxv, double *slack_sol, double *tgtf_out, int32_t *eq2bv,
+                          uint32_t *iters, uint32_t *pivots)
+{
+    cudaStream_t s = ctx->stream;
+    const int Cm = n + m + 1, prow = s1.prow;
+    const bool aux = !s1.pos || s1.bneg;
+    int rc = 0;
     if (maxv) *maxv = 0.0;
     if (iters) *iters = 0;
     if (pivots) *pivots = 0;
-    // the caller's LP in device scratch (the only bulk upload of the call)
-    void *scr = nullptr;
-    const size_t in_elems = (size_t)m * (n + 1) + (n + 1) + m;
-    int rc = xp_ctx_scratch(ctx, in_elems * sizeof(double), &scr);
-    if (rc) return rc;
-    double *d_leq = (double *)scr, *d_tg = d_leq + (size_t)m * (n + 1), *d_b = d_tg + (n + 1);
-    XP_CUDA_OK(ctx, cudaMemcpyAsync(d_tg, tgtf, (n + 1) * sizeof(double), cudaMemcpyHostToDevice, s));
-    XP_CUDA_OK(ctx, cudaMemcpyAsync(d_b, h_b, (size_t)m * sizeof(double), cudaMemcpyHostToDevice, s));
     unsigned n_piv = 0;
     LpRef A, M;
     rc = cached_handle(ctx, &ctx->cached_lp, m, Cm, &M.lp);
@@ -3534,7 +3545,7 @@ extern "C" int xp_six_two_stage_f64_large_vc(xp_ctx *ctx, int m, int n, const do
     if (!aux) {
         rc = set_vc(M.lp, vc_diag, vc_rhs, n, -1); // (only the optimal exit reads it)
         if (rc) return rc;
-        streamed = two_stage_streamed(ctx, M.lp, m, n, leq, d_leq, d_tg, d_b, max_iter);
+        if (leq) streamed = two_stage_streamed(ctx, M.lp, m, n, leq, d_leq, d_tg, d_b, max_iter);
         if (streamed < 0) return streamed;
     }
     if (!streamed) {
@@ -3543,7 +3554,7 @@ extern "C" int xp_six_two_stage_f64_large_vc(xp_ctx *ctx, int m, int n, const do
     // byte has arrived.  Phase 1 (rare) needs the whole LP first: one copy.
     const size_t row_bytes = (size_t)(n + 1) * sizeof(double);
     int n_chunks = 1;
-    if (!aux && (size_t)m * row_bytes >= ((size_t)64 << 20)) n_chunks = XP_PIPE_MAX < m ? XP_PIPE_MAX : m;
+    if (leq && !aux && (size_t)m * row_bytes >= ((size_t)64 << 20)) n_chunks = XP_PIPE_MAX < m ? XP_PIPE_MAX : m;
     if (n_chunks > 1) {
         rc = xp_ctx_pipe(ctx);
         if (rc) return rc;
@@ -3555,7 +3566,7 @@ extern "C" int xp_six_two_stage_f64_large_vc(xp_ctx *ctx, int m, int n, const do
                                             (size_t)(r1 - r0) * row_bytes, cudaMemcpyHostToDevice, ctx->pipe_copy));
             XP_CUDA_OK(ctx, cudaEventRecord(ctx->pipe_up[c], ctx->pipe_copy));
         }
-    } else {
+    } else if (leq) {
         XP_CUDA_OK(ctx, cudaMemcpyAsync(d_leq, leq, (size_t)m * row_bytes, cudaMemcpyHostToDevice, s));
     }
     if (!aux) {
@@ -3640,6 +3651,82 @@ extern "C" int xp_six_two_stage_f64_large_vc(xp_ctx *ctx, int m, int n, const do
     if (pivots) *pivots = n_piv + it;
     *status = st;
     return 0;
+}
+
+
+extern "C" int xp_six_two_stage_f64_large_vc(xp_ctx *ctx, int m, int n, const double *leq, const double *tgtf,
+                                             const double *vc_diag, const double *vc_rhs, uint32_t max_iter,
+                                             int rule, int32_t *status, double *maxv, double *slack_sol,
+                                             double *tgtf_out, int32_t *eq2bv, uint32_t *iters, uint32_t *pivots)
+{
+    if (!ctx || m < 1 || n < 1 || !leq || !tgtf || !status) return XP_ERR_BAD_ARG;
+    if (rule != XP_RULE_REFERENCE) return XP_ERR_BAD_ARG;
+    XP_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    // stage1 decision on the caller's arrays, :1794-1803 (the constant column is gathered into a
+    // small pinned buffer on the way: the piecewise upload sends it ahead of the matrix)
+    if (ctx->stage_bytes < (size_t)m * sizeof(double)) {
+        if (ctx->stage) cudaFreeHost(ctx->stage);
+        ctx->stage = nullptr;
+        ctx->stage_bytes = 0;
+        XP_CUDA_OK(ctx, cudaMallocHost(&ctx->stage, (size_t)m * sizeof(double)));
+        ctx->stage_bytes = (size_t)m * sizeof(double);
+    }
+    double *h_b = (double *)ctx->stage;
+    Stage1 s1;
+    for (int j = 0; j < n; j++) s1.pos |= tgtf[j] > 0.0;
+    for (int i = 0; i < m; i++) {
+        const double b = leq[(size_t)i * (n + 1) + n];
+        h_b[i] = b;
+        s1.bneg |= b < 0.0;
+        if (h_b[s1.prow] > b) s1.prow = i;
+    }
+    // the caller's LP in device scratch (the only bulk upload of the call)
+    void *scr = nullptr;
+    const size_t in_elems = (size_t)m * (n + 1) + (n + 1) + m;
+    int rc = xp_ctx_scratch(ctx, in_elems * sizeof(double), &scr);
+    if (rc) return rc;
+    double *d_leq = (double *)scr, *d_tg = d_leq + (size_t)m * (n + 1), *d_b = d_tg + (n + 1);
+    XP_CUDA_OK(ctx, cudaMemcpyAsync(d_tg, tgtf, (n + 1) * sizeof(double), cudaMemcpyHostToDevice, s));
+    XP_CUDA_OK(ctx, cudaMemcpyAsync(d_b, h_b, (size_t)m * sizeof(double), cudaMemcpyHostToDevice, s));
+    return two_stage_impl(ctx, m, n, leq, s1, d_leq, d_tg, d_b, vc_diag, vc_rhs, max_iter, rule, status, maxv,
+                          slack_sol, tgtf_out, eq2bv, iters, pivots);
+}
+
+// TwoStageMethod on the explicit DUAL of a normalised primal LP (SIX::minm, lpsol.h:1661-1732 with
+// calcDualMaxm :1585-1655), the dual built on the device: the caller hands over the PRIMAL
+// (leq mp x (np+1), tgtf np+1; x >= 0, no equalities) exactly as it would to the max entry, the
+// transposition -A^T, the dual objective -b and its slack form never exist on the host.  Outputs
+// are those of the dual LP (np rows, mp variables): slack_sol / tgtf_out mp+np+1 entries, eq2bv np.
+extern "C" int xp_six_two_stage_f64_large_dual(xp_ctx *ctx, int mp, int np, const double *leq, const double *tgtf,
+                                               uint32_t max_iter, int rule, int32_t *status, double *maxv,
+                                               double *slack_sol, double *tgtf_out, int32_t *eq2bv,
+                                               uint32_t *iters, uint32_t *pivots)
+{
+    if (!ctx || mp < 1 || np < 1 || !leq || !tgtf || !status) return XP_ERR_BAD_ARG;
+    if (rule != XP_RULE_REFERENCE) return XP_ERR_BAD_ARG;
+    XP_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    const int m = np, n = mp; // the dual's shape
+    Stage1 s1;                // dual objective -b_j, dual constant column c_i
+    for (int j = 0; j < mp; j++) s1.pos |= -leq[(size_t)j * (np + 1) + np] > 0.0;
+    for (int i = 0; i < np; i++) {
+        s1.bneg |= tgtf[i] < 0.0;
+        if (tgtf[s1.prow] > tgtf[i]) s1.prow = i;
+    }
+    void *scr = nullptr;
+    const size_t prim = (size_t)mp * (np + 1) + (np + 1), dual = (size_t)m * (n + 1) + (n + 1) + m;
+    int rc = xp_ctx_scratch(ctx, (prim + dual) * sizeof(double), &scr);
+    if (rc) return rc;
+    double *d_leq = (double *)scr, *d_tg = d_leq + (size_t)m * (n + 1), *d_b = d_tg + (n + 1);
+    double *p_leq = d_b + m, *p_tg = p_leq + (size_t)mp * (np + 1);
+    XP_CUDA_OK(ctx, cudaMemcpyAsync(p_leq, leq, (size_t)mp * (np + 1) * sizeof(double), cudaMemcpyHostToDevice, s));
+    XP_CUDA_OK(ctx, cudaMemcpyAsync(p_tg, tgtf, (size_t)(np + 1) * sizeof(double), cudaMemcpyHostToDevice, s));
+    k_build_dual<<<ctx->sm_count * 4, 256, 0, s>>>(p_leq, p_tg, mp, np, d_leq, d_tg, d_b);
+    ctx->launches++;
+    XP_CUDA_OK(ctx, cudaGetLastError());
+    return two_stage_impl(ctx, m, n, nullptr, s1, d_leq, d_tg, d_b, nullptr, nullptr, max_iter, rule, status, maxv,
+                          slack_sol, tgtf_out, eq2bv, iters, pivots);
 }
 
 // Position-keyed checksums (xp_lp_f64_checksum) of the tableau and objective row the last
