@@ -441,3 +441,32 @@ def test_minm_large_dual_built_on_device(ctx, monkeypatch):
         same_f64(ctx.six_solve("f64", 1, l3, t3, max_iter=300), o, ("lb-min", s_))
         seen.add(o["status"])
     assert len(seen) >= 1
+
+
+def test_has_solution_device_resident_vs_lockstep_and_oracle(ctx, monkeypatch):
+    """Lineq::has_solution with the whole query on the device (one warp per query: both MIPs, DFS
+    branch & bound, every node relaxation in registers) against the lock-step host path
+    (XP_HS_HOST=1) on 6 000 random dependence systems, and against the oracle on a sample; all
+    four (is_int_sol, is_unique_sol) combinations."""
+    r = np.random.RandomState(4711)
+    systems = []
+    for k in range(6000):
+        nq, mq = int(r.randint(1, 7)), int(r.randint(1, 10))
+        sysm = np.zeros((mq, nq + 1), dtype=np.int64)
+        sysm[:, :nq] = r.randint(-3, 5, size=(mq, nq)) * (r.uniform(size=(mq, nq)) < 0.7)
+        sysm[:, nq] = r.randint(-4, 25, size=mq)
+        systems.append((sysm, None))
+    for is_int in (True, False):
+        for is_unique in (True, False):
+            dev = ctx.has_solution_ragged(systems, is_int=is_int, is_unique=is_unique)
+            monkeypatch.setenv("XP_HS_HOST", "1")
+            host = ctx.has_solution_ragged(systems, is_int=is_int, is_unique=is_unique)
+            monkeypatch.delenv("XP_HS_HOST")
+            bad = np.nonzero(dev != host)[0]
+            assert len(bad) == 0, (is_int, is_unique, bad[:10], dev[bad[:10]], host[bad[:10]])
+            for k in range(0, 6000, 11):
+                a0 = H.appro_count("oracle")
+                o = H.has_solution("oracle", H.to_rat(systems[k][0]), is_int=is_int, is_unique=is_unique)
+                if H.appro_count("oracle") == a0:
+                    assert dev[k] == o, (is_int, is_unique, k, dev[k], o)
+            assert set(np.unique(dev).tolist()) >= {0, 1}

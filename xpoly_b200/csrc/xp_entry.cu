@@ -785,6 +785,11 @@ extern "C" int xp_mip_solve_rat_batch(xp_ctx *ctx, int is_min, int is_bin, int b
 }
 
 // ---- Lineq::has_solution (linsys.cpp:830-906), batched ----
+int xp_has_solution_device(xp_ctx *ctx, const std::vector<int> &sel, const int32_t *ns, const int32_t *ms,
+                           const int64_t *leq_off, const xp_rat *leq_pool, int is_int_sol, int is_unique_sol,
+                           int32_t *result);
+bool xp_has_solution_device_fits(int n, int m, int k, const xp_rat *leq);
+
 namespace {
 
 // Systems Ls[b] (leq, may be empty) / Es[b] (eq, may be empty) over ns[b] variables, vc = -I.
@@ -869,10 +874,11 @@ extern "C" int xp_has_solution_rat_batch(xp_ctx *ctx, int batch, int m, int n, c
 {
     XP_ENTRY_GUARD(ctx);
     if (batch < 0 || m < 1 || n < 1 || !leq || !result) return XP_ERR_BAD_ARG;
-    std::vector<Mat<Q>> Ls(batch), Es(batch);
-    std::vector<int> ns(batch, n);
-    for (int b = 0; b < batch; b++) Ls[b] = mat_q(m, n + 1, leq + (size_t)b * m * (n + 1));
-    int rc = has_solution_core(ctx, Ls, Es, ns, is_int_sol, is_unique_sol, result);
+    std::vector<int32_t> ns(batch, n), ms(batch, m);
+    std::vector<int64_t> off(batch);
+    for (int b = 0; b < batch; b++) off[b] = (int64_t)b * m * (n + 1);
+    int rc = xp_has_solution_rat_ragged(ctx, batch, ns.data(), ms.data(), off.data(), leq, (size_t)batch * m * (n + 1),
+                                        nullptr, nullptr, nullptr, 0, is_int_sol, is_unique_sol, result);
     if (rc) return rc;
     for (int b = 0; b < batch; b++)
         if (result[b] < 0) return result[b]; // uniform API: any failing system fails the call
@@ -890,8 +896,6 @@ extern "C" int xp_has_solution_rat_ragged(xp_ctx *ctx, int batch, const int32_t 
 {
     XP_ENTRY_GUARD(ctx);
     if (batch < 0 || !ns || !ms || !result) return XP_ERR_BAD_ARG;
-    std::vector<Mat<Q>> Ls(batch), Es(batch);
-    std::vector<int> nv(batch);
     for (int b = 0; b < batch; b++) {
         const int n = ns[b], m = ms[b], k = ks ? ks[b] : 0;
         if (n < 1 || m < 0 || k < 0) return XP_ERR_BAD_ARG;
@@ -899,9 +903,37 @@ extern "C" int xp_has_solution_rat_ragged(xp_ctx *ctx, int batch, const int32_t 
         // every system must lie inside its pool (offsets and lengths in xp_rat elements)
         if (m > 0 && (leq_off[b] < 0 || (size_t)leq_off[b] + (size_t)m * (n + 1) > leq_pool_len)) return XP_ERR_BAD_ARG;
         if (k > 0 && (eq_off[b] < 0 || (size_t)eq_off[b] + (size_t)k * (n + 1) > eq_pool_len)) return XP_ERR_BAD_ARG;
-        nv[b] = n;
-        if (m > 0) Ls[b] = mat_q(m, n + 1, leq_pool + leq_off[b]);
-        if (k > 0) Es[b] = mat_q(k, n + 1, eq_pool + eq_off[b]);
     }
-    return has_solution_core(ctx, Ls, Es, nv, is_int_sol, is_unique_sol, result);
+    // Queries of the dependence-feasibility shape (integer rows, no equalities, small) are answered
+    // whole on the device, one warp per query (xp_has_solution_dev.cu); the others -- equalities,
+    // rational inputs, larger systems -- and any query that overflowed int64 there go through the
+    // lock-step path below (host B&B state machine, batched node relaxations).
+    std::vector<int> dev_sel, host_sel;
+    const bool no_dev = getenv("XP_HS_HOST") != nullptr;
+    for (int b = 0; b < batch; b++) {
+        const int k = ks ? ks[b] : 0;
+        if (!no_dev && ms[b] > 0 && xp_has_solution_device_fits(ns[b], ms[b], k, leq_pool + leq_off[b])) dev_sel.push_back(b);
+        else host_sel.push_back(b);
+    }
+    if (!dev_sel.empty()) {
+        int rc = xp_has_solution_device(ctx, dev_sel, ns, ms, leq_off, leq_pool, is_int_sol, is_unique_sol, result);
+        if (rc) return rc;
+        for (int b : dev_sel)
+            if (result[b] == XP_ERR_OVERFLOW || result[b] == XP_ERR_TOO_LARGE) host_sel.push_back(b);
+    }
+    if (host_sel.empty()) return 0;
+    const int hb = (int)host_sel.size();
+    std::vector<Mat<Q>> Ls(hb), Es(hb);
+    std::vector<int> nv(hb);
+    for (int s = 0; s < hb; s++) {
+        const int b = host_sel[s], n = ns[b], m = ms[b], k = ks ? ks[b] : 0;
+        nv[s] = n;
+        if (m > 0) Ls[s] = mat_q(m, n + 1, leq_pool + leq_off[b]);
+        if (k > 0) Es[s] = mat_q(k, n + 1, eq_pool + eq_off[b]);
+    }
+    std::vector<int32_t> hres(hb, 0);
+    int rc = has_solution_core(ctx, Ls, Es, nv, is_int_sol, is_unique_sol, hres.data());
+    if (rc) return rc;
+    for (int s = 0; s < hb; s++) result[host_sel[s]] = hres[s];
+    return 0;
 }
