@@ -826,31 +826,20 @@ def run_ours(args):
             details["batched"] = run_batched(ctx, xp, torch, dev, with_cpu=not args.no_cpu)
             details.update(run_exact_and_bnb(ctx, xp, torch, dev, with_cpu=not args.no_cpu))
     else:
-        # ---- e2e at N GPUs: every rank moves ITS column slice of the host tableau through the
-        # C-ABI handle calls (upload of the full host arrays keeps the rank's slice, download
-        # writes the rank's columns back), pinned host buffers, all copies inside the timed
-        # region; wall clock between barriers, max over ranks.
-        tab_bytes = m * Ccols * 8
-        hp_in, hp_out = C.c_void_p(), C.c_void_p()
-        ctx.check(lib.xp_host_alloc(ctx._h, C.c_size_t(tab_bytes), C.byref(hp_in)))
-        ctx.check(lib.xp_host_alloc(ctx._h, C.c_size_t(tab_bytes), C.byref(hp_out)))
+        # ---- e2e at N GPUs: the LP starts in (pinned) host memory as the caller's leq / tgtf; every
+        # rank uploads the columns of leq that fall into its slice (xp_lp_f64_upload_leq on the sharded
+        # handle: 2-D copy over its own PCIe link, slack columns generated on the device), the ranks
+        # solve together, O(C) comes down; all copies inside the timed region, wall clock between
+        # barriers, max over ranks
+        from xpoly_b200.synth import dense_lp
+        leq_h, tg_h = dense_lp(SEED, m, n)
+        hp_in = C.c_void_p()
+        ctx.check(lib.xp_host_alloc(ctx._h, C.c_size_t(leq_h.nbytes), C.byref(hp_in)))
+        h_leq = np.ctypeslib.as_array(C.cast(hp_in, C.POINTER(C.c_double)), shape=leq_h.shape)
+        h_leq[...] = leq_h
         lp.set_block(args.block)
-        lp.fill_synthetic(SEED)
-        st0 = lp.download(want_tab=False)
-        ctx.check(lib.xp_lp_f64_download(lp._h, hp_in, None, None, None, None, None, None, None,
-                                         None, None, 0))
-        h_in = np.ctypeslib.as_array(C.cast(hp_in, C.POINTER(C.c_double)), shape=(m, Ccols))
-        # replicated inputs every rank needs whole: the constant column and the objective row
-        rhs = torch.from_numpy(np.ascontiguousarray(h_in[:, Ccols - 1])).to(dev)
-        dist.broadcast(rhs, src=world - 1)
-        h_in[:, Ccols - 1] = rhs.cpu().numpy()
-        tgt = torch.from_numpy(st0["tgtf"].copy()).to(dev)
-        dist.all_reduce(tgt)  # slices are disjoint, the rest of each rank's row is zero
-        tg0 = tgt.cpu().numpy()
-        nv0, b2e0, e2b0 = st0["nvset"].copy(), st0["bv2eq"].copy(), st0["eq2bv"].copy()
-        bvs0 = st0["bvset"].copy()
-        tg1, nv1, bvs1 = np.zeros(Ccols), np.zeros_like(nv0), np.zeros_like(bvs0)
-        b2e1, e2b1 = np.zeros_like(b2e0), np.zeros_like(e2b0)
+        tg1 = np.zeros(Ccols)
+        e2b1 = np.zeros(m, dtype=np.int32)
         maxv, sol = np.zeros(1), np.zeros(Ccols)
         iters = np.zeros(1, dtype=np.uint32)
         p = lambda a: a.ctypes.data_as(C.c_void_p)
@@ -858,32 +847,33 @@ def run_ours(args):
         def e2e_step():
             barrier()
             t0 = time.perf_counter()
-            ctx.check(lib.xp_lp_f64_upload(lp._h, hp_in, p(tg0), p(nv0), p(bvs0), p(b2e0), p(e2b0),
-                                           None, None))
+            ctx.check(lib.xp_lp_f64_upload_leq(lp._h, hp_in, p(tg_h), n))
             st = ctx.check(lib.xp_lp_f64_solve(lp._h, C.c_uint32(P), 0))
-            ctx.check(lib.xp_lp_f64_download(lp._h, hp_out, p(tg1), p(nv1), p(bvs1), p(b2e1),
-                                             p(e2b1), p(maxv), p(sol), p(iters), None, 0))
+            ctx.check(lib.xp_lp_f64_download(lp._h, None, p(tg1), None, None, None, p(e2b1), p(maxv), p(sol), p(iters),
+                                             None, 0))
             barrier()
             return time.perf_counter() - t0, int(iters[0]), st
         e2e_step()
         ts, its = [], 0
-        for _ in range(max(2, min(args.steps, 4))):
+        for _ in range(max(3, min(args.steps, 8))):
             dt, it, _st = e2e_step()
             ts.append(dt)
             its += it
         tt = torch.tensor([sum(ts)], dtype=torch.float64, device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        small = Ccols * 8 + (Ccols - 1) * (1 + 4) + m * 4
+        a_lo, a_hi = min(lp.col0, n), min(lp.col0 + local_cols, n)
+        up = torch.tensor([float(m * max(a_hi - a_lo, 0) * 8 + m * 8 + (n + 1) * 8)], dtype=torch.float64, device=dev)
+        dist.all_reduce(up)
         line["e2e"] = {"value": its / float(tt.item()), "unit": "pivots/s",
-                       "h2d_bytes_per_step": int(tab_bytes + world * small + (world - 1) * m * 8),
-                       "d2h_bytes_per_step": int(tab_bytes + world * (small + Ccols * 8)),
+                       "h2d_bytes_per_step": int(up.item()),
+                       "d2h_bytes_per_step": int(world * (2 * Ccols * 8 + m * 4 + 64)),
                        "ms_per_step": 1000.0 * float(tt.item()) / len(ts), "pivots_per_step": P,
-                       "api": "xp_lp_f64_upload + xp_lp_f64_solve + xp_lp_f64_download on the "
-                              "column-sharded handle (pinned host buffers, each rank moves its "
-                              "own column slice over its own PCIe link)",
+                       "api": "xp_lp_f64_upload_leq + xp_lp_f64_solve + xp_lp_f64_download on the column-sharded "
+                              "handle (pinned host leq; every rank uploads the columns of its slice over its own "
+                              "PCIe link, slack form on the device)",
                        "basis_matches_device_run": bool(np.array_equal(e2b1, e2b_K)) if P == Kp else None}
         ctx.check(lib.xp_host_free(ctx._h, hp_in))
-        ctx.check(lib.xp_host_free(ctx._h, hp_out))
+        del h_leq
         barrier()
         lp.close()
         barrier()

@@ -112,7 +112,8 @@ int xp_lp_f64_upload(xp_lp_f64 *lp, const double *tableau, const double *tgtf,
                      const int32_t *eq2bv, const double *vc_diag, const double *vc_rhs);
 /* Build the slack form [A | I | b] of a normalised LP (leq m x (n+1), b >= 0)
  * directly on the device: SIX::slack + the identity basis of stage1
- * (lpsol.h:1405-1433, :1821-1841).  Requires C == n + m + 1. */
+ * (lpsol.h:1405-1433, :1821-1841).  Requires C == n + m + 1.  On a sharded handle every
+ * rank passes the same full `leq` and uploads only the columns that fall into its slice. */
 int xp_lp_f64_upload_leq(xp_lp_f64 *lp, const double *leq, const double *tgtf, int n);
 /* Fill with the synthetic dense family of SURVEY 8(d) on the device
  * (A_ij~U(0,1), b_i = 1 + U*n, c_j~U(0,1); counter-based generator). */

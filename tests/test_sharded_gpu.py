@@ -126,6 +126,38 @@ def test_inproc_windowed_leader(G, window):
         assert_same_state(g, H.slack_solve_oracle("f64", *sf, max_iter=K), ("wshard-resume", G, window, K))
 
 
+@pytest.mark.parametrize("G", [1, 2, 3])
+def test_upload_leq_on_shards(G):
+    """xp_lp_f64_upload_leq on a (sharded) handle: every rank uploads only the columns of leq that
+    fall into its slice and generates the slack columns on the device -- same state as uploading the
+    host-built slack form."""
+    for seed, (m, n) in enumerate([(16, 15), (33, 20), (12, 40)]):
+        leq, tg = H.gen_dense_lp(7300 + seed, m, n)
+        sf = xp.slack_form(leq, tg)
+        ctxs = [xp.Context(0) for _ in range(G)]
+        lps = [c.large_lp(m, n + m + 1, r, G) for r, c in enumerate(ctxs)]
+        for lp in lps:
+            if G > 1:
+                lp.peer_attach_local(lps)
+            lp.upload_leq(leq, tg)
+        st = [None] * G
+        th = [threading.Thread(target=lambda r=r: st.__setitem__(r, lps[r].solve(H.NO_LIMIT))) for r in range(G)]
+        [t.start() for t in th]
+        [t.join() for t in th]
+        o = H.slack_solve_oracle("f64", *sf)
+        for lp in lps:
+            g = lp.download(log_cap=1 << 16)
+            sl = slice(lp.col0, lp.col0 + lp.local_cols)
+            assert st[lp.rank] == o["status"] and g["iters"] == o["iters"]
+            assert np.array_equal(H.bits(g["tab"][:, sl]), H.bits(o["tab"][:, sl]))
+            assert np.array_equal(H.bits(g["tgtf"][sl]), H.bits(o["tgtf"][sl]))
+            assert np.array_equal(g["eq2bv"], o["eq2bv"]) and np.array_equal(H.bits(g["sol"]), H.bits(o["sol"]))
+        for lp in lps:
+            lp.close()
+        for c in ctxs:
+            c.close()
+
+
 @pytest.mark.parametrize("G", [2, 4])
 def test_inproc_mixed_sign_slow_paths(G):
     """disableNV retries, the pass-2 ratio test and the findPivotNVandBVPair search

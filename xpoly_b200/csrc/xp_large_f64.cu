@@ -178,10 +178,21 @@ __device__ __forceinline__ double *Fptr(const LpDev &d, int r, int par, int s)
 {
     return (double *)(d.xb[r] + xoff_F(d, par, s));
 }
-// Column range of rank r: even split in units of two columns (128-bit accesses).
+// Column range of rank r, in units of two columns (128-bit accesses).  An even split, except that
+// rank 0 -- the leader of windowed runs, whose slice must hold the pricing window -- keeps at least
+// LEADER_MIN columns when the even share would be smaller (8 GPUs at c3: 3072 + 7 x 1902 instead of
+// 8 x 2048: the entering column of the dense family climbs past 2048 after ~3 600 pivots, and every
+// pivot outside the window costs two NVLink exchanges).  Mirrored by sharded.shard_bounds().
+constexpr int LEADER_MIN = 3072;
 __host__ __device__ __forceinline__ int shard_lo(int C, int G, int r)
 {
-    long long pairs = (C + 1) / 2;
+    const long long pairs = (C + 1) / 2;
+    if (G > 2 && pairs / G < LEADER_MIN / 2 && pairs >= LEADER_MIN) { // (needs room for the peers as well)
+        if (r == 0) return 0;
+        const long long rest = pairs - LEADER_MIN / 2;
+        const long long lo = LEADER_MIN + 2 * (rest * (r - 1) / (G - 1));
+        return lo > C ? C : (int)lo;
+    }
     long long lo = 2 * (pairs * r / G);
     return lo > C ? C : (int)lo;
 }
@@ -189,6 +200,7 @@ __device__ __forceinline__ int owner_of(const LpDev &d, int j)
 {
     if (d.G == 1) return 0;
     int r = (int)(((long long)(j / 2) * d.G) / ((d.C + 1) / 2));
+    if (r >= d.G) r = d.G - 1;
     while (r + 1 < d.G && shard_lo(d.C, d.G, r + 1) <= j) r++;
     while (r > 0 && shard_lo(d.C, d.G, r) > j) r--;
     return r;
@@ -2698,6 +2710,40 @@ extern "C" int xp_lp_f64_upload(xp_lp_f64 *lp, const double *tableau, const doub
     return lp_reset(lp);
 }
 
+namespace {
+// Slack form of this rank's slice from a COMPACT copy of the A-columns it owns: `A` holds columns
+// [a_lo, a_lo + wa) of leq (m x wa), b the constant column, tg the objective.  Replicated state
+// (basis maps, constant-column replica) is written by every rank.
+__global__ void k_slack_form_slice(LpDev d, const double *A, int wa, int a_lo, const double *b, const double *tg, int n)
+{
+    const int m = d.m, C = d.C, Cl = d.Cl;
+    const size_t total = (size_t)m * Cl;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        const int i = (int)(e / Cl), j = d.col0 + (int)(e % Cl);
+        double v;
+        if (j < n) v = A[(size_t)i * wa + (j - a_lo)];
+        else if (j < n + m) v = (j - n == i) ? 1.0 : 0.0;
+        else v = b[i];
+        d.tab[e] = v;
+    }
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < C; j += gridDim.x * blockDim.x) {
+        if (j >= d.col0 && j < d.col0 + Cl) d.tgtf[j - d.col0] = j < n ? tg[j] : (j < n + m ? 0.0 : tg[n]);
+        if (j < n + m) {
+            d.nvset[j] = j < n;
+            d.bv2eq[j] = j < n ? -1 : j - n;
+        }
+        if (j < m) {
+            d.eq2bv[j] = n + j;
+            d.rhsbuf[j] = b[j];
+        }
+        if (j == 0) d.st->tg_rhs = tg[n];
+    }
+}
+} // namespace
+
+// Works on a sharded handle too: every rank uploads only the columns of leq that fall into its
+// slice (a 2-D copy; pinned host memory gives the full PCIe rate) plus the constant column and
+// the objective; slack columns are generated on the device.
 extern "C" int xp_lp_f64_upload_leq(xp_lp_f64 *lp, const double *leq, const double *tgtf, int n)
 {
     if (!lp || !leq || !tgtf) return XP_ERR_BAD_ARG;
@@ -2706,19 +2752,33 @@ extern "C" int xp_lp_f64_upload_leq(xp_lp_f64 *lp, const double *leq, const doub
     const int m = d.m;
     if (d.C != n + m + 1) return XP_ERR_BAD_ARG;
     XP_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    const int a_lo = d.col0 < n ? d.col0 : n, a_hi = d.col0 + d.Cl < n ? d.col0 + d.Cl : n;
+    const int wa = a_hi > a_lo ? a_hi - a_lo : 0;
+    if (ctx->stage_bytes < (size_t)m * sizeof(double)) {
+        if (ctx->stage) cudaFreeHost(ctx->stage);
+        ctx->stage = nullptr;
+        ctx->stage_bytes = 0;
+        XP_CUDA_OK(ctx, cudaMallocHost(&ctx->stage, (size_t)m * sizeof(double)));
+        ctx->stage_bytes = (size_t)m * sizeof(double);
+    }
+    double *h_b = (double *)ctx->stage;
+    for (int i = 0; i < m; i++) h_b[i] = leq[(size_t)i * (n + 1) + n];
     void *scr = nullptr;
-    size_t bytes = ((size_t)m * (n + 1) + (n + 1)) * sizeof(double);
+    const size_t bytes = ((size_t)m * (wa > 0 ? wa : 1) + m + (n + 1)) * sizeof(double);
     int rc = xp_ctx_scratch(ctx, bytes, &scr);
     if (rc) return rc;
-    double *d_leq = (double *)scr, *d_tg = d_leq + (size_t)m * (n + 1);
+    double *d_A = (double *)scr, *d_b = d_A + (size_t)m * (wa > 0 ? wa : 1), *d_tg = d_b + m;
     cudaStream_t s = ctx->stream;
-    XP_CUDA_OK(ctx, cudaMemcpyAsync(d_leq, leq, (size_t)m * (n + 1) * sizeof(double),
-                                    cudaMemcpyHostToDevice, s));
+    if (wa > 0)
+        XP_CUDA_OK(ctx, cudaMemcpy2DAsync(d_A, (size_t)wa * sizeof(double), leq + a_lo, (size_t)(n + 1) * sizeof(double),
+                                          (size_t)wa * sizeof(double), m, cudaMemcpyHostToDevice, s));
+    XP_CUDA_OK(ctx, cudaMemcpyAsync(d_b, h_b, (size_t)m * sizeof(double), cudaMemcpyHostToDevice, s));
     XP_CUDA_OK(ctx, cudaMemcpyAsync(d_tg, tgtf, (n + 1) * sizeof(double), cudaMemcpyHostToDevice, s));
-    k_slack_form<<<ctx->sm_count * 4, 256, 0, s>>>(d, d_leq, d_tg, n, 0, d.m);
+    k_slack_form_slice<<<ctx->sm_count * 4, 256, 0, s>>>(d, d_A, wa, a_lo, d_b, d_tg, n);
     ctx->launches++;
     d.vc_diag = d.vc_rhs = nullptr;
     XP_CUDA_OK(ctx, cudaGetLastError());
+    XP_CUDA_OK(ctx, cudaStreamSynchronize(s)); // the staging buffer is reused by the next call
     return lp_reset(lp);
 }
 

@@ -8,11 +8,19 @@ are host bytes)."""
 import numpy as np
 
 
+LEADER_MIN = 3072  # columns rank 0 keeps at least (it leads the windowed runs); shard_lo() in xp_large_f64.cu
+
+
 def shard_bounds(C, nranks):
-    """Column range [lo, hi) of every rank: even split in units of two columns
-    (the kernels use 128-bit accesses).  Mirrors shard_lo() in xp_large_f64.cu."""
+    """Column range [lo, hi) of every rank, in units of two columns (the kernels use 128-bit
+    accesses): an even split, except that rank 0 keeps at least LEADER_MIN columns when the even
+    share would be smaller.  Mirrors shard_lo() in xp_large_f64.cu."""
     pairs = (C + 1) // 2
-    lo = [min(C, 2 * (pairs * r // nranks)) for r in range(nranks)] + [C]
+    if nranks > 2 and pairs // nranks < LEADER_MIN // 2 and pairs >= LEADER_MIN:
+        rest = pairs - LEADER_MIN // 2
+        lo = [0] + [min(C, LEADER_MIN + 2 * (rest * (r - 1) // (nranks - 1))) for r in range(1, nranks)] + [C]
+    else:
+        lo = [min(C, 2 * (pairs * r // nranks)) for r in range(nranks)] + [C]
     return [(lo[r], lo[r + 1]) for r in range(nranks)]
 
 
