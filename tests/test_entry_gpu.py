@@ -451,7 +451,7 @@ def test_has_solution_device_resident_vs_lockstep_and_oracle(ctx, monkeypatch):
     r = np.random.RandomState(4711)
     systems = []
     for k in range(6000):
-        nq, mq = int(r.randint(1, 7)), int(r.randint(1, 10))
+        nq, mq = int(r.randint(1, 7)), int(r.randint(1, 16))  # up to 15 rows: both kernel sizes and, beyond 24 rows at the deepest node, the host path
         sysm = np.zeros((mq, nq + 1), dtype=np.int64)
         sysm[:, :nq] = r.randint(-3, 5, size=(mq, nq)) * (r.uniform(size=(mq, nq)) < 0.7)
         sysm[:, nq] = r.randint(-4, 25, size=mq)

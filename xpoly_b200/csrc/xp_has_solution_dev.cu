@@ -21,8 +21,10 @@
 // Values are exact rationals num / D (D = common denominator of the LP that produced them);
 // comparisons cross-multiply in 128 bits -- the value semantics of the reference's Rational
 // wherever that one stays exact.  An int64 overflow anywhere reports XP_ERR_OVERFLOW for the query.
-// Queries that do not fit (equalities, rational inputs, more than 16 rows / 32 columns at the
-// deepest node) are answered by the lock-step path of xp_entry.cu.
+// Queries that do not fit (equalities, rational inputs, more than 24 rows / 32 columns at the
+// deepest node) are answered by the lock-step path of xp_entry.cu.  Two instantiations: 16 rows
+// (237 registers) and 24 rows (255 registers, a few spilled words) for the larger dependence
+// polyhedra (13 rows x 4 variables after the reference's pre-filter, tests/golden/deppoly_queries.json).
 #include "xp_batch_warp_i64.cuh"
 
 #include <vector>
@@ -31,8 +33,8 @@ namespace {
 
 using namespace xpwi;
 
-constexpr int HS_MR = 16;   // rows of the deepest node LP (and variables of its dual)
-constexpr int HS_N1 = 16;   // n + 1 at most
+constexpr int HS_MRMAX = 24; // rows of the deepest node LP (and variables of its dual): kernels for 16 and 24
+constexpr int HS_N1 = 16;    // n + 1 at most
 constexpr int HS_DEPTH = 18;
 
 struct HsArgs {
@@ -50,9 +52,10 @@ struct HsFrame {
     i64 tv_num, tv_den; // value of the floor child (tmpv, :2527-2543)
 };
 
+template <int HS_MR>
 struct HsWarp {
     i64 leq[HS_MR * HS_N1];        // node LP: the query's rows, then one branching row per level
-    i64 dual[HS_MR * (HS_MR + 1)]; // explicit dual of the node LP (min problems)
+    i64 dual[HS_N1 * (HS_MR + 1)]; // explicit dual of the node LP (min problems): n rows x (m + 1)
     i64 tg[HS_N1], dtg[HS_MR + 1];
     i64 sol[HS_N1];                // numerators of the node's final solution over D
     HsFrame fr[HS_DEPTH];
@@ -64,7 +67,8 @@ __device__ __forceinline__ bool q_le(i64 an, i64 ad, i64 bn, i64 bd) { return (i
 
 // One node relaxation: SIX::maxm / minm on rows [0, m) of S.leq.  Returns the SIX status; on
 // SIX_SUCC S.sol[0..n] holds the solution numerators over D and (v_num, D) the objective value.
-__device__ int solve_node(HsWarp &S, LP<HS_MR, 1> &W, const XpBatchArgs &A, bool is_max, int m, int n, i64 &v_num,
+template <int HS_MR>
+__device__ int solve_node(HsWarp<HS_MR> &S, LP<HS_MR, 1> &W, const XpBatchArgs &A, bool is_max, int m, int n, i64 &v_num,
                           i64 &D, bool &ovf)
 {
     const int lane = W.lane;
@@ -103,7 +107,8 @@ __device__ int solve_node(HsWarp &S, LP<HS_MR, 1> &W, const XpBatchArgs &A, bool
 }
 
 // MIP::maxm / minm (RecusivePart, lpsol.h:2426-2612) on the query in S.leq[0..m0).  Returns the IP status.
-__device__ int run_mip(HsWarp &S, LP<HS_MR, 1> &W, const XpBatchArgs &A, bool is_max, bool is_int, int m0, int n)
+template <int HS_MR>
+__device__ int run_mip(HsWarp<HS_MR> &S, LP<HS_MR, 1> &W, const XpBatchArgs &A, bool is_max, bool is_int, int m0, int n)
 {
     const int lane = W.lane;
     if (lane <= HS_N1) S.fork[lane] = 0;
@@ -205,10 +210,11 @@ __device__ int run_mip(HsWarp &S, LP<HS_MR, 1> &W, const XpBatchArgs &A, bool is
     }
 }
 
+template <int HS_MR>
 __global__ void __launch_bounds__(32 * WARPS) k_has_solution(HsArgs H)
 {
     __shared__ __align__(16) i64 scratch[WARPS][32];
-    __shared__ HsWarp state[WARPS];
+    __shared__ HsWarp<HS_MR> state[WARPS];
     LP<HS_MR, 1> W;
     W.c1 = W.sol1 = 0;
     W.t1 = 0ull;
@@ -216,7 +222,7 @@ __global__ void __launch_bounds__(32 * WARPS) k_has_solution(HsArgs H)
     W.b2e1 = -1;
     W.lane = threadIdx.x & 31;
     W.sc = scratch[threadIdx.x >> 5];
-    HsWarp &S = state[threadIdx.x >> 5];
+    HsWarp<HS_MR> &S = state[threadIdx.x >> 5];
     XpBatchArgs A;
     A.max_iter = 10000u; // six.set_param(m_indent, 10000), :2441
     const int lane = W.lane;
@@ -256,14 +262,36 @@ __global__ void __launch_bounds__(32 * WARPS) k_has_solution(HsArgs H)
 } // namespace
 
 // Host side: `sel` lists the queries of the batch that qualify (integer entries, no equalities,
-// small enough); their rows are packed as int64 and answered by one launch.
-int xp_has_solution_device(xp_ctx *ctx, const std::vector<int> &sel, const int32_t *ns, const int32_t *ms,
+// small enough); their rows are packed as int64 and answered by one launch per kernel size.
+template <int HS_MR>
+static int hs_launch(xp_ctx *ctx, const HsArgs &H, int B)
+{
+    int occ = 1;
+    XP_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_has_solution<HS_MR>, 32 * WARPS, 0));
+    if (occ < 1) occ = 1;
+    long long g = (long long)occ * ctx->sm_count;
+    const long long need = ((long long)B + WARPS - 1) / WARPS;
+    if (g > need) g = need;
+    k_has_solution<HS_MR><<<(unsigned)g, 32 * WARPS, 0, ctx->stream>>>(H);
+    ctx->launches++;
+    return 0;
+}
+
+int xp_has_solution_device(xp_ctx *ctx, const std::vector<int> &sel_in, const int32_t *ns, const int32_t *ms,
                            const int64_t *leq_off, const xp_rat *leq_pool, int is_int_sol, int is_unique_sol,
                            int32_t *result)
 {
-    const int B = (int)sel.size();
-    if (B == 0) return 0;
+    if (sel_in.empty()) return 0;
     XP_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    // queries whose deepest node has at most 16 rows first, the 17..24-row ones after them
+    std::vector<int> sel;
+    sel.reserve(sel_in.size());
+    for (int b : sel_in)
+        if (ms[b] + ns[b] <= 16) sel.push_back(b);
+    const int B16 = (int)sel.size();
+    for (int b : sel_in)
+        if (ms[b] + ns[b] > 16) sel.push_back(b);
+    const int B = (int)sel.size();
     std::vector<int32_t> hn(B), hm(B);
     std::vector<int64_t> off(B);
     size_t total = 0;
@@ -281,7 +309,7 @@ int xp_has_solution_device(xp_ctx *ctx, const std::vector<int> &sel, const int32
         for (size_t e = 0; e < cnt; e++) d[e] = p[e].num; // den == 1 (pre-screened)
     }
     auto pad = [](size_t b) { return (b + 255) & ~(size_t)255; };
-    const size_t bytes = pad(total * 8) + 2 * pad((size_t)B * 4) + pad((size_t)B * 8) + pad((size_t)B * 4) + 512;
+    const size_t bytes = pad(total * 8) + 2 * pad((size_t)B * 4) + pad((size_t)B * 8) + pad((size_t)B * 4) + 1024;
     void *scr = nullptr;
     int rc = xp_ctx_scratch(ctx, bytes, &scr);
     if (rc) return rc;
@@ -296,32 +324,30 @@ int xp_has_solution_device(xp_ctx *ctx, const std::vector<int> &sel, const int32
     int32_t *d_n = (int32_t *)take((size_t)B * 4), *d_m = (int32_t *)take((size_t)B * 4);
     int64_t *d_off = (int64_t *)take((size_t)B * 8);
     int32_t *d_res = (int32_t *)take((size_t)B * 4);
-    unsigned *d_q = (unsigned *)take(256);
+    unsigned *d_q = (unsigned *)take(512);
     cudaStream_t s = ctx->stream;
     XP_CUDA_OK(ctx, cudaMemcpyAsync(d_pool, pool.data(), total * 8, cudaMemcpyHostToDevice, s));
     XP_CUDA_OK(ctx, cudaMemcpyAsync(d_n, hn.data(), (size_t)B * 4, cudaMemcpyHostToDevice, s));
     XP_CUDA_OK(ctx, cudaMemcpyAsync(d_m, hm.data(), (size_t)B * 4, cudaMemcpyHostToDevice, s));
     XP_CUDA_OK(ctx, cudaMemcpyAsync(d_off, off.data(), (size_t)B * 8, cudaMemcpyHostToDevice, s));
-    XP_CUDA_OK(ctx, cudaMemsetAsync(d_q, 0, sizeof(unsigned), s));
+    XP_CUDA_OK(ctx, cudaMemsetAsync(d_q, 0, 512, s));
+    XP_CUDA_OK(ctx, cudaEventRecord(ctx->ev0, s));
     HsArgs H;
-    H.batch = B;
-    H.ns = d_n;
-    H.ms = d_m;
-    H.off = d_off;
     H.pool = d_pool;
     H.is_int = is_int_sol;
     H.is_unique = is_unique_sol;
-    H.result = d_res;
-    H.queue = d_q;
-    int occ = 1;
-    XP_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_has_solution, 32 * WARPS, 0));
-    if (occ < 1) occ = 1;
-    long long g = (long long)occ * ctx->sm_count;
-    const long long need = ((long long)B + WARPS - 1) / WARPS;
-    if (g > need) g = need;
-    XP_CUDA_OK(ctx, cudaEventRecord(ctx->ev0, s));
-    k_has_solution<<<(unsigned)g, 32 * WARPS, 0, s>>>(H);
-    ctx->launches++;
+    if (B16 > 0) {
+        H.batch = B16;
+        H.ns = d_n, H.ms = d_m, H.off = d_off, H.result = d_res, H.queue = d_q;
+        rc = hs_launch<16>(ctx, H, B16);
+        if (rc) return rc;
+    }
+    if (B > B16) {
+        H.batch = B - B16;
+        H.ns = d_n + B16, H.ms = d_m + B16, H.off = d_off + B16, H.result = d_res + B16, H.queue = d_q + 64;
+        rc = hs_launch<HS_MRMAX>(ctx, H, B - B16);
+        if (rc) return rc;
+    }
     XP_CUDA_OK(ctx, cudaEventRecord(ctx->ev1, s));
     XP_CUDA_OK(ctx, cudaGetLastError());
     std::vector<int32_t> hres(B);
@@ -338,7 +364,7 @@ bool xp_has_solution_device_fits(int n, int m, int k, const xp_rat *leq)
     if (k != 0 || n < 1 || m < 1) return false;
     // deepest node: one branching row per variable (fork_count allows each variable once)
     const int rows = m + n;
-    if (n + 1 > HS_N1 || rows > HS_MR || n > HS_MR) return false;
+    if (n + 1 > HS_N1 || rows > HS_MRMAX) return false;
     if (n + rows + 2 > 32) return false; // columns incl. slacks, auxiliary variable and constant (primal and dual alike)
     const size_t cnt = (size_t)m * (n + 1);
     for (size_t e = 0; e < cnt; e++)
