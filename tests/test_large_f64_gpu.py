@@ -367,14 +367,21 @@ def test_flush_variants_bitwise(ctx, env, monkeypatch):
     lp.close()
 
 
-@pytest.mark.parametrize("m,n,window,K", [(300, 1500, 512, 128), (300, 1500, 256, 100), (300, 1500, 1024, 64),
-                                          (520, 2100, 512, 120), (520, 2101, 512, 120), (257, 1300, 768, 97)])
-def test_two_stage_large_streamed_upload(ctx, m, n, window, K, monkeypatch):
+@pytest.mark.parametrize("m,n,window,K,first", [(300, 1500, 512, 128, 0), (300, 1500, 256, 100, 0),
+                                                (300, 1500, 1024, 64, 0), (520, 2100, 512, 120, 0),
+                                                (520, 2101, 512, 120, 0), (257, 1300, 768, 97, 0),
+                                                (300, 3500, 1024, 128, 512), (300, 3500, 768, 200, 256),
+                                                (280, 4100, 1024, 256, 768)])
+def test_two_stage_large_streamed_upload(ctx, m, n, window, K, first, monkeypatch):
     """xp_six_two_stage_f64_large uploading behind the solve: window columns first, the bounded
-    solve runs on the early tiles while the rest of A is still on its way, the late tiles replay
-    the closed blocks out of the ring.  Bit for bit against the oracle, for runs the window decides
-    alone and for runs a pricing scan leaves it (the full-width solve then continues)."""
+    solve runs on the early tiles while the rest of A is still on its way, the late pieces (one to
+    three, `first` < window: the streamed run decides in a narrower window than the resident
+    solve) replay the closed blocks out of the ring.  Bit for bit against the oracle, for runs the
+    window decides alone and for runs a pricing scan leaves it (the full-width solve then
+    continues)."""
     monkeypatch.setenv("XP_STREAM_MIN_MB", "0")
+    if first:
+        monkeypatch.setenv("XP_STREAM_FIRST", str(first))
     ctx.set_window(window)
     try:
         for seed in range(3):

@@ -3383,15 +3383,16 @@ struct LpRef { // handles live on the ctx (cached_handle): nothing to release on
 } // namespace
 
 // Upload behind the solve (no phase 1, bounded run of at most NH blocks).  The pricing window
-// holds the columns that can enter, so the caller's LP goes up in two column pieces: the window
-// [0, w) first, the rest of A -- [w, n) -- while the device is already deciding.  The "early"
-// tiles (window + slack identity + constant column, the latter two generated on the device)
-// run the whole bounded solve: k_wpanel decides, k_prow_bulk / k_flush_w keep the early tiles up
-// to date and every closed block stays in the ring (F, records, pivot-row marks).  When the
-// late piece has landed its tiles replay the closed blocks in order -- the same operations per
-// entry in the same order, only later.  Anything the window cannot decide (a pricing scan that
-// leaves it, a failing ratio test) simply leaves the block open: by the time the host looks,
-// the late tiles have caught up and the ordinary full-width solve continues from that state.
+// holds the columns that can enter, so the caller's LP goes up in column pieces: a window
+// [0, ws) first, the rest of A -- [ws, n) -- in up to three more while the device is already
+// deciding.  The "early" tiles (window + slack identity + constant column, the latter two
+// generated on the device) run the whole bounded solve: k_wpanel decides, k_prow_bulk /
+// k_flush_w keep the early tiles up to date and every closed block stays in the ring (F, records,
+// pivot-row marks).  Each late piece, once landed, replays the closed blocks in order on its
+// tiles -- the same operations per entry in the same order, only later.  Anything the window
+// cannot decide (a pricing scan that leaves it, a failing ratio test) simply leaves the block
+// open: by the time the host looks, the late tiles have caught up and the ordinary full-width
+// solve continues from that state.
 // Returns 1 if it took the job (state ready for xp_lp_f64_solve), 0 if the shape does not
 // qualify (caller uploads the plain way), < 0 on error.
 static int two_stage_streamed(xp_ctx *ctx, xp_lp_f64 *lp, int m, int n, const double *leq, double *d_leq,
@@ -3414,33 +3415,66 @@ static int two_stage_streamed(xp_ctx *ctx, xp_lp_f64 *lp, int m, int n, const do
     const int late_end = ((n + TCW - 1) / TCW) * TCW < C ? ((n + TCW - 1) / TCW) * TCW : C;
     const int tiles = (C + TCW - 1) / TCW;
     const size_t pitch = (size_t)(n + 1) * sizeof(double);
+    // Column pieces, in upload order.  The first is the window the bounded run decides in: the
+    // sooner it lands the sooner the device starts, so it is narrower than the resident solve's
+    // window (a run of at most NH blocks enters low columns; leaving the window is handled, only
+    // slower).  The last is small -- its replay is all that remains once the upload ends -- and
+    // the columns between go up in two halves so the first half replays while the second lands.
+    int ws = w > 3 * 1024 ? 3 * 1024 : w;
+    if (const char *e = getenv("XP_STREAM_FIRST")) { // (tests)
+        const int v = atoi(e) / TCW * TCW;
+        if (v >= TCW && v <= w) ws = v;
+    }
+    int cut[5], np = 0;
+    cut[np++] = 0;
+    cut[np++] = ws;
+    {
+        const int rt = (late_end - ws) / TCW; // late tiles
+        if (rt >= 12) {
+            const int last = 4, mid = rt - last;
+            cut[np++] = ws + (mid / 2) * TCW;
+            cut[np++] = ws + mid * TCW;
+        } else if (rt >= 6) {
+            cut[np++] = ws + (rt - 2) * TCW;
+        }
+        cut[np++] = late_end;
+    }
+    const int npieces = np - 1; // <= 4 <= XP_PIPE_MAX
     const bool dbg = getenv("XP_STREAM_DBG") != nullptr;
-    cudaEvent_t te[6] = {};
+    cudaEvent_t te[12] = {};
     if (dbg)
         for (auto &e : te) cudaEventCreate(&e);
     XP_CUDA_OK(ctx, cudaEventRecord(ctx->pipe_begin, s)); // d_tg, d_b and the previous call's kernels
     XP_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->pipe_copy, ctx->pipe_begin, 0));
     if (dbg) cudaEventRecord(te[0], ctx->pipe_copy);
-    XP_CUDA_OK(ctx, cudaMemcpy2DAsync(d_leq, pitch, leq, pitch, (size_t)w * sizeof(double), m, cudaMemcpyHostToDevice,
-                                      ctx->pipe_copy));
-    XP_CUDA_OK(ctx, cudaEventRecord(ctx->pipe_up[0], ctx->pipe_copy));
-    if (dbg) cudaEventRecord(te[1], ctx->pipe_copy);
-    XP_CUDA_OK(ctx, cudaMemcpy2DAsync(d_leq + w, pitch, leq + w, pitch, (size_t)(n - w) * sizeof(double), m,
-                                      cudaMemcpyHostToDevice, ctx->pipe_copy));
-    XP_CUDA_OK(ctx, cudaEventRecord(ctx->pipe_up[1], ctx->pipe_copy));
-    if (dbg) cudaEventRecord(te[2], ctx->pipe_copy);
+    for (int p = 0; p < npieces; p++) {
+        const int c0 = cut[p], c1 = cut[p + 1] < n ? cut[p + 1] : n;
+        if (c1 > c0)
+            XP_CUDA_OK(ctx, cudaMemcpy2DAsync(d_leq + c0, pitch, leq + c0, pitch, (size_t)(c1 - c0) * sizeof(double), m,
+                                              cudaMemcpyHostToDevice, ctx->pipe_copy));
+        XP_CUDA_OK(ctx, cudaEventRecord(ctx->pipe_up[p], ctx->pipe_copy));
+        if (dbg) cudaEventRecord(te[1 + p], ctx->pipe_copy);
+    }
     rc = lp_reset(lp);
     if (rc) return rc;
+    const int w_full = d.w, wwpc_full = d.wwpc;
+    d.w = ws;
+    d.wwpc = (ws + WNC - 1) / WNC;
+    struct Restore {
+        LpDev &d;
+        int w, wwpc;
+        ~Restore() { d.w = w, d.wwpc = wwpc; }
+    } restore{d, w_full, wwpc_full};
     // ---- early tiles: slack form, then the whole bounded solve ----
     XP_CUDA_OK(ctx, cudaStreamWaitEvent(s, ctx->pipe_up[0], 0));
     const int g = ctx->sm_count * 4;
-    k_slack_form_cols<<<g, 256, 0, s>>>(d, d_leq, d_b, d_tg, n, 0, w, 1);
+    k_slack_form_cols<<<g, 256, 0, s>>>(d, d_leq, d_b, d_tg, n, 0, ws, 1);
     if (late_end < C) k_slack_form_cols<<<g, 256, 0, s>>>(d, d_leq, d_b, d_tg, n, late_end, C, 0);
     k_init<<<1, 32, 0, s>>>(d, max_iter, lp->kblk == 0 ? -kblk : kblk, 0);
     k_first_price_window<<<1, 1024, 0, s>>>(d);
     ctx->launches += 4;
     ColSet early;
-    early.ct0a = 0, early.ct1a = w / TCW, early.ct0b = late_end / TCW, early.ct1b = late_end < C ? tiles : late_end / TCW;
+    early.ct0a = 0, early.ct1a = ws / TCW, early.ct0b = late_end / TCW, early.ct1b = late_end < C ? tiles : late_end / TCW;
     early.slot = -1, early.close = 1;
     for (unsigned b = 0; b < nb; b++) {
         XP_CUDA_OK(ctx, wpanel_launch(lp, late_end, C));
@@ -3449,41 +3483,50 @@ static int two_stage_streamed(xp_ctx *ctx, xp_lp_f64 *lp, int m, int n, const do
         rc = flush_w_launch(lp, kblk, &early);
         if (rc) return rc;
     }
-    // ---- late tiles: slack form when they have landed, then the closed blocks in order ----
-    if (dbg) cudaEventRecord(te[3], s);
-    XP_CUDA_OK(ctx, cudaStreamWaitEvent(s, ctx->pipe_up[1], 0));
-    if (dbg) cudaEventRecord(te[4], s);
-    k_slack_form_cols<<<g, 256, 0, s>>>(d, d_leq, d_b, d_tg, n, w, late_end, 0);
-    ctx->launches++;
-    ColSet late;
-    late.ct0a = w / TCW, late.ct1a = late_end / TCW, late.ct0b = late.ct1b = 0;
-    late.close = 0;
-    int bg = (late_end - w + WB_TH - 1) / WB_TH;
-    if (bg > 2 * ctx->sm_count) bg = 2 * ctx->sm_count;
-    for (unsigned b = 0; b < nb; b++) {
-        k_prow_bulk<<<bg, WB_TH, 2 * KMAX * WB_TH * sizeof(double), s>>>(d, 1, (int)b, w, late_end);
+    // ---- late pieces: slack form when each has landed, then the closed blocks in order ----
+    if (dbg) cudaEventRecord(te[6], s);
+    auto bulk_grid = [&](int c0, int c1) {
+        int bg = (c1 - c0 + WB_TH - 1) / WB_TH;
+        return bg > 2 * ctx->sm_count ? 2 * ctx->sm_count : bg;
+    };
+    for (int p = 1; p < npieces; p++) {
+        const int c0 = cut[p], c1 = cut[p + 1];
+        XP_CUDA_OK(ctx, cudaStreamWaitEvent(s, ctx->pipe_up[p], 0));
+        k_slack_form_cols<<<g, 256, 0, s>>>(d, d_leq, d_b, d_tg, n, c0, c1, 0);
         ctx->launches++;
-        late.slot = (int)b;
-        rc = flush_w_launch(lp, kblk, &late);
-        if (rc) return rc;
+        ColSet late;
+        late.ct0a = c0 / TCW, late.ct1a = c1 / TCW, late.ct0b = late.ct1b = 0;
+        late.close = 0;
+        for (unsigned b = 0; b < nb; b++) {
+            k_prow_bulk<<<bulk_grid(c0, c1), WB_TH, 2 * KMAX * WB_TH * sizeof(double), s>>>(d, 1, (int)b, c0, c1);
+            ctx->launches++;
+            late.slot = (int)b;
+            rc = flush_w_launch(lp, kblk, &late);
+            if (rc) return rc;
+        }
+        if (dbg) cudaEventRecord(te[6 + p], s);
     }
     XP_CUDA_OK(ctx, cudaGetLastError());
-    if (dbg) cudaEventRecord(te[5], s);
     XP_CUDA_OK(ctx, cudaMemcpyAsync(lp->h_st, d.st, sizeof(LpState), cudaMemcpyDeviceToHost, s));
     XP_CUDA_OK(ctx, cudaStreamSynchronize(s));
     if (dbg) {
-        float a = 0, b = 0, c = 0, e = 0, f = 0;
-        cudaEventElapsedTime(&a, te[0], te[1]);
-        cudaEventElapsedTime(&b, te[0], te[2]);
-        cudaEventElapsedTime(&c, te[0], te[3]);
-        cudaEventElapsedTime(&e, te[0], te[4]);
-        cudaEventElapsedTime(&f, te[0], te[5]);
-        fprintf(stderr, "[xp stream] window piece up at %.2f ms, late piece at %.2f; early solve done at %.2f, late replay "
-                        "%.2f -> %.2f ms (cnt %u, t %d, status %d)\n", a, b, c, e, f, lp->h_st->cnt, lp->h_st->t, lp->h_st->status);
+        float t = 0;
+        fprintf(stderr, "[xp stream] pieces");
+        for (int p = 0; p < npieces; p++) {
+            cudaEventElapsedTime(&t, te[0], te[1 + p]);
+            fprintf(stderr, " [%d,%d) up at %.2f ms;", cut[p], cut[p + 1], t);
+        }
+        cudaEventElapsedTime(&t, te[0], te[6]);
+        fprintf(stderr, " early solve done at %.2f;", t);
+        for (int p = 1; p < npieces; p++) {
+            cudaEventElapsedTime(&t, te[0], te[6 + p]);
+            fprintf(stderr, " replay %d done at %.2f;", p, t);
+        }
+        fprintf(stderr, " (cnt %u, t %d, status %d)\n", lp->h_st->cnt, lp->h_st->t, lp->h_st->status);
         for (auto &ev : te) cudaEventDestroy(ev);
     }
     if (lp->h_st->t > 0) { // a block was left open (exception inside the window run): its pivot rows for the late tiles
-        k_prow_bulk<<<bg, WB_TH, 2 * KMAX * WB_TH * sizeof(double), s>>>(d, 2, 0, w, late_end);
+        k_prow_bulk<<<bulk_grid(ws, late_end), WB_TH, 2 * KMAX * WB_TH * sizeof(double), s>>>(d, 2, 0, ws, late_end);
         ctx->launches++;
         XP_CUDA_OK(ctx, cudaGetLastError());
     }
