@@ -678,10 +678,16 @@ def run_ours(args):
     r1_sweep_ms = r1["flush_ms"] / max(r1["flushes"], 1)
     fp64_ops = k_eff * 2.0 * m * local_cols  # non-fused operations of one launch (DMUL + DADD per entry and pivot)
     ach = fp64_ops / (flush_avg_ms * 1e-3) if flush_avg_ms > 0 else 0.0
+    n_sm = ctx_sm_count(torch, dev)
+    shared_sms = int(lib.xp_lp_f64_pass_shared_sms(lp._h)) if world == 1 else 0
     roofline = {
-        "bound": "fp64_pipe_nonfused", "kernel": "k_flush_w (rank-k tableau pass, k pivots per launch, DMUL + DADD per entry and pivot)",
+        "bound": "fp64_pipe_nonfused", "kernel": "k_flush_w (rank-k tableau pass, k pivots per launch, DMUL + DADD per entry and pivot)"
+                 + (f"; lookahead: each pass runs beside the {shared_sms}-CTA k_wpanel cluster deciding the next block and is timed "
+                    "from the cluster's launch to its own end" if shared_sms else ""),
         "achieved": ach / 1e12, "peak": fp64_peak / 1e12, "unit": "Tops/s",
         "frac": ach / fp64_peak if fp64_peak > 0 else None,
+        "sms_shared_with_panel": shared_sms,
+        "frac_of_sms_held": (ach / (fp64_peak * (n_sm - shared_sms) / n_sm)) if fp64_peak > 0 else None,
         "peak_source": f"measured in this run (xp_probe_fp64_nonfused, {pms.value:.1f} ms; nominal 64 lanes/clk/SM = "
                        f"{fp64_nominal / 1e12:.2f})",
         "traffic": traffic, "ops_per_launch": fp64_ops, "pivots_per_launch": k_eff,

@@ -84,6 +84,40 @@ def test_windowed_panel_bounded_and_resume(ctx):
         lp.close()
 
 
+@pytest.mark.parametrize("m,n,window", [(300, 1501, 512), (257, 1300, 256), (200, 2101, 768), (130, 701, 512)])  # m + n odd: even row stride
+def test_lookahead_flush(ctx, m, n, window, monkeypatch):
+    """Lookahead: the live pass of k_flush_w closes a block on the window tiles only, the tiles
+    beyond take it one step later beside the next block's k_wpanel (programmatic dependent
+    launch).  Whole state against the oracle -- runs to termination, runs the window cannot decide
+    alone (mixed signs: the slow path and the full-width panel work on the caught-up tableau),
+    bounded runs resumed in the middle of a block -- and against the same run with the lookahead off."""
+    for seed in range(2):
+        leq, tg = H.gen_dense_lp(8600 + seed, m, n)
+        run_both(ctx, leq, tg, max_iter=600, tag=("look", m, n, seed), blocks=(0, 12, 32), windows=(window,))
+    leq, tg = H.gen_mixed_lp(8650, m, n)
+    leq[:, n] = np.abs(leq[:, n])
+    tg[:n] = np.abs(tg[:n])
+    run_both(ctx, leq, tg, max_iter=600, tag=("look-mixed", m, n), blocks=(0, 32), windows=(window,))
+    leq, tg = H.gen_dense_lp(8660, m, n)
+    sf = xp.slack_form(leq, tg)
+    sums = {}
+    for off in (False, True):
+        if off:
+            monkeypatch.setenv("XP_NO_LOOKAHEAD", "1")
+        lp = ctx.large_lp(*sf[0].shape)
+        lp.set_window(window)
+        lp.set_block(32)
+        lp.upload(*sf)
+        for K in (3, 40, 45, 100, 101, 170):
+            st = lp.solve(K)
+            g = lp.download(log_cap=1 << 16)
+            g["status"] = st
+            assert_same_state(g, H.slack_solve_oracle("f64", *sf, max_iter=K), ("look-resume", off, K))
+        sums[off] = lp.checksum()
+        lp.close()
+    assert sums[False] == sums[True]
+
+
 @pytest.mark.parametrize("m,n", [(2, 2), (6, 5), (8, 7), (10, 9), (16, 15), (33, 20), (7, 40)])
 def test_small_dense_to_termination(ctx, m, n):
     seen = set()

@@ -92,6 +92,8 @@ struct LpState {
     int n_touched;
     int touched[KMAX]; // rows with last_piv >= 0
     int hist_t[NH];    // pivots of the closed blocks still in the ring (k_block_snapshot)
+    int rest_pending;  // lookahead: the block in ring slot rest_slot is closed on the window tiles only,
+    int rest_slot;     // the tiles beyond the window still owe it (k_flush_w, slot == SLOT_LAG)
     double r, cq, prow_rhs;
     double maxv;
     double tg_rhs; // replica of the objective row's constant term
@@ -217,6 +219,12 @@ __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned l
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 __device__ __forceinline__ double ld_cg(const double *p) { return __ldcg(p); }
+__device__ __forceinline__ unsigned ld_acquire_gpu_u32(const unsigned *p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 
 // Size of the next block of a bounded run (max_iter known): as few passes over the tableau as
 // the upper bound allows, sizes in multiples of 8 (the flush kernel's unrolled step count) and
@@ -1299,9 +1307,19 @@ k_panel(LpDev d, PanA *partA, PanB *partB, unsigned long long *bar, unsigned lon
 // marks of that block, no closing) on the tiles that arrived late.
 struct ColSet {
     int ct0a, ct1a, ct0b, ct1b; // tile ranges [ct0a, ct1a) u [ct0b, ct1b)
-    int slot;                   // -1: the open block (live); >= 0: ring slot of a closed block
+    int slot;                   // -1: the open block (live); >= 0: ring slot of a closed block; SLOT_LAG: see below
     int close;                  // the last CTA closes the block
 };
+// Lookahead (one GPU, windowed panel): a finished block is closed by k_block_close before any
+// tile has taken it (rest_pending / rest_slot), and the pass over the tableau is launched with
+// slot == SLOT_LAG *beside* the next block's k_wpanel -- programmatic dependent launch, the
+// cluster holds 16 SMs, the pass the others.  It replays the owed block out of the ring exactly
+// as the streamed upload's late tiles do, range a (the window tiles) first; k_wpanel spins until
+// ctr[4] says they are all in place.  Apart from those window tiles k_wpanel touches the ring
+// slot of the block it is deciding, the P rows of the window columns and the replicas (rhsbuf,
+// objective row of the window); the pass touches the owed block's slot and the P rows of the
+// columns beyond the window: no word in common.
+constexpr int SLOT_LAG = -2;
 
 #include "xp_large_wpanel.cuh"
 
@@ -1339,6 +1357,30 @@ __global__ void k_block_snapshot(LpDev d)
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < d.m; i += gridDim.x * blockDim.x)
         d.hist_lp[(size_t)slot * d.m + i] = d.last_piv[i];
     if (blockIdx.x == 0 && threadIdx.x == 0) st->hist_t[slot] = t;
+}
+
+// Lookahead: the same snapshot, and the block is closed right here -- before any tile has taken
+// it.  The whole pass is then owed (rest_pending) and runs out of the ring slot beside the next
+// block's k_wpanel, window tiles first (ctr[4] counts them for the cluster).  One CTA.
+__global__ void __launch_bounds__(1024) k_block_close(LpDev d)
+{
+    LpState *st = d.st;
+    const int t = st->t;
+    if (t == 0 || (t < st->kblk && st->status == XPI_RUNNING)) return; // nothing to close
+    const int slot = st->blk & (NH - 1);
+    for (int i = threadIdx.x; i < d.m; i += blockDim.x) d.hist_lp[(size_t)slot * d.m + i] = d.last_piv[i];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        st->hist_t[slot] = t;
+        st->rest_pending = 1;
+        st->rest_slot = slot;
+        d.ctr[4] = 0;
+        for (int k = 0; k < st->n_touched; k++) d.last_piv[st->touched[k]] = -1;
+        st->n_touched = 0;
+        st->t = 0;
+        st->blk += 1;
+        next_block(st);
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -1707,21 +1749,41 @@ __global__ void __launch_bounds__(LANES *GROUPS, 2) k_flush_w(LpDev d, ColSet cs
     constexpr int THREADS = LANES * GROUPS, TC = 4 * LANES;
     constexpr int TPB = FT_ROWS / (GROUPS * TR); // tiles per unit and row group
     LpState *st = d.st;
-    const bool live = cs.slot < 0;
-    const int t = live ? st->t : st->hist_t[cs.slot];
-    if (t == 0) return;
-    if (live && t < st->kblk && st->status == XPI_RUNNING) return; // block still open
-    const int par = live ? (st->blk & (NH - 1)) : cs.slot, Cl = d.Cl, m = d.m, tid = threadIdx.x;
-    const int32_t *marks = live ? d.last_piv : d.hist_lp + (size_t)cs.slot * m;
+    const bool live = cs.slot == -1, lag = cs.slot == SLOT_LAG;
+    // The lagging pass is launched beside k_wpanel (programmatic stream serialization) and never
+    // needs its results -- but the kernels behind it in the stream do, and they only wait for
+    // THIS grid: one CTA of the lagging pass (the last to finish; CTA 0 if there is nothing to
+    // do) therefore leaves through griddepcontrol.wait, so the grid cannot complete before the
+    // cluster has (a no-op when launched the plain way).  The others exit at once: the cluster
+    // waits for the window tiles of every CTA, so no CTA may wait for the cluster while it
+    // keeps another one from starting.
+    auto leave = [&]() {
+        if (lag) asm volatile("griddepcontrol.wait;" ::: "memory");
+    };
+    if (lag && !st->rest_pending) {
+        if (blockIdx.x == 0) leave();
+        return;
+    }
+    const int slot = lag ? st->rest_slot : cs.slot;
+    const int t = live ? st->t : st->hist_t[slot];
+    if (t == 0 || (live && t < st->kblk && st->status == XPI_RUNNING)) { // nothing owed / block still open
+        if (blockIdx.x == 0) leave();
+        return;
+    }
+    const int par = live ? (st->blk & (NH - 1)) : slot, Cl = d.Cl, m = d.m, tid = threadIdx.x;
+    const int32_t *marks = live ? d.last_piv : d.hist_lp + (size_t)slot * m;
     const int lane = tid % LANES, grp = tid / LANES;
     double *sP = sm, *sF = sm + (size_t)t * TC;
     int *s_lp = (int *)(sF + (size_t)nbuf * t * FT_ROWS);
     const double *sPl0 = sP + 2 * lane, *sPl1 = sP + 2 * LANES + 2 * lane;
     const int nrb = (m + FT_ROWS - 1) / FT_ROWS;
-    const int nta = cs.ct1a - cs.ct0a, ctiles = nta + (cs.ct1b - cs.ct0b); // tiles of the set, in order
-    const long long units = (long long)ctiles * nrb;
-    const int u0 = (int)(units * blockIdx.x / gridDim.x), u1 = (int)(units * (blockIdx.x + 1) / gridDim.x);
-    auto tile_of = [&](int k) { return k < nta ? cs.ct0a + k : cs.ct0b + (k - nta); };
+    const int nta = cs.ct1a - cs.ct0a, ntb = cs.ct1b - cs.ct0b;
+    // Work units = (column tile, block of FT_ROWS rows), tile-major over the tiles of the set;
+    // every CTA takes one contiguous share.  The lagging pass does so twice: first over range a
+    // (the window tiles: every CTA gets its share of them, so they are done as early as they
+    // can be, and their completion is counted in ctr[4] for the k_wpanel spinning beside us),
+    // then over range b.
+    const int nph = lag ? 2 : 1;
     auto load_P = [&](int ct) {
         for (int e = tid; e < t * (TC / 2); e += THREADS) {
             const int s = e / (TC / 2), l = e - s * (TC / 2);
@@ -1761,11 +1823,17 @@ __global__ void __launch_bounds__(LANES *GROUPS, 2) k_flush_w(LpDev d, ColSet cs
     }
     __syncthreads();
     const bool mb = t >= 12 && nbuf == 3;
-    int cti = u0 < u1 ? u0 / nrb : 0, rb = u0 < u1 ? (u0 % nrb) * FT_ROWS : 0; // tile index in the set
+    int lu = 0; // units this CTA has taken so far (selects the multiplier buffer and the mbarrier phase)
+    for (int ph = 0; ph < nph; ph++) {
+    const int pt0 = (lag && ph == 1) ? nta : 0, pnt = lag ? (ph == 0 ? nta : ntb) : nta + ntb; // tiles of this phase (set order)
+    const long long units = (long long)pnt * nrb;
+    const int u0 = (int)(units * blockIdx.x / gridDim.x), u1 = (int)(units * (blockIdx.x + 1) / gridDim.x);
+    auto tile_of = [&](int k) { k += pt0; return k < nta ? cs.ct0a + k : cs.ct0b + (k - nta); };
+    int cti = u0 < u1 ? u0 / nrb : 0, rb = u0 < u1 ? (u0 % nrb) * FT_ROWS : 0; // tile index in the phase
     int ct = tile_of(cti);
     if (u0 < u1) {
         load_P(ct);
-        copy_F(rb, 0);
+        copy_F(rb, lu % nbuf);
         prefetch_tile(ct, rb, 0);
     }
     if (!mb) cp_async_wait_all();
@@ -1779,7 +1847,7 @@ __global__ void __launch_bounds__(LANES *GROUPS, 2) k_flush_w(LpDev d, ColSet cs
         }
         const int j0 = ct * TC + 2 * lane, j1 = j0 + 2 * LANES;
         const bool act0 = j0 < Cl, act1 = j1 < Cl; // Cl is even on this path
-        const int lu = u - u0, buf = lu % nbuf;
+        const int buf = lu % nbuf;
         const double *sFu = sF + (size_t)buf * t * FT_ROWS;
         const int *lpu = s_lp + buf * FT_ROWS;
         const bool more = u + 1 < u1;
@@ -1885,8 +1953,19 @@ __global__ void __launch_bounds__(LANES *GROUPS, 2) k_flush_w(LpDev d, ColSet cs
         ct = ct1;
         cti = cti1;
         rb = rb1;
+        lu++;
     }
-    if (!cs.close) return;
+    if (lag && ph == 0) { // this CTA's window units are in place
+        __syncthreads();
+        if (tid == 0 && u1 > u0) {
+            __threadfence();
+            atomicAdd(&d.ctr[4], (unsigned)(u1 - u0));
+        }
+    } else if (ph + 1 < nph) {
+        __syncthreads();
+    }
+    } // phases
+    if (!cs.close && !lag) return;
     if (tid == 0) {
         __threadfence();
         s_flag = atomicAdd(&d.ctr[2], 1u) == gridDim.x - 1;
@@ -1895,6 +1974,10 @@ __global__ void __launch_bounds__(LANES *GROUPS, 2) k_flush_w(LpDev d, ColSet cs
     if (!s_flag) return;
     if (tid == 0) {
         d.ctr[2] = 0;
+        if (lag) { // (runs beside k_wpanel: touches nothing but these two words)
+            st->rest_pending = 0;
+            return leave();
+        }
         for (int k = 0; k < st->n_touched; k++) d.last_piv[st->touched[k]] = -1;
         st->n_touched = 0;
         st->t = 0;
@@ -2045,6 +2128,7 @@ __global__ void k_init(LpDev d, unsigned max_iter, int kblk, int fresh)
             st->blk = 0; // ring slots restart (the previous solve is over on every rank)
             st->wb_pending = 0;
             for (int k = 0; k < NH; k++) st->hist_t[k] = 0;
+            st->rest_pending = 0;
         } else {
             if (st->status == XP_SIX_TIME_OUT && st->cnt < max_iter) st->status = XPI_RUNNING; // resume
             if (kblk != 0 && st->t == 0) { // kblk < 0: adaptive with upper bound -kblk
@@ -2222,6 +2306,7 @@ struct xp_lp_f64 {
     bool wpanel_ready = false; // kernel attributes set
     // optional per-launch timing of the flush kernel (CUDA events on the ctx stream)
     bool profile = false;
+    int shared_sms = 0; // SMs the last solve's tableau passes left to k_wpanel (lookahead), else 0
     std::vector<cudaEvent_t> evs;
     uint64_t prof_sweeps = 0;
     double prof_sweep_ms = 0.0, prof_gap_ms = 0.0;
@@ -2278,7 +2363,7 @@ static ColSet all_tiles(const LpDev &d)
     return cs;
 }
 
-static int flush_w_launch(xp_lp_f64 *lp, int kblk, const ColSet *set = nullptr)
+static int flush_w_launch(xp_lp_f64 *lp, int kblk, const ColSet *set = nullptr, int sm_reserve = 0, bool beside = false)
 {
     xp_ctx *ctx = lp->ctx;
     const LpDev &d = lp->d;
@@ -2303,10 +2388,24 @@ static int flush_w_launch(xp_lp_f64 *lp, int kblk, const ColSet *set = nullptr)
     const size_t smem = flush_t_smem(kblk, lp->fw_nbuf);
     const int ctiles = (cs.ct1a - cs.ct0a) + (cs.ct1b - cs.ct0b);
     const long long units = (long long)ctiles * ((d.m + FT_ROWS - 1) / FT_ROWS);
-    long long grid = (long long)lp->fw_occ * ctx->sm_count;
+    long long grid = (long long)lp->fw_occ * (ctx->sm_count - sm_reserve); // one resident wave on the SMs it gets
     if (grid > units) grid = units;
     if (grid < 1) return 0;
-    kern<<<(unsigned)grid, FT_THREADS, smem, ctx->stream>>>(d, cs, lp->fw_nbuf);
+    if (beside) { // may start as soon as the kernel in front (k_wpanel) has, and never waits for it
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)grid);
+        cfg.blockDim = dim3(FT_THREADS);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = ctx->stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        XP_CUDA_OK(ctx, cudaLaunchKernelEx(&cfg, kern, d, cs, lp->fw_nbuf));
+    } else {
+        kern<<<(unsigned)grid, FT_THREADS, smem, ctx->stream>>>(d, cs, lp->fw_nbuf);
+    }
     ctx->launches++;
     return 0;
 }
@@ -2858,7 +2957,10 @@ static int window_config(xp_lp_f64 *lp)
     return 0;
 }
 
-static cudaError_t wpanel_launch(xp_lp_f64 *lp, int bulk_lo = -1, int bulk_hi = -1)
+// `beside` (lookahead): a pass of k_flush_w launched right behind the cluster that starts as
+// soon as the cluster has and runs on the other SMs; `after` is recorded behind that pass.
+static cudaError_t wpanel_launch(xp_lp_f64 *lp, int bulk_lo = -1, int bulk_hi = -1, const ColSet *beside = nullptr,
+                                 int kblk = 0, cudaEvent_t after = nullptr)
 {
     const LpDev &d = lp->d;
     cudaStream_t s = lp->ctx->stream;
@@ -2876,12 +2978,17 @@ static cudaError_t wpanel_launch(xp_lp_f64 *lp, int bulk_lo = -1, int bulk_hi = 
         at[0].val.clusterDim.y = at[0].val.clusterDim.z = 1;
         cfg.attrs = at;
         cfg.numAttrs = 1;
-        e = cudaLaunchKernelEx(&cfg, k_wpanel, d, lp->wpanel_dbg);
+        const unsigned wait_units = beside ? (unsigned)((beside->ct1a - beside->ct0a) * ((d.m + FT_ROWS - 1) / FT_ROWS)) : 0u;
+        e = cudaLaunchKernelEx(&cfg, k_wpanel, d, lp->wpanel_dbg, wait_units);
     } else {
         k_wpanel_peer<<<1, 32, 0, s>>>(d);
         e = cudaGetLastError();
     }
     if (e != cudaSuccess) return e;
+    if (beside) {
+        if (flush_w_launch(lp, kblk, beside, WNC, true)) return cudaErrorLaunchFailure;
+        if (after && (e = cudaEventRecord(after, s)) != cudaSuccess) return e;
+    }
     // the columns the window left out (and, on peers, the replicated bookkeeping)
     const int jl0 = bulk_lo >= 0 ? bulk_lo : (d.w - d.col0 > 0 ? d.w - d.col0 : 0);
     const int jl1 = bulk_hi >= 0 ? bulk_hi : d.Cl;
@@ -2935,8 +3042,50 @@ extern "C" int xp_lp_f64_solve(xp_lp_f64 *lp, uint32_t max_iter, int rule)
         blocks = need > 8 ? 8 : (int)need;
     }
     int n_prof = 0; // flushes bracketed by events in this call
+    // Lookahead (one GPU, windowed panel, k_flush_w): a finished block is closed at once
+    // (k_block_close) and the tableau takes it one step later, beside the next block's k_wpanel.
+    constexpr int TCW = 4 * FW_LANES;
+    const int tiles = (d.Cl + TCW - 1) / TCW;
+    const bool look = lp->use_panel && d.w > 0 && d.G == 1 && (d.Cl & 1) == 0 && lp->ft_wide && kblk >= lp->ft_min &&
+                      kblk >= lp->ft_balanced_min && d.w % TCW == 0 && d.w / TCW <= tiles && ctx->sm_count > 2 * WNC &&
+                      !getenv("XP_NO_LOOKAHEAD");
+    lp->shared_sms = look ? WNC : 0;
+    ColSet owed_pass; // window tiles first, then the others
+    owed_pass.ct0a = 0, owed_pass.ct1a = look ? d.w / TCW : 0, owed_pass.ct0b = owed_pass.ct1a, owed_pass.ct1b = tiles;
+    owed_pass.slot = SLOT_LAG, owed_pass.close = 0;
+    bool owed = false; // a closed block may be waiting for the tableau pass
+    const bool dbg_tl = look && getenv("XP_BLOCK_DBG") != nullptr; // stderr: where one block's time goes
+    bool dbg_done = false;
+    cudaEvent_t dbg_ev[8] = {};
+    if (dbg_tl)
+        for (auto &e : dbg_ev) cudaEventCreate(&e);
     for (;;) {
         for (int b = 0; b < blocks; b++) {
+            if (look) {
+                // k_wpanel decides this block || the tableau takes the previous one; then the
+                // deferred columns' pivot rows, the slow-path pair, the full-width panel
+                const bool prof = owed && lp->profile && n_prof < PROF_MAX_SWEEPS;
+                const bool tl = dbg_tl && b == 3 && !dbg_done;
+                if (prof) XP_CUDA_OK(ctx, cudaEventRecord(lp->evs[2 * n_prof], s));
+                if (tl) cudaEventRecord(dbg_ev[0], s);
+                if (!owed) XP_CUDA_OK(ctx, wpanel_launch(lp)); // first block of the call: nothing is owed (every call ends drained)
+                else XP_CUDA_OK(ctx, wpanel_launch(lp, -1, -1, &owed_pass, kblk, prof ? lp->evs[2 * n_prof + 1] : nullptr));
+                if (prof) n_prof++;
+                owed = true;
+                if (tl) cudaEventRecord(dbg_ev[1], s);
+                k_pcol<<<d.gridA, TH, 0, s>>>(d);
+                if (tl) cudaEventRecord(dbg_ev[2], s);
+                k_prow<<<d.gridB, TH, 0, s>>>(d);
+                if (tl) cudaEventRecord(dbg_ev[3], s);
+                XP_CUDA_OK(ctx, wpanel_launch(lp));
+                if (tl) cudaEventRecord(dbg_ev[4], s);
+                XP_CUDA_OK(ctx, panel_launch(lp));
+                if (tl) cudaEventRecord(dbg_ev[5], s);
+                k_block_close<<<1, 1024, 0, s>>>(d);
+                if (tl) cudaEventRecord(dbg_ev[6], s), dbg_done = true;
+                ctx->launches += 4;
+                continue;
+            }
             if (lp->use_panel && d.w > 0) {
                 // windowed fast path (one cluster decides the whole block inside the window, the
                 // deferred columns follow in bulk); the pair in the middle takes whatever single
@@ -2984,6 +3133,29 @@ extern "C" int xp_lp_f64_solve(xp_lp_f64 *lp, uint32_t max_iter, int rule)
         blocks = (unsigned long long)want > need ? (int)need : want;
         if (blocks < 1) blocks = 1;
     }
+    if (dbg_tl) {
+        if (dbg_done) {
+            cudaStreamSynchronize(s);
+            static const char *nm[6] = {"k_wpanel || k_flush_w, k_prow_bulk", "k_pcol", "k_prow", "k_wpanel, k_prow_bulk (2nd)",
+                                        "k_panel", "k_block_close"};
+            for (int k = 0; k < 6; k++) {
+                float ms = 0.f;
+                cudaEventElapsedTime(&ms, dbg_ev[k], dbg_ev[k + 1]);
+                fprintf(stderr, "[xp block] %-40s %8.1f us\n", nm[k], ms * 1e3);
+            }
+        }
+        for (auto &e : dbg_ev) cudaEventDestroy(e);
+    }
+    if (look) { // the last closed block
+        const bool prof = lp->profile && n_prof < PROF_MAX_SWEEPS;
+        if (prof) XP_CUDA_OK(ctx, cudaEventRecord(lp->evs[2 * n_prof], s));
+        int frc = flush_w_launch(lp, kblk, &owed_pass);
+        if (frc) return frc;
+        if (prof) {
+            XP_CUDA_OK(ctx, cudaEventRecord(lp->evs[2 * n_prof + 1], s));
+            n_prof++;
+        }
+    }
     if (lp->profile) {
         for (int k = 0; k < n_prof; k++) {
             float ms = 0.f;
@@ -3026,6 +3198,8 @@ extern "C" int xp_lp_f64_profile(xp_lp_f64 *lp, int enable)
     lp->prof_sweep_ms = lp->prof_gap_ms = 0.0;
     return 0;
 }
+
+extern "C" int xp_lp_f64_pass_shared_sms(const xp_lp_f64 *lp) { return lp ? lp->shared_sms : 0; }
 
 extern "C" int xp_lp_f64_profile_read(xp_lp_f64 *lp, uint64_t *n_sweeps, double *sweep_ms,
                                       double *gap_ms)

@@ -71,7 +71,7 @@ struct WXchg {
     unsigned c[2][WNC]; //   candidate | anypos << 31
 };
 
-__global__ void __launch_bounds__(WTHB, 1) k_wpanel(LpDev d, unsigned long long *dbg)
+__global__ void __launch_bounds__(WTHB, 1) k_wpanel(LpDev d, unsigned long long *dbg, unsigned wait_units)
 {
     cg::cluster_group cl = cg::this_cluster();
     extern __shared__ double s_dyn[];
@@ -82,6 +82,14 @@ __global__ void __launch_bounds__(WTHB, 1) k_wpanel(LpDev d, unsigned long long 
     __shared__ double s_pq[KMAX], s_fp[KMAX];
     __shared__ int s_bad;
     LpState *st = d.st;
+    // Lookahead: the previous block may still be owed to the tableau (k_block_close).  The pass
+    // that applies it -- k_flush_w with SLOT_LAG, launched behind this kernel with programmatic
+    // stream serialization -- may start now, on the SMs this cluster leaves; it takes the window
+    // tiles first and counts them in ctr[4].  (The flag is read before the trigger: the pass
+    // clears it when it is through.)
+    const bool owed = wait_units != 0 && st->rest_pending != 0;
+    __syncthreads();
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int c = (int)cl.block_rank();
     const bool worker = tid < WTH;
@@ -97,6 +105,33 @@ __global__ void __launch_bounds__(WTHB, 1) k_wpanel(LpDev d, unsigned long long 
                     q < d.w && t < kblk && cnt < max_iter;
     if (c == 0 && tid == 0) st->wb_pending = 0; // (k_prow_bulk of the previous run is over; nobody else reads it here)
     if (!go) return;
+    if (owed) { // the window columns (and nothing else of the tableau) are read below
+        // CTA 0 watches the counter for the whole cluster.  If the pass does not show up -- the
+        // driver may serialise the two launches (profilers do) -- the cluster leaves without
+        // having touched anything: the pass then runs behind it, and the second k_wpanel of
+        // the block's launch sequence finds the tableau complete and does the work.
+        if (c == 0 && tid == 0) {
+            unsigned long long t0, t1;
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
+            unsigned spins = 0;
+            int ok = 1;
+            while (ld_acquire_gpu_u32(&d.ctr[4]) < wait_units) {
+                if ((++spins & 255u) == 0) {
+                    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
+                    if (t1 - t0 > 20000000ULL) { // 20 ms
+                        ok = 0;
+                        break;
+                    }
+                }
+            }
+            s_bad = !ok;
+        }
+        cl.sync();
+        const int bad0 = *cl.map_shared_rank(&s_bad, 0);
+        cl.sync(); // (s_bad is reused below)
+        if (bad0) return;
+        __threadfence(); // order the tableau reads below behind CTA 0's acquire
+    }
     const int t_in = t;
     const unsigned wseq = st->wseq + 1; // number of this windowed launch
     double tg_rhs = st->tg_rhs;
