@@ -152,9 +152,9 @@ int xp_ctx_set_window(xp_ctx *ctx, int width); /* for xp_six_slack_f64 / xp_six_
 int xp_lp_f64_profile(xp_lp_f64 *lp, int enable);
 int xp_lp_f64_profile_read(xp_lp_f64 *lp, uint64_t *n_sweeps, double *sweep_ms, double *gap_ms);
 /* SMs the timed tableau passes of the last xp_lp_f64_solve shared with the deciding kernel: 0 --
- * each pass had the device to itself -- or 16 when the lookahead was on (one GPU, windowed
- * panel: a finished block is applied to the tableau beside the 16-CTA cluster that decides the
- * next one; the pass is then timed from the cluster's launch to its own end).  The environment
+ * each pass had the device to itself -- or 16 when the lookahead was on (windowed panel, on the
+ * rank that runs it: a finished block is applied to the tableau beside the 16-CTA cluster that
+ * decides the next one; the pass is then timed from the cluster's launch to its own end).  The environment
  * variable XP_NO_LOOKAHEAD=1 turns the lookahead off. */
 int xp_lp_f64_pass_shared_sms(const xp_lp_f64 *lp);
 /* Order-independent 64-bit checksum of the device tableau bits (parity at full size). */

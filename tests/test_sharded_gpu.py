@@ -126,6 +126,25 @@ def test_inproc_windowed_leader(G, window):
         assert_same_state(g, H.slack_solve_oracle("f64", *sf, max_iter=K), ("wshard-resume", G, window, K))
 
 
+@pytest.mark.parametrize("G,m,n,window", [(2, 300, 1501, 512), (2, 257, 1300, 256), (3, 200, 2499, 512)])
+def test_inproc_lookahead_leader(G, m, n, window):
+    """Lookahead on the leader of a sharded LP: rank 0 closes a block at once and applies it to
+    its slice beside the next k_wpanel (its slice is wider than the window), the peers keep the
+    plain order.  Dense runs, a mixed-sign run (slow paths on the caught-up tableau), resumes."""
+    for seed in range(2):
+        leq, tg = H.gen_dense_lp(8700 + seed, m, n)
+        sf = xp.slack_form(leq, tg)
+        g = solve_sharded_inproc(G, sf, [400], block=(32, 0)[seed], window=window)[0]
+        assert_same_state(g, H.slack_solve_oracle("f64", *sf, max_iter=400), ("lookshard", G, m, n, seed))
+    leq, tg = H.gen_mixed_lp(8750, m, n)
+    leq[:, n] = np.abs(leq[:, n])
+    tg[:n] = np.abs(tg[:n])
+    sf = xp.slack_form(leq, tg)
+    outs = solve_sharded_inproc(G, sf, [45, 100, 333], block=32, window=window)
+    for K, g in zip((45, 100, 333), outs):
+        assert_same_state(g, H.slack_solve_oracle("f64", *sf, max_iter=K), ("lookshard-mixed", G, K))
+
+
 @pytest.mark.parametrize("G", [1, 2, 3])
 def test_upload_leq_on_shards(G):
     """xp_lp_f64_upload_leq on a (sharded) handle: every rank uploads only the columns of leq that

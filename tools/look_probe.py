@@ -8,9 +8,9 @@ import xpoly_b200 as xp
 
 ctx = xp.Context(0)
 m, n = 8192, 8191
-for mode in ("look", "nolook"):
-    if mode == "nolook":
-        os.environ["XP_NO_LOOKAHEAD"] = "1"
+modes = [("look", {})] + [("chunk%s" % c, {"XP_LAG_CHUNK": c}) for c in sys.argv[1:]] + [("nolook", {"XP_NO_LOOKAHEAD": "1"})]
+for mode, env in modes:
+    os.environ.update(env)
     lp = ctx.large_lp(m, n + m + 1)
     lp.fill_synthetic(2024)
     lp.solve(600)
@@ -20,5 +20,5 @@ for mode in ("look", "nolook"):
         done += 224
         lp.solve(done)
         ms += ctx.last_kernel_ms
-    print(mode, "pivots/s %.0f" % (2240 / (ms * 1e-3)), "us per 32-pivot block %.1f" % (ms * 1e3 / 70), lp.checksum())
+    print(mode, "pivots/s %.0f" % (2240 / (ms * 1e-3)), "us per 32-pivot block %.1f" % (ms * 1e3 / 70), lp.checksum(), flush=True)
     lp.close()

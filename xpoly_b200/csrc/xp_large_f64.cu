@@ -1309,8 +1309,9 @@ struct ColSet {
     int ct0a, ct1a, ct0b, ct1b; // tile ranges [ct0a, ct1a) u [ct0b, ct1b)
     int slot;                   // -1: the open block (live); >= 0: ring slot of a closed block; SLOT_LAG: see below
     int close;                  // the last CTA closes the block
+    int chunk = 0;              // SLOT_LAG: row blocks per work chunk (0: default)
 };
-// Lookahead (one GPU, windowed panel): a finished block is closed by k_block_close before any
+// Lookahead (windowed panel, on the rank that runs k_wpanel): a finished block is closed by k_block_close before any
 // tile has taken it (rest_pending / rest_slot), and the pass over the tableau is launched with
 // slot == SLOT_LAG *beside* the next block's k_wpanel -- programmatic dependent launch, the
 // cluster holds 16 SMs, the pass the others.  It replays the owed block out of the ring exactly
@@ -1374,7 +1375,8 @@ __global__ void __launch_bounds__(1024) k_block_close(LpDev d)
         st->hist_t[slot] = t;
         st->rest_pending = 1;
         st->rest_slot = slot;
-        d.ctr[4] = 0;
+        d.ctr[4] = 0; // window units of the owed pass in place
+        d.ctr[5] = 0; // chunks of the owed pass handed out
         for (int k = 0; k < st->n_touched; k++) d.last_piv[st->touched[k]] = -1;
         st->n_touched = 0;
         st->t = 0;
@@ -1778,12 +1780,16 @@ __global__ void __launch_bounds__(LANES *GROUPS, 2) k_flush_w(LpDev d, ColSet cs
     const double *sPl0 = sP + 2 * lane, *sPl1 = sP + 2 * LANES + 2 * lane;
     const int nrb = (m + FT_ROWS - 1) / FT_ROWS;
     const int nta = cs.ct1a - cs.ct0a, ntb = cs.ct1b - cs.ct0b;
-    // Work units = (column tile, block of FT_ROWS rows), tile-major over the tiles of the set;
-    // every CTA takes one contiguous share.  The lagging pass does so twice: first over range a
-    // (the window tiles: every CTA gets its share of them, so they are done as early as they
-    // can be, and their completion is counted in ctr[4] for the k_wpanel spinning beside us),
-    // then over range b.
-    const int nph = lag ? 2 : 1;
+    // Work units = (column tile, block of FT_ROWS rows), tile-major over the tiles of the set
+    // (range a, then range b).  Ordinarily every CTA takes one contiguous share.  The lagging
+    // pass hands them out as it goes instead -- ctr[5] counts chunks of cs.chunk row blocks of one
+    // tile, single units over the last two tiles -- because its CTAs do not run alike: the
+    // ones on the 16 SMs of the k_wpanel cluster only start when the cluster is through.  The
+    // window tiles (range a) come first; their completion is counted in ctr[4] for the cluster.
+    const int nt = nta + ntb, CH = cs.chunk > 0 ? cs.chunk : 4;
+    const int cpt = (nrb + CH - 1) / CH, tail_t = nt < 2 ? nt : 2;
+    const int nbig = (nt - tail_t) * cpt, nchunks = nbig + tail_t * nrb;
+    __shared__ int s_chunk;
     auto load_P = [&](int ct) {
         for (int e = tid; e < t * (TC / 2); e += THREADS) {
             const int s = e / (TC / 2), l = e - s * (TC / 2);
@@ -1824,15 +1830,29 @@ __global__ void __launch_bounds__(LANES *GROUPS, 2) k_flush_w(LpDev d, ColSet cs
     __syncthreads();
     const bool mb = t >= 12 && nbuf == 3;
     int lu = 0; // units this CTA has taken so far (selects the multiplier buffer and the mbarrier phase)
-    for (int ph = 0; ph < nph; ph++) {
-    const int pt0 = (lag && ph == 1) ? nta : 0, pnt = lag ? (ph == 0 ? nta : ntb) : nta + ntb; // tiles of this phase (set order)
-    const long long units = (long long)pnt * nrb;
-    const int u0 = (int)(units * blockIdx.x / gridDim.x), u1 = (int)(units * (blockIdx.x + 1) / gridDim.x);
-    auto tile_of = [&](int k) { k += pt0; return k < nta ? cs.ct0a + k : cs.ct0b + (k - nta); };
-    int cti = u0 < u1 ? u0 / nrb : 0, rb = u0 < u1 ? (u0 % nrb) * FT_ROWS : 0; // tile index in the phase
+    int cur_tile = -1; // tile whose pivot rows sP holds
+    auto tile_of = [&](int k) { return k < nta ? cs.ct0a + k : cs.ct0b + (k - nta); };
+    for (int it = 0;; it++) {
+    int u0, u1, sig = 0; // this share: units [u0, u1) in set order; units to report in ctr[4]
+    if (!lag) {
+        if (it > 0) break;
+        const long long units = (long long)nt * nrb;
+        u0 = (int)(units * blockIdx.x / gridDim.x), u1 = (int)(units * (blockIdx.x + 1) / gridDim.x);
+    } else {
+        if (tid == 0) s_chunk = (int)atomicAdd(&d.ctr[5], 1u);
+        __syncthreads();
+        const int c = s_chunk;
+        if (c >= nchunks) break;
+        int k, r0, r1;
+        if (c < nbig) k = c / cpt, r0 = (c - k * cpt) * CH, r1 = min(r0 + CH, nrb);
+        else k = (nt - tail_t) + (c - nbig) / nrb, r0 = (c - nbig) % nrb, r1 = r0 + 1;
+        u0 = k * nrb + r0, u1 = k * nrb + r1;
+        if (k < nta) sig = u1 - u0;
+    }
+    int cti = u0 < u1 ? u0 / nrb : 0, rb = u0 < u1 ? (u0 % nrb) * FT_ROWS : 0; // tile index in the set
     int ct = tile_of(cti);
     if (u0 < u1) {
-        load_P(ct);
+        if (ct != cur_tile) load_P(ct), cur_tile = ct;
         copy_F(rb, lu % nbuf);
         prefetch_tile(ct, rb, 0);
     }
@@ -1944,6 +1964,7 @@ __global__ void __launch_bounds__(LANES *GROUPS, 2) k_flush_w(LpDev d, ColSet cs
         if (more && ct1 != ct) {
             __syncthreads();
             load_P(ct1);
+            cur_tile = ct1;
             __syncthreads();
         }
         if (!mb) {
@@ -1955,16 +1976,14 @@ __global__ void __launch_bounds__(LANES *GROUPS, 2) k_flush_w(LpDev d, ColSet cs
         rb = rb1;
         lu++;
     }
-    if (lag && ph == 0) { // this CTA's window units are in place
+    if (lag) { // everybody is through with this share (sP, s_chunk); window units are reported
         __syncthreads();
-        if (tid == 0 && u1 > u0) {
+        if (tid == 0 && sig) {
             __threadfence();
-            atomicAdd(&d.ctr[4], (unsigned)(u1 - u0));
+            atomicAdd(&d.ctr[4], (unsigned)sig);
         }
-    } else if (ph + 1 < nph) {
-        __syncthreads();
     }
-    } // phases
+    } // shares
     if (!cs.close && !lag) return;
     if (tid == 0) {
         __threadfence();
@@ -2610,6 +2629,8 @@ static int lp_create_fill(xp_ctx *ctx, int m, int C, int rank, int G, xp_lp_f64 
     XP_CUDA_OK(ctx, cudaFuncGetAttributes(&fa, k_prow_bulk));
     XP_CUDA_OK(ctx, cudaFuncGetAttributes(&fa, k_flush_t<FT_TR, FT_LANES, FT_HALVES>));
     XP_CUDA_OK(ctx, cudaFuncGetAttributes(&fa, k_flush_w<FT_TR, 64, 4>));
+    XP_CUDA_OK(ctx, cudaFuncGetAttributes(&fa, k_block_close));
+    XP_CUDA_OK(ctx, cudaFuncGetAttributes(&fa, k_block_snapshot));
     XP_CUDA_OK(ctx, cudaFuncGetAttributes(&fa, k_init));
     XP_CUDA_OK(ctx, cudaFuncGetAttributes(&fa, k_feas_sol));
     XP_CUDA_OK(ctx, cudaFuncGetAttributes(&fa, k_feas_rows));
@@ -2986,7 +3007,8 @@ static cudaError_t wpanel_launch(xp_lp_f64 *lp, int bulk_lo = -1, int bulk_hi = 
     }
     if (e != cudaSuccess) return e;
     if (beside) {
-        if (flush_w_launch(lp, kblk, beside, WNC, true)) return cudaErrorLaunchFailure;
+        if (flush_w_launch(lp, kblk, beside, 0, true)) return cudaErrorLaunchFailure; // (work is handed out as it goes: the CTAs
+                                                                                       // that wait for the cluster's SMs join late)
         if (after && (e = cudaEventRecord(after, s)) != cudaSuccess) return e;
     }
     // the columns the window left out (and, on peers, the replicated bookkeeping)
@@ -3042,17 +3064,20 @@ extern "C" int xp_lp_f64_solve(xp_lp_f64 *lp, uint32_t max_iter, int rule)
         blocks = need > 8 ? 8 : (int)need;
     }
     int n_prof = 0; // flushes bracketed by events in this call
-    // Lookahead (one GPU, windowed panel, k_flush_w): a finished block is closed at once
-    // (k_block_close) and the tableau takes it one step later, beside the next block's k_wpanel.
+    // Lookahead (windowed panel, k_flush_w; on the rank that runs k_wpanel): a finished block is
+    // closed at once (k_block_close) and the tableau slice takes it one step later, beside the
+    // next block's k_wpanel.  The peers of a sharded LP keep the plain order -- the launches that
+    // talk to each other (k_wpanel / k_wpanel_peer, k_pcol, k_prow, k_panel) stay paired.
     constexpr int TCW = 4 * FW_LANES;
     const int tiles = (d.Cl + TCW - 1) / TCW;
-    const bool look = lp->use_panel && d.w > 0 && d.G == 1 && (d.Cl & 1) == 0 && lp->ft_wide && kblk >= lp->ft_min &&
+    const bool look = lp->use_panel && d.w > 0 && d.rank == 0 && (d.Cl & 1) == 0 && lp->ft_wide && kblk >= lp->ft_min &&
                       kblk >= lp->ft_balanced_min && d.w % TCW == 0 && d.w / TCW <= tiles && ctx->sm_count > 2 * WNC &&
                       !getenv("XP_NO_LOOKAHEAD");
     lp->shared_sms = look ? WNC : 0;
     ColSet owed_pass; // window tiles first, then the others
     owed_pass.ct0a = 0, owed_pass.ct1a = look ? d.w / TCW : 0, owed_pass.ct0b = owed_pass.ct1a, owed_pass.ct1b = tiles;
     owed_pass.slot = SLOT_LAG, owed_pass.close = 0;
+    if (const char *e = getenv("XP_LAG_CHUNK")) owed_pass.chunk = atoi(e); // (tuning)
     bool owed = false; // a closed block may be waiting for the tableau pass
     const bool dbg_tl = look && getenv("XP_BLOCK_DBG") != nullptr; // stderr: where one block's time goes
     bool dbg_done = false;
@@ -3200,6 +3225,19 @@ extern "C" int xp_lp_f64_profile(xp_lp_f64 *lp, int enable)
 }
 
 extern "C" int xp_lp_f64_pass_shared_sms(const xp_lp_f64 *lp) { return lp ? lp->shared_sms : 0; }
+
+// (debugging aid, not in the header) status, cnt, t, kblk, blk, q, slow, pivot_pending, wseq,
+// wb_pending, rest_pending, rest_slot, n_touched, xseq, xs, cseq of the device state
+extern "C" int xp_lp_f64_debug_state(xp_lp_f64 *lp, long long *out16)
+{
+    if (!lp || !out16) return XP_ERR_BAD_ARG;
+    LpState h;
+    if (cudaMemcpy(&h, lp->d.st, sizeof h, cudaMemcpyDeviceToHost) != cudaSuccess) return XP_ERR_CUDA;
+    const long long v[16] = {h.status, h.cnt, h.t, h.kblk, h.blk, h.q, h.slow, h.pivot_pending, h.wseq, h.wb_pending,
+                             h.rest_pending, h.rest_slot, h.n_touched, h.xseq, h.xs, h.cseq};
+    for (int k = 0; k < 16; k++) out16[k] = v[k];
+    return 0;
+}
 
 extern "C" int xp_lp_f64_profile_read(xp_lp_f64 *lp, uint64_t *n_sweeps, double *sweep_ms,
                                       double *gap_ms)
