@@ -655,6 +655,7 @@ def run_ours(args):
 
     sampler.wait_ready()
     main = timed_run(args.block, P, args.steps, args.warmup, load_s=0.5)
+    shared_sms = int(lib.xp_lp_f64_pass_shared_sms(lp._h))  # (sharded: rank 0 -- the rank whose launches are timed here)
     sampler.stop()
     clocks = sampler.window(main["t0"], main["t2"])
     clocks["window"] = ("timed region" if main["extra_steps"] == 0 else
@@ -679,7 +680,6 @@ def run_ours(args):
     fp64_ops = k_eff * 2.0 * m * local_cols  # non-fused operations of one launch (DMUL + DADD per entry and pivot)
     ach = fp64_ops / (flush_avg_ms * 1e-3) if flush_avg_ms > 0 else 0.0
     n_sm = ctx_sm_count(torch, dev)
-    shared_sms = int(lib.xp_lp_f64_pass_shared_sms(lp._h))  # (sharded: rank 0 -- the rank whose launches are timed here)
     roofline = {
         "bound": "fp64_pipe_nonfused", "kernel": "k_flush_w (rank-k tableau pass, k pivots per launch, DMUL + DADD per entry and pivot)"
                  + (f"; lookahead: each pass runs beside the {shared_sms}-CTA k_wpanel cluster deciding the next block and is timed "

@@ -114,6 +114,14 @@ def test_lookahead_flush(ctx, m, n, window, monkeypatch):
             g["status"] = st
             assert_same_state(g, H.slack_solve_oracle("f64", *sf, max_iter=K), ("look-resume", off, K))
         sums[off] = lp.checksum()
+        # bounded calls back to back: each leaves its last block owed, the next call applies it
+        # beside its first k_wpanel; only the download at the end drains
+        lp.upload(*sf)
+        for K in (40, 80, 81, 120):
+            st = lp.solve(K)
+        g = lp.download(log_cap=1 << 16)
+        g["status"] = st
+        assert_same_state(g, H.slack_solve_oracle("f64", *sf, max_iter=120), ("look-chain", off))
         lp.close()
     assert sums[False] == sums[True]
 

@@ -2326,6 +2326,11 @@ struct xp_lp_f64 {
     // optional per-launch timing of the flush kernel (CUDA events on the ctx stream)
     bool profile = false;
     int shared_sms = 0; // SMs the last solve's tableau passes left to k_wpanel (lookahead), else 0
+    // lookahead: xp_lp_f64_solve returned SIX_TIME_OUT with the last closed block still owed to the
+    // tableau -- the next solve applies it beside its first k_wpanel, anything else drains first (lp_drain)
+    bool owed = false;
+    ColSet owed_pass;
+    int owed_kblk = 0;
     std::vector<cudaEvent_t> evs;
     uint64_t prof_sweeps = 0;
     double prof_sweep_ms = 0.0, prof_gap_ms = 0.0;
@@ -2503,6 +2508,7 @@ static cudaError_t preload_flush()
 
 static int lp_create_fill(xp_ctx *ctx, int m, int C, int rank, int G, xp_lp_f64 *lp);
 static int window_config(xp_lp_f64 *lp);
+static int lp_drain(xp_lp_f64 *lp);
 
 static int lp_create(xp_ctx *ctx, int m, int C, int rank, int G, xp_lp_f64 **out)
 {
@@ -2661,6 +2667,7 @@ extern "C" int xp_lp_f64_create_sharded(xp_ctx *ctx, int m, int C, int rank, int
 extern "C" int xp_lp_f64_set_block(xp_lp_f64 *lp, int pivots_per_flush)
 {
     if (!lp || pivots_per_flush < 0 || pivots_per_flush > KMAX) return XP_ERR_BAD_ARG;
+    if (int rc = lp_drain(lp)) return rc;
     lp->kblk = pivots_per_flush;
     return 0;
 }
@@ -2668,6 +2675,7 @@ extern "C" int xp_lp_f64_set_block(xp_lp_f64 *lp, int pivots_per_flush)
 extern "C" int xp_lp_f64_set_window(xp_lp_f64 *lp, int width)
 {
     if (!lp) return XP_ERR_BAD_ARG;
+    if (int rc = lp_drain(lp)) return rc;
     lp->window = width;
     return window_config(lp);
 }
@@ -2778,10 +2786,23 @@ extern "C" void xp_lp_f64_destroy(xp_lp_f64 *lp)
     delete lp;
 }
 
+// The pass a bounded solve left owed (lookahead), on the handle's stream.  Every entry point that
+// reads or reshapes the tableau calls this first.
+static int lp_drain(xp_lp_f64 *lp)
+{
+    if (!lp->owed) return 0;
+    lp->owed = false;
+    const int rc = flush_w_launch(lp, lp->owed_kblk, &lp->owed_pass);
+    if (rc) return rc;
+    XP_CUDA_OK(lp->ctx, cudaGetLastError());
+    return 0;
+}
+
 static int lp_reset(xp_lp_f64 *lp)
 {
     xp_ctx *ctx = lp->ctx;
     lp->cnt_host = 0;
+    lp->owed = false; // (a fresh LP: k_init clears rest_pending)
     const int k = lp->kblk > 0 ? lp->kblk : auto_block(lp->d);
     k_init<<<ctx->sm_count * 2, 256, 0, ctx->stream>>>(lp->d, 0u, k, 1);
     ctx->launches++;
@@ -3036,7 +3057,9 @@ static cudaError_t panel_launch(xp_lp_f64 *lp)
                                        panel_smem_bytes(rpc, cpc), lp->ctx->stream);
 }
 
-extern "C" int xp_lp_f64_solve(xp_lp_f64 *lp, uint32_t max_iter, int rule)
+// defer: a run that stops at max_iter may leave its last closed block owed to the tableau
+// (lookahead; the next solve applies it beside its first k_wpanel, lp_drain() otherwise).
+static int lp_solve(xp_lp_f64 *lp, uint32_t max_iter, int rule, bool defer)
 {
     if (!lp) return XP_ERR_BAD_ARG;
     if (rule != XP_RULE_REFERENCE) return XP_ERR_BAD_ARG;
@@ -3078,7 +3101,10 @@ extern "C" int xp_lp_f64_solve(xp_lp_f64 *lp, uint32_t max_iter, int rule)
     owed_pass.ct0a = 0, owed_pass.ct1a = look ? d.w / TCW : 0, owed_pass.ct0b = owed_pass.ct1a, owed_pass.ct1b = tiles;
     owed_pass.slot = SLOT_LAG, owed_pass.close = 0;
     if (const char *e = getenv("XP_LAG_CHUNK")) owed_pass.chunk = atoi(e); // (tuning)
-    bool owed = false; // a closed block may be waiting for the tableau pass
+    if (lp->owed && (!look || lp->owed_kblk != kblk || lp->owed_pass.ct1a != owed_pass.ct1a || lp->owed_pass.chunk != owed_pass.chunk))
+        if (int rc = lp_drain(lp)) return rc; // (the schedule changed since the call that left it)
+    bool owed = lp->owed; // a closed block may be waiting for the tableau pass
+    lp->owed = false;
     const bool dbg_tl = look && getenv("XP_BLOCK_DBG") != nullptr; // stderr: where one block's time goes
     bool dbg_done = false;
     cudaEvent_t dbg_ev[8] = {};
@@ -3171,7 +3197,11 @@ extern "C" int xp_lp_f64_solve(xp_lp_f64 *lp, uint32_t max_iter, int rule)
         }
         for (auto &e : dbg_ev) cudaEventDestroy(e);
     }
-    if (look) { // the last closed block
+    if (look && defer && lp->h_st->status == XP_SIX_TIME_OUT) { // resumable: leave it to the next call
+        lp->owed = true;
+        lp->owed_pass = owed_pass;
+        lp->owed_kblk = kblk;
+    } else if (look) { // the last closed block
         const bool prof = lp->profile && n_prof < PROF_MAX_SWEEPS;
         if (prof) XP_CUDA_OK(ctx, cudaEventRecord(lp->evs[2 * n_prof], s));
         int frc = flush_w_launch(lp, kblk, &owed_pass);
@@ -3209,6 +3239,8 @@ extern "C" int xp_lp_f64_solve(xp_lp_f64 *lp, uint32_t max_iter, int rule)
     lp->cnt_host = lp->h_st->cnt;
     return lp->h_st->status;
 }
+
+extern "C" int xp_lp_f64_solve(xp_lp_f64 *lp, uint32_t max_iter, int rule) { return lp_solve(lp, max_iter, rule, true); }
 
 extern "C" int xp_lp_f64_profile(xp_lp_f64 *lp, int enable)
 {
@@ -3259,6 +3291,7 @@ extern "C" int xp_lp_f64_download(xp_lp_f64 *lp, double *tableau, double *tgtf, 
     xp_ctx *ctx = lp->ctx;
     LpDev &d = lp->d;
     XP_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    if (int rc = lp_drain(lp)) return rc;
     cudaStream_t s = ctx->stream;
 #define D2H(dst, src, bytes) \
     if (dst) XP_CUDA_OK(ctx, cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyDeviceToHost, s))
@@ -3300,6 +3333,7 @@ extern "C" int xp_lp_f64_checksum(xp_lp_f64 *lp, uint64_t *sum_tableau, uint64_t
     xp_ctx *ctx = lp->ctx;
     LpDev &d = lp->d;
     XP_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    if (int rc = lp_drain(lp)) return rc;
     void *scr = nullptr;
     int rc = xp_ctx_scratch(ctx, 16, &scr);
     if (rc) return rc;
@@ -3343,7 +3377,7 @@ extern "C" int xp_six_slack_f64(xp_ctx *ctx, double *tableau, double *tgtf, int 
     }
     rc = xp_lp_f64_upload(lp, tableau, tgtf, nvset, bvset, bv2eq, eq2bv, vc_diag, vc_rhs);
     if (rc) return rc;
-    int st = xp_lp_f64_solve(lp, max_iter, rule);
+    int st = lp_solve(lp, max_iter, rule, false);
     if (st >= 0) {
         rc = xp_lp_f64_download(lp, tableau, tgtf, nvset, bvset, bv2eq, eq2bv, maxv, sol, iters,
                                 pivot_log, log_cap);
@@ -3685,15 +3719,29 @@ static int two_stage_streamed(xp_ctx *ctx, xp_lp_f64 *lp, int m, int n, const do
     k_init<<<1, 32, 0, s>>>(d, max_iter, lp->kblk == 0 ? -kblk : kblk, 0);
     k_first_price_window<<<1, 1024, 0, s>>>(d);
     ctx->launches += 4;
+    // (lookahead, as in xp_lp_f64_solve: a finished block is closed at once and the early tiles
+    // take it beside the next block's k_wpanel, window tiles first)
     ColSet early;
     early.ct0a = 0, early.ct1a = ws / TCW, early.ct0b = late_end / TCW, early.ct1b = late_end < C ? tiles : late_end / TCW;
-    early.slot = -1, early.close = 1;
-    for (unsigned b = 0; b < nb; b++) {
-        XP_CUDA_OK(ctx, wpanel_launch(lp, late_end, C));
-        k_block_snapshot<<<32, 256, 0, s>>>(d);
-        ctx->launches++;
-        rc = flush_w_launch(lp, kblk, &early);
+    if (!getenv("XP_NO_LOOKAHEAD")) {
+        early.slot = SLOT_LAG, early.close = 0;
+        for (unsigned b = 0; b < nb; b++) {
+            if (b == 0) XP_CUDA_OK(ctx, wpanel_launch(lp, late_end, C));
+            else XP_CUDA_OK(ctx, wpanel_launch(lp, late_end, C, &early, kblk));
+            k_block_close<<<1, 1024, 0, s>>>(d);
+            ctx->launches++;
+        }
+        rc = flush_w_launch(lp, kblk, &early); // the last closed block
         if (rc) return rc;
+    } else {
+        early.slot = -1, early.close = 1;
+        for (unsigned b = 0; b < nb; b++) {
+            XP_CUDA_OK(ctx, wpanel_launch(lp, late_end, C));
+            k_block_snapshot<<<32, 256, 0, s>>>(d);
+            ctx->launches++;
+            rc = flush_w_launch(lp, kblk, &early);
+            if (rc) return rc;
+        }
     }
     // ---- late pieces: slack form when each has landed, then the closed blocks in order ----
     if (dbg) cudaEventRecord(te[6], s);
@@ -3910,7 +3958,7 @@ static int two_stage_impl(xp_ctx *ctx, int m, int n, const double *leq, Stage1 s
         n_piv++;
         rc = lp_reset(A.lp);
         if (rc) return rc;
-        int st = xp_lp_f64_solve(A.lp, max_iter, rule);
+        int st = lp_solve(A.lp, max_iter, rule, false);
         if (st < 0) return st;
         n_piv += A.lp->h_st->cnt;
         if (pivots) *pivots = n_piv;
@@ -3956,7 +4004,7 @@ static int two_stage_impl(xp_ctx *ctx, int m, int n, const double *leq, Stage1 s
     rc = lp_reset(M.lp);
     if (rc) return rc;
     } // !streamed
-    int st = xp_lp_f64_solve(M.lp, max_iter, rule);
+    int st = lp_solve(M.lp, max_iter, rule, false);
     if (st < 0) return st;
     uint32_t it = 0;
     rc = xp_lp_f64_download(M.lp, nullptr, tgtf_out, nullptr, nullptr, nullptr, eq2bv, maxv, slack_sol, &it,
