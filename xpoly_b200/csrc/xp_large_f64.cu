@@ -92,6 +92,7 @@ struct LpState {
     int n_touched;
     int touched[KMAX]; // rows with last_piv >= 0
     int hist_t[NH];    // pivots of the closed blocks still in the ring (k_block_snapshot)
+    unsigned wcnt;     // pivots made by k_wpanel so far (cnt - wcnt: pivots that needed the full-width kernels)
     int rest_pending;  // lookahead: the block in ring slot rest_slot is closed on the window tiles only,
     int rest_slot;     // the tiles beyond the window still owe it (k_flush_w, slot == SLOT_LAG)
     double r, cq, prow_rhs;
@@ -1367,17 +1368,24 @@ __global__ void __launch_bounds__(1024) k_block_close(LpDev d)
 {
     LpState *st = d.st;
     const int t = st->t;
-    if (t == 0 || (t < st->kblk && st->status == XPI_RUNNING)) return; // nothing to close
-    const int slot = st->blk & (NH - 1);
+    // while (cnt < m_max_iter), lpsol.h:1039 -- what the next k_pcol would find (nothing between
+    // here and there changes the state once the count is reached); said here, a bounded run needs no
+    // extra round of launches to report it
+    const bool timeout = st->status == XPI_RUNNING && st->cnt >= st->max_iter;
+    const bool running = st->status == XPI_RUNNING && !timeout;
+    __syncthreads();
+    if (timeout && threadIdx.x == 0) st->status = XP_SIX_TIME_OUT;
+    if (t == 0 || (t < st->kblk && running)) return; // nothing to close
+    const int slot = st->blk & (NH - 1), nt = st->n_touched;
     for (int i = threadIdx.x; i < d.m; i += blockDim.x) d.hist_lp[(size_t)slot * d.m + i] = d.last_piv[i];
     __syncthreads();
+    for (int k = threadIdx.x; k < nt; k += blockDim.x) d.last_piv[st->touched[k]] = -1;
     if (threadIdx.x == 0) {
         st->hist_t[slot] = t;
         st->rest_pending = 1;
         st->rest_slot = slot;
         d.ctr[4] = 0; // window units of the owed pass in place
         d.ctr[5] = 0; // chunks of the owed pass handed out
-        for (int k = 0; k < st->n_touched; k++) d.last_piv[st->touched[k]] = -1;
         st->n_touched = 0;
         st->t = 0;
         st->blk += 1;
@@ -1995,6 +2003,7 @@ __global__ void __launch_bounds__(LANES *GROUPS, 2) k_flush_w(LpDev d, ColSet cs
         d.ctr[2] = 0;
         if (lag) { // (runs beside k_wpanel: touches nothing but these two words)
             st->rest_pending = 0;
+            st->wcnt = 0;
             return leave();
         }
         for (int k = 0; k < st->n_touched; k++) d.last_piv[st->touched[k]] = -1;
@@ -2331,6 +2340,8 @@ struct xp_lp_f64 {
     bool owed = false;
     ColSet owed_pass;
     int owed_kblk = 0;
+    bool pess = true;      // the next batch of blocks carries the general-path kernels (see lp_solve)
+    unsigned gen_seen = 0; // pivots made outside k_wpanel as of the last poll
     std::vector<cudaEvent_t> evs;
     uint64_t prof_sweeps = 0;
     double prof_sweep_ms = 0.0, prof_gap_ms = 0.0;
@@ -2803,6 +2814,8 @@ static int lp_reset(xp_lp_f64 *lp)
     xp_ctx *ctx = lp->ctx;
     lp->cnt_host = 0;
     lp->owed = false; // (a fresh LP: k_init clears rest_pending)
+    lp->pess = true;  // (the first pricing of a solve is the slow path's)
+    lp->gen_seen = 0;
     const int k = lp->kblk > 0 ? lp->kblk : auto_block(lp->d);
     k_init<<<ctx->sm_count * 2, 256, 0, ctx->stream>>>(lp->d, 0u, k, 1);
     ctx->launches++;
@@ -3105,6 +3118,28 @@ static int lp_solve(xp_lp_f64 *lp, uint32_t max_iter, int rule, bool defer)
         if (int rc = lp_drain(lp)) return rc; // (the schedule changed since the call that left it)
     bool owed = lp->owed; // a closed block may be waiting for the tableau pass
     lp->owed = false;
+    const bool self_timeout = look && d.G == 1; // k_block_close reports SIX_TIME_OUT: no extra block for it
+    if (self_timeout && max_iter != XP_NO_ITER_LIMIT && max_iter > lp->cnt_host) {
+        const unsigned long long need = ((unsigned long long)max_iter - lp->cnt_host + kblk - 1) / kblk;
+        blocks = need > 8 ? 8 : (int)need;
+    }
+    // Optimistic batches (one GPU): as long as k_wpanel decides every pivot alone, the kernels of
+    // the general path (k_pcol, k_prow, the second k_wpanel, k_panel) find nothing to do -- five
+    // empty launches per block.  The host leaves them out while the state it polls says the last
+    // batch needed none (every pivot counted by k_wpanel, the next one decidable inside the window)
+    // and puts them back for the next batch otherwise.  A batch that meets an exception without
+    // them simply stops deciding there -- every remaining launch finds the block open and
+    // returns -- until the host has looked.
+    const bool may_skip = look && d.G == 1 && !getenv("XP_NO_OPTIMISTIC");
+    bool pess = !may_skip || lp->pess;
+    unsigned gen_seen = lp->gen_seen; // pivots not made by k_wpanel, as of the last poll
+    auto general_needed = [&](const LpState &h) {
+        const bool go = !h.slow && !h.pivot_pending && h.q != INT_BIG && h.q < d.w;
+        const unsigned gen = h.cnt - h.wcnt;
+        const bool moved = gen != gen_seen;
+        gen_seen = gen;
+        return !go || moved;
+    };
     const bool dbg_tl = look && getenv("XP_BLOCK_DBG") != nullptr; // stderr: where one block's time goes
     bool dbg_done = false;
     cudaEvent_t dbg_ev[8] = {};
@@ -3124,17 +3159,22 @@ static int lp_solve(xp_lp_f64 *lp, uint32_t max_iter, int rule, bool defer)
                 if (prof) n_prof++;
                 owed = true;
                 if (tl) cudaEventRecord(dbg_ev[1], s);
-                k_pcol<<<d.gridA, TH, 0, s>>>(d);
-                if (tl) cudaEventRecord(dbg_ev[2], s);
-                k_prow<<<d.gridB, TH, 0, s>>>(d);
-                if (tl) cudaEventRecord(dbg_ev[3], s);
-                XP_CUDA_OK(ctx, wpanel_launch(lp));
-                if (tl) cudaEventRecord(dbg_ev[4], s);
-                XP_CUDA_OK(ctx, panel_launch(lp));
+                if (pess) { // (optimistic batches leave these out: see below)
+                    k_pcol<<<d.gridA, TH, 0, s>>>(d);
+                    if (tl) cudaEventRecord(dbg_ev[2], s);
+                    k_prow<<<d.gridB, TH, 0, s>>>(d);
+                    if (tl) cudaEventRecord(dbg_ev[3], s);
+                    XP_CUDA_OK(ctx, wpanel_launch(lp));
+                    if (tl) cudaEventRecord(dbg_ev[4], s);
+                    XP_CUDA_OK(ctx, panel_launch(lp));
+                    ctx->launches += 3;
+                } else if (tl) {
+                    cudaEventRecord(dbg_ev[2], s), cudaEventRecord(dbg_ev[3], s), cudaEventRecord(dbg_ev[4], s);
+                }
                 if (tl) cudaEventRecord(dbg_ev[5], s);
                 k_block_close<<<1, 1024, 0, s>>>(d);
                 if (tl) cudaEventRecord(dbg_ev[6], s), dbg_done = true;
-                ctx->launches += 4;
+                ctx->launches++;
                 continue;
             }
             if (lp->use_panel && d.w > 0) {
@@ -3177,10 +3217,11 @@ static int lp_solve(xp_lp_f64 *lp, uint32_t max_iter, int rule, bool defer)
         XP_CUDA_OK(ctx, cudaGetLastError());
         XP_CUDA_OK(ctx, cudaMemcpyAsync(lp->h_st, d.st, sizeof(LpState), cudaMemcpyDeviceToHost, s));
         XP_CUDA_OK(ctx, cudaStreamSynchronize(s));
+        pess = general_needed(*lp->h_st) || !may_skip;
         if (lp->h_st->status != XPI_RUNNING) break;
         unsigned long long left = (unsigned long long)max_iter - lp->h_st->cnt;
         int want = blocks < 8 ? blocks * 2 : 8;
-        unsigned long long need = left / kblk + 1; // the extra block reports TIME_OUT
+        unsigned long long need = self_timeout ? (left + kblk - 1) / kblk : left / kblk + 1; // the extra block reports TIME_OUT
         blocks = (unsigned long long)want > need ? (int)need : want;
         if (blocks < 1) blocks = 1;
     }
@@ -3197,6 +3238,8 @@ static int lp_solve(xp_lp_f64 *lp, uint32_t max_iter, int rule, bool defer)
         }
         for (auto &e : dbg_ev) cudaEventDestroy(e);
     }
+    lp->pess = pess;
+    lp->gen_seen = gen_seen;
     if (look && defer && lp->h_st->status == XP_SIX_TIME_OUT) { // resumable: leave it to the next call
         lp->owed = true;
         lp->owed_pass = owed_pass;

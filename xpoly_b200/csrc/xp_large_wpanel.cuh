@@ -458,6 +458,7 @@ __global__ void __launch_bounds__(WTHB, 1) k_wpanel(LpDev d, unsigned long long 
             st->n_log = n_log;
             st->n_touched = n_touched;
             st->wseq = wseq;
+            st->wcnt += (unsigned)(t - t_in);
             st->wb_t0 = t_in;
             st->wb_pending = t > t_in;
             if (bad) st->status = XP_ERR_PEER;
