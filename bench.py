@@ -673,6 +673,20 @@ def run_ours(args):
                 break
             except Exception:
                 traffic = None
+    # the same blocked run with the lookahead off: every pass has the device to itself (the kernel's
+    # own roofline figure, beside the one of the schedule `value` is measured on)
+    alone = None
+    shared_any = shared_sms  # (sharded: only the leader reports it, every rank must run the same steps)
+    if world > 1:
+        t = torch.tensor([shared_sms], dtype=torch.int64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        shared_any = int(t.item())
+    if shared_any:
+        os.environ["XP_NO_LOOKAHEAD"] = "1"
+        try:
+            alone = timed_run(args.block, P, 5, 3)
+        finally:
+            del os.environ["XP_NO_LOOKAHEAD"]
     # the reference's own schedule (one tableau pass per pivot), same kernels with k = 1
     r1 = timed_run(1, args.rank1_pivots, 3, 1)
     r1_value = r1["pivots"] / (r1["dev_ms"] * 1e-3)
@@ -700,6 +714,12 @@ def run_ours(args):
         "rank1_pivots_per_s": r1_value,
         "rank1_kernel_hbm_frac": (B_pivot / (r1_sweep_ms * 1e-3) / 1e9 / peak) if r1_sweep_ms > 0 else None,
         "rank1_whole_pivot_frac_of_8TBps": r1_value * B_pivot / 8e12}
+    if alone and alone["flushes"] and alone["flush_ms"] > 0:
+        a_ops = alone["pivots"] / alone["flushes"] * 2.0 * m * local_cols
+        a_ms = alone["flush_ms"] / alone["flushes"]
+        roofline["alone_frac"] = a_ops / (a_ms * 1e-3) / fp64_peak if fp64_peak > 0 else None
+        roofline["alone_avg_launch_ms"] = a_ms
+        roofline["alone_pivots_per_s"] = alone["pivots"] / (alone["dev_ms"] * 1e-3)
 
     # ---- parity, in the run: the state after 200 pivots against the CPU side ----
     sys.path.insert(0, os.path.join(ROOT, "tests"))

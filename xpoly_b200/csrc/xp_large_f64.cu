@@ -3103,11 +3103,12 @@ static int lp_solve(xp_lp_f64 *lp, uint32_t max_iter, int rule, bool defer)
     // Lookahead (windowed panel, k_flush_w; on the rank that runs k_wpanel): a finished block is
     // closed at once (k_block_close) and the tableau slice takes it one step later, beside the
     // next block's k_wpanel.  The peers of a sharded LP keep the plain order -- the launches that
-    // talk to each other (k_wpanel / k_wpanel_peer, k_pcol, k_prow, k_panel) stay paired.
+    // talk to each other (k_wpanel / k_wpanel_peer, k_pcol, k_prow, k_panel) stay paired -- and so
+    // does a leader whose slice ends with the window (4 and 8 GPUs at c3: nothing to overlap).
     constexpr int TCW = 4 * FW_LANES;
     const int tiles = (d.Cl + TCW - 1) / TCW;
     const bool look = lp->use_panel && d.w > 0 && d.rank == 0 && (d.Cl & 1) == 0 && lp->ft_wide && kblk >= lp->ft_min &&
-                      kblk >= lp->ft_balanced_min && d.w % TCW == 0 && d.w / TCW <= tiles && ctx->sm_count > 2 * WNC &&
+                      kblk >= lp->ft_balanced_min && d.w % TCW == 0 && d.w / TCW < tiles && ctx->sm_count > 2 * WNC &&
                       !getenv("XP_NO_LOOKAHEAD");
     lp->shared_sms = look ? WNC : 0;
     ColSet owed_pass; // window tiles first, then the others
@@ -3240,7 +3241,9 @@ static int lp_solve(xp_lp_f64 *lp, uint32_t max_iter, int rule, bool defer)
     }
     lp->pess = pess;
     lp->gen_seen = gen_seen;
-    if (look && defer && lp->h_st->status == XP_SIX_TIME_OUT) { // resumable: leave it to the next call
+    if (!lp->h_st->rest_pending) {
+        // nothing owed (the polled state is final: no launch since)
+    } else if (look && defer && lp->h_st->status == XP_SIX_TIME_OUT) { // resumable: leave it to the next call
         lp->owed = true;
         lp->owed_pass = owed_pass;
         lp->owed_kblk = kblk;
