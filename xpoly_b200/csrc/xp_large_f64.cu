@@ -2980,6 +2980,8 @@ static int window_config(xp_lp_f64 *lp)
         XP_CUDA_OK(ctx, cudaFuncSetAttribute(k_wpanel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
         XP_CUDA_OK(ctx, cudaFuncSetAttribute(k_wpanel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)ctx->smem_optin - 8192));
+        XP_CUDA_OK(ctx, cudaFuncSetAttribute(k_prow_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)(2 * KMAX * WB_TH * sizeof(double))));
         lp->wpanel_ready = true;
     }
     if (d.rank == 0) { // can the device hold one such cluster at all?
@@ -3049,7 +3051,7 @@ static cudaError_t wpanel_launch(xp_lp_f64 *lp, int bulk_lo = -1, int bulk_hi = 
     int grid = (jl1 - jl0 + WB_TH - 1) / WB_TH;
     if (grid < 1) grid = 1;
     if (grid > 2 * lp->ctx->sm_count) grid = 2 * lp->ctx->sm_count;
-    k_prow_bulk<<<grid, WB_TH, 0, s>>>(d, 0, 0, jl0, jl1);
+    k_prow_bulk<<<grid, WB_TH, 2 * KMAX * WB_TH * sizeof(double), s>>>(d, 0, 0, jl0, jl1);
     return cudaGetLastError();
 }
 
@@ -3802,7 +3804,7 @@ static int two_stage_streamed(xp_ctx *ctx, xp_lp_f64 *lp, int m, int n, const do
         late.ct0a = c0 / TCW, late.ct1a = c1 / TCW, late.ct0b = late.ct1b = 0;
         late.close = 0;
         for (unsigned b = 0; b < nb; b++) {
-            k_prow_bulk<<<bulk_grid(c0, c1), WB_TH, 0, s>>>(d, 1, (int)b, c0, c1);
+            k_prow_bulk<<<bulk_grid(c0, c1), WB_TH, 2 * KMAX * WB_TH * sizeof(double), s>>>(d, 1, (int)b, c0, c1);
             ctx->launches++;
             late.slot = (int)b;
             rc = flush_w_launch(lp, kblk, &late);
@@ -3830,7 +3832,7 @@ static int two_stage_streamed(xp_ctx *ctx, xp_lp_f64 *lp, int m, int n, const do
         for (auto &ev : te) cudaEventDestroy(ev);
     }
     if (lp->h_st->t > 0) { // a block was left open (exception inside the window run): its pivot rows for the late tiles
-        k_prow_bulk<<<bulk_grid(ws, late_end), WB_TH, 0, s>>>(d, 2, 0, ws, late_end);
+        k_prow_bulk<<<bulk_grid(ws, late_end), WB_TH, 2 * KMAX * WB_TH * sizeof(double), s>>>(d, 2, 0, ws, late_end);
         ctx->launches++;
         XP_CUDA_OK(ctx, cudaGetLastError());
     }

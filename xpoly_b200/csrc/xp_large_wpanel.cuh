@@ -537,6 +537,7 @@ constexpr int WB_TH = 128;
 // mode 2: every pivot so far of the OPEN block (all made by k_wpanel), for such columns.
 __global__ void __launch_bounds__(WB_TH) k_prow_bulk(LpDev d, int mode, int slot, int jlo, int jhi)
 {
+    extern __shared__ double s_bulk[]; // sA[KMAX][WB_TH] | sPr[KMAX][WB_TH]
     __shared__ double s_L[KMAX][KMAX]; // s_L[s][u] = F[u][p_s], u < s
     __shared__ WRec s_rec[KMAX];
     LpState *st = d.st;
@@ -553,48 +554,31 @@ __global__ void __launch_bounds__(WB_TH) k_prow_bulk(LpDev d, int mode, int slot
         s_L[s][u] = u < s ? ld_cg(Fptr(d, d.rank, par, u) + s_rec[s].p) : 0.0;
     }
     __syncthreads();
+    double *sA = s_bulk, *sPr = s_bulk + (size_t)KMAX * WB_TH;
     const int ld = d.Cl;
-    // One column per thread.  P[s][j] = scale_s(A[p_s][j] (+) sum over u < s of L[s][u] * P[u][j]), the
-    // sum taken left to right (and restarting from P[s0p][j] when row p_s was itself the pivot row
-    // of step s0p).  The chains of different s only meet in P[u], which is final after step u - 1:
-    // all of them advance together, one u at a time, so the dependent path is t1 (mul, add) pairs
-    // instead of t1^2 / 2 -- the values stay in registers (v[]), every step is fully unrolled.
     for (int jb = jlo + blockIdx.x * WB_TH; jb < Cl; jb += gridDim.x * WB_TH) {
         const int jl = jb + tid;
-        if (jl >= Cl) continue;
-        const int g = d.col0 + jl;
-        double v[KMAX];
-        int s0v[KMAX];
-#pragma unroll
-        for (int s = 0; s < KMAX; s++) {
-            const bool on = s >= t0 && s < t1;
-            v[s] = on ? d.tab[(size_t)s_rec[on ? s : t0].p * ld + jl] : 0.0;
-            s0v[s] = on ? s_rec[s].s0p : KMAX; // (KMAX: never touched)
-        }
-        double tg = d.tgtf[jl];
-#pragma unroll
-        for (int u = 0; u < KMAX; u++) {
-            if (u >= t1) break;
-            double pu;
-            if (u < t0) {
-                pu = ld_cg(d.P + (size_t)u * ld + jl);
-            } else {
-                const double r = s_rec[u].r, cq = s_rec[u].cq;
-                pu = xp_scale(v[u], r, xp_feq(r, 1.0), xp_feq(r, 0.0));
-                d.P[(size_t)u * ld + jl] = pu;
-                double tt = xp_mul(pu, -1.0);
+        if (jl < Cl) {
+            const int g = d.col0 + jl;
+            for (int s = t0; s < t1; s++) sA[s * WB_TH + tid] = d.tab[(size_t)s_rec[s].p * ld + jl];
+            for (int u = 0; u < t0; u++) sPr[u * WB_TH + tid] = ld_cg(d.P + (size_t)u * ld + jl);
+            double tg = d.tgtf[jl];
+            for (int s = t0; s < t1; s++) {
+                const WRec rc = s_rec[s];
+                double v = sA[s * WB_TH + tid];
+                if (rc.s0p >= 0) v = sPr[rc.s0p * WB_TH + tid];
+#pragma unroll 8
+                for (int u = rc.s0p + 1; u < s; u++) v = xp_add(v, xp_mul(s_L[s][u], sPr[u * WB_TH + tid]));
+                const double xv = xp_scale(v, rc.r, xp_feq(rc.r, 1.0), xp_feq(rc.r, 0.0));
+                sPr[s * WB_TH + tid] = xv;
+                d.P[(size_t)s * ld + jl] = xv;
+                double tt = xp_mul(xv, -1.0);
                 if (g >= n) tt = -tt;
-                tt = xp_feq(cq, 0.0) ? 0.0 : (xp_feq(cq, 1.0) ? tt : xp_mul(tt, cq));
+                tt = xp_feq(rc.cq, 0.0) ? 0.0 : (xp_feq(rc.cq, 1.0) ? tt : xp_mul(tt, rc.cq));
                 tg = xp_add(tt, tg); // no zeroing out here: the scan stopped inside the window (zero_upto <= q < w)
             }
-#pragma unroll
-            for (int s = u + 1; s < KMAX; s++) {
-                if (s >= t1) break;
-                const double acc = xp_add(v[s], xp_mul(s_L[s][u], pu));
-                v[s] = u == s0v[s] ? pu : (u > s0v[s] ? acc : v[s]);
-            }
+            d.tgtf[jl] = tg;
         }
-        d.tgtf[jl] = tg;
     }
     if (d.rank > 0 && mode == 0) { // replicated state the leader kept while deciding
         for (int i = blockIdx.x * WB_TH + tid; i < d.m; i += gridDim.x * WB_TH) {
