@@ -8,7 +8,7 @@ import xpoly_b200 as xp
 
 ctx = xp.Context(0)
 m, n = 8192, 8191
-modes = [("look", {})] + [("chunk%s" % c, {"XP_LAG_CHUNK": c}) for c in sys.argv[1:]] + [("nolook", {"XP_NO_LOOKAHEAD": "1"})]
+modes = [("look", {})] + [(a, dict([a.split("=")])) for a in sys.argv[1:]] + [("nolook", {"XP_NO_LOOKAHEAD": "1"})] + [("nolook," + a, dict([a.split("=")])) for a in sys.argv[1:] if a.startswith("XP_FLUSH")]
 for mode, env in modes:
     os.environ.update(env)
     lp = ctx.large_lp(m, n + m + 1)
