@@ -1,6 +1,8 @@
 """Parity of the HBM-resident FP64 path (xp_six_slack_f64 / xp_lp_f64_*) against
 the oracle's solveSlackForm, bit for bit: status, iteration count, pivot
 sequence, basis maps, whole tableau, objective row, solution."""
+import os
+
 import numpy as np
 import pytest
 
@@ -8,6 +10,7 @@ import harness as H
 import xpoly_b200 as xp
 
 pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def assert_same_state(g, o, tag):
@@ -124,6 +127,35 @@ def test_lookahead_flush(ctx, m, n, window, monkeypatch):
         assert_same_state(g, H.slack_solve_oracle("f64", *sf, max_iter=120), ("look-chain", off))
         lp.close()
     assert sums[False] == sums[True]
+
+
+def test_lookahead_serialised_launches():
+    """What a profiler that serialises kernels makes of the lookahead: the pass cannot start
+    beside the cluster, the cluster gives up waiting for it (20 ms) without having touched anything,
+    the pass runs behind it and the next k_wpanel decides the block.  Slower, same bits.  (Own
+    process: the switch is read once.)"""
+    import subprocess
+    import sys
+    code = (
+        "import os, sys, numpy as np\n"
+        "sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "import harness as H, xpoly_b200 as xp\n"
+        "ctx = xp.Context(0)\n"
+        "leq, tg = H.gen_dense_lp(8600, 257, 1300)\n"
+        "leq2, tg2 = H.gen_dense_lp(8660, 257, 1300)\n"
+        "for (l, t, K) in ((leq, tg, 600), (leq2, tg2, 100)):\n"
+        "    sf = xp.slack_form(l, t)\n"
+        "    o = H.slack_solve_oracle('f64', *sf, max_iter=K)\n"
+        "    lp = ctx.large_lp(*sf[0].shape); lp.set_window(256); lp.set_block(16); lp.upload(*sf)\n"
+        "    st = lp.solve(K); g = lp.download(log_cap=1 << 16)\n"
+        "    assert st == o['status'] and g['iters'] == o['iters'], (st, o['status'], g['iters'], o['iters'])\n"
+        "    for k in ('tab', 'tgtf', 'sol'):\n"
+        "        assert np.array_equal(H.bits(g[k]), H.bits(o[k])), k\n"
+        "    assert np.array_equal(g['eq2bv'], o['eq2bv'])\n"
+        "print('serial-ok')\n") % (ROOT, os.path.join(ROOT, "tests"))
+    env = dict(os.environ, XP_LOOKAHEAD_SERIAL="1")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "serial-ok" in out.stdout, out.stdout + out.stderr
 
 
 @pytest.mark.parametrize("m,n", [(2, 2), (6, 5), (8, 7), (10, 9), (16, 15), (33, 20), (7, 40)])

@@ -3041,8 +3041,11 @@ static cudaError_t wpanel_launch(xp_lp_f64 *lp, int bulk_lo = -1, int bulk_hi = 
     }
     if (e != cudaSuccess) return e;
     if (beside) {
-        if (flush_w_launch(lp, kblk, beside, 0, true)) return cudaErrorLaunchFailure; // (work is handed out as it goes: the CTAs
-                                                                                       // that wait for the cluster's SMs join late)
+        // (work is handed out as it goes: the CTAs that wait for the cluster's SMs join late).
+        // XP_LOOKAHEAD_SERIAL=1 launches the pass the plain way -- what a profiler that serialises
+        // kernels makes of it: the cluster gives up waiting and the next k_wpanel does the work (tests)
+        static const bool serial = getenv("XP_LOOKAHEAD_SERIAL") != nullptr;
+        if (flush_w_launch(lp, kblk, beside, 0, !serial)) return cudaErrorLaunchFailure;
         if (after && (e = cudaEventRecord(after, s)) != cudaSuccess) return e;
     }
     // the columns the window left out (and, on peers, the replicated bookkeeping)
