@@ -101,6 +101,10 @@ def test_lookahead_flush(ctx, m, n, window, monkeypatch):
     leq[:, n] = np.abs(leq[:, n])
     tg[:n] = np.abs(tg[:n])
     run_both(ctx, leq, tg, max_iter=600, tag=("look-mixed", m, n), blocks=(0, 32), windows=(window,))
+    for seed in (8651, 8652):  # mixed-sign objective as well: ratio tests fail inside the window run (-> disableNV)
+        leq, tg = H.gen_mixed_lp(seed, m, n)
+        leq[:, n] = np.abs(leq[:, n])
+        run_both(ctx, leq, tg, max_iter=400, tag=("look-mixed2", m, n, seed), blocks=(0, 32), windows=(window,))
     leq, tg = H.gen_dense_lp(8660, m, n)
     sf = xp.slack_form(leq, tg)
     sums = {}

@@ -93,6 +93,7 @@ struct LpState {
     int touched[KMAX]; // rows with last_piv >= 0
     int hist_t[NH];    // pivots of the closed blocks still in the ring (k_block_snapshot)
     unsigned wcnt;     // pivots made by k_wpanel so far (cnt - wcnt: pivots that needed the full-width kernels)
+    int wfail;         // the last k_wpanel run ended on a failing ratio test (k_pcol takes that column)
     int rest_pending;  // lookahead: the block in ring slot rest_slot is closed on the window tiles only,
     int rest_slot;     // the tiles beyond the window still owe it (k_flush_w, slot == SLOT_LAG)
     double r, cq, prow_rhs;
@@ -115,7 +116,7 @@ struct XHdr {
     // the peers its exit state + one record per pivot (xoff_rec) + the multiplier columns
     unsigned long long wflag;       // leader -> peer: number of the windowed launch whose results are in place
     unsigned long long wack[MAXR];  // peer -> leader: last windowed launch the peer has consumed
-    int wexit[8];                   // leader -> peer: t, q, anypos, zero_upto, slow, status
+    int wexit[8];                   // leader -> peer: t, q, anypos, zero_upto, slow, status, ratio test failed
 };
 constexpr size_t XHDR_BYTES = 1024;
 static_assert(sizeof(XHdr) <= XHDR_BYTES, "exchange header");
@@ -1361,6 +1362,16 @@ __global__ void k_block_snapshot(LpDev d)
     if (blockIdx.x == 0 && threadIdx.x == 0) st->hist_t[slot] = t;
 }
 
+// while (cnt < m_max_iter), lpsol.h:1039 -- what the next k_pcol would find (nothing between here and
+// there changes the state once the count is reached).  Said before the pass over the tableau, a
+// bounded run needs no extra round of launches to report it, and the pass closes the last,
+// partial block right away.
+__global__ void k_timeout(LpDev d)
+{
+    LpState *st = d.st;
+    if (st->status == XPI_RUNNING && st->cnt >= st->max_iter) st->status = XP_SIX_TIME_OUT;
+}
+
 // Lookahead: the same snapshot, and the block is closed right here -- before any tile has taken
 // it.  The whole pass is then owed (rest_pending) and runs out of the ring slot beside the next
 // block's k_wpanel, window tiles first (ctr[4] counts them for the cluster).  One CTA.
@@ -2004,6 +2015,7 @@ __global__ void __launch_bounds__(LANES *GROUPS, 2) k_flush_w(LpDev d, ColSet cs
         if (lag) { // (runs beside k_wpanel: touches nothing but these two words)
             st->rest_pending = 0;
             st->wcnt = 0;
+            st->wfail = 0;
             return leave();
         }
         for (int k = 0; k < st->n_touched; k++) d.last_piv[st->touched[k]] = -1;
@@ -2647,6 +2659,7 @@ static int lp_create_fill(xp_ctx *ctx, int m, int C, int rank, int G, xp_lp_f64 
     XP_CUDA_OK(ctx, cudaFuncGetAttributes(&fa, k_flush_t<FT_TR, FT_LANES, FT_HALVES>));
     XP_CUDA_OK(ctx, cudaFuncGetAttributes(&fa, k_flush_w<FT_TR, 64, 4>));
     XP_CUDA_OK(ctx, cudaFuncGetAttributes(&fa, k_block_close));
+    XP_CUDA_OK(ctx, cudaFuncGetAttributes(&fa, k_timeout));
     XP_CUDA_OK(ctx, cudaFuncGetAttributes(&fa, k_block_snapshot));
     XP_CUDA_OK(ctx, cudaFuncGetAttributes(&fa, k_init));
     XP_CUDA_OK(ctx, cudaFuncGetAttributes(&fa, k_feas_sol));
@@ -3122,27 +3135,33 @@ static int lp_solve(xp_lp_f64 *lp, uint32_t max_iter, int rule, bool defer)
         if (int rc = lp_drain(lp)) return rc; // (the schedule changed since the call that left it)
     bool owed = lp->owed; // a closed block may be waiting for the tableau pass
     lp->owed = false;
-    const bool self_timeout = look && d.G == 1; // k_block_close reports SIX_TIME_OUT: no extra block for it
+    const bool windowed = lp->use_panel && d.w > 0; // (the same on every rank of a sharded LP)
+    const bool self_timeout = windowed; // k_block_close / k_timeout report SIX_TIME_OUT: no extra block for it
     if (self_timeout && max_iter != XP_NO_ITER_LIMIT && max_iter > lp->cnt_host) {
         const unsigned long long need = ((unsigned long long)max_iter - lp->cnt_host + kblk - 1) / kblk;
         blocks = need > 8 ? 8 : (int)need;
     }
-    // Optimistic batches (one GPU): as long as k_wpanel decides every pivot alone, the kernels of
+    // Optimistic batches: as long as k_wpanel decides every pivot alone, the kernels of
     // the general path (k_pcol, k_prow, the second k_wpanel, k_panel) find nothing to do -- five
     // empty launches per block.  The host leaves them out while the state it polls says the last
     // batch needed none (every pivot counted by k_wpanel, the next one decidable inside the window)
     // and puts them back for the next batch otherwise.  A batch that meets an exception without
     // them simply stops deciding there -- every remaining launch finds the block open and
-    // returns -- until the host has looked.
-    const bool may_skip = look && d.G == 1 && !getenv("XP_NO_OPTIMISTIC");
+    // returns -- until the host has looked.  Sharded: every rank polls the same replicated words
+    // after the same batch, hence takes the same decision (the kernels left out are the ones
+    // that talk to each other).
+    const bool may_skip = windowed && !getenv("XP_NO_OPTIMISTIC");
     bool pess = !may_skip || lp->pess;
     unsigned gen_seen = lp->gen_seen; // pivots not made by k_wpanel, as of the last poll
+    unsigned cnt_seen = lp->cnt_host;
     auto general_needed = [&](const LpState &h) {
-        const bool go = !h.slow && !h.pivot_pending && h.q != INT_BIG && h.q < d.w;
+        const bool go = !h.slow && !h.wfail && !h.pivot_pending && h.q != INT_BIG && h.q < d.w;
         const unsigned gen = h.cnt - h.wcnt;
         const bool moved = gen != gen_seen;
+        const bool stalled = h.cnt == cnt_seen; // (whatever the reason: a batch without a single pivot)
         gen_seen = gen;
-        return !go || moved;
+        cnt_seen = h.cnt;
+        return !go || moved || stalled;
     };
     const bool dbg_tl = look && getenv("XP_BLOCK_DBG") != nullptr; // stderr: where one block's time goes
     bool dbg_done = false;
@@ -3187,11 +3206,15 @@ static int lp_solve(xp_lp_f64 *lp, uint32_t max_iter, int rule, bool defer)
                 // pivot needs the slow path or lies outside the window; the full-width panel
                 // finishes a block the window cannot
                 XP_CUDA_OK(ctx, wpanel_launch(lp));
-                k_pcol<<<d.gridA, TH, 0, s>>>(d);
-                k_prow<<<d.gridB, TH, 0, s>>>(d);
-                XP_CUDA_OK(ctx, wpanel_launch(lp));
-                XP_CUDA_OK(ctx, panel_launch(lp));
-                ctx->launches += 3;
+                if (pess) {
+                    k_pcol<<<d.gridA, TH, 0, s>>>(d);
+                    k_prow<<<d.gridB, TH, 0, s>>>(d);
+                    XP_CUDA_OK(ctx, wpanel_launch(lp));
+                    XP_CUDA_OK(ctx, panel_launch(lp));
+                    ctx->launches += 3;
+                }
+                k_timeout<<<1, 1, 0, s>>>(d);
+                ctx->launches++;
             } else if (lp->use_panel) {
                 // fast path: all pivots of the block in one persistent kernel; the pair in
                 // the middle takes whatever single pivot needs the slow path

@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(WTHB, 1) k_wpanel(LpDev d, unsigned long long 
     }
     int cur = 0;      // s_rh buffer holding the constant column as of now
     unsigned xn = 0;  // exchanges so far (slot = xn & 1)
-    int slow_out = 0;
+    int slow_out = 0, fail_out = 0; // how the run ended: re-price on the slow path / the ratio test on q failed
     WRec *recs[MAXR];
     for (int r = 0; r < G; r++) recs[r] = (WRec *)(d.xb[r] + xoff_rec(d, par));
 
@@ -306,7 +306,10 @@ __global__ void __launch_bounds__(WTHB, 1) k_wpanel(LpDev d, unsigned long long 
             if (p != INT_BIG) break;
         }
         WPANEL_T(1)
-        if (p == INT_BIG) break; // ratio test failed: k_pcol redoes this column and takes the slow path
+        if (p == INT_BIG) { // ratio test failed: k_pcol redoes this column and takes the slow path
+            fail_out = 1;
+            break;
+        }
         const double r = xp_div(1.0, piv_a); // mulOfRow(eqnum, 1 / pivot), :1471
         const bool r_one = xp_feq(r, 1.0), r_zero = xp_feq(r, 0.0);
         const bool cq_zero = xp_feq(cq, 0.0), cq_one = xp_feq(cq, 1.0);
@@ -454,6 +457,7 @@ __global__ void __launch_bounds__(WTHB, 1) k_wpanel(LpDev d, unsigned long long 
             st->anypos = anypos;
             st->zero_upto = zero_upto;
             st->slow = slow_out;
+            st->wfail = fail_out;
             st->tg_rhs = tg_rhs;
             st->n_log = n_log;
             st->n_touched = n_touched;
@@ -466,7 +470,7 @@ __global__ void __launch_bounds__(WTHB, 1) k_wpanel(LpDev d, unsigned long long 
         if (G > 1 && lane > 0 && lane < G) { // exit state for peer `lane`, then the flag
             XHdr *H = (XHdr *)d.xb[lane];
             H->wexit[0] = t, H->wexit[1] = q, H->wexit[2] = anypos, H->wexit[3] = zero_upto;
-            H->wexit[4] = slow_out, H->wexit[5] = bad ? XP_ERR_PEER : XPI_RUNNING;
+            H->wexit[4] = slow_out, H->wexit[5] = bad ? XP_ERR_PEER : XPI_RUNNING, H->wexit[6] = fail_out;
         }
     }
     if (G > 1) {
@@ -512,9 +516,11 @@ __global__ void k_wpanel_peer(LpDev d)
     st->anypos = we[2];
     st->zero_upto = we[3];
     st->slow = we[4];
+    st->wfail = we[6];
     if (we[5] != XPI_RUNNING) st->status = we[5];
     st->wb_t0 = t;
     st->wb_pending = t1 > t;
+    st->wcnt += (unsigned)(t1 - t);
     st->t = t1; // cnt, n_log, tg_rhs, basis maps, tabu table: replayed from the records by k_prow_bulk
     __threadfence_system();
     st_release_sys(&((XHdr *)d.xb[0])->wack[d.rank], (unsigned long long)wseq);
