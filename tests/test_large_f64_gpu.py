@@ -133,6 +133,28 @@ def test_lookahead_flush(ctx, m, n, window, monkeypatch):
     assert sums[False] == sums[True]
 
 
+def test_c3_window_follows_entering_column(ctx, monkeypatch):
+    """Automatic window at full size: it starts at the configured 4096 columns, follows the entering
+    column down (1.5 x the highest column seen lately + 256) and up again; the run is the same,
+    bit for bit, as with the width fixed (checksum of all 134 M doubles after every call)."""
+    m, n = 8192, 8191
+    sums, widths = {}, {}
+    for fixed in (False, True):
+        if fixed:
+            monkeypatch.setenv("XP_WINDOW_FIXED", "1")
+        lp = ctx.large_lp(m, n + m + 1)
+        lp.fill_synthetic(2024)
+        sums[fixed], widths[fixed] = [], []
+        for K in range(200, 2001, 200):
+            assert lp.solve(K) == xp.SIX_TIME_OUT
+            widths[fixed].append(lp.window)
+            sums[fixed].append(lp.checksum())
+        lp.close()
+    assert sums[False] == sums[True]
+    assert set(widths[True]) == {4096}
+    assert min(widths[False]) <= 2048 and max(widths[False]) <= 4096, widths[False]
+
+
 def test_lookahead_serialised_launches():
     """What a profiler that serialises kernels makes of the lookahead: the pass cannot start
     beside the cluster, the cluster gives up waiting for it (20 ms) without having touched anything,

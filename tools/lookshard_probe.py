@@ -43,7 +43,7 @@ th = [threading.Thread(target=run, args=(r,)) for r in range(G)]
 [t.join() for t in th]
 print("status", st)
 lib = xp.lib()
-names = "status cnt t kblk blk q slow pivot_pending wseq wb_pending rest_pending rest_slot n_touched xseq xs cseq".split()
+names = "status cnt t kblk blk q slow pivot_pending wseq wb_pending rest_pending rest_slot n_touched wcnt qmax wfail".split()
 for r, lp in enumerate(lps):
     out = (C.c_longlong * 16)()
     lib.xp_lp_f64_debug_state(lp._h, out)

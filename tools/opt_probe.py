@@ -25,7 +25,7 @@ lp.set_window(window)
 lp.set_block(block)
 lp.upload(*sf)
 lib = xp.lib()
-names = "status cnt t kblk blk q slow pivot_pending wseq wb_pending rest_pending rest_slot n_touched xseq xs cseq".split()
+names = "status cnt t kblk blk q slow pivot_pending wseq wb_pending rest_pending rest_slot n_touched wcnt qmax wfail".split()
 done = []
 
 

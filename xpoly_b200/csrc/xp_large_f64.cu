@@ -94,6 +94,7 @@ struct LpState {
     int hist_t[NH];    // pivots of the closed blocks still in the ring (k_block_snapshot)
     unsigned wcnt;     // pivots made by k_wpanel so far (cnt - wcnt: pivots that needed the full-width kernels)
     int wfail;         // the last k_wpanel run ended on a failing ratio test (k_pcol takes that column)
+    int qmax;          // highest entering column k_wpanel has used since the host last looked (k_qmax_reset)
     int rest_pending;  // lookahead: the block in ring slot rest_slot is closed on the window tiles only,
     int rest_slot;     // the tiles beyond the window still owe it (k_flush_w, slot == SLOT_LAG)
     double r, cq, prow_rhs;
@@ -116,7 +117,7 @@ struct XHdr {
     // the peers its exit state + one record per pivot (xoff_rec) + the multiplier columns
     unsigned long long wflag;       // leader -> peer: number of the windowed launch whose results are in place
     unsigned long long wack[MAXR];  // peer -> leader: last windowed launch the peer has consumed
-    int wexit[8];                   // leader -> peer: t, q, anypos, zero_upto, slow, status, ratio test failed
+    int wexit[8];                   // leader -> peer: t, q, anypos, zero_upto, slow, status, ratio test failed, highest q
 };
 constexpr size_t XHDR_BYTES = 1024;
 static_assert(sizeof(XHdr) <= XHDR_BYTES, "exchange header");
@@ -762,6 +763,7 @@ __global__ void __launch_bounds__(TH) k_prow(LpDev d)
         if (s0p < 0) st->touched[st->n_touched++] = p;
         st->t = t + 1;
         st->cnt += 1;
+        if (q > st->qmax) st->qmax = q;
         st->pivot_pending = 0;
         st->q = cand;
         st->anypos = anypos;
@@ -957,6 +959,7 @@ k_panel(LpDev d, PanA *partA, PanB *partB, unsigned long long *bar, unsigned lon
     int slow_out = 0;
     int q_prev = -1, bv_prev = -1; // the pivot whose basis swap CTA 0 may still be writing
     bool dirty = false;
+    int qmx = -1; // highest entering column of this launch (the host sizes the pricing window by it)
     if (go) {
         for (int i = r_lo + tid; i < r_hi; i += TH) {
             s_e2b[i - r_lo] = d.eq2bv[i];
@@ -1268,6 +1271,7 @@ k_panel(LpDev d, PanA *partA, PanB *partB, unsigned long long *bar, unsigned lon
             t++;
             cnt++;
             dirty = true;
+            if (q > qmx) qmx = q;
             q_prev = q;
             bv_prev = bv;
             q = cd;
@@ -1291,6 +1295,7 @@ k_panel(LpDev d, PanA *partA, PanB *partB, unsigned long long *bar, unsigned lon
         st->tg_rhs = tg_rhs;
         st->n_log = n_log;
         st->n_touched = n_touched;
+        if (qmx > st->qmax) st->qmax = qmx;
     }
     if (c == 0 && tid == 0 && go) { // exchange counters advance even if no pivot completed
         st->xseq = xseq;
@@ -1371,6 +1376,8 @@ __global__ void k_timeout(LpDev d)
     LpState *st = d.st;
     if (st->status == XPI_RUNNING && st->cnt >= st->max_iter) st->status = XP_SIX_TIME_OUT;
 }
+
+__global__ void k_qmax_reset(LpDev d) { d.st->qmax = 0; }
 
 // Lookahead: the same snapshot, and the block is closed right here -- before any tile has taken
 // it.  The whole pass is then owed (rest_pending) and runs out of the ring slot beside the next
@@ -2014,8 +2021,6 @@ __global__ void __launch_bounds__(LANES *GROUPS, 2) k_flush_w(LpDev d, ColSet cs
         d.ctr[2] = 0;
         if (lag) { // (runs beside k_wpanel: touches nothing but these two words)
             st->rest_pending = 0;
-            st->wcnt = 0;
-            st->wfail = 0;
             return leave();
         }
         for (int k = 0; k < st->n_touched; k++) d.last_piv[st->touched[k]] = -1;
@@ -2169,6 +2174,9 @@ __global__ void k_init(LpDev d, unsigned max_iter, int kblk, int fresh)
             st->wb_pending = 0;
             for (int k = 0; k < NH; k++) st->hist_t[k] = 0;
             st->rest_pending = 0;
+            st->wcnt = 0;
+            st->wfail = 0;
+            st->qmax = 0;
         } else {
             if (st->status == XP_SIX_TIME_OUT && st->cnt < max_iter) st->status = XPI_RUNNING; // resume
             if (kblk != 0 && st->t == 0) { // kblk < 0: adaptive with upper bound -kblk
@@ -2352,6 +2360,9 @@ struct xp_lp_f64 {
     bool owed = false;
     ColSet owed_pass;
     int owed_kblk = 0;
+    // automatic window: it follows the entering column (see lp_solve); w_max is the configured width
+    int w_max = 0, wwpc_max = 0, q_prev = 0;
+    bool w_auto = false;
     bool pess = true;      // the next batch of blocks carries the general-path kernels (see lp_solve)
     unsigned gen_seen = 0; // pivots made outside k_wpanel as of the last poll
     std::vector<cudaEvent_t> evs;
@@ -2660,6 +2671,7 @@ static int lp_create_fill(xp_ctx *ctx, int m, int C, int rank, int G, xp_lp_f64 
     XP_CUDA_OK(ctx, cudaFuncGetAttributes(&fa, k_flush_w<FT_TR, 64, 4>));
     XP_CUDA_OK(ctx, cudaFuncGetAttributes(&fa, k_block_close));
     XP_CUDA_OK(ctx, cudaFuncGetAttributes(&fa, k_timeout));
+    XP_CUDA_OK(ctx, cudaFuncGetAttributes(&fa, k_qmax_reset));
     XP_CUDA_OK(ctx, cudaFuncGetAttributes(&fa, k_block_snapshot));
     XP_CUDA_OK(ctx, cudaFuncGetAttributes(&fa, k_init));
     XP_CUDA_OK(ctx, cudaFuncGetAttributes(&fa, k_feas_sol));
@@ -2829,6 +2841,11 @@ static int lp_reset(xp_lp_f64 *lp)
     lp->owed = false; // (a fresh LP: k_init clears rest_pending)
     lp->pess = true;  // (the first pricing of a solve is the slow path's)
     lp->gen_seen = 0;
+    if (lp->w_max > 0) { // the window starts at its configured width
+        lp->d.w = lp->w_max;
+        lp->d.wwpc = lp->wwpc_max;
+        lp->q_prev = lp->w_max;
+    }
     const int k = lp->kblk > 0 ? lp->kblk : auto_block(lp->d);
     k_init<<<ctx->sm_count * 2, 256, 0, ctx->stream>>>(lp->d, 0u, k, 1);
     ctx->launches++;
@@ -2971,6 +2988,8 @@ static int window_config(xp_lp_f64 *lp)
     xp_ctx *ctx = lp->ctx;
     LpDev &d = lp->d;
     d.w = d.wrpc = d.wwpc = 0;
+    lp->w_max = lp->wwpc_max = 0;
+    lp->w_auto = false;
     int want = lp->window;
     if (const char *e = getenv("XP_WINDOW"))
         if (want == 0) want = atoi(e);
@@ -3022,6 +3041,10 @@ static int window_config(xp_lp_f64 *lp)
     d.w = w;
     d.wrpc = rpc;
     d.wwpc = wpc;
+    lp->w_max = w;
+    lp->wwpc_max = wpc;
+    lp->q_prev = w;
+    lp->w_auto = want == 0 && !getenv("XP_WINDOW_FIXED");
     return 0;
 }
 
@@ -3130,6 +3153,32 @@ static int lp_solve(xp_lp_f64 *lp, uint32_t max_iter, int rule, bool defer)
     ColSet owed_pass; // window tiles first, then the others
     owed_pass.ct0a = 0, owed_pass.ct1a = look ? d.w / TCW : 0, owed_pass.ct0b = owed_pass.ct1a, owed_pass.ct1b = tiles;
     owed_pass.slot = SLOT_LAG, owed_pass.close = 0;
+    // Automatic window: it follows the entering column.  The reference enters the lowest-index
+    // column with c_j > 0, which on the dense family climbs slowly (0.6 columns per pivot at c3 after
+    // a burst in the first 200); everything the window holds has to be in place before the next
+    // block can be decided, so a window of 1.5 x the highest column seen lately (+ 256, in tiles,
+    // never above the configured width) keeps that serial part short.  Decided where the host polls
+    // the state anyway, from replicated words (every rank of a sharded LP arrives at the same width);
+    // a fresh LP starts at the configured width.  The width is a schedule, not an approximation: a
+    // pivot outside the window takes the full-width kernels, and the window grows.
+    auto adapt_window = [&](const LpState &h) {
+        if (!lp->w_auto || lp->w_max <= 0 || d.w <= 0) return cudaSuccess;
+        int q_hi = h.qmax;
+        if (h.q != INT_BIG && h.q > q_hi) q_hi = h.q;
+        const int q_ref = q_hi > lp->q_prev ? q_hi : lp->q_prev;
+        lp->q_prev = q_hi;
+        long long w_new = ((long long)q_ref + q_ref / 2 + 257 + TCW - 1) / TCW * TCW;
+        if (w_new < 2 * TCW) w_new = 2 * TCW;
+        if (w_new >= lp->w_max) w_new = lp->w_max;
+        if ((int)w_new != d.w) {
+            d.w = (int)w_new;
+            d.wwpc = d.w == lp->w_max ? lp->wwpc_max : (d.w + WNC - 1) / WNC;
+            if (look) owed_pass.ct1a = owed_pass.ct0b = (d.w + TCW - 1) / TCW < tiles ? (d.w + TCW - 1) / TCW : tiles;
+        }
+        k_qmax_reset<<<1, 1, 0, s>>>(d);
+        ctx->launches++;
+        return cudaGetLastError();
+    };
     if (const char *e = getenv("XP_LAG_CHUNK")) owed_pass.chunk = atoi(e); // (tuning)
     if (lp->owed && (!look || lp->owed_kblk != kblk || lp->owed_pass.ct1a != owed_pass.ct1a || lp->owed_pass.chunk != owed_pass.chunk))
         if (int rc = lp_drain(lp)) return rc; // (the schedule changed since the call that left it)
@@ -3244,6 +3293,7 @@ static int lp_solve(xp_lp_f64 *lp, uint32_t max_iter, int rule, bool defer)
         XP_CUDA_OK(ctx, cudaGetLastError());
         XP_CUDA_OK(ctx, cudaMemcpyAsync(lp->h_st, d.st, sizeof(LpState), cudaMemcpyDeviceToHost, s));
         XP_CUDA_OK(ctx, cudaStreamSynchronize(s));
+        XP_CUDA_OK(ctx, adapt_window(*lp->h_st));
         pess = general_needed(*lp->h_st) || !may_skip;
         if (lp->h_st->status != XPI_RUNNING) break;
         unsigned long long left = (unsigned long long)max_iter - lp->h_st->cnt;
@@ -3331,14 +3381,14 @@ extern "C" int xp_lp_f64_profile(xp_lp_f64 *lp, int enable)
 extern "C" int xp_lp_f64_pass_shared_sms(const xp_lp_f64 *lp) { return lp ? lp->shared_sms : 0; }
 
 // (debugging aid, not in the header) status, cnt, t, kblk, blk, q, slow, pivot_pending, wseq,
-// wb_pending, rest_pending, rest_slot, n_touched, xseq, xs, cseq of the device state
+// wb_pending, rest_pending, rest_slot, n_touched, wcnt, qmax, wfail of the device state
 extern "C" int xp_lp_f64_debug_state(xp_lp_f64 *lp, long long *out16)
 {
     if (!lp || !out16) return XP_ERR_BAD_ARG;
     LpState h;
     if (cudaMemcpy(&h, lp->d.st, sizeof h, cudaMemcpyDeviceToHost) != cudaSuccess) return XP_ERR_CUDA;
     const long long v[16] = {h.status, h.cnt, h.t, h.kblk, h.blk, h.q, h.slow, h.pivot_pending, h.wseq, h.wb_pending,
-                             h.rest_pending, h.rest_slot, h.n_touched, h.xseq, h.xs, h.cseq};
+                             h.rest_pending, h.rest_slot, h.n_touched, h.wcnt, h.qmax, h.wfail};
     for (int k = 0; k < 16; k++) out16[k] = v[k];
     return 0;
 }
@@ -3717,7 +3767,7 @@ static int two_stage_streamed(xp_ctx *ctx, xp_lp_f64 *lp, int m, int n, const do
                               const double *d_tg, const double *d_b, uint32_t max_iter)
 {
     LpDev &d = lp->d;
-    const int TCW = 4 * FW_LANES, C = d.C, w = d.w;
+    const int TCW = 4 * FW_LANES, C = d.C, w = lp->w_max > 0 ? lp->w_max : d.w; // (the configured width: a fresh LP starts there)
     const int kblk = lp->kblk > 0 ? lp->kblk : auto_block(d);
     if (getenv("XP_NO_STREAM_UPLOAD")) return 0;
     if (!lp->use_panel || w <= 0 || w % TCW || n <= w + TCW || !lp->ft_wide || (d.Cl & 1)) return 0;

@@ -195,6 +195,7 @@ __global__ void __launch_bounds__(WTHB, 1) k_wpanel(LpDev d, unsigned long long 
     int cur = 0;      // s_rh buffer holding the constant column as of now
     unsigned xn = 0;  // exchanges so far (slot = xn & 1)
     int slow_out = 0, fail_out = 0; // how the run ended: re-price on the slow path / the ratio test on q failed
+    int qmx = q; // highest entering column of this run (the host sizes the window by it)
     WRec *recs[MAXR];
     for (int r = 0; r < G; r++) recs[r] = (WRec *)(d.xb[r] + xoff_rec(d, par));
 
@@ -436,6 +437,7 @@ __global__ void __launch_bounds__(WTHB, 1) k_wpanel(LpDev d, unsigned long long 
         cnt++;
         cur ^= 1;
         q = cd;
+        if (cd != INT_BIG && cd > qmx) qmx = cd;
         anypos = ap;
         cq = cq_next;
         zero_upto = cd == INT_BIG ? 0 : cd;
@@ -458,6 +460,7 @@ __global__ void __launch_bounds__(WTHB, 1) k_wpanel(LpDev d, unsigned long long 
             st->zero_upto = zero_upto;
             st->slow = slow_out;
             st->wfail = fail_out;
+            if (qmx > st->qmax) st->qmax = qmx;
             st->tg_rhs = tg_rhs;
             st->n_log = n_log;
             st->n_touched = n_touched;
@@ -470,7 +473,7 @@ __global__ void __launch_bounds__(WTHB, 1) k_wpanel(LpDev d, unsigned long long 
         if (G > 1 && lane > 0 && lane < G) { // exit state for peer `lane`, then the flag
             XHdr *H = (XHdr *)d.xb[lane];
             H->wexit[0] = t, H->wexit[1] = q, H->wexit[2] = anypos, H->wexit[3] = zero_upto;
-            H->wexit[4] = slow_out, H->wexit[5] = bad ? XP_ERR_PEER : XPI_RUNNING, H->wexit[6] = fail_out;
+            H->wexit[4] = slow_out, H->wexit[5] = bad ? XP_ERR_PEER : XPI_RUNNING, H->wexit[6] = fail_out, H->wexit[7] = qmx;
         }
     }
     if (G > 1) {
@@ -517,6 +520,7 @@ __global__ void k_wpanel_peer(LpDev d)
     st->zero_upto = we[3];
     st->slow = we[4];
     st->wfail = we[6];
+    if (we[7] > st->qmax) st->qmax = we[7];
     if (we[5] != XPI_RUNNING) st->status = we[5];
     st->wb_t0 = t;
     st->wb_pending = t1 > t;
