@@ -3044,7 +3044,9 @@ static int window_config(xp_lp_f64 *lp)
     lp->w_max = w;
     lp->wwpc_max = wpc;
     lp->q_prev = w;
-    lp->w_auto = want == 0 && !getenv("XP_WINDOW_FIXED");
+    // (following the entering column pays where the slice of rank 0 is much wider than the window,
+    // so that the pass over the rest hides the cluster: measured at c3, 2 GPUs +11 %, 4 GPUs -4 %)
+    lp->w_auto = want == 0 && Cl0 >= 2 * w && !getenv("XP_WINDOW_FIXED");
     return 0;
 }
 
@@ -3143,11 +3145,12 @@ static int lp_solve(xp_lp_f64 *lp, uint32_t max_iter, int rule, bool defer)
     // closed at once (k_block_close) and the tableau slice takes it one step later, beside the
     // next block's k_wpanel.  The peers of a sharded LP keep the plain order -- the launches that
     // talk to each other (k_wpanel / k_wpanel_peer, k_pcol, k_prow, k_panel) stay paired -- and so
-    // does a leader whose slice ends with the window (4 and 8 GPUs at c3: nothing to overlap).
+    // does a leader whose slice is (nearly) all window: with less than a quarter of its tiles
+    // to overlap, the pass is better off with the whole device and no cluster beside it.
     constexpr int TCW = 4 * FW_LANES;
     const int tiles = (d.Cl + TCW - 1) / TCW;
     const bool look = lp->use_panel && d.w > 0 && d.rank == 0 && (d.Cl & 1) == 0 && lp->ft_wide && kblk >= lp->ft_min &&
-                      kblk >= lp->ft_balanced_min && d.w % TCW == 0 && d.w / TCW < tiles && ctx->sm_count > 2 * WNC &&
+                      kblk >= lp->ft_balanced_min && d.w % TCW == 0 && 4 * (d.w / TCW) <= 3 * tiles && ctx->sm_count > 2 * WNC &&
                       !getenv("XP_NO_LOOKAHEAD");
     lp->shared_sms = look ? WNC : 0;
     ColSet owed_pass; // window tiles first, then the others
