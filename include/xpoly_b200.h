@@ -140,8 +140,11 @@ int xp_ctx_set_block(xp_ctx *ctx, int pivots_per_flush); /* for xp_six_slack_f64
  * rows for that window only, and everything to its right is brought up to date once per
  * block.  Same operations per entry in the same order, hence the same bits; a pricing
  * scan that leaves the window falls back to the full-width kernels for that pivot.
- * width: 0 = automatic (on for large LPs), < 0 = off, > 0 = forced.  Every rank of a
- * sharded LP must make the same call; takes effect at the next solve. */
+ * width: 0 = automatic (on for large LPs: at most 4096 columns, and where rank 0's slice is at
+ * least twice that the width follows the entering column -- 1.5 x the highest column used lately
+ * + 256 -- since everything inside the window has to be in place before the next block can be
+ * decided), < 0 = off, > 0 = forced.  xp_lp_f64_window() returns the width in use right now.
+ * Every rank of a sharded LP must make the same call; takes effect at the next solve. */
 int xp_lp_f64_set_window(xp_lp_f64 *lp, int width);
 int xp_lp_f64_window(const xp_lp_f64 *lp); /* width in use (0 = off) */
 int xp_ctx_set_window(xp_ctx *ctx, int width); /* for xp_six_slack_f64 / xp_six_two_stage_f64_large */
