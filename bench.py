@@ -665,7 +665,9 @@ def run_ours(args):
     flush_avg_ms = main["flush_ms"] / max(main["flushes"], 1)
     moved = 2.0 * m * local_cols * 8  # one read + one write of the slice per launch
     traffic = None
-    for prof in ("r02_flush_ncu_full.json", "r01_flush_ncu_full.json"):
+    # (the kernel as the timed schedule launches it: replaying out of the ring beside the cluster
+    # when the lookahead is on, the plain pass otherwise)
+    for prof in (("r02_flush_lag_ncu_full.json",) if shared_sms else ()) + ("r02_flush_ncu_full.json", "r01_flush_ncu_full.json"):
         pth = os.path.join(ROOT, "profiles", prof)
         if os.path.exists(pth) and world == 1:
             try:
