@@ -237,12 +237,14 @@ def run_batched(ctx, xp, torch, dev, with_cpu=True, rank=0, world=1, dist=None):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-    g = torch.Generator(device=dev)
-    g.manual_seed(SEED + rank)
-    leq = torch.rand((B, m, n + 1), dtype=torch.float64, device=dev, generator=g)
-    leq[:, :, n] = 1.0 + leq[:, :, n] * n
-    tg = torch.rand((B, n + 1), dtype=torch.float64, device=dev, generator=g)
-    tg[:, n] = 0.0
+    # LP k of the batch comes from std::mt19937_64(2024 + k) (A_ij ~ U(0,1) row by row
+    # with b_i = 1 + U * n, then c_j ~ U(0,1)); generated on the host, outside any timed region
+    from xpoly_b200 import synth
+    lo_k = Btot * rank // world
+    h_leq, h_tg = synth.dense_lp_batch(2024 + lo_k, B, m, n)
+    leq = torch.from_numpy(h_leq).to(dev)
+    tg = torch.from_numpy(h_tg).to(dev)
+    del h_leq, h_tg
     status = torch.zeros(B, dtype=torch.int32, device=dev)
     maxv = torch.zeros(B, dtype=torch.float64, device=dev)
     pivots = torch.zeros(B, dtype=torch.int32, device=dev)
@@ -322,7 +324,7 @@ def run_batched(ctx, xp, torch, dev, with_cpu=True, rank=0, world=1, dist=None):
     fp64_ops = tot_piv * 2.0 * (m + 1) * (n + m + 1)
     fp64_peak = ctx_sm_count(torch, dev) * 64 * sm_clock_hz(torch, dev)
     return {
-        "metric": "small LPs/s", "workload": f"c2: {Btot} LPs, tableau {m}x{n + m + 1}, FP64"
+        "metric": "small LPs/s", "workload": f"c2: {Btot} LPs, tableau {m}x{n + m + 1}, FP64, LP k drawn from std::mt19937_64(2024 + k)"
                                              + (f", split over {world} GPUs" if world > 1 else ""),
         "value": Btot / (dev_ms * 1e-3), "unit": "LPs/s", "ms": dev_ms, "scaling": "strong",
         "pivots_total": tot_piv, "pivots_per_s": tot_piv / (dev_ms * 1e-3),

@@ -131,11 +131,10 @@ def test_c2_full_batch_100k(ctx):
     in the batch (reversed order gives the reversed results, bit for bit); (b) a ragged launch of
     the same LPs agrees with the uniform one; (c) a random sample of 200 LPs equals the oracle."""
     B, m, n = 100_000, 32, 31
+    from xpoly_b200 import synth
     r = np.random.RandomState(2024)
-    leq = r.uniform(0, 1, size=(B, m, n + 1))
-    leq[:, :, n] = 1.0 + leq[:, :, n] * n
-    tg = r.uniform(0, 1, size=(B, n + 1))
-    tg[:, n] = 0.0
+    leq, tg = synth.dense_lp_batch(2024, B, m, n)  # SURVEY 8(d): LP k from std::mt19937_64(2024 + k)
+    mix = None
     a = ctx.two_stage_f64_batch(leq, tg)
     b = ctx.two_stage_f64_batch(leq[::-1].copy(), tg[::-1].copy())
     # (d) the shared-memory CTA kernel, forced, gives the same bits on all 100 000 LPs as the
@@ -150,6 +149,8 @@ def test_c2_full_batch_100k(ctx):
     for k in ("maxv", "slack_sol", "tgtf"):
         assert np.array_equal(H.bits(a[k]), H.bits(b[k][::-1])), k
     assert set(np.unique(a["status"])) <= {0, 1, 3}
+    mix = {k: float((a["status"] == k).mean()) for k in (0, 1, 3)}
+    assert 0.40 < mix[0] < 0.60 and 0.40 < mix[3] < 0.60 and mix[1] < 0.05, mix  # SURVEY: ~49 / 50 / 1.6 %
     idx = r.choice(B, size=200, replace=False)
     rag = ctx.two_stage_f64_ragged([(leq[k], tg[k]) for k in idx[:64]])
     for j, k in enumerate(idx[:64]):
